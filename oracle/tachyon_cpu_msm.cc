@@ -1,0 +1,885 @@
+// ORACLE — TEST INFRASTRUCTURE ONLY.  Not part of the product.
+//
+// CPU restatement of Tachyon's variable-base MSM path (the parity oracle and
+// the timed CPU baseline).  Only tests/, __graft_entry__.smoke() and bench.py's
+// cpu_baseline / --impl reference legs may load this library.  The product
+// (tachyon_b200/csrc) never links, loads or calls anything in here.
+//
+// The reference itself cannot be built in this image (Bazel 6.3 + generated
+// headers + abseil/glog/gmp/perfetto, none present), so this file restates the
+// algorithm; every function cites the reference file:line it follows (paths
+// relative to /root/reference).  Pinning: the reference holds no fixed-input
+// MSM vector (all of its MSM tests draw from a non-deterministically seeded
+// RNG), so the oracle is pinned against what the reference's tests DO fix:
+//   * the GF(7) toy-curve KATs of short_weierstrass/point_xyzz_unittest.cc:77-166
+//     (add / mixed add / double / negate / conversions), run through the same
+//     templates with a GF(7) field (tests/test_oracle_kats.py);
+//   * the curve/field constants in bn/bn254/BUILD.bazel and
+//     bls12/bls12_381/BUILD.bazel (moduli, b, generators);
+//   * the decimal KATs of vendors/circom/circomlib/zkey/zkey_unittest.cc:57-80
+//     against the Montgomery bytes of vendors/circom/examples/multiplier_3.zkey
+//     (pins R = 2^256, limb order, from-Montgomery);
+//   * the reference's relation tests restated with fixed seeds
+//     (MSM == naive sum, all Pippenger strategies agree), plus an independent
+//     pure-Python big-int model (oracle/pymodel.py).
+//
+// Build: see oracle/Makefile (g++ -O3 -march=x86-64-v3 -fopenmp -shared -fPIC).
+
+#include <stddef.h>
+#include <stdint.h>
+#include <string.h>
+
+#include <algorithm>
+#include <cmath>
+#include <vector>
+
+#if defined(_OPENMP)
+#include <omp.h>
+#endif
+
+namespace {
+
+using u64 = uint64_t;
+using u128 = unsigned __int128;
+
+// ---------------------------------------------------------------------------
+// BigInt<N>  (tachyon/math/base/big_int.h)
+// ---------------------------------------------------------------------------
+template <size_t N>
+struct BigInt {
+  u64 v[N];
+
+  static BigInt Zero() {
+    BigInt r;
+    for (size_t i = 0; i < N; ++i) r.v[i] = 0;
+    return r;
+  }
+  static BigInt One() {
+    BigInt r = Zero();
+    r.v[0] = 1;
+    return r;
+  }
+  bool IsZero() const {
+    u64 acc = 0;
+    for (size_t i = 0; i < N; ++i) acc |= v[i];
+    return acc == 0;
+  }
+  bool operator==(const BigInt& o) const {
+    for (size_t i = 0; i < N; ++i)
+      if (v[i] != o.v[i]) return false;
+    return true;
+  }
+  // lexicographic from the most significant limb (big_int.h operator<)
+  bool operator<(const BigInt& o) const {
+    for (size_t i = N; i-- > 0;) {
+      if (v[i] != o.v[i]) return v[i] < o.v[i];
+    }
+    return false;
+  }
+  bool operator>=(const BigInt& o) const { return !(*this < o); }
+
+  // returns carry out
+  u64 AddInPlace(const BigInt& o) {
+    u64 carry = 0;
+    for (size_t i = 0; i < N; ++i) {
+      u128 t = (u128)v[i] + o.v[i] + carry;
+      v[i] = (u64)t;
+      carry = (u64)(t >> 64);
+    }
+    return carry;
+  }
+  // returns borrow out
+  u64 SubInPlace(const BigInt& o) {
+    u64 borrow = 0;
+    for (size_t i = 0; i < N; ++i) {
+      u128 t = (u128)v[i] - o.v[i] - borrow;
+      v[i] = (u64)t;
+      borrow = (u64)(t >> 64) & 1;
+    }
+    return borrow;
+  }
+  u64 MulBy2InPlace() {
+    u64 carry = 0;
+    for (size_t i = 0; i < N; ++i) {
+      u64 nc = v[i] >> 63;
+      v[i] = (v[i] << 1) | carry;
+      carry = nc;
+    }
+    return carry;
+  }
+  void DivBy2InPlace() {
+    for (size_t i = 0; i < N; ++i) {
+      u64 hi = (i + 1 < N) ? (v[i + 1] << 63) : 0;
+      v[i] = (v[i] >> 1) | hi;
+    }
+  }
+  bool Bit(size_t i) const { return (v[i / 64] >> (i % 64)) & 1; }
+
+  // big_int.h:1015-1039 ExtractBits<uint64_t>: bit_count bits starting at
+  // bit_offset, straddling at most two limbs, zero-extended past the top.
+  u64 ExtractBits64(size_t bit_offset, size_t bit_count) const {
+    size_t limb_idx = bit_offset / 64;
+    size_t bit_idx = bit_offset % 64;
+    u64 ret;
+    if (limb_idx >= N) return 0;  // (reference never reads past N-1; W*c may)
+    if (bit_idx < 64 - bit_count || limb_idx == N - 1) {
+      ret = v[limb_idx] >> bit_idx;
+    } else {
+      ret = (v[limb_idx] >> bit_idx) | (v[limb_idx + 1] << (64 - bit_idx));
+    }
+    u64 mask = (u64{1} << bit_count) - 1;
+    return ret & mask;
+  }
+};
+
+// ---------------------------------------------------------------------------
+// Montgomery prime field (tachyon/math/finite_fields/prime_field_fallback.h,
+// constants per finite_fields/modulus.h:45-87)
+// ---------------------------------------------------------------------------
+template <size_t N_>
+struct FieldParams {
+  static constexpr size_t N = N_;
+  BigInt<N> modulus;
+  u64 inv64;      // -p^-1 mod 2^64               (modulus.h Inverse<uint64_t>)
+  BigInt<N> r;    // 2^(64N) mod p  == One()      (modulus.h MontgomeryR)
+  BigInt<N> r2;   // 2^(128N) mod p               (modulus.h MontgomeryR2)
+  unsigned bits;  // kModulusBits
+
+  void Init(const u64* mod) {
+    for (size_t i = 0; i < N; ++i) modulus.v[i] = mod[i];
+    // Newton iteration for p^-1 mod 2^64, then negate.
+    u64 inv = 1;
+    for (int i = 0; i < 63; ++i) {
+      inv *= inv;
+      inv *= mod[0];
+    }
+    inv64 = ~inv + 1;
+    // R and R^2 by repeated modular doubling.
+    BigInt<N> x = BigInt<N>::One();
+    for (size_t i = 0; i < 128 * N; ++i) {
+      u64 c = x.MulBy2InPlace();
+      if (c || x >= modulus) x.SubInPlace(modulus);
+      if (i + 1 == 64 * N) r = x;
+    }
+    r2 = x;
+    bits = 0;
+    for (size_t i = 0; i < 64 * N; ++i)
+      if (modulus.Bit(i)) bits = (unsigned)i + 1;
+  }
+};
+
+// Tag types give each field its own static parameter block.
+template <typename Tag, size_t N_>
+struct Fp {
+  static constexpr size_t N = N_;
+  static FieldParams<N_> P;
+  BigInt<N> v;  // Montgomery form, fully reduced
+
+  static Fp Zero() { return Fp{BigInt<N>::Zero()}; }
+  static Fp One() { return Fp{P.r}; }
+  bool IsZero() const { return v.IsZero(); }
+  bool IsOne() const { return v == P.r; }
+  bool operator==(const Fp& o) const { return v == o.v; }
+  bool operator!=(const Fp& o) const { return !(v == o.v); }
+
+  // big_int.h:279-291 Clamp: subtract p once if carry or value >= p.
+  static void Clamp(BigInt<N>* x, u64 carry) {
+    if (carry || *x >= P.modulus) x->SubInPlace(P.modulus);
+  }
+  // prime_field_fallback.h:199-206
+  Fp Add(const Fp& o) const {
+    Fp r = *this;
+    u64 c = r.v.AddInPlace(o.v);
+    Clamp(&r.v, c);
+    return r;
+  }
+  // :216-223
+  Fp Double() const {
+    Fp r = *this;
+    u64 c = r.v.MulBy2InPlace();
+    Clamp(&r.v, c);
+    return r;
+  }
+  // :234-243
+  Fp Sub(const Fp& o) const {
+    Fp r = *this;
+    if (r.v < o.v) r.v.AddInPlace(P.modulus);
+    r.v.SubInPlace(o.v);
+    return r;
+  }
+  // :253-260
+  Fp Neg() const {
+    if (IsZero()) return *this;
+    Fp r{P.modulus};
+    r.v.SubInPlace(v);
+    return r;
+  }
+  // :331-355 DoFastMul — CIOS with interleaved reduction; final Clamp.
+  // Carry handling is written for the general case (one extra word) so the
+  // same template also serves moduli without a spare bit and GF(7).
+  Fp Mul(const Fp& o) const {
+    u64 t[N + 2];
+    for (size_t i = 0; i < N + 2; ++i) t[i] = 0;
+    for (size_t i = 0; i < N; ++i) {
+      u64 carry = 0;
+      for (size_t j = 0; j < N; ++j) {
+        u128 x = (u128)v.v[j] * o.v.v[i] + t[j] + carry;
+        t[j] = (u64)x;
+        carry = (u64)(x >> 64);
+      }
+      u128 s = (u128)t[N] + carry;
+      t[N] = (u64)s;
+      t[N + 1] = (u64)(s >> 64);
+      u64 k = t[0] * P.inv64;
+      u128 x = (u128)k * P.modulus.v[0] + t[0];
+      carry = (u64)(x >> 64);
+      for (size_t j = 1; j < N; ++j) {
+        x = (u128)k * P.modulus.v[j] + t[j] + carry;
+        t[j - 1] = (u64)x;
+        carry = (u64)(x >> 64);
+      }
+      s = (u128)t[N] + carry;
+      t[N - 1] = (u64)s;
+      t[N] = t[N + 1] + (u64)(s >> 64);
+    }
+    Fp r;
+    for (size_t i = 0; i < N; ++i) r.v.v[i] = t[i];
+    Clamp(&r.v, t[N]);
+    return r;
+  }
+  // :364-394 DoSquareImpl (same value as Mul(*this); kept as Mul for brevity)
+  Fp Square() const { return Mul(*this); }
+
+  // Canonical (non-Montgomery) integer. prime_field_fallback.h:166-169 ->
+  // big_int.h:1049-1076 FromMontgomery: N rounds of word-wise reduction.
+  BigInt<N> ToBigInt() const {
+    u64 t[N];
+    for (size_t i = 0; i < N; ++i) t[i] = v.v[i];
+    for (size_t i = 0; i < N; ++i) {
+      u64 k = t[0] * P.inv64;
+      u128 x = (u128)k * P.modulus.v[0] + t[0];
+      u64 carry = (u64)(x >> 64);
+      for (size_t j = 1; j < N; ++j) {
+        x = (u128)k * P.modulus.v[j] + t[j] + carry;
+        t[j - 1] = (u64)x;
+        carry = (u64)(x >> 64);
+      }
+      t[N - 1] = carry;
+    }
+    BigInt<N> r;
+    for (size_t i = 0; i < N; ++i) r.v[i] = t[i];
+    return r;
+  }
+  // canonical -> Montgomery: x * R^2 * R^-1
+  static Fp FromBigInt(const BigInt<N>& x) { return Fp{x}.Mul(Fp{P.r2}); }
+  static Fp FromU64(u64 x) {
+    BigInt<N> b = BigInt<N>::Zero();
+    b.v[0] = x;
+    return FromBigInt(b);
+  }
+  // Reference uses a Bernstein-Yang inverter (prime_field_fallback.h:309-316);
+  // the inverse is unique, so Fermat gives the identical field element.
+  Fp Inverse() const {
+    BigInt<N> e = P.modulus;
+    BigInt<N> two = BigInt<N>::Zero();
+    two.v[0] = 2;
+    e.SubInPlace(two);
+    Fp result = One();
+    for (size_t i = P.bits; i-- > 0;) {
+      result = result.Square();
+      if (e.Bit(i)) result = result.Mul(*this);
+    }
+    return result;
+  }
+};
+template <typename Tag, size_t N_>
+FieldParams<N_> Fp<Tag, N_>::P;
+
+// ---------------------------------------------------------------------------
+// Short-Weierstrass points, a = 0
+// (tachyon/math/elliptic_curves/short_weierstrass/*)
+// ---------------------------------------------------------------------------
+template <typename Fq>
+struct Affine {
+  Fq x, y;
+  // affine_point.h:125 — the identity is encoded as (0, 0)
+  bool IsZero() const { return x.IsZero() && y.IsZero(); }
+  // affine_point.h:168
+  Affine Neg() const { return Affine{x, y.Neg()}; }
+};
+
+template <typename Fq>
+struct Jacobian {
+  Fq x, y, z;
+};
+
+template <typename Fq>
+struct XYZZ {
+  Fq x, y, zz, zzz;
+
+  // point_xyzz.h:37-39 / Zero(): (1, 1, 0, 0)
+  static XYZZ Zero() { return XYZZ{Fq::One(), Fq::One(), Fq::Zero(), Fq::Zero()}; }
+  // point_xyzz.h:193
+  bool IsZero() const { return zz.IsZero(); }
+  static XYZZ FromAffine(const Affine<Fq>& p) {
+    if (p.IsZero()) return Zero();
+    return XYZZ{p.x, p.y, Fq::One(), Fq::One()};
+  }
+  XYZZ Neg() const { return XYZZ{x, y.Neg(), zz, zzz}; }
+
+  // point_xyzz_impl.h:199-236 DoDoubleImpl (dbl-2008-s-1, a = 0)
+  XYZZ Double() const {
+    if (IsZero()) return Zero();
+    Fq u = y.Double();
+    Fq vv = u.Square();
+    Fq w = u.Mul(vv);
+    Fq s = x.Mul(vv);
+    Fq m = x.Square();
+    m = m.Add(m.Double());
+    XYZZ r;
+    r.x = m.Square().Sub(s.Double());
+    r.y = m.Mul(s.Sub(r.x)).Sub(w.Mul(y));
+    r.zz = vv.Mul(zz);
+    r.zzz = w.Mul(zzz);
+    return r;
+  }
+
+  // point_xyzz_impl.h:14-97 Add / DoAdd (add-2008-s)
+  XYZZ Add(const XYZZ& b) const {
+    if (IsZero()) return b;
+    if (b.IsZero()) return *this;
+    Fq u1 = x.Mul(b.zz);
+    Fq s1 = y.Mul(b.zzz);
+    Fq p = b.x.Mul(zz).Sub(u1);
+    Fq r = b.y.Mul(zzz).Sub(s1);
+    if (p.IsZero() && r.IsZero()) return Double();
+    Fq pp = p.Square();
+    Fq ppp = p.Mul(pp);
+    Fq q = u1.Mul(pp);
+    XYZZ c;
+    c.x = r.Square().Sub(ppp).Sub(q.Double());
+    c.y = r.Mul(q.Sub(c.x)).Sub(s1.Mul(ppp));
+    c.zz = zz.Mul(b.zz).Mul(pp);
+    c.zzz = zzz.Mul(b.zzz).Mul(ppp);
+    return c;
+  }
+
+  // point_xyzz_impl.h:99-176 Add(AffinePoint) / DoAdd (madd-2008-s)
+  XYZZ AddAffine(const Affine<Fq>& b) const {
+    if (IsZero()) return FromAffine(b);
+    if (b.IsZero()) return *this;
+    Fq p = b.x.Mul(zz).Sub(x);
+    Fq r = b.y.Mul(zzz).Sub(y);
+    if (p.IsZero() && r.IsZero()) return Double();
+    Fq pp = p.Square();
+    Fq ppp = p.Mul(pp);
+    Fq q = x.Mul(pp);
+    XYZZ c;
+    c.x = r.Square().Sub(ppp).Sub(q.Double());
+    c.y = r.Mul(q.Sub(c.x)).Sub(y.Mul(ppp));
+    c.zz = zz.Mul(pp);
+    c.zzz = zzz.Mul(ppp);
+    return c;
+  }
+
+  // point_xyzz.h:199-213 ToAffine: (X/ZZ, Y/ZZZ)
+  Affine<Fq> ToAffine() const {
+    if (IsZero()) return Affine<Fq>{Fq::Zero(), Fq::Zero()};
+    if (zz.IsOne()) return Affine<Fq>{x, y};
+    Fq z_inv_cubic = zzz.Inverse();
+    Fq z_inv_square = z_inv_cubic.Mul(zz).Square();
+    return Affine<Fq>{x.Mul(z_inv_square), y.Mul(z_inv_cubic)};
+  }
+  // point_xyzz.h:228-237 ToJacobian: (X*ZZZ*Z, Y*ZZ*Z^2, Z = ZZ*ZZZ)
+  Jacobian<Fq> ToJacobian() const {
+    if (IsZero()) return Jacobian<Fq>{Fq::One(), Fq::One(), Fq::Zero()};
+    if (zz.IsOne()) return Jacobian<Fq>{x, y, Fq::One()};
+    Fq z = zz.Mul(zzz);
+    return Jacobian<Fq>{x.Mul(zzz).Mul(z), y.Mul(zz).Mul(z.Square()), z};
+  }
+};
+
+// jacobian_point.h:201-213 ToAffine: (X/Z^2, Y/Z^3); identity -> (0,0)
+template <typename Fq>
+Affine<Fq> JacobianToAffine(const Jacobian<Fq>& p) {
+  if (p.z.IsZero()) return Affine<Fq>{Fq::Zero(), Fq::Zero()};
+  if (p.z.IsOne()) return Affine<Fq>{p.x, p.y};
+  Fq zi = p.z.Inverse();
+  Fq zi2 = zi.Square();
+  return Affine<Fq>{p.x.Mul(zi2), p.y.Mul(zi2.Mul(zi))};
+}
+
+// ---------------------------------------------------------------------------
+// MSM  (tachyon/math/elliptic_curves/msm/*)
+// ---------------------------------------------------------------------------
+
+// msm_ctx.h:31-43
+unsigned ComputeWindowsBits(size_t size) {
+  if (size < 32) return 3;
+  return (unsigned)(std::log2((double)size) * 69 / 100) + 2;
+}
+// msm_ctx.h:45-48
+unsigned ComputeWindowsCount(unsigned modulus_bits, unsigned window_bits) {
+  return (modulus_bits + window_bits - 1) / window_bits;
+}
+
+// pippenger.h:27-51 FillDigits
+template <size_t N>
+void FillDigits(const BigInt<N>& scalar, size_t window_bits, int64_t* digits,
+                size_t num_digits) {
+  u64 radix = u64{1} << window_bits;
+  u64 carry = 0;
+  size_t bit_offset = 0;
+  for (size_t i = 0; i < num_digits; ++i) {
+    u64 bits = scalar.ExtractBits64(bit_offset, window_bits);
+    u64 coeff = carry + bits;
+    carry = (coeff + radix / 2) >> window_bits;
+    digits[i] = (int64_t)coeff - (int64_t)(carry << window_bits);
+    bit_offset += window_bits;
+  }
+  digits[num_digits - 1] += (int64_t)(carry << window_bits);
+}
+
+template <typename Fq>
+XYZZ<Fq> AccumulateBuckets(const std::vector<XYZZ<Fq>>& buckets) {
+  // pippenger_base.h:36-57: running sum from the top bucket down.
+  XYZZ<Fq> running = XYZZ<Fq>::Zero();
+  XYZZ<Fq> window = XYZZ<Fq>::Zero();
+  for (size_t k = buckets.size(); k-- > 0;) {
+    running = running.Add(buckets[k]);
+    window = window.Add(running);
+  }
+  return window;
+}
+
+template <typename Fq>
+XYZZ<Fq> AccumulateWindowSums(const std::vector<XYZZ<Fq>>& sums, size_t c) {
+  // pippenger_base.h:59-77: Horner from the highest window; `lowest` is added
+  // last without doubling.
+  XYZZ<Fq> total = XYZZ<Fq>::Zero();
+  for (size_t w = sums.size(); w-- > 1;) {
+    total = total.Add(sums[w]);
+    for (size_t i = 0; i < c; ++i) total = total.Double();
+  }
+  return sums[0].Add(total);
+}
+
+// pippenger.h:68-110 Run with use_msm_window_naf_ = true (affine bases:
+// kNegationIsCheap), windows optionally in parallel (:155-169).
+template <typename Fq, typename Fr>
+XYZZ<Fq> Pippenger(const Affine<Fq>* bases, const Fr* scalars, size_t n,
+                   bool parallel_windows) {
+  unsigned c = ComputeWindowsBits(n);
+  unsigned W = ComputeWindowsCount(Fr::P.bits, c);
+  // pippenger.h:91-96
+  std::vector<int64_t> digits(n * (size_t)W);
+  for (size_t i = 0; i < n; ++i) {
+    auto s = scalars[i].ToBigInt();
+    FillDigits(s, c, &digits[i * W], W);  // :143-153
+  }
+  std::vector<XYZZ<Fq>> window_sums(W);
+  auto one_window = [&](size_t w) {
+    // pippenger.h:112-135 AccumulateSingleWindowNAFSum
+    size_t nb = (w == W - 1) ? (size_t{1} << c) : (size_t{1} << (c - 1));
+    std::vector<XYZZ<Fq>> buckets(nb, XYZZ<Fq>::Zero());
+    for (size_t j = 0; j < n; ++j) {
+      int64_t d = digits[j * W + w];
+      if (d > 0) {
+        buckets[(size_t)(d - 1)] = buckets[(size_t)(d - 1)].AddAffine(bases[j]);
+      } else if (d < 0) {
+        buckets[(size_t)(-d - 1)] =
+            buckets[(size_t)(-d - 1)].AddAffine(bases[j].Neg());
+      }
+    }
+    window_sums[w] = AccumulateBuckets(buckets);
+  };
+  if (parallel_windows) {
+#pragma omp parallel for schedule(dynamic, 1)
+    for (size_t w = 0; w < W; ++w) one_window(w);
+  } else {
+    for (size_t w = 0; w < W; ++w) one_window(w);
+  }
+  return AccumulateWindowSums(window_sums, c);
+}
+
+// pippenger_adapter.h:27-116, strategy kParallelTerm (the default of
+// VariableBaseMSM::Run, variable_base_msm.h:20-36): contiguous chunks of
+// ceil(n / threads) (base/openmp_util.h:38-48, base/parallelize.h:194-210),
+// one independent Pippenger per chunk, partial sums added in order.
+template <typename Fq, typename Fr>
+XYZZ<Fq> MsmParallelTerm(const Affine<Fq>* bases, const Fr* scalars, size_t n,
+                         int threads) {
+  if (n == 0) return XYZZ<Fq>::Zero();  // :62-65
+  if (threads < 1) threads = 1;
+  size_t chunk = (n + (size_t)threads - 1) / (size_t)threads;
+  size_t num_chunks = (n + chunk - 1) / chunk;
+  std::vector<XYZZ<Fq>> partial(num_chunks);
+#pragma omp parallel for num_threads(threads) schedule(static, 1)
+  for (size_t i = 0; i < num_chunks; ++i) {
+    size_t start = i * chunk;
+    size_t len = std::min(chunk, n - start);
+    partial[i] = Pippenger<Fq, Fr>(bases + start, scalars + start, len, false);
+  }
+  XYZZ<Fq> total = XYZZ<Fq>::Zero();
+  for (size_t i = 0; i < num_chunks; ++i) total = total.Add(partial[i]);
+  return total;
+}
+
+// The naive answer of the reference's tests
+// (msm/test/variable_base_msm_test_set.h:96-104): sum of base * scalar by
+// double-and-add over the canonical scalar bits.
+template <typename Fq, size_t NS>
+XYZZ<Fq> ScalarMul(const XYZZ<Fq>& p, const BigInt<NS>& k) {
+  XYZZ<Fq> acc = XYZZ<Fq>::Zero();
+  for (size_t i = 64 * NS; i-- > 0;) {
+    acc = acc.Double();
+    if (k.Bit(i)) acc = acc.Add(p);
+  }
+  return acc;
+}
+template <typename Fq, typename Fr>
+XYZZ<Fq> MsmNaive(const Affine<Fq>* bases, const Fr* scalars, size_t n) {
+  XYZZ<Fq> total = XYZZ<Fq>::Zero();
+  for (size_t i = 0; i < n; ++i) {
+    total = total.Add(ScalarMul(XYZZ<Fq>::FromAffine(bases[i]), scalars[i].ToBigInt()));
+  }
+  return total;
+}
+
+// ---------------------------------------------------------------------------
+// Deterministic synthetic inputs.  The reference's generators
+// (elliptic_curves/test/random.h:11-29, big_int.h:107-116) are mirrored with a
+// fixed-seed SplitMix64 so that every run sees identical bytes.
+// ---------------------------------------------------------------------------
+inline u64 SplitMix64At(u64 seed, u64 index) {
+  u64 z = seed + (index + 1) * 0x9E3779B97F4A7C15ull;
+  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+  z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+  return z ^ (z >> 31);
+}
+
+constexpr size_t kChainLog = 12;  // points per doubling chain = 2^12
+
+template <typename Fq, typename Fr>
+void GeneratePoints(const Affine<Fq>& gen, u64 seed, size_t first, size_t n,
+                    Affine<Fq>* out) {
+  // point index i lives in chain j = i >> 12 at depth d = i & 4095:
+  //   P_i = 2^d * [h_j] G,   h_j = SplitMix64(seed ^ "pt", j) | 1
+  // Each chain is normalised with one shared inversion (Montgomery's trick);
+  // the affine values equal per-point ToAffine() since inverses are unique.
+  size_t chain_len = size_t{1} << kChainLog;
+  size_t last = first + n;
+  size_t j0 = first / chain_len, j1 = (last + chain_len - 1) / chain_len;
+#pragma omp parallel for schedule(dynamic, 1)
+  for (size_t j = j0; j < j1; ++j) {
+    BigInt<1> h;
+    h.v[0] = SplitMix64At(seed ^ 0x7074ull, j) | 1;
+    XYZZ<Fq> p = ScalarMul(XYZZ<Fq>::FromAffine(gen), h);
+    size_t lo = j * chain_len, hi = std::min(last, lo + chain_len);
+    std::vector<XYZZ<Fq>> pts(hi - lo);
+    std::vector<Fq> prefix(hi - lo);
+    Fq run = Fq::One();
+    for (size_t i = lo; i < hi; ++i) {
+      pts[i - lo] = p;
+      run = run.Mul(p.zzz);
+      prefix[i - lo] = run;
+      p = p.Double();
+    }
+    Fq inv = run.Inverse();
+    for (size_t i = hi; i-- > lo;) {
+      Fq zi3 = (i > lo) ? inv.Mul(prefix[i - lo - 1]) : inv;
+      inv = inv.Mul(pts[i - lo].zzz);
+      if (i >= first) {
+        Fq zi2 = zi3.Mul(pts[i - lo].zz).Square();
+        out[i - first] = Affine<Fq>{pts[i - lo].x.Mul(zi2), pts[i - lo].y.Mul(zi3)};
+      }
+    }
+  }
+}
+
+enum ScalarDist { kUniform = 0, kNonUniform = 1, kWitness = 2 };
+
+template <typename Fr>
+Fr RandomScalarAt(u64 seed, u64 i) {
+  // big_int.h:107-116 Random(max): N random limbs, halve until < max.
+  BigInt<Fr::N> x;
+  for (size_t k = 0; k < Fr::N; ++k) x.v[k] = SplitMix64At(seed ^ 0x7363ull, i * Fr::N + k);
+  while (x >= Fr::P.modulus) x.DivBy2InPlace();
+  return Fr::FromBigInt(x);
+}
+
+template <typename Fr>
+void GenerateScalars(u64 seed, int dist, size_t first, size_t n, Fr* out) {
+#pragma omp parallel for schedule(static)
+  for (size_t k = 0; k < n; ++k) {
+    u64 i = first + k;
+    if (dist == kNonUniform) {
+      out[k] = RandomScalarAt<Fr>(seed, 0);  // benchmark/msm/msm_config.h:43-46
+    } else if (dist == kWitness) {
+      u64 sel = SplitMix64At(seed ^ 0x7769ull, i) % 10;
+      if (sel < 4) {
+        out[k] = Fr::Zero();
+      } else if (sel < 7) {
+        out[k] = Fr::One();
+      } else if (sel < 9) {
+        out[k] = Fr::FromU64(SplitMix64At(seed ^ 0x7363ull, i * Fr::N) & 0xffffffffull);
+      } else {
+        out[k] = RandomScalarAt<Fr>(seed, i);
+      }
+    } else {
+      out[k] = RandomScalarAt<Fr>(seed, i);
+    }
+  }
+}
+
+// Folds every doubling chain's scalars into one: S_j = sum_d s_{j,d} 2^d mod r,
+// so that MSM(P, s) == MSM(chain heads, S) — the size-independent check used
+// at full benchmark sizes.  (Not in the reference; follows from P_i = 2^d H_j.)
+template <typename Fr>
+void FoldChainScalars(const Fr* scalars, size_t n, Fr* out) {
+  size_t chain_len = size_t{1} << kChainLog;
+  size_t chains = (n + chain_len - 1) / chain_len;
+#pragma omp parallel for schedule(static)
+  for (size_t j = 0; j < chains; ++j) {
+    size_t lo = j * chain_len, hi = std::min(n, lo + chain_len);
+    Fr acc = Fr::Zero();
+    for (size_t i = hi; i-- > lo;) acc = acc.Double().Add(scalars[i]);
+    out[j] = acc;
+  }
+}
+
+// ---------------------------------------------------------------------------
+// Field tags and one-time initialisation
+// ---------------------------------------------------------------------------
+struct Bn254FqTag {};
+struct Bn254FrTag {};
+struct Bls381FqTag {};
+struct Bls381FrTag {};
+struct Gf7Tag {};
+
+using Bn254Fq = Fp<Bn254FqTag, 4>;
+using Bn254Fr = Fp<Bn254FrTag, 4>;
+using Bls381Fq = Fp<Bls381FqTag, 6>;
+using Bls381Fr = Fp<Bls381FrTag, 4>;
+using Gf7 = Fp<Gf7Tag, 1>;
+
+Affine<Bn254Fq> g_bn254_gen;
+Affine<Bls381Fq> g_bls381_gen;
+
+struct Init {
+  Init() {
+    // bn/bn254/BUILD.bazel:27-60 (Fq, Fr), :119-148 (G1: a=0, b=3, G=(1,2))
+    static const u64 bn_q[4] = {0x3c208c16d87cfd47ull, 0x97816a916871ca8dull,
+                                0xb85045b68181585dull, 0x30644e72e131a029ull};
+    static const u64 bn_r[4] = {0x43e1f593f0000001ull, 0x2833e84879b97091ull,
+                                0xb85045b68181585dull, 0x30644e72e131a029ull};
+    // bls12/bls12_381/BUILD.bazel:36-71 (Fq, Fr), :117-151 (G1: a=0, b=4, G)
+    static const u64 bls_q[6] = {0xb9feffffffffaaabull, 0x1eabfffeb153ffffull,
+                                 0x6730d2a0f6b0f624ull, 0x64774b84f38512bfull,
+                                 0x4b1ba7b6434bacd7ull, 0x1a0111ea397fe69aull};
+    static const u64 bls_r[4] = {0xffffffff00000001ull, 0x53bda402fffe5bfeull,
+                                 0x3339d80809a1d805ull, 0x73eda753299d7d48ull};
+    static const u64 seven[1] = {7};
+    Bn254Fq::P.Init(bn_q);
+    Bn254Fr::P.Init(bn_r);
+    Bls381Fq::P.Init(bls_q);
+    Bls381Fr::P.Init(bls_r);
+    Gf7::P.Init(seven);
+
+    g_bn254_gen = Affine<Bn254Fq>{Bn254Fq::FromU64(1), Bn254Fq::FromU64(2)};
+    BigInt<6> gx{{0xfb3af00adb22c6bbull, 0x6c55e83ff97a1aefull, 0xa14e3a3f171bac58ull,
+                  0xc3688c4f9774b905ull, 0x2695638c4fa9ac0full, 0x17f1d3a73197d794ull}};
+    BigInt<6> gy{{0x0caa232946c5e7e1ull, 0xd03cc744a2888ae4ull, 0x00db18cb2c04b3edull,
+                  0xfcf5e095d5d00af6ull, 0xa09e30ed741d8ae4ull, 0x08b3f481e3aaa0f1ull}};
+    g_bls381_gen = Affine<Bls381Fq>{Bls381Fq::FromBigInt(gx), Bls381Fq::FromBigInt(gy)};
+  }
+} g_init;
+
+template <typename Fq>
+void StoreXYZZ(const XYZZ<Fq>& p, u64* out) {
+  memcpy(out, &p, sizeof(p));
+}
+
+}  // namespace
+
+// ---------------------------------------------------------------------------
+// C ABI (ctypes).  All field elements are little-endian u64 limbs in
+// Montgomery form unless a name says "canonical".
+// ---------------------------------------------------------------------------
+#define ORACLE_CURVE_API(PFX, FQ, FR, GEN)                                                  \
+  extern "C" {                                                                               \
+  int oracle_##PFX##_fq_limbs() { return (int)FQ::N; }                                       \
+  int oracle_##PFX##_fr_limbs() { return (int)FR::N; }                                       \
+  void oracle_##PFX##_constants(u64* fq_mod, u64* fq_r, u64* fq_r2, u64* fq_inv, u64* fr_mod, \
+                                u64* fr_r, u64* fr_r2, u64* fr_inv, u64* gen_xy) {            \
+    memcpy(fq_mod, &FQ::P.modulus, sizeof(u64) * FQ::N);                                      \
+    memcpy(fq_r, &FQ::P.r, sizeof(u64) * FQ::N);                                              \
+    memcpy(fq_r2, &FQ::P.r2, sizeof(u64) * FQ::N);                                            \
+    *fq_inv = FQ::P.inv64;                                                                    \
+    memcpy(fr_mod, &FR::P.modulus, sizeof(u64) * FR::N);                                      \
+    memcpy(fr_r, &FR::P.r, sizeof(u64) * FR::N);                                              \
+    memcpy(fr_r2, &FR::P.r2, sizeof(u64) * FR::N);                                            \
+    *fr_inv = FR::P.inv64;                                                                    \
+    memcpy(gen_xy, &GEN, sizeof(GEN));                                                        \
+  }                                                                                          \
+  /* op: 0 add, 1 sub, 2 mul, 3 square(a), 4 neg(a), 5 double(a), 6 inverse(a) */             \
+  void oracle_##PFX##_fq_op(int op, const u64* a, const u64* b, u64* out, size_t n) {         \
+    const FQ* A = (const FQ*)a;                                                               \
+    const FQ* B = (const FQ*)b;                                                               \
+    FQ* O = (FQ*)out;                                                                         \
+    for (size_t i = 0; i < n; ++i) {                                                          \
+      switch (op) {                                                                           \
+        case 0: O[i] = A[i].Add(B[i]); break;                                                 \
+        case 1: O[i] = A[i].Sub(B[i]); break;                                                 \
+        case 2: O[i] = A[i].Mul(B[i]); break;                                                 \
+        case 3: O[i] = A[i].Square(); break;                                                  \
+        case 4: O[i] = A[i].Neg(); break;                                                     \
+        case 5: O[i] = A[i].Double(); break;                                                  \
+        case 6: O[i] = A[i].Inverse(); break;                                                 \
+      }                                                                                       \
+    }                                                                                         \
+  }                                                                                          \
+  void oracle_##PFX##_fq_to_mont(const u64* a, u64* out, size_t n) {                          \
+    for (size_t i = 0; i < n; ++i)                                                            \
+      ((FQ*)out)[i] = FQ::FromBigInt(((const BigInt<FQ::N>*)a)[i]);                           \
+  }                                                                                          \
+  void oracle_##PFX##_fq_from_mont(const u64* a, u64* out, size_t n) {                        \
+    for (size_t i = 0; i < n; ++i)                                                            \
+      ((BigInt<FQ::N>*)out)[i] = ((const FQ*)a)[i].ToBigInt();                                \
+  }                                                                                          \
+  void oracle_##PFX##_fr_to_mont(const u64* a, u64* out, size_t n) {                          \
+    for (size_t i = 0; i < n; ++i)                                                            \
+      ((FR*)out)[i] = FR::FromBigInt(((const BigInt<FR::N>*)a)[i]);                           \
+  }                                                                                          \
+  void oracle_##PFX##_fr_from_mont(const u64* a, u64* out, size_t n) {                        \
+    for (size_t i = 0; i < n; ++i)                                                            \
+      ((BigInt<FR::N>*)out)[i] = ((const FR*)a)[i].ToBigInt();                                \
+  }                                                                                          \
+  /* digits of ONE Montgomery scalar, reference window rule for `chunk_n` points */           \
+  void oracle_##PFX##_fill_digits(const u64* scalar_mont, size_t window_bits,                 \
+                                  size_t num_digits, int64_t* digits) {                       \
+    FillDigits(((const FR*)scalar_mont)->ToBigInt(), window_bits, digits, num_digits);        \
+  }                                                                                          \
+  void oracle_##PFX##_xyzz_add(const u64* a, const u64* b, u64* out) {                        \
+    StoreXYZZ(((const XYZZ<FQ>*)a)->Add(*(const XYZZ<FQ>*)b), out);                           \
+  }                                                                                          \
+  void oracle_##PFX##_xyzz_madd(const u64* a, const u64* b_affine, u64* out) {                \
+    StoreXYZZ(((const XYZZ<FQ>*)a)->AddAffine(*(const Affine<FQ>*)b_affine), out);            \
+  }                                                                                          \
+  void oracle_##PFX##_xyzz_double(const u64* a, u64* out) {                                   \
+    StoreXYZZ(((const XYZZ<FQ>*)a)->Double(), out);                                           \
+  }                                                                                          \
+  void oracle_##PFX##_xyzz_to_affine(const u64* a, u64* out) {                                \
+    Affine<FQ> r = ((const XYZZ<FQ>*)a)->ToAffine();                                          \
+    memcpy(out, &r, sizeof(r));                                                               \
+  }                                                                                          \
+  void oracle_##PFX##_xyzz_to_jacobian(const u64* a, u64* out) {                              \
+    Jacobian<FQ> r = ((const XYZZ<FQ>*)a)->ToJacobian();                                      \
+    memcpy(out, &r, sizeof(r));                                                               \
+  }                                                                                          \
+  void oracle_##PFX##_jacobian_to_affine(const u64* a, u64* out) {                            \
+    Affine<FQ> r = JacobianToAffine(*(const Jacobian<FQ>*)a);                                 \
+    memcpy(out, &r, sizeof(r));                                                               \
+  }                                                                                          \
+  /* k: canonical FR::N-limb scalar */                                                        \
+  void oracle_##PFX##_scalar_mul(const u64* p_affine, const u64* k, u64* out_xyzz) {          \
+    StoreXYZZ(ScalarMul(XYZZ<FQ>::FromAffine(*(const Affine<FQ>*)p_affine),                   \
+                        *(const BigInt<FR::N>*)k),                                            \
+              out_xyzz);                                                                      \
+  }                                                                                          \
+  unsigned oracle_##PFX##_window_bits(size_t n) { return ComputeWindowsBits(n); }             \
+  unsigned oracle_##PFX##_window_count(unsigned c) {                                          \
+    return ComputeWindowsCount(FR::P.bits, c);                                                \
+  }                                                                                          \
+  /* strategy: 0 kNone, 1 kParallelWindow, 2 kParallelTerm (default) */                       \
+  void oracle_##PFX##_msm(const u64* bases, const u64* scalars, size_t n, int strategy,       \
+                          int threads, u64* out_xyzz) {                                       \
+    const Affine<FQ>* B = (const Affine<FQ>*)bases;                                           \
+    const FR* S = (const FR*)scalars;                                                         \
+    XYZZ<FQ> r;                                                                               \
+    if (n == 0) {                                                                             \
+      r = XYZZ<FQ>::Zero();                                                                   \
+    } else if (strategy == 2) {                                                               \
+      r = MsmParallelTerm<FQ, FR>(B, S, n, threads);                                          \
+    } else {                                                                                  \
+      r = Pippenger<FQ, FR>(B, S, n, strategy == 1);                                          \
+    }                                                                                         \
+    StoreXYZZ(r, out_xyzz);                                                                   \
+  }                                                                                          \
+  void oracle_##PFX##_msm_naive(const u64* bases, const u64* scalars, size_t n,               \
+                                u64* out_xyzz) {                                              \
+    StoreXYZZ(MsmNaive<FQ, FR>((const Affine<FQ>*)bases, (const FR*)scalars, n), out_xyzz);   \
+  }                                                                                          \
+  void oracle_##PFX##_generate_points(u64 seed, size_t first, size_t n, u64* out) {           \
+    GeneratePoints<FQ, FR>(GEN, seed, first, n, (Affine<FQ>*)out);                            \
+  }                                                                                          \
+  void oracle_##PFX##_generate_scalars(u64 seed, int dist, size_t first, size_t n,            \
+                                       u64* out) {                                            \
+    GenerateScalars<FR>(seed, dist, first, n, (FR*)out);                                      \
+  }                                                                                          \
+  void oracle_##PFX##_fold_chain_scalars(const u64* scalars, size_t n, u64* out) {            \
+    FoldChainScalars<FR>((const FR*)scalars, n, (FR*)out);                                    \
+  }                                                                                          \
+  }
+
+ORACLE_CURVE_API(bn254, Bn254Fq, Bn254Fr, g_bn254_gen)
+ORACLE_CURVE_API(bls12_381, Bls381Fq, Bls381Fr, g_bls381_gen)
+
+// GF(7) toy curve y^2 = x^3 + 5 (short_weierstrass/test/sw_curve_config.h:31-45):
+// the same XYZZ/Jacobian templates run over a 1-limb Montgomery field so that
+// the reference's hard-coded KATs can be replayed.  Values cross the ABI as
+// plain small integers (canonical), one u64 per coordinate.
+namespace {
+Gf7 G7(u64 x) { return Gf7::FromU64(x % 7); }
+u64 G7out(const Gf7& x) { return x.ToBigInt().v[0]; }
+XYZZ<Gf7> G7xyzz(const u64* p) { return XYZZ<Gf7>{G7(p[0]), G7(p[1]), G7(p[2]), G7(p[3])}; }
+void G7store(const XYZZ<Gf7>& p, u64* out) {
+  out[0] = G7out(p.x);
+  out[1] = G7out(p.y);
+  out[2] = G7out(p.zz);
+  out[3] = G7out(p.zzz);
+}
+}  // namespace
+
+extern "C" {
+void oracle_gf7_xyzz_add(const u64* a, const u64* b, u64* out) {
+  G7store(G7xyzz(a).Add(G7xyzz(b)), out);
+}
+void oracle_gf7_xyzz_madd(const u64* a, const u64* b_affine, u64* out) {
+  G7store(G7xyzz(a).AddAffine(Affine<Gf7>{G7(b_affine[0]), G7(b_affine[1])}), out);
+}
+void oracle_gf7_xyzz_double(const u64* a, u64* out) { G7store(G7xyzz(a).Double(), out); }
+void oracle_gf7_xyzz_neg(const u64* a, u64* out) { G7store(G7xyzz(a).Neg(), out); }
+void oracle_gf7_xyzz_to_affine(const u64* a, u64* out) {
+  Affine<Gf7> r = G7xyzz(a).ToAffine();
+  out[0] = G7out(r.x);
+  out[1] = G7out(r.y);
+}
+void oracle_gf7_xyzz_to_jacobian(const u64* a, u64* out) {
+  Jacobian<Gf7> r = G7xyzz(a).ToJacobian();
+  out[0] = G7out(r.x);
+  out[1] = G7out(r.y);
+  out[2] = G7out(r.z);
+}
+void oracle_gf7_jacobian_to_affine(const u64* a, u64* out) {
+  Affine<Gf7> r = JacobianToAffine(Jacobian<Gf7>{G7(a[0]), G7(a[1]), G7(a[2])});
+  out[0] = G7out(r.x);
+  out[1] = G7out(r.y);
+}
+// k * (x, y) by double-and-add, returned affine (point_xyzz_unittest.cc:128-142)
+void oracle_gf7_scalar_mul(const u64* p_affine, u64 k, u64* out_affine) {
+  BigInt<1> kk{{k}};
+  Affine<Gf7> r =
+      ScalarMul(XYZZ<Gf7>::FromAffine(Affine<Gf7>{G7(p_affine[0]), G7(p_affine[1])}), kk)
+          .ToAffine();
+  out_affine[0] = G7out(r.x);
+  out_affine[1] = G7out(r.y);
+}
+int oracle_max_threads() {
+#if defined(_OPENMP)
+  return omp_get_max_threads();
+#else
+  return 1;
+#endif
+}
+}
