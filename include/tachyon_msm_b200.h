@@ -1,0 +1,155 @@
+/*
+ * tachyon_msm_b200.h — C ABI of the B200-native variable-base MSM engine.
+ *
+ * Part 1 is the drop-in boundary: exactly the symbols and struct layouts that
+ * the reference generates from
+ *   tachyon/c/math/elliptic_curves/generator/msm_gpu.h.tpl:17-56   (GPU MSM API)
+ *   tachyon/c/math/elliptic_curves/generator/point.h.tpl:22-117    (point structs, _init)
+ *   tachyon/c/math/finite_fields/generator/.../prime_field.h.tpl:36-38 (limb structs)
+ * instantiated for %{type} in {bn254, bls12_381}
+ * (tachyon/c/math/elliptic_curves/generator/build_defs.bzl:93-170).
+ * A caller of libtachyon's MSM-GPU API (vendors/scroll_halo2/src/bn254_msm_gpu.cc:11-34,
+ * benchmark/msm/msm_benchmark_gpu.cc:61-66) links against this library unchanged.
+ *
+ * Part 2 (prefix tachyon_b200_ / *_b200) is this engine's own extension:
+ * device-resident inputs, explicit device/stream selection, stage timings,
+ * synthetic test-set generation and the element-wise parity hooks.
+ *
+ * All field elements are little-endian u64 limbs in Montgomery form
+ * (R = 2^(64*limbs)), fully reduced; the affine identity is (0, 0); a Jacobian
+ * point with z == 0 is the identity.
+ */
+#ifndef TACHYON_MSM_B200_H_
+#define TACHYON_MSM_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#if defined(__GNUC__)
+#define TACHYON_C_EXPORT __attribute__((visibility("default")))
+#else
+#define TACHYON_C_EXPORT
+#endif
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ------------------------------------------------------------------------- */
+/* Part 1 — the reference's MSM-GPU C API                                     */
+/* ------------------------------------------------------------------------- */
+
+#define TACHYON_B200_DECLARE_CURVE(C, FQ_LIMBS)                                              \
+  struct tachyon_##C##_fr { uint64_t limbs[4]; };              /* prime_field.h.tpl:36-38 */ \
+  struct tachyon_##C##_fq { uint64_t limbs[FQ_LIMBS]; };                                     \
+  struct tachyon_##C##_g1_affine { struct tachyon_##C##_fq x, y; };     /* point.h.tpl:22-25 */ \
+  struct tachyon_##C##_g1_point2 { struct tachyon_##C##_fq x, y; };     /* point.h.tpl:78-81 */ \
+  struct tachyon_##C##_g1_jacobian { struct tachyon_##C##_fq x, y, z; };/* point.h.tpl:50-54 */ \
+  struct tachyon_##C##_g1_xyzz { struct tachyon_##C##_fq x, y, zz, zzz; };/* point.h.tpl:64-69 */ \
+  typedef struct tachyon_##C##_g1_msm_gpu* tachyon_##C##_g1_msm_gpu_ptr; /* msm_gpu.h.tpl:17 */ \
+                                                                                             \
+  /* point.h.tpl:117 — idempotent, cheap; callers invoke it before anything else */         \
+  TACHYON_C_EXPORT void tachyon_##C##_g1_init(void);                                         \
+  /* msm_gpu.h.tpl:26 — degree = log2(max size), advisory (reference never reads it,        \
+     c/math/elliptic_curves/msm/msm_gpu.h:35).  Prints "CreateMSMGpuApi()" and honours      \
+     TACHYON_MSM_GPU_INPUT_DIR / TACHYON_LOG_MSM like msm_gpu.h:36-52.  Aborts on CUDA       \
+     failure (msm_gpu.h:59-62). */                                                           \
+  TACHYON_C_EXPORT tachyon_##C##_g1_msm_gpu_ptr tachyon_##C##_g1_create_msm_gpu(uint8_t degree); \
+  /* msm_gpu.h.tpl:32 */                                                                     \
+  TACHYON_C_EXPORT void tachyon_##C##_g1_destroy_msm_gpu(tachyon_##C##_g1_msm_gpu_ptr ptr);  \
+  /* msm_gpu.h.tpl:42-44.  bases/scalars: `size` elements each, host memory (pageable or    \
+     pinned) or device memory (icicle_msm_bn254_g1.cc:38-45).  Returns a heap object made   \
+     with C++ `new`, owned by the caller (msm_gpu.h:81).  Any failure aborts (msm_gpu.h:79). */ \
+  TACHYON_C_EXPORT struct tachyon_##C##_g1_jacobian* tachyon_##C##_g1_point2_msm_gpu(        \
+      tachyon_##C##_g1_msm_gpu_ptr ptr, const struct tachyon_##C##_g1_point2* bases,         \
+      const struct tachyon_##C##_fr* scalars, size_t size);                                  \
+  /* msm_gpu.h.tpl:54-56 — same code path as point2 (msm_input_provider.h:23-29) */          \
+  TACHYON_C_EXPORT struct tachyon_##C##_g1_jacobian* tachyon_##C##_g1_affine_msm_gpu(        \
+      tachyon_##C##_g1_msm_gpu_ptr ptr, const struct tachyon_##C##_g1_affine* bases,         \
+      const struct tachyon_##C##_fr* scalars, size_t size);                                  \
+                                                                                             \
+  /* ---- Part 2: extensions ---------------------------------------------------------- */  \
+  /* Context on a given CUDA device, silent (no banner).  NULL on failure. */               \
+  TACHYON_C_EXPORT tachyon_##C##_g1_msm_gpu_ptr tachyon_##C##_g1_create_msm_gpu_b200(        \
+      uint8_t degree, int device);                                                           \
+  /* Run all work of this context on an existing CUDA stream (a cudaStream_t) of the        \
+     context's device instead of its own stream.  0 on success. */                           \
+  TACHYON_C_EXPORT int tachyon_##C##_g1_msm_gpu_set_stream_b200(                             \
+      tachyon_##C##_g1_msm_gpu_ptr ptr, void* cuda_stream);                                  \
+  /* name: "window_bits" (0 = automatic), "segment" (max entries per accumulation task),    \
+     "devices" (point-range sharding over the first k devices; 1 = this context's device). */ \
+  TACHYON_C_EXPORT int tachyon_##C##_g1_msm_gpu_set_option_b200(                             \
+      tachyon_##C##_g1_msm_gpu_ptr ptr, const char* name, long value);                       \
+  /* MSM returning the un-normalised XYZZ sum by value into *out; returns 0 or a negative   \
+     error code instead of aborting.  Pointers as for *_affine_msm_gpu. */                   \
+  TACHYON_C_EXPORT int tachyon_##C##_g1_msm_gpu_xyzz_b200(                                   \
+      tachyon_##C##_g1_msm_gpu_ptr ptr, const struct tachyon_##C##_g1_affine* bases,         \
+      const struct tachyon_##C##_fr* scalars, size_t size, struct tachyon_##C##_g1_xyzz* out); \
+  /* Stage timings of the last call on this context (CUDA events on its stream). */         \
+  TACHYON_C_EXPORT int tachyon_##C##_g1_msm_gpu_last_timing_b200(                            \
+      tachyon_##C##_g1_msm_gpu_ptr ptr, struct tachyon_b200_msm_timing* out);                \
+  /* Deterministic synthetic test set written to DEVICE memory of the current device:       \
+     points first..first+n of the doubling-chain stream, scalars of distribution dist       \
+     (0 uniform, 1 non_uniform, 2 witness).  Mirrors msm/test/variable_base_msm_test_set.h. */ \
+  TACHYON_C_EXPORT int tachyon_##C##_g1_generate_bases_b200(uint64_t seed, size_t first,     \
+                                                            size_t n, void* device_out);     \
+  TACHYON_C_EXPORT int tachyon_##C##_g1_generate_scalars_b200(uint64_t seed, int dist,       \
+                                                              size_t first, size_t n,        \
+                                                              void* device_out);             \
+  /* Element-wise parity hooks on HOST arrays (copied to the current device and back).      \
+     fq/fr op: 0 add 1 sub 2 mul 3 square 4 neg 5 double 6 inverse 7 from_mont 8 to_mont.   \
+     point op: 0 xyzz+xyzz 1 xyzz+affine 2 xyzz-affine 3 double. */                          \
+  TACHYON_C_EXPORT int tachyon_##C##_fq_op_b200(int op, const uint64_t* a, const uint64_t* b, \
+                                                uint64_t* out, size_t n);                    \
+  TACHYON_C_EXPORT int tachyon_##C##_fr_op_b200(int op, const uint64_t* a, const uint64_t* b, \
+                                                uint64_t* out, size_t n);                    \
+  TACHYON_C_EXPORT int tachyon_##C##_g1_point_op_b200(int op, const uint64_t* a,             \
+                                                      const uint64_t* b, uint64_t* out,      \
+                                                      size_t n);                             \
+  /* Host-only helpers (no GPU needed): out = a + b on XYZZ points — how per-GPU / per-rank  \
+     partial sums are combined (pippenger_adapter.h:110-113) — and XYZZ -> Jacobian           \
+     (point_xyzz.h:228-237), the conversion applied to every MSM result. */                  \
+  TACHYON_C_EXPORT void tachyon_##C##_g1_xyzz_add_b200(const struct tachyon_##C##_g1_xyzz* a, \
+                                                       const struct tachyon_##C##_g1_xyzz* b, \
+                                                       struct tachyon_##C##_g1_xyzz* out);   \
+  TACHYON_C_EXPORT void tachyon_##C##_g1_xyzz_to_jacobian_b200(                              \
+      const struct tachyon_##C##_g1_xyzz* a, struct tachyon_##C##_g1_jacobian* out);
+
+struct tachyon_b200_msm_timing {
+  float h2d_ms;         /* host->device copies of bases/scalars (0 for device inputs) */
+  float sort_ms;        /* recode + histogram + scan + task build + scatter */
+  float accumulate_ms;  /* bucket accumulation (+ folding of split buckets) */
+  float reduce_ms;      /* bucket reduction levels + device->host of window sums */
+  float total_ms;       /* first enqueue .. last device->host copy */
+  float host_ms;        /* host epilogue (window Horner, partial adds), wall clock */
+  uint32_t window_bits;
+  uint32_t windows;
+  uint32_t tasks;       /* accumulation tasks (threads of the hot kernel) */
+  uint32_t entries;     /* non-zero digits = mixed additions performed */
+  uint32_t kernel_launches; /* kernels of this library launched by the call */
+  uint32_t devices;
+};
+
+TACHYON_B200_DECLARE_CURVE(bn254, 4)
+TACHYON_B200_DECLARE_CURVE(bls12_381, 6)
+
+/* Number of CUDA devices visible, or a negative error. */
+TACHYON_C_EXPORT int tachyon_b200_device_count(void);
+/* Text of the last error recorded by an extension call on this thread. */
+TACHYON_C_EXPORT const char* tachyon_b200_last_error(void);
+/* Measured INT32 multiply-pipe peak of `device`: 32x32->64 multiply-adds per second
+   (best of `repeats`), variant 0 = IMAD.WIDE chains, 1 = IMAD.WIDE.X carry chains.
+   Negative on error. */
+TACHYON_C_EXPORT double tachyon_b200_imad_peak(int device, int variant, int repeats);
+/* Window size the engine picks for an n-point MSM over a scalar field of `scalar_bits`
+   bits, and the matching window count (host-only). */
+TACHYON_C_EXPORT uint32_t tachyon_b200_window_bits(size_t n, uint32_t scalar_bits);
+TACHYON_C_EXPORT uint32_t tachyon_b200_window_count(uint32_t scalar_bits, uint32_t window_bits);
+/* Total kernels launched by this library in this process (all contexts). */
+TACHYON_C_EXPORT uint64_t tachyon_b200_kernel_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+
+#endif /* TACHYON_MSM_B200_H_ */

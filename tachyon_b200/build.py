@@ -1,0 +1,65 @@
+"""Builds libtachyon_msm_b200.so in-tree with nvcc for sm_100a.
+
+    python -m tachyon_b200.build [--verbose]
+
+The shared library is the product: a C-ABI (include/tachyon_msm_b200.h) with the
+CUDA runtime linked statically, so any host language can bind it.
+"""
+import os
+import subprocess
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(HERE, "csrc")
+LIB_DIR = os.path.join(HERE, "lib")
+LIB = os.path.join(LIB_DIR, "libtachyon_msm_b200.so")
+SOURCES = ["msm_api.cu"]
+HEADERS = ["fp.cuh", "xyzz.cuh", "msm_kernels.cuh", "msm_engine.cuh", "host_math.h",
+           "field_constants.h", os.path.join("..", "..", "include", "tachyon_msm_b200.h")]
+
+NVCC_FLAGS = [
+    "-O3", "-std=c++17",
+    "-gencode", "arch=compute_100a,code=sm_100a",
+    "-lineinfo",
+    "-Xcompiler", "-fPIC,-fvisibility=hidden",
+    "-cudart", "static",
+    "-shared",
+]
+
+
+def nvcc():
+    for cand in (os.environ.get("NVCC"), "/usr/local/cuda/bin/nvcc", "nvcc"):
+        if cand and (os.path.isabs(cand) and os.path.exists(cand) or not os.path.isabs(cand)):
+            return cand
+    return "nvcc"
+
+
+def up_to_date():
+    if not os.path.exists(LIB):
+        return False
+    t = os.path.getmtime(LIB)
+    deps = [os.path.join(CSRC, f) for f in SOURCES + HEADERS] + [os.path.abspath(__file__)]
+    return all(os.path.getmtime(d) <= t for d in deps)
+
+
+def build(force=False, verbose=False):
+    if not force and up_to_date():
+        return LIB
+    os.makedirs(LIB_DIR, exist_ok=True)
+    cmd = [nvcc()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + \
+          ["-o", LIB] + [os.path.join(CSRC, s) for s in SOURCES]
+    env = dict(os.environ)
+    # nvcc's host compiler must be the system g++ (the image's CXX lacks libstdc++ specs)
+    env.pop("CXX", None)
+    env.pop("CC", None)
+    res = subprocess.run(cmd, cwd=CSRC, env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    if verbose or res.returncode != 0:
+        sys.stderr.write(res.stdout)
+    if res.returncode != 0:
+        raise RuntimeError("nvcc failed building libtachyon_msm_b200.so")
+    return LIB
+
+
+if __name__ == "__main__":
+    build(force=True, verbose="--verbose" in sys.argv)
+    print(LIB)

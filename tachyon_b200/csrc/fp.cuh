@@ -1,0 +1,335 @@
+// Montgomery prime-field arithmetic on 32-bit limbs for sm_100a.
+//
+// Replaces, for the device side of the MSM path, what the reference reaches
+// through tachyon/math/finite_fields/prime_field_gpu.h:327-429 (MulLimbs /
+// MadNRedc / Clamp) and kernels/prime_field_ops_internal.cu.h:13-131.  Values
+// are little-endian u32 limbs, Montgomery form with R = 2^(32*N) (identical
+// bytes to the reference's u64-limb R = 2^(64*N/2)), always fully reduced to
+// [0, p) on function exit so that zero/equality tests are plain limb compares.
+//
+// The multiplier is written so that every 32x32->64 product is one
+// IMAD.WIDE.U32(.X) with the carry riding the predicate: products of one row
+// are split by column parity into two accumulators whose 64-bit words never
+// straddle (ptxas fuses each mad.lo.cc/madc.hi.cc pair below into a single
+// IMAD.WIDE.U32.X — checked with cuobjdump -sass).  Per N-limb multiply:
+// 2*N*N + N products (136 for BN254, 300 for BLS12-381), which is exactly the
+// per-modmul figure SURVEY.md §8(d) uses for the IMAD roofline.
+#pragma once
+#include <stdint.h>
+
+#include "field_constants.h"
+
+namespace tb200 {
+
+#define TB_DEV __device__ __forceinline__
+
+// ---- carry-chain primitives (CC flag lives across consecutive statements) --
+TB_DEV uint32_t add_cc(uint32_t a, uint32_t b) {
+  uint32_t r;
+  asm volatile("add.cc.u32 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b));
+  return r;
+}
+TB_DEV uint32_t addc_cc(uint32_t a, uint32_t b) {
+  uint32_t r;
+  asm volatile("addc.cc.u32 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b));
+  return r;
+}
+TB_DEV uint32_t addc(uint32_t a, uint32_t b) {
+  uint32_t r;
+  asm volatile("addc.u32 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b));
+  return r;
+}
+TB_DEV uint32_t sub_cc(uint32_t a, uint32_t b) {
+  uint32_t r;
+  asm volatile("sub.cc.u32 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b));
+  return r;
+}
+TB_DEV uint32_t subc_cc(uint32_t a, uint32_t b) {
+  uint32_t r;
+  asm volatile("subc.cc.u32 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b));
+  return r;
+}
+TB_DEV uint32_t subc(uint32_t a, uint32_t b) {
+  uint32_t r;
+  asm volatile("subc.u32 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b));
+  return r;
+}
+TB_DEV uint32_t mad_lo_cc(uint32_t a, uint32_t b, uint32_t c) {
+  uint32_t r;
+  asm volatile("mad.lo.cc.u32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(c));
+  return r;
+}
+TB_DEV uint32_t madc_lo_cc(uint32_t a, uint32_t b, uint32_t c) {
+  uint32_t r;
+  asm volatile("madc.lo.cc.u32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(c));
+  return r;
+}
+TB_DEV uint32_t madc_hi_cc(uint32_t a, uint32_t b, uint32_t c) {
+  uint32_t r;
+  asm volatile("madc.hi.cc.u32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(c));
+  return r;
+}
+TB_DEV void mul_wide(uint32_t& lo, uint32_t& hi, uint32_t a, uint32_t b) {
+  asm volatile("{\n\t.reg .u64 t;\n\tmul.wide.u32 t, %2, %3;\n\tmov.b64 {%0, %1}, t;\n\t}"
+               : "=r"(lo), "=r"(hi)
+               : "r"(a), "r"(b));
+}
+
+// F is one of the *Params structs of field_constants.h.
+template <class F>
+struct Fp {
+  static constexpr int N = F::kLimbs32;
+  uint32_t l[N];
+};
+
+template <class F>
+TB_DEV void fp_set_zero(Fp<F>& r) {
+#pragma unroll
+  for (int i = 0; i < Fp<F>::N; ++i) r.l[i] = 0;
+}
+template <class F>
+TB_DEV void fp_set_one(Fp<F>& r) {
+#pragma unroll
+  for (int i = 0; i < Fp<F>::N; ++i) r.l[i] = F::one(i);
+}
+template <class F>
+TB_DEV bool fp_is_zero(const Fp<F>& a) {
+  uint32_t acc = 0;
+#pragma unroll
+  for (int i = 0; i < Fp<F>::N; ++i) acc |= a.l[i];
+  return acc == 0;
+}
+template <class F>
+TB_DEV bool fp_eq(const Fp<F>& a, const Fp<F>& b) {
+  uint32_t acc = 0;
+#pragma unroll
+  for (int i = 0; i < Fp<F>::N; ++i) acc |= a.l[i] ^ b.l[i];
+  return acc == 0;
+}
+
+// r = t - p if t >= p else t, for t < 2p  (the Clamp of big_int.h:279-291).
+template <class F>
+TB_DEV void fp_reduce_once(Fp<F>& r, const uint32_t (&t)[Fp<F>::N]) {
+  constexpr int N = Fp<F>::N;
+  uint32_t u[N];
+  u[0] = sub_cc(t[0], F::mod(0));
+#pragma unroll
+  for (int i = 1; i < N; ++i) u[i] = subc_cc(t[i], F::mod(i));
+  uint32_t borrow = subc(0u, 0u);  // 0xffffffff when t < p
+#pragma unroll
+  for (int i = 0; i < N; ++i) r.l[i] = borrow ? t[i] : u[i];
+}
+
+// r = a + b mod p   (prime_field_fallback.h:199-206)
+template <class F>
+TB_DEV void fp_add(Fp<F>& r, const Fp<F>& a, const Fp<F>& b) {
+  constexpr int N = Fp<F>::N;
+  uint32_t t[N];
+  t[0] = add_cc(a.l[0], b.l[0]);
+#pragma unroll
+  for (int i = 1; i < N - 1; ++i) t[i] = addc_cc(a.l[i], b.l[i]);
+  t[N - 1] = addc(a.l[N - 1], b.l[N - 1]);  // p < 2^(32N-1): no carry out
+  fp_reduce_once<F>(r, t);
+}
+template <class F>
+TB_DEV void fp_dbl(Fp<F>& r, const Fp<F>& a) {
+  fp_add<F>(r, a, a);
+}
+
+// r = a - b mod p   (prime_field_fallback.h:234-243)
+template <class F>
+TB_DEV void fp_sub(Fp<F>& r, const Fp<F>& a, const Fp<F>& b) {
+  constexpr int N = Fp<F>::N;
+  uint32_t t[N];
+  t[0] = sub_cc(a.l[0], b.l[0]);
+#pragma unroll
+  for (int i = 1; i < N; ++i) t[i] = subc_cc(a.l[i], b.l[i]);
+  uint32_t borrow = subc(0u, 0u);  // all-ones when a < b
+  r.l[0] = add_cc(t[0], F::mod(0) & borrow);
+#pragma unroll
+  for (int i = 1; i < N - 1; ++i) r.l[i] = addc_cc(t[i], F::mod(i) & borrow);
+  r.l[N - 1] = addc(t[N - 1], F::mod(N - 1) & borrow);
+}
+
+// r = -a mod p, with -0 = 0   (prime_field_fallback.h:253-260)
+template <class F>
+TB_DEV void fp_neg(Fp<F>& r, const Fp<F>& a) {
+  constexpr int N = Fp<F>::N;
+  uint32_t nz = 0;
+#pragma unroll
+  for (int i = 0; i < N; ++i) nz |= a.l[i];
+  uint32_t mask = nz ? 0xffffffffu : 0u;
+  r.l[0] = sub_cc(F::mod(0) & mask, a.l[0]);
+#pragma unroll
+  for (int i = 1; i < N - 1; ++i) r.l[i] = subc_cc(F::mod(i) & mask, a.l[i]);
+  r.l[N - 1] = subc(F::mod(N - 1) & mask, a.l[N - 1]);
+}
+// r = neg ? -a : a
+template <class F>
+TB_DEV void fp_cneg(Fp<F>& r, const Fp<F>& a, bool neg) {
+  Fp<F> n;
+  fp_neg<F>(n, a);
+#pragma unroll
+  for (int i = 0; i < Fp<F>::N; ++i) r.l[i] = neg ? n.l[i] : a.l[i];
+}
+
+// ---------------------------------------------------------------------------
+// Montgomery multiplication, row-interleaved, parity-split accumulators.
+//
+// The running value V (N+1 limbs) is held as  V = X + (Y << 32)  where X and Y
+// are N-limb arrays read as N/2 64-bit words, so a product a_j*b_i always
+// lands on a whole word of one of them (even j -> X, odd j -> Y).  After the
+// Montgomery row (adding m*p with m = X[0]*inv) limb X[0] is zero and the
+// implicit division by 2^32 swaps the roles: Y becomes the aligned array and
+// X, moved down one word, the offset one.  That move is folded into the next
+// row's first chain (the addend is read two limbs ahead), so it costs no
+// instruction; only X[1], the half word left behind, needs one add.
+// Carries out of the aligned chain go to Y's top limb; carries out of the
+// offset chain cannot occur because V < 2^(32(N+1)) throughout
+// (V < 2p + 2^33 p and p < 2^(32N-2) for both curves).
+// ---------------------------------------------------------------------------
+template <class F, int N>
+TB_DEV void mont_reduce_row(uint32_t (&X)[N], uint32_t (&Y)[N]) {
+  uint32_t m = X[0] * F::kInv32;
+  Y[0] = mad_lo_cc(F::mod(1), m, Y[0]);
+  Y[1] = madc_hi_cc(F::mod(1), m, Y[1]);
+#pragma unroll
+  for (int j = 2; j < N; j += 2) {
+    Y[j] = madc_lo_cc(F::mod(j + 1), m, Y[j]);
+    Y[j + 1] = madc_hi_cc(F::mod(j + 1), m, Y[j + 1]);
+  }
+  X[0] = mad_lo_cc(F::mod(0), m, X[0]);
+  X[1] = madc_hi_cc(F::mod(0), m, X[1]);
+#pragma unroll
+  for (int j = 2; j < N; j += 2) {
+    X[j] = madc_lo_cc(F::mod(j), m, X[j]);
+    X[j + 1] = madc_hi_cc(F::mod(j), m, X[j + 1]);
+  }
+  Y[N - 1] = addc(Y[N - 1], 0u);
+}
+
+// One row i >= 1.  On entry Y is the previous row's aligned array (Y[0] == 0).
+template <class F, int N>
+TB_DEV void mont_mul_row(uint32_t (&X)[N], uint32_t (&Y)[N], const uint32_t (&a)[N],
+                         uint32_t bi) {
+  X[0] = add_cc(X[0], Y[1]);
+#pragma unroll
+  for (int j = 0; j < N; j += 2) {
+    uint32_t c_lo = (j + 2 < N) ? Y[j + 2] : 0u;
+    uint32_t c_hi = (j + 3 < N) ? Y[j + 3] : 0u;
+    Y[j] = madc_lo_cc(a[j + 1], bi, c_lo);
+    Y[j + 1] = madc_hi_cc(a[j + 1], bi, c_hi);
+  }
+  X[0] = mad_lo_cc(a[0], bi, X[0]);
+  X[1] = madc_hi_cc(a[0], bi, X[1]);
+#pragma unroll
+  for (int j = 2; j < N; j += 2) {
+    X[j] = madc_lo_cc(a[j], bi, X[j]);
+    X[j + 1] = madc_hi_cc(a[j], bi, X[j + 1]);
+  }
+  Y[N - 1] = addc(Y[N - 1], 0u);
+  mont_reduce_row<F, N>(X, Y);
+}
+
+// r = a * b * R^-1 mod p, a, b < p  (value of prime_field_fallback.h:331-355)
+template <class F>
+TB_DEV void fp_mul(Fp<F>& r, const Fp<F>& a, const Fp<F>& b) {
+  constexpr int N = Fp<F>::N;
+  static_assert(N % 2 == 0, "limb count must be even");
+  uint32_t E[N], O[N];
+#pragma unroll
+  for (int j = 0; j < N; j += 2) {
+    mul_wide(E[j], E[j + 1], a.l[j], b.l[0]);
+    mul_wide(O[j], O[j + 1], a.l[j + 1], b.l[0]);
+  }
+  mont_reduce_row<F, N>(E, O);
+#pragma unroll
+  for (int i = 1; i < N; i += 2) {
+    mont_mul_row<F, N>(O, E, a.l, b.l[i]);
+    if (i + 1 < N) mont_mul_row<F, N>(E, O, a.l, b.l[i + 1]);
+  }
+  // last row had X = O (O[0] == 0), Y = E:  result = E + (O >> 32)
+  uint32_t t[N];
+  t[0] = add_cc(E[0], O[1]);
+#pragma unroll
+  for (int j = 1; j < N - 1; ++j) t[j] = addc_cc(E[j], O[j + 1]);
+  t[N - 1] = addc(E[N - 1], 0u);
+  fp_reduce_once<F>(r, t);
+}
+
+template <class F>
+TB_DEV void fp_sqr(Fp<F>& r, const Fp<F>& a) {
+  fp_mul<F>(r, a, a);
+}
+
+// Montgomery -> canonical: a * 1 * R^-1  (value of big_int.h:1049-1076
+// FromMontgomery).  Fully reduced for every modulus, including BLS12-381 Fr
+// which has a single spare bit (the lazy [0,2p) form of
+// prime_field_gpu.h:256 would not be valid there).
+template <class F>
+TB_DEV void fp_from_mont(Fp<F>& r, const Fp<F>& a) {
+  Fp<F> one;
+#pragma unroll
+  for (int i = 0; i < Fp<F>::N; ++i) one.l[i] = (i == 0) ? 1u : 0u;
+  fp_mul<F>(r, a, one);
+}
+
+template <class F>
+TB_DEV void fp_to_mont(Fp<F>& r, const Fp<F>& a) {
+  Fp<F> r2;
+#pragma unroll
+  for (int i = 0; i < Fp<F>::N; ++i) r2.l[i] = F::r2(i);
+  fp_mul<F>(r, a, r2);
+}
+
+// a^(p-2): only used by test/bench utilities (point normalisation).
+template <class F>
+__device__ __noinline__ void fp_inv(Fp<F>& r, const Fp<F>& a) {
+  constexpr int N = Fp<F>::N;
+  uint32_t e[N];
+  e[0] = sub_cc(F::mod(0), 2u);
+#pragma unroll
+  for (int i = 1; i < N; ++i) e[i] = subc_cc(F::mod(i), 0u);
+  Fp<F> acc;
+  fp_set_one<F>(acc);
+  for (int i = F::kBits - 1; i >= 0; --i) {
+    fp_sqr<F>(acc, acc);
+    if ((e[i >> 5] >> (i & 31)) & 1) fp_mul<F>(acc, acc, a);
+  }
+  r = acc;
+}
+
+// 128-bit vector load/store of a field element (address must be 16-B aligned)
+template <class F>
+TB_DEV void fp_load(Fp<F>& r, const void* p) {
+  const uint4* q = reinterpret_cast<const uint4*>(p);
+#pragma unroll
+  for (int i = 0; i < Fp<F>::N / 4; ++i) {
+    uint4 v = __ldg(q + i);
+    r.l[4 * i] = v.x;
+    r.l[4 * i + 1] = v.y;
+    r.l[4 * i + 2] = v.z;
+    r.l[4 * i + 3] = v.w;
+  }
+}
+template <class F>
+TB_DEV void fp_load_rw(Fp<F>& r, const void* p) {
+  const uint4* q = reinterpret_cast<const uint4*>(p);
+#pragma unroll
+  for (int i = 0; i < Fp<F>::N / 4; ++i) {
+    uint4 v = q[i];
+    r.l[4 * i] = v.x;
+    r.l[4 * i + 1] = v.y;
+    r.l[4 * i + 2] = v.z;
+    r.l[4 * i + 3] = v.w;
+  }
+}
+template <class F>
+TB_DEV void fp_store(void* p, const Fp<F>& a) {
+  uint4* q = reinterpret_cast<uint4*>(p);
+#pragma unroll
+  for (int i = 0; i < Fp<F>::N / 4; ++i)
+    q[i] = make_uint4(a.l[4 * i], a.l[4 * i + 1], a.l[4 * i + 2], a.l[4 * i + 3]);
+}
+
+}  // namespace tb200

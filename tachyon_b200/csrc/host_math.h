@@ -1,0 +1,179 @@
+// Host-side field / point arithmetic for the MSM epilogue (window Horner,
+// combination of per-GPU partials, XYZZ -> Jacobian), on u64 limbs.
+// Follows tachyon/math/elliptic_curves/msm/algorithms/pippenger/pippenger_base.h:59-77
+// (AccumulateWindowSums) and short_weierstrass/point_xyzz.h:228-237 (ToJacobian);
+// independent of oracle/ (which is test infrastructure and never linked here).
+#pragma once
+#include <stddef.h>
+#include <stdint.h>
+#include <string.h>
+
+#include "field_constants.h"
+
+namespace tb200 {
+
+template <class F>
+struct HostFp {
+  static constexpr int N = F::kLimbs64;
+  uint64_t v[N];
+
+  static HostFp Zero() {
+    HostFp r;
+    for (int i = 0; i < N; ++i) r.v[i] = 0;
+    return r;
+  }
+  static HostFp One() {
+    HostFp r;
+    for (int i = 0; i < N; ++i) r.v[i] = F::kOne64[i];
+    return r;
+  }
+  bool IsZero() const {
+    uint64_t acc = 0;
+    for (int i = 0; i < N; ++i) acc |= v[i];
+    return acc == 0;
+  }
+  bool IsOne() const {
+    uint64_t acc = 0;
+    for (int i = 0; i < N; ++i) acc |= v[i] ^ F::kOne64[i];
+    return acc == 0;
+  }
+  static bool Geq(const uint64_t* a, const uint64_t* b) {
+    for (int i = N; i-- > 0;) {
+      if (a[i] != b[i]) return a[i] > b[i];
+    }
+    return true;
+  }
+  static void SubMod(uint64_t* a) {
+    unsigned __int128 borrow = 0;
+    for (int i = 0; i < N; ++i) {
+      unsigned __int128 t = (unsigned __int128)a[i] - F::kMod64[i] - (uint64_t)borrow;
+      a[i] = (uint64_t)t;
+      borrow = (t >> 64) & 1;
+    }
+  }
+  HostFp Add(const HostFp& o) const {
+    HostFp r;
+    unsigned __int128 carry = 0;
+    for (int i = 0; i < N; ++i) {
+      unsigned __int128 t = (unsigned __int128)v[i] + o.v[i] + (uint64_t)carry;
+      r.v[i] = (uint64_t)t;
+      carry = t >> 64;
+    }
+    if (carry || Geq(r.v, F::kMod64)) SubMod(r.v);
+    return r;
+  }
+  HostFp Dbl() const { return Add(*this); }
+  HostFp Sub(const HostFp& o) const {
+    HostFp r;
+    unsigned __int128 borrow = 0;
+    for (int i = 0; i < N; ++i) {
+      unsigned __int128 t = (unsigned __int128)v[i] - o.v[i] - (uint64_t)borrow;
+      r.v[i] = (uint64_t)t;
+      borrow = (t >> 64) & 1;
+    }
+    if (borrow) {
+      unsigned __int128 carry = 0;
+      for (int i = 0; i < N; ++i) {
+        unsigned __int128 t = (unsigned __int128)r.v[i] + F::kMod64[i] + (uint64_t)carry;
+        r.v[i] = (uint64_t)t;
+        carry = t >> 64;
+      }
+    }
+    return r;
+  }
+  HostFp Mul(const HostFp& o) const {
+    uint64_t t[N + 2];
+    for (int i = 0; i < N + 2; ++i) t[i] = 0;
+    for (int i = 0; i < N; ++i) {
+      uint64_t carry = 0;
+      for (int j = 0; j < N; ++j) {
+        unsigned __int128 x = (unsigned __int128)v[j] * o.v[i] + t[j] + carry;
+        t[j] = (uint64_t)x;
+        carry = (uint64_t)(x >> 64);
+      }
+      unsigned __int128 s = (unsigned __int128)t[N] + carry;
+      t[N] = (uint64_t)s;
+      t[N + 1] = (uint64_t)(s >> 64);
+      uint64_t m = t[0] * F::kInv64;
+      unsigned __int128 x = (unsigned __int128)m * F::kMod64[0] + t[0];
+      carry = (uint64_t)(x >> 64);
+      for (int j = 1; j < N; ++j) {
+        x = (unsigned __int128)m * F::kMod64[j] + t[j] + carry;
+        t[j - 1] = (uint64_t)x;
+        carry = (uint64_t)(x >> 64);
+      }
+      s = (unsigned __int128)t[N] + carry;
+      t[N - 1] = (uint64_t)s;
+      t[N] = t[N + 1] + (uint64_t)(s >> 64);
+    }
+    HostFp r;
+    for (int i = 0; i < N; ++i) r.v[i] = t[i];
+    if (t[N] || Geq(r.v, F::kMod64)) SubMod(r.v);
+    return r;
+  }
+  HostFp Sqr() const { return Mul(*this); }
+};
+
+template <class F>
+struct HostXYZZ {
+  HostFp<F> x, y, zz, zzz;
+
+  static HostXYZZ Zero() {
+    return HostXYZZ{HostFp<F>::One(), HostFp<F>::One(), HostFp<F>::Zero(), HostFp<F>::Zero()};
+  }
+  bool IsZero() const { return zz.IsZero(); }
+
+  HostXYZZ Dbl() const {
+    if (IsZero()) return *this;
+    HostFp<F> u = y.Dbl(), v = u.Sqr(), w = u.Mul(v), s = x.Mul(v);
+    HostFp<F> m = x.Sqr();
+    m = m.Add(m.Dbl());
+    HostXYZZ r;
+    r.x = m.Sqr().Sub(s.Dbl());
+    r.y = m.Mul(s.Sub(r.x)).Sub(w.Mul(y));
+    r.zz = v.Mul(zz);
+    r.zzz = w.Mul(zzz);
+    return r;
+  }
+  HostXYZZ Add(const HostXYZZ& b) const {
+    if (IsZero()) return b;
+    if (b.IsZero()) return *this;
+    HostFp<F> u1 = x.Mul(b.zz), s1 = y.Mul(b.zzz);
+    HostFp<F> p = b.x.Mul(zz).Sub(u1), r = b.y.Mul(zzz).Sub(s1);
+    if (p.IsZero() && r.IsZero()) return Dbl();
+    HostFp<F> pp = p.Sqr(), ppp = p.Mul(pp), q = u1.Mul(pp);
+    HostXYZZ c;
+    c.x = r.Sqr().Sub(ppp).Sub(q.Dbl());
+    c.y = r.Mul(q.Sub(c.x)).Sub(s1.Mul(ppp));
+    c.zz = zz.Mul(b.zz).Mul(pp);
+    c.zzz = zzz.Mul(b.zzz).Mul(ppp);
+    return c;
+  }
+};
+
+template <class F>
+struct HostJacobian {
+  HostFp<F> x, y, z;
+};
+
+// point_xyzz.h:228-237
+template <class F>
+HostJacobian<F> ToJacobian(const HostXYZZ<F>& p) {
+  if (p.IsZero()) return HostJacobian<F>{HostFp<F>::One(), HostFp<F>::One(), HostFp<F>::Zero()};
+  if (p.zz.IsOne()) return HostJacobian<F>{p.x, p.y, HostFp<F>::One()};
+  HostFp<F> z = p.zz.Mul(p.zzz);
+  return HostJacobian<F>{p.x.Mul(p.zzz).Mul(z), p.y.Mul(p.zz).Mul(z.Sqr()), z};
+}
+
+// pippenger_base.h:59-77: Horner over window sums, c doublings per window.
+template <class F>
+HostXYZZ<F> CombineWindows(const HostXYZZ<F>* sums, uint32_t windows, uint32_t c) {
+  HostXYZZ<F> total = HostXYZZ<F>::Zero();
+  for (uint32_t w = windows; w-- > 1;) {
+    total = total.Add(sums[w]);
+    for (uint32_t i = 0; i < c; ++i) total = total.Dbl();
+  }
+  return sums[0].Add(total);
+}
+
+}  // namespace tb200

@@ -1,0 +1,524 @@
+// C ABI of the engine: the reference's MSM-GPU entry points
+// (tachyon/c/math/elliptic_curves/generator/msm_gpu.cc.tpl:8-33,
+//  tachyon/c/math/elliptic_curves/msm/msm_gpu.h:22-122) and this library's
+// extensions, for bn254 and bls12_381.  See include/tachyon_msm_b200.h.
+#include <cuda_runtime.h>
+
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <fstream>
+#include <iostream>
+#include <memory>
+#include <string>
+#include <thread>
+#include <vector>
+
+#include "../../include/tachyon_msm_b200.h"
+#include "msm_engine.cuh"
+
+namespace tb200 {
+
+std::atomic<uint64_t> g_kernel_launches{0};
+thread_local std::string g_last_error;
+
+static int Fail(const CudaError& e) {
+  char buf[512];
+  snprintf(buf, sizeof(buf), "%s:%d: %s -> %s (%d)", e.file, e.line, e.what,
+           cudaGetErrorString(e.code), (int)e.code);
+  g_last_error = buf;
+  return -(int)(e.code ? e.code : 1);
+}
+
+[[noreturn]] static void Die(const CudaError& e) {
+  // The reference CHECK()s at the C boundary (msm_gpu.h:79, :59-62): abort loudly.
+  Fail(e);
+  fprintf(stderr, "tachyon_msm_b200: fatal: %s\n", g_last_error.c_str());
+  abort();
+}
+
+// Context behind tachyon_<curve>_g1_msm_gpu_ptr (MSMGpuApi of msm_gpu.h:22-67).
+template <class C>
+struct MsmGpuContext {
+  using Engine = MsmEngine<C>;
+  using Point = typename Engine::Point;
+
+  std::vector<std::unique_ptr<Engine>> engines;  // [0] = primary device
+  int primary_device = 0;
+  MsmTiming timing;
+  std::string input_dir;  // TACHYON_MSM_GPU_INPUT_DIR (msm_gpu.h:44-48)
+  bool log_msm = false;   // TACHYON_LOG_MSM          (msm_gpu.h:49-52)
+  size_t idx = 0;
+
+  explicit MsmGpuContext(int device) : primary_device(device) {
+    engines.emplace_back(new Engine(device));
+  }
+
+  void SetDevices(int k) {
+    int avail = 0;
+    TB_CUDA(cudaGetDeviceCount(&avail));
+    if (k < 1 || k > avail) throw CudaError{cudaErrorInvalidDevice, "devices option", __FILE__, __LINE__};
+    while ((int)engines.size() > k) engines.pop_back();
+    while ((int)engines.size() < k) {
+      int dev = (primary_device + (int)engines.size()) % avail;
+      engines.emplace_back(new Engine(dev));
+      engines.back()->options() = engines[0]->options();
+    }
+  }
+
+  // Point-range sharding (the split of pippenger_adapter.h:82-113 across GPUs
+  // instead of threads): device g takes [g*n/G, (g+1)*n/G); partial sums are
+  // added on the host.  Device-resident inputs stay on the primary device.
+  Point Run(const void* bases, const void* scalars, size_t n) {
+    size_t G = engines.size();
+    bool host_inputs = true;
+    {
+      cudaPointerAttributes a;
+      if (cudaPointerGetAttributes(&a, bases) == cudaSuccess &&
+          (a.type == cudaMemoryTypeDevice || a.type == cudaMemoryTypeManaged))
+        host_inputs = false;
+      else
+        cudaGetLastError();
+      if (cudaPointerGetAttributes(&a, scalars) == cudaSuccess &&
+          (a.type == cudaMemoryTypeDevice || a.type == cudaMemoryTypeManaged))
+        host_inputs = false;
+      else
+        cudaGetLastError();
+    }
+    if (G == 1 || !host_inputs || n < 2 * G) {
+      Point r = engines[0]->Run(bases, scalars, n);
+      timing = engines[0]->timing();
+      return r;
+    }
+    std::vector<Point> parts(G);
+    std::vector<CudaError> errs(G, CudaError{cudaSuccess, "", "", 0});
+    std::vector<std::thread> threads;
+    for (size_t g = 0; g < G; ++g) {
+      threads.emplace_back([&, g] {
+        size_t lo = n * g / G, hi = n * (g + 1) / G;
+        try {
+          parts[g] = engines[g]->Run(
+              static_cast<const char*>(bases) + lo * Engine::kAffineBytes,
+              static_cast<const char*>(scalars) + lo * Engine::kScalarBytes, hi - lo);
+        } catch (const CudaError& e) {
+          errs[g] = e;
+        }
+      });
+    }
+    for (auto& t : threads) t.join();
+    for (auto& e : errs)
+      if (e.code != cudaSuccess) throw e;
+    Point total = parts[0];
+    for (size_t g = 1; g < G; ++g) total = total.Add(parts[g]);
+    timing = MsmTiming{};
+    for (size_t g = 0; g < G; ++g) {
+      const MsmTiming& t = engines[g]->timing();
+      timing.h2d_ms = std::max(timing.h2d_ms, t.h2d_ms);
+      timing.sort_ms = std::max(timing.sort_ms, t.sort_ms);
+      timing.accumulate_ms = std::max(timing.accumulate_ms, t.accumulate_ms);
+      timing.reduce_ms = std::max(timing.reduce_ms, t.reduce_ms);
+      timing.total_ms = std::max(timing.total_ms, t.total_ms);
+      timing.host_ms = std::max(timing.host_ms, t.host_ms);
+      timing.window_bits = t.window_bits;
+      timing.windows = t.windows;
+      timing.tasks += t.tasks;
+      timing.entries += t.entries;
+      timing.kernel_launches += t.kernel_launches;
+    }
+    timing.devices = (uint32_t)G;
+    TB_CUDA(cudaSetDevice(primary_device));
+    return total;
+  }
+};
+
+template <class F>
+static std::string FpHex(const HostFp<F>& montgomery) {
+  // canonical value, big-endian hex (what ToHexString prints)
+  HostFp<F> one = HostFp<F>::Zero();
+  one.v[0] = 1;
+  HostFp<F> c = montgomery.Mul(one);
+  std::string s = "0x";
+  char buf[17];
+  for (int i = HostFp<F>::N; i-- > 0;) {
+    snprintf(buf, sizeof(buf), "%016llx", (unsigned long long)c.v[i]);
+    s += buf;
+  }
+  return s;
+}
+
+// Dump format of msm_gpu.h:99-119 / msm_gpu_replay.cc:19-37: u64 count, then
+// every field element as canonical little-endian u64 limbs.
+template <class C>
+static void MaybeLogAndDump(MsmGpuContext<C>& ctx, const void* bases, const void* scalars,
+                            size_t size, const HostJacobian<typename C::Fq>& jac) {
+  using Fq = typename C::Fq;
+  using Fr = typename C::Fr;
+  if (ctx.log_msm) {
+    std::cout << "\033[33mDoMSMGpu()" << ctx.idx << "\033[0m" << std::endl;
+    std::cout << "(" << FpHex<Fq>(jac.x) << ", " << FpHex<Fq>(jac.y) << ", " << FpHex<Fq>(jac.z)
+              << ")" << std::endl;
+  }
+  ctx.idx++;
+  if (!ctx.input_dir.empty()) {
+    cudaPointerAttributes a;
+    bool dev = cudaPointerGetAttributes(&a, bases) == cudaSuccess && a.type == cudaMemoryTypeDevice;
+    cudaGetLastError();
+    if (dev) return;  // device-resident SRS is not dumped
+    auto write = [&](const char* stem, auto tag, const void* data, size_t per) {
+      using F = decltype(tag);
+      std::string path = ctx.input_dir + "/" + stem + std::to_string(ctx.idx - 1) + ".txt";
+      {
+        std::ofstream f(path, std::ios::binary);
+        uint64_t count = size;
+        f.write(reinterpret_cast<const char*>(&count), 8);
+      }
+      std::ofstream f(path, std::ios::binary | std::ios::app);
+      HostFp<F> one = HostFp<F>::Zero();
+      one.v[0] = 1;
+      const uint64_t* src = static_cast<const uint64_t*>(data);
+      for (size_t i = 0; i < size * per; ++i) {
+        HostFp<F> m;
+        memcpy(m.v, src + i * HostFp<F>::N, sizeof(m.v));
+        HostFp<F> c = m.Mul(one);
+        f.write(reinterpret_cast<const char*>(c.v), sizeof(c.v));
+      }
+    };
+    write("bases", Fq{}, bases, 2);
+    write("scalars", Fr{}, scalars, 1);
+  }
+}
+
+template <class C, class CJacobian>
+static CJacobian* DoMsmGpu(MsmGpuContext<C>* ctx, const void* bases, const void* scalars,
+                           size_t size) {
+  using Fq = typename C::Fq;
+  try {
+    auto sum = ctx->Run(bases, scalars, size);
+    HostJacobian<Fq> jac = ToJacobian<Fq>(sum);
+    static_assert(sizeof(CJacobian) == sizeof(jac), "layout");
+    CJacobian* ret = new CJacobian();  // caller deletes (msm_gpu.h:81)
+    memcpy(ret, &jac, sizeof(jac));
+    MaybeLogAndDump<C>(*ctx, bases, scalars, size, jac);
+    return ret;
+  } catch (const CudaError& e) {
+    Die(e);
+  }
+}
+
+template <class Ctx>
+static Ctx* CreateContext(int device, bool banner) {
+  if (banner) {
+    // msm_gpu.h:36-42
+    std::cout << "\033[32mCreateMSMGpuApi()\033[0m" << std::endl;
+  }
+  auto* ctx = new Ctx(device);
+  if (const char* d = getenv("TACHYON_MSM_GPU_INPUT_DIR")) ctx->input_dir = d;
+  if (const char* l = getenv("TACHYON_LOG_MSM")) ctx->log_msm = std::string(l) == "1";
+  if (const char* w = getenv("TACHYON_B200_MSM_WINDOW_BITS"))
+    ctx->engines[0]->options().window_bits = (uint32_t)atoi(w);
+  if (const char* g = getenv("TACHYON_B200_MSM_DEVICES")) ctx->SetDevices(atoi(g));
+  return ctx;
+}
+
+// ---- element-wise hooks ------------------------------------------------------
+template <class F>
+static int FieldOpGpu(int op, const uint64_t* a, const uint64_t* b, uint64_t* out, size_t n) {
+  try {
+    if (n == 0) return 0;
+    size_t bytes = n * F::kLimbs64 * 8;
+    uint32_t *da, *db, *dout;
+    TB_CUDA(cudaMalloc(&da, bytes));
+    TB_CUDA(cudaMalloc(&db, bytes));
+    TB_CUDA(cudaMalloc(&dout, bytes));
+    TB_CUDA(cudaMemcpy(da, a, bytes, cudaMemcpyHostToDevice));
+    TB_CUDA(cudaMemcpy(db, b ? b : a, bytes, cudaMemcpyHostToDevice));
+    field_op_kernel<F><<<(uint32_t)((n + 127) / 128), 128>>>(op, da, db, dout, (uint32_t)n);
+    g_kernel_launches.fetch_add(1);
+    TB_CUDA(cudaGetLastError());
+    TB_CUDA(cudaMemcpy(out, dout, bytes, cudaMemcpyDeviceToHost));
+    cudaFree(da);
+    cudaFree(db);
+    cudaFree(dout);
+    return 0;
+  } catch (const CudaError& e) {
+    return Fail(e);
+  }
+}
+
+template <class C>
+static int PointOpGpu(int op, const uint64_t* a, const uint64_t* b, uint64_t* out, size_t n) {
+  using Fq = typename C::Fq;
+  try {
+    if (n == 0) return 0;
+    size_t fe = Fq::kLimbs64 * 8;
+    size_t abytes = n * 4 * fe, bbytes = n * (op == 0 ? 4 : 2) * fe;
+    uint32_t *da, *db, *dout;
+    TB_CUDA(cudaMalloc(&da, abytes));
+    TB_CUDA(cudaMalloc(&db, bbytes));
+    TB_CUDA(cudaMalloc(&dout, abytes));
+    TB_CUDA(cudaMemcpy(da, a, abytes, cudaMemcpyHostToDevice));
+    if (b) TB_CUDA(cudaMemcpy(db, b, bbytes, cudaMemcpyHostToDevice));
+    point_op_kernel<C><<<(uint32_t)((n + 63) / 64), 64>>>(op, da, db, dout, (uint32_t)n);
+    g_kernel_launches.fetch_add(1);
+    TB_CUDA(cudaGetLastError());
+    TB_CUDA(cudaMemcpy(out, dout, abytes, cudaMemcpyDeviceToHost));
+    cudaFree(da);
+    cudaFree(db);
+    cudaFree(dout);
+    return 0;
+  } catch (const CudaError& e) {
+    return Fail(e);
+  }
+}
+
+template <class C>
+static int GenerateBases(uint64_t seed, size_t first, size_t n, void* device_out) {
+  using Fq = typename C::Fq;
+  try {
+    if (n == 0) return 0;
+    const size_t chain = size_t(1) << kChainLog;
+    if (first % chain) throw CudaError{cudaErrorInvalidValue, "first must be a multiple of 4096", __FILE__, __LINE__};
+    // in slabs, so the XYZZ scratch stays bounded
+    const size_t slab = size_t(1) << 22;
+    uint32_t* scratch;
+    size_t scratch_pts = n < slab ? n : slab;
+    TB_CUDA(cudaMalloc(&scratch, scratch_pts * 4 * Fq::kLimbs64 * 8));
+    for (size_t off = 0; off < n; off += slab) {
+      size_t len = n - off < slab ? n - off : slab;
+      uint32_t chains = (uint32_t)((len + chain - 1) / chain);
+      generate_chains_kernel<C><<<(chains + 31) / 32, 32>>>(
+          seed, (uint32_t)((first + off) / chain), chains, (uint32_t)len, scratch);
+      TB_CUDA(cudaGetLastError());
+      normalize_kernel<C><<<(uint32_t)((len + 127) / 128), 128>>>(
+          scratch, (uint32_t)len,
+          reinterpret_cast<uint32_t*>(static_cast<char*>(device_out) + off * 2 * Fq::kLimbs64 * 8));
+      TB_CUDA(cudaGetLastError());
+      g_kernel_launches.fetch_add(2);
+    }
+    TB_CUDA(cudaDeviceSynchronize());
+    cudaFree(scratch);
+    return 0;
+  } catch (const CudaError& e) {
+    return Fail(e);
+  }
+}
+
+template <class C>
+static int GenerateScalars(uint64_t seed, int dist, size_t first, size_t n, void* device_out) {
+  try {
+    if (n == 0) return 0;
+    generate_scalars_kernel<C><<<(uint32_t)((n + 255) / 256), 256>>>(
+        seed, dist, (uint64_t)first, (uint32_t)n, static_cast<uint32_t*>(device_out));
+    g_kernel_launches.fetch_add(1);
+    TB_CUDA(cudaGetLastError());
+    TB_CUDA(cudaDeviceSynchronize());
+    return 0;
+  } catch (const CudaError& e) {
+    return Fail(e);
+  }
+}
+
+}  // namespace tb200
+
+using namespace tb200;
+
+struct tachyon_bn254_g1_msm_gpu : public MsmGpuContext<Bn254Curve> {
+  using MsmGpuContext<Bn254Curve>::MsmGpuContext;
+};
+struct tachyon_bls12_381_g1_msm_gpu : public MsmGpuContext<Bls381Curve> {
+  using MsmGpuContext<Bls381Curve>::MsmGpuContext;
+};
+
+#define TB200_DEFINE_CURVE_API(CN, CURVE)                                                      \
+  void tachyon_##CN##_g1_init(void) {}                                                         \
+  tachyon_##CN##_g1_msm_gpu_ptr tachyon_##CN##_g1_create_msm_gpu(uint8_t degree) {             \
+    (void)degree; /* advisory, unread by the reference too (msm_gpu.h:35) */                   \
+    try {                                                                                      \
+      int dev = 0;                                                                             \
+      if (cudaGetDevice(&dev) != cudaSuccess) dev = 0;                                         \
+      return CreateContext<tachyon_##CN##_g1_msm_gpu>(dev, true);      \
+    } catch (const CudaError& e) {                                                             \
+      Die(e);                                                                                  \
+    }                                                                                          \
+  }                                                                                            \
+  tachyon_##CN##_g1_msm_gpu_ptr tachyon_##CN##_g1_create_msm_gpu_b200(uint8_t degree,          \
+                                                                     int device) {             \
+    (void)degree;                                                                              \
+    try {                                                                                      \
+      return CreateContext<tachyon_##CN##_g1_msm_gpu>(device, false);  \
+    } catch (const CudaError& e) {                                                             \
+      Fail(e);                                                                                 \
+      return nullptr;                                                                          \
+    }                                                                                          \
+  }                                                                                            \
+  void tachyon_##CN##_g1_destroy_msm_gpu(tachyon_##CN##_g1_msm_gpu_ptr ptr) {                  \
+    delete ptr;                                            \
+  }                                                                                            \
+  tachyon_##CN##_g1_jacobian* tachyon_##CN##_g1_point2_msm_gpu(                                \
+      tachyon_##CN##_g1_msm_gpu_ptr ptr, const tachyon_##CN##_g1_point2* bases,                \
+      const tachyon_##CN##_fr* scalars, size_t size) {                                         \
+    return DoMsmGpu<CURVE, tachyon_##CN##_g1_jacobian>(ptr, bases, scalars, size);             \
+  }                                                                                            \
+  tachyon_##CN##_g1_jacobian* tachyon_##CN##_g1_affine_msm_gpu(                                \
+      tachyon_##CN##_g1_msm_gpu_ptr ptr, const tachyon_##CN##_g1_affine* bases,                \
+      const tachyon_##CN##_fr* scalars, size_t size) {                                         \
+    return DoMsmGpu<CURVE, tachyon_##CN##_g1_jacobian>(ptr, bases, scalars, size);             \
+  }                                                                                            \
+  int tachyon_##CN##_g1_msm_gpu_set_stream_b200(tachyon_##CN##_g1_msm_gpu_ptr ptr,             \
+                                                void* cuda_stream) {                           \
+    if (!ptr || ptr->engines.size() != 1) return -1;                                           \
+    ptr->engines[0]->SetStream(static_cast<cudaStream_t>(cuda_stream));                        \
+    return 0;                                                                                  \
+  }                                                                                            \
+  int tachyon_##CN##_g1_msm_gpu_set_option_b200(tachyon_##CN##_g1_msm_gpu_ptr ptr,             \
+                                                const char* name, long value) {                \
+    if (!ptr || !name) return -1;                                                              \
+    try {                                                                                      \
+      std::string k(name);                                                                     \
+      if (k == "window_bits") {                                                                \
+        for (auto& e : ptr->engines) e->options().window_bits = (uint32_t)value;               \
+      } else if (k == "segment") {                                                             \
+        for (auto& e : ptr->engines) e->options().segment = (uint32_t)value;                   \
+      } else if (k == "devices") {                                                             \
+        ptr->SetDevices((int)value);                                                           \
+      } else {                                                                                 \
+        g_last_error = "unknown option " + k;                                                  \
+        return -1;                                                                             \
+      }                                                                                        \
+      return 0;                                                                                \
+    } catch (const CudaError& e) {                                                             \
+      return Fail(e);                                                                          \
+    }                                                                                          \
+  }                                                                                            \
+  int tachyon_##CN##_g1_msm_gpu_xyzz_b200(tachyon_##CN##_g1_msm_gpu_ptr ptr,                   \
+                                          const tachyon_##CN##_g1_affine* bases,               \
+                                          const tachyon_##CN##_fr* scalars, size_t size,       \
+                                          tachyon_##CN##_g1_xyzz* out) {                       \
+    if (!ptr || !out) return -1;                                                               \
+    try {                                                                                      \
+      auto sum = ptr->Run(bases, scalars, size);                                               \
+      static_assert(sizeof(*out) == sizeof(sum), "layout");                                    \
+      memcpy(out, &sum, sizeof(sum));                                                          \
+      return 0;                                                                                \
+    } catch (const CudaError& e) {                                                             \
+      return Fail(e);                                                                          \
+    }                                                                                          \
+  }                                                                                            \
+  int tachyon_##CN##_g1_msm_gpu_last_timing_b200(tachyon_##CN##_g1_msm_gpu_ptr ptr,            \
+                                                 tachyon_b200_msm_timing* out) {               \
+    if (!ptr || !out) return -1;                                                               \
+    const MsmTiming& t = ptr->timing;                                                          \
+    out->h2d_ms = t.h2d_ms;                                                                    \
+    out->sort_ms = t.sort_ms;                                                                  \
+    out->accumulate_ms = t.accumulate_ms;                                                      \
+    out->reduce_ms = t.reduce_ms;                                                              \
+    out->total_ms = t.total_ms;                                                                \
+    out->host_ms = t.host_ms;                                                                  \
+    out->window_bits = t.window_bits;                                                          \
+    out->windows = t.windows;                                                                  \
+    out->tasks = t.tasks;                                                                      \
+    out->entries = t.entries;                                                                  \
+    out->kernel_launches = t.kernel_launches;                                                  \
+    out->devices = t.devices;                                                                  \
+    return 0;                                                                                  \
+  }                                                                                            \
+  int tachyon_##CN##_g1_generate_bases_b200(uint64_t seed, size_t first, size_t n,             \
+                                            void* device_out) {                                \
+    return GenerateBases<CURVE>(seed, first, n, device_out);                                   \
+  }                                                                                            \
+  int tachyon_##CN##_g1_generate_scalars_b200(uint64_t seed, int dist, size_t first, size_t n, \
+                                              void* device_out) {                              \
+    return GenerateScalars<CURVE>(seed, dist, first, n, device_out);                           \
+  }                                                                                            \
+  int tachyon_##CN##_fq_op_b200(int op, const uint64_t* a, const uint64_t* b, uint64_t* out,   \
+                                size_t n) {                                                    \
+    return FieldOpGpu<CURVE::Fq>(op, a, b, out, n);                                            \
+  }                                                                                            \
+  int tachyon_##CN##_fr_op_b200(int op, const uint64_t* a, const uint64_t* b, uint64_t* out,   \
+                                size_t n) {                                                    \
+    return FieldOpGpu<CURVE::Fr>(op, a, b, out, n);                                            \
+  }                                                                                            \
+  int tachyon_##CN##_g1_point_op_b200(int op, const uint64_t* a, const uint64_t* b,            \
+                                      uint64_t* out, size_t n) {                               \
+    return PointOpGpu<CURVE>(op, a, b, out, n);                                                \
+  }                                                                                            \
+  void tachyon_##CN##_g1_xyzz_add_b200(const tachyon_##CN##_g1_xyzz* a,                        \
+                                       const tachyon_##CN##_g1_xyzz* b,                        \
+                                       tachyon_##CN##_g1_xyzz* out) {                          \
+    HostXYZZ<CURVE::Fq> x, y;                                                                  \
+    memcpy(&x, a, sizeof(x));                                                                  \
+    memcpy(&y, b, sizeof(y));                                                                  \
+    HostXYZZ<CURVE::Fq> r = x.Add(y);                                                          \
+    memcpy(out, &r, sizeof(r));                                                                \
+  }                                                                                            \
+  void tachyon_##CN##_g1_xyzz_to_jacobian_b200(const tachyon_##CN##_g1_xyzz* a,                \
+                                               tachyon_##CN##_g1_jacobian* out) {              \
+    HostXYZZ<CURVE::Fq> x;                                                                     \
+    memcpy(&x, a, sizeof(x));                                                                  \
+    HostJacobian<CURVE::Fq> j = ToJacobian<CURVE::Fq>(x);                                      \
+    memcpy(out, &j, sizeof(j));                                                                \
+  }
+
+extern "C" {
+
+TB200_DEFINE_CURVE_API(bn254, Bn254Curve)
+TB200_DEFINE_CURVE_API(bls12_381, Bls381Curve)
+
+int tachyon_b200_device_count(void) {
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    return -(int)e;
+  }
+  return n;
+}
+
+uint32_t tachyon_b200_window_bits(size_t n, uint32_t scalar_bits) {
+  return ChooseWindowBits(n, scalar_bits);
+}
+uint32_t tachyon_b200_window_count(uint32_t scalar_bits, uint32_t window_bits) {
+  return WindowsFor(scalar_bits, window_bits);
+}
+
+const char* tachyon_b200_last_error(void) { return g_last_error.c_str(); }
+
+uint64_t tachyon_b200_kernel_launch_count(void) { return g_kernel_launches.load(); }
+
+double tachyon_b200_imad_peak(int device, int variant, int repeats) {
+  try {
+    TB_CUDA(cudaSetDevice(device));
+    int sms = 0;
+    TB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));
+    uint32_t* out;
+    TB_CUDA(cudaMalloc(&out, 4));
+    cudaEvent_t e0, e1;
+    TB_CUDA(cudaEventCreate(&e0));
+    TB_CUDA(cudaEventCreate(&e1));
+    const uint32_t iters = 4096, blocks = sms * 8, threads = 256;
+    double best = 0;
+    for (int r = 0; r < repeats + 1; ++r) {
+      TB_CUDA(cudaEventRecord(e0));
+      if (variant == 0)
+        imad_peak_kernel<0><<<blocks, threads>>>(iters, 12345u + r, out);
+      else
+        imad_peak_kernel<1><<<blocks, threads>>>(iters, 12345u + r, out);
+      TB_CUDA(cudaEventRecord(e1));
+      TB_CUDA(cudaEventSynchronize(e1));
+      g_kernel_launches.fetch_add(1);
+      float ms;
+      TB_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+      double products = (double)blocks * threads * iters * 16.0;
+      double rate = products / (ms * 1e-3);
+      if (r > 0 && rate > best) best = rate;  // r == 0 is warm-up
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    cudaFree(out);
+    return best;
+  } catch (const CudaError& e) {
+    return (double)Fail(e);
+  }
+}
+
+}  // extern "C"

@@ -1,0 +1,372 @@
+// Host-side MSM engine: owns the device workspace and stream of one GPU and
+// enqueues the kernel pipeline of msm_kernels.cuh.  Plays the role of
+// tachyon/math/elliptic_curves/msm/variable_base_msm_gpu.h:11-31 +
+// algorithms/icicle/icicle_msm.h:35-76 (context = mem pool + stream, Run(bases,
+// scalars) -> one point), without icicle.
+#pragma once
+#include <cuda_runtime.h>
+
+#include <atomic>
+#include <chrono>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <string>
+#include <vector>
+
+#include "host_math.h"
+#include "msm_kernels.cuh"
+
+namespace tb200 {
+
+extern std::atomic<uint64_t> g_kernel_launches;
+
+struct CudaError {
+  cudaError_t code;
+  const char* what;
+  const char* file;
+  int line;
+};
+
+#define TB_CUDA(expr)                                                         \
+  do {                                                                        \
+    cudaError_t e_ = (expr);                                                  \
+    if (e_ != cudaSuccess) throw CudaError{e_, #expr, __FILE__, __LINE__};    \
+  } while (0)
+
+// Grow-only device buffer.
+struct DeviceBuffer {
+  void* ptr = nullptr;
+  size_t bytes = 0;
+  void Reserve(size_t want) {
+    if (want <= bytes) return;
+    if (ptr) TB_CUDA(cudaFree(ptr));
+    ptr = nullptr;
+    bytes = 0;
+    // round up to 2 MiB, 12.5 % slack so slightly larger follow-up calls reuse it
+    size_t sz = want + want / 8;
+    sz = (sz + (size_t(2) << 20) - 1) & ~((size_t(2) << 20) - 1);
+    TB_CUDA(cudaMalloc(&ptr, sz));
+    bytes = sz;
+  }
+  void Free() {
+    if (ptr) cudaFree(ptr);
+    ptr = nullptr;
+    bytes = 0;
+  }
+  template <class T>
+  T* as() const {
+    return reinterpret_cast<T*>(ptr);
+  }
+};
+
+struct MsmTiming {
+  float h2d_ms = 0, sort_ms = 0, accumulate_ms = 0, reduce_ms = 0, total_ms = 0, host_ms = 0;
+  uint32_t window_bits = 0, windows = 0, tasks = 0, entries = 0, kernel_launches = 0, devices = 1;
+};
+
+struct MsmOptions {
+  uint32_t window_bits = 0;  // 0 = choose from n
+  uint32_t segment = 0;      // 0 = default
+};
+
+// Window choice.  Cost in units of one mixed addition:
+//   accumulation  n * W
+//   reduction     W * 2^(c-1) * 2 full additions (1.4 madd each), run at lower
+//                 occupancy than the hot kernel (factor kReduceInefficiency)
+// W is the smallest count with W * c >= bits + 1, so the signed top digit
+// never carries out (see for_each_digit).
+inline uint32_t WindowsFor(uint32_t bits, uint32_t c) { return (bits + 1 + c - 1) / c; }
+
+inline uint32_t ChooseWindowBits(size_t n, uint32_t scalar_bits) {
+  constexpr double kReduceInefficiency = 1.5;
+  constexpr uint32_t kMaxBuckets = 1u << 24;  // scan_top_kernel capacity
+  double best = 1e300;
+  uint32_t best_c = 2;
+  for (uint32_t c = 2; c <= 22; ++c) {
+    uint32_t W = WindowsFor(scalar_bits, c);
+    double buckets = (double)W * (double)(1u << (c - 1));
+    if (buckets > kMaxBuckets) break;
+    double cost = (double)n * W + buckets * 2.0 * 1.4 * kReduceInefficiency;
+    if (cost < best) {
+      best = cost;
+      best_c = c;
+    }
+  }
+  return best_c;
+}
+
+template <class C>
+class MsmEngine {
+ public:
+  using Fq = typename C::Fq;
+  using Fr = typename C::Fr;
+  using Point = HostXYZZ<Fq>;
+  static constexpr size_t kAffineBytes = 2 * Fq::kLimbs64 * 8;
+  static constexpr size_t kScalarBytes = Fr::kLimbs64 * 8;
+  static constexpr size_t kXyzzBytes = 4 * Fq::kLimbs64 * 8;
+  static constexpr int kXyzzWords = 4 * Fq::kLimbs32;
+  // n * W must stay below 2^32 (u32 offsets) and n below 2^31 (sign bit)
+  static constexpr size_t kMaxChunk = size_t(1) << 26;
+
+  explicit MsmEngine(int device) : device_(device) {
+    TB_CUDA(cudaSetDevice(device_));
+    TB_CUDA(cudaStreamCreateWithFlags(&own_stream_, cudaStreamNonBlocking));
+    stream_ = own_stream_;
+    for (auto& e : ev_) TB_CUDA(cudaEventCreate(&e));
+    TB_CUDA(cudaMallocHost(&host_out_, kHostOutBytes));
+    TB_CUDA(cudaMalloc(&totals_, sizeof(MsmTotals)));
+    int sms = 0;
+    TB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device_));
+    sm_count_ = sms;
+  }
+  ~MsmEngine() {
+    cudaSetDevice(device_);
+    cudaStreamSynchronize(stream_);
+    for (DeviceBuffer* b : {&bases_stage_, &scalars_stage_, &count_, &offset_, &cursor_,
+                            &task_base_, &tasks_, &multi_, &sorted_, &task_out_, &block_sums_,
+                            &lvl_a_[0], &lvl_a_[1], &lvl_c_[0], &lvl_c_[1]})
+      b->Free();
+    if (totals_) cudaFree(totals_);
+    if (host_out_) cudaFreeHost(host_out_);
+    for (auto& e : ev_) cudaEventDestroy(e);
+    cudaStreamDestroy(own_stream_);
+  }
+  MsmEngine(const MsmEngine&) = delete;
+  MsmEngine& operator=(const MsmEngine&) = delete;
+
+  int device() const { return device_; }
+  void SetStream(cudaStream_t s) { stream_ = s ? s : own_stream_; }
+  MsmOptions& options() { return options_; }
+  const MsmTiming& timing() const { return timing_; }
+
+  // bases / scalars: n elements each, host (pageable or pinned) or device
+  // memory of this engine's device.  Blocking.
+  Point Run(const void* bases, const void* scalars, size_t n) {
+    TB_CUDA(cudaSetDevice(device_));
+    timing_ = MsmTiming{};
+    Point total = Point::Zero();
+    if (n == 0) return total;  // pippenger_adapter.h:62-65
+    // Sequential chunks only when the index arithmetic requires it; unlike
+    // icicle_msm_bn254_g1.cc:56-62 the last chunk keeps its remainder.
+    for (size_t off = 0; off < n; off += kMaxChunk) {
+      size_t len = n - off < kMaxChunk ? n - off : kMaxChunk;
+      Point part = RunChunk(static_cast<const char*>(bases) + off * kAffineBytes,
+                            static_cast<const char*>(scalars) + off * kScalarBytes, len);
+      total = (off == 0) ? part : total.Add(part);
+    }
+    return total;
+  }
+
+ private:
+  static bool IsDevicePointer(const void* p) {
+    cudaPointerAttributes attr;
+    cudaError_t e = cudaPointerGetAttributes(&attr, p);
+    if (e != cudaSuccess) {
+      cudaGetLastError();
+      return false;
+    }
+    return attr.type == cudaMemoryTypeDevice || attr.type == cudaMemoryTypeManaged;
+  }
+
+  template <class K, class... Args>
+  void Launch(K kernel, uint32_t grid, uint32_t block, Args... args) {
+    kernel<<<grid, block, 0, stream_>>>(args...);
+    TB_CUDA(cudaGetLastError());
+    ++launches_;
+    g_kernel_launches.fetch_add(1, std::memory_order_relaxed);
+  }
+
+  MsmPlan MakePlan(size_t n) const {
+    MsmPlan p{};
+    p.n = (uint32_t)n;
+    p.c = options_.window_bits ? options_.window_bits : ChooseWindowBits(n, Fr::kBits);
+    if (p.c < 2) p.c = 2;
+    if (p.c > 24) p.c = 24;
+    p.W = WindowsFor(Fr::kBits, p.c);
+    p.B = 1u << (p.c - 1);
+    p.TB = p.W * p.B;
+    p.seg = options_.segment ? options_.segment : 128;
+    uint64_t entries = (uint64_t)n * p.W;
+    uint64_t nonempty = entries < p.TB ? entries : p.TB;
+    p.max_tasks = (uint32_t)(nonempty + entries / p.seg);
+    return p;
+  }
+
+  Point RunChunk(const void* bases, const void* scalars, size_t n) {
+    auto wall0 = std::chrono::steady_clock::now();
+    MsmPlan plan = MakePlan(n);
+    launches_ = 0;
+    TB_CUDA(cudaEventRecord(ev_[0], stream_));
+
+    // ---- inputs -----------------------------------------------------------
+    const uint32_t* d_bases;
+    const uint32_t* d_scalars;
+    if (IsDevicePointer(scalars)) {
+      d_scalars = static_cast<const uint32_t*>(scalars);
+    } else {
+      scalars_stage_.Reserve(n * kScalarBytes);
+      TB_CUDA(cudaMemcpyAsync(scalars_stage_.ptr, scalars, n * kScalarBytes,
+                              cudaMemcpyHostToDevice, stream_));
+      d_scalars = scalars_stage_.as<uint32_t>();
+    }
+    if (IsDevicePointer(bases)) {
+      d_bases = static_cast<const uint32_t*>(bases);
+    } else {
+      bases_stage_.Reserve(n * kAffineBytes);
+      TB_CUDA(cudaMemcpyAsync(bases_stage_.ptr, bases, n * kAffineBytes, cudaMemcpyHostToDevice,
+                              stream_));
+      d_bases = bases_stage_.as<uint32_t>();
+    }
+    TB_CUDA(cudaEventRecord(ev_[1], stream_));
+
+    // ---- workspace --------------------------------------------------------
+    uint32_t scan_blocks = (plan.TB + kScanItems - 1) / kScanItems;
+    if (scan_blocks > (uint32_t)kScanItems) throw CudaError{cudaErrorInvalidValue, "too many buckets", __FILE__, __LINE__};
+    count_.Reserve((size_t)(plan.TB + 1) * 4);
+    offset_.Reserve((size_t)(plan.TB + 1) * 4);
+    cursor_.Reserve((size_t)(plan.TB + 1) * 4);
+    task_base_.Reserve((size_t)plan.TB * 4);
+    tasks_.Reserve((size_t)plan.max_tasks * sizeof(uint2));
+    multi_.Reserve((size_t)plan.TB * 4);
+    sorted_.Reserve((size_t)n * plan.W * 4);
+    task_out_.Reserve((size_t)plan.max_tasks * kXyzzBytes);
+    block_sums_.Reserve((size_t)scan_blocks * 8);
+
+    // ---- sort: histogram, scan, tasks, scatter ----------------------------
+    TB_CUDA(cudaMemsetAsync(count_.ptr, 0, (size_t)(plan.TB + 1) * 4, stream_));
+    uint32_t sgrid = (plan.n + 255) / 256;
+    Launch(digits_hist_kernel<C>, sgrid, 256, d_scalars, plan, count_.as<uint32_t>());
+    Launch(scan_block_sums_kernel, scan_blocks, kScanThreads, count_.as<uint32_t>(), plan.TB,
+           plan.seg, block_sums_.as<uint64_t>());
+    Launch(scan_top_kernel, 1, kScanThreads, block_sums_.as<uint64_t>(), scan_blocks, totals_);
+    Launch(scan_apply_build_tasks_kernel, scan_blocks, kScanThreads, count_.as<uint32_t>(),
+           plan.TB, plan.seg, block_sums_.as<uint64_t>(), offset_.as<uint32_t>(),
+           cursor_.as<uint32_t>(), task_base_.as<uint32_t>(), tasks_.as<uint2>(),
+           multi_.as<uint32_t>(), totals_);
+    Launch(digits_scatter_kernel<C>, sgrid, 256, d_scalars, plan, cursor_.as<uint32_t>(),
+           sorted_.as<uint32_t>());
+    TB_CUDA(cudaEventRecord(ev_[2], stream_));
+
+    // ---- accumulate -------------------------------------------------------
+    uint32_t agrid = (plan.max_tasks + kAccThreads - 1) / kAccThreads;
+    Launch(accumulate_kernel<C>, agrid, kAccThreads, d_bases, sorted_.as<uint32_t>(),
+           tasks_.as<uint2>(), totals_, task_out_.as<uint32_t>());
+    Launch(fold_partials_kernel<C>, sm_count_ * 4, kFoldThreads, multi_.as<uint32_t>(), totals_,
+           offset_.as<uint32_t>(), task_base_.as<uint32_t>(), plan.seg,
+           task_out_.as<uint32_t>());
+    TB_CUDA(cudaEventRecord(ev_[3], stream_));
+
+    // ---- bucket reduction levels -------------------------------------------
+    uint32_t n_in = plan.B;
+    uint32_t shift = 0;
+    int level = 0;
+    const uint32_t* in_a = task_out_.as<uint32_t>();
+    const uint32_t* in_c = nullptr;
+    uint32_t* out_a = nullptr;
+    uint32_t* out_c = nullptr;
+    while (true) {
+      uint32_t L = ChooseLevelLength(level, n_in, plan.W);
+      uint32_t n_out = (n_in + L - 1) / L;
+      DeviceBuffer& ba = lvl_a_[level & 1];
+      DeviceBuffer& bc = lvl_c_[level & 1];
+      ba.Reserve((size_t)plan.W * n_out * kXyzzBytes);
+      bc.Reserve((size_t)plan.W * n_out * kXyzzBytes);
+      out_a = ba.as<uint32_t>();
+      out_c = bc.as<uint32_t>();
+      uint32_t threads = plan.W * n_out;
+      uint32_t grid = (threads + kReduceThreads - 1) / kReduceThreads;
+      if (level == 0) {
+        Launch(reduce_level_kernel<C, true>, grid, kReduceThreads, in_a, in_c,
+               offset_.as<uint32_t>(), task_base_.as<uint32_t>(), n_in, n_out, L, shift, plan.W,
+               out_a, out_c);
+      } else {
+        Launch(reduce_level_kernel<C, false>, grid, kReduceThreads, in_a, in_c,
+               (const uint32_t*)nullptr, (const uint32_t*)nullptr, n_in, n_out, L, shift, plan.W,
+               out_a, out_c);
+      }
+      shift += Log2(L);
+      n_in = n_out;
+      in_a = out_a;
+      in_c = out_c;
+      ++level;
+      if (n_out == 1) break;
+    }
+    // window sums S_w = A_w + C_w, finished on the host
+    size_t win_bytes = (size_t)plan.W * kXyzzBytes;
+    TB_CUDA(cudaMemcpyAsync(host_out_, out_a, win_bytes, cudaMemcpyDeviceToHost, stream_));
+    TB_CUDA(cudaMemcpyAsync(host_out_ + win_bytes, out_c, win_bytes, cudaMemcpyDeviceToHost,
+                            stream_));
+    TB_CUDA(cudaMemcpyAsync(host_out_ + 2 * win_bytes, totals_, sizeof(MsmTotals),
+                            cudaMemcpyDeviceToHost, stream_));
+    TB_CUDA(cudaEventRecord(ev_[4], stream_));
+    TB_CUDA(cudaStreamSynchronize(stream_));
+
+    // ---- host epilogue (pippenger_base.h:59-77) ----------------------------
+    auto host0 = std::chrono::steady_clock::now();
+    std::vector<Point> sums(plan.W);
+    const Point* ha = reinterpret_cast<const Point*>(host_out_);
+    const Point* hc = reinterpret_cast<const Point*>(host_out_ + win_bytes);
+    for (uint32_t w = 0; w < plan.W; ++w) sums[w] = ha[w].Add(hc[w]);
+    Point result = CombineWindows<Fq>(sums.data(), plan.W, plan.c);
+    auto host1 = std::chrono::steady_clock::now();
+
+    MsmTotals tot;
+    memcpy(&tot, host_out_ + 2 * win_bytes, sizeof(tot));
+    float ms;
+    TB_CUDA(cudaEventElapsedTime(&ms, ev_[0], ev_[1]));
+    timing_.h2d_ms += ms;
+    TB_CUDA(cudaEventElapsedTime(&ms, ev_[1], ev_[2]));
+    timing_.sort_ms += ms;
+    TB_CUDA(cudaEventElapsedTime(&ms, ev_[2], ev_[3]));
+    timing_.accumulate_ms += ms;
+    TB_CUDA(cudaEventElapsedTime(&ms, ev_[3], ev_[4]));
+    timing_.reduce_ms += ms;
+    TB_CUDA(cudaEventElapsedTime(&ms, ev_[0], ev_[4]));
+    timing_.total_ms += ms;
+    timing_.host_ms += std::chrono::duration<float, std::milli>(host1 - host0).count();
+    timing_.window_bits = plan.c;
+    timing_.windows = plan.W;
+    timing_.tasks += tot.tasks;
+    timing_.entries += tot.entries;
+    timing_.kernel_launches += launches_;
+    (void)wall0;
+    return result;
+  }
+
+  static uint32_t Log2(uint32_t x) {
+    uint32_t r = 0;
+    while ((1u << r) < x) ++r;
+    return r;
+  }
+
+  // Level 0 is throughput-bound (many buckets): blocks as long as the grid
+  // still fills the chip.  Later levels are latency-bound chains of full
+  // additions: keep them short.
+  uint32_t ChooseLevelLength(int level, uint32_t n_in, uint32_t windows) const {
+    if (level > 0) return n_in < 4 ? n_in : 4;
+    uint64_t items = (uint64_t)n_in * windows;
+    uint64_t want_threads = (uint64_t)sm_count_ * 512;
+    uint32_t L = 64;
+    while (L > 4 && items / L < want_threads) L >>= 1;
+    if (L > n_in) L = n_in;
+    return L;
+  }
+
+  static constexpr size_t kHostOutBytes = 64 * 2 * 192 + 64;  // <= 64 windows x (A, C) + totals
+
+  int device_;
+  int sm_count_ = 148;
+  cudaStream_t own_stream_ = nullptr;
+  cudaStream_t stream_ = nullptr;
+  cudaEvent_t ev_[5];
+  MsmOptions options_;
+  MsmTiming timing_;
+  uint32_t launches_ = 0;
+  MsmTotals* totals_ = nullptr;
+  char* host_out_ = nullptr;
+  DeviceBuffer bases_stage_, scalars_stage_, count_, offset_, cursor_, task_base_, tasks_, multi_,
+      sorted_, task_out_, block_sums_, lvl_a_[2], lvl_c_[2];
+};
+
+}  // namespace tb200

@@ -1,0 +1,633 @@
+// sm_100a kernels of the variable-base MSM pipeline (bucket method).
+//
+// This is the from-scratch replacement of the single external call the
+// reference makes at
+//   tachyon/math/elliptic_curves/msm/algorithms/icicle/icicle_msm_bn254_g1.cc:12-17
+// (and the bls12_381 twin), and computes the same group element as the CPU
+// path tachyon/math/elliptic_curves/msm/algorithms/pippenger/pippenger.h:68-169.
+//
+//   digits_hist     scalar de-Montgomery + signed-window recode -> bucket sizes
+//   scan_*          exclusive scan of sizes (bucket offsets) and task counts
+//   build_tasks     bucket -> fixed-max-length segments ("tasks")
+//   digits_scatter  counting-sort scatter of (point index | sign) by bucket
+//   accumulate      per task: sum of +-P over its segment, XYZZ mixed adds  (HOT)
+//   fold_partials   buckets that were split into several tasks
+//   reduce_level    sum_k (k+1) B_k per window, blocked running sums
+//
+// Layouts (all in HBM, SoA where a kernel streams, AoS where it gathers):
+//   bases    n x {x, y}           Montgomery u32 limbs, 64 B (BN254) / 96 B (BLS)
+//   scalars  n x 8 u32            Montgomery Fr
+//   count    TB+1 u32             TB = W * 2^(c-1) buckets, key = w * 2^(c-1) + |d| - 1
+//   sorted   <= n*W u32           point index | sign << 31, grouped by key
+//   tasks    uint2 {start, len}   len <= seg
+//   task_out T x XYZZ             128 B / 192 B
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "xyzz.cuh"
+
+namespace tb200 {
+
+struct Bn254Curve {
+  using Fq = Bn254FqParams;
+  using Fr = Bn254FrParams;
+  using Gen = Bn254G1Generator;
+  static constexpr const char* kName = "bn254";
+};
+struct Bls381Curve {
+  using Fq = Bls381FqParams;
+  using Fr = Bls381FrParams;
+  using Gen = Bls381G1Generator;
+  static constexpr const char* kName = "bls12_381";
+};
+
+struct MsmPlan {
+  uint32_t n;        // points
+  uint32_t c;        // window bits
+  uint32_t W;        // windows, W * c >= scalar bits + 1
+  uint32_t B;        // buckets per window = 2^(c-1)
+  uint32_t TB;       // W * B
+  uint32_t seg;      // max entries per task
+  uint32_t max_tasks;
+};
+
+// totals written by the scan: [0] = entries (non-zero digits), [1] = tasks,
+// [2] = number of split buckets (filled by build_tasks)
+struct MsmTotals {
+  uint32_t entries;
+  uint32_t tasks;
+  uint32_t multi;
+  uint32_t pad;
+};
+
+// ---------------------------------------------------------------------------
+// Scalar recoding.  Same digits as pippenger.h:27-51 FillDigits up to the
+// representation of +-2^(c-1) (taken as +2^(c-1) here, -2^(c-1) there; both
+// name the same multiple) and with W chosen so the top digit never carries
+// out, hence every window has exactly 2^(c-1) buckets.
+// ---------------------------------------------------------------------------
+template <class Fr>
+TB_DEV void load_scalar_canonical(Fp<Fr>& s, const uint32_t* scalars, uint32_t i) {
+  Fp<Fr> m;
+  fp_load<Fr>(m, scalars + (size_t)i * Fp<Fr>::N);
+  fp_from_mont<Fr>(s, m);
+}
+
+// Pops the low c bits and shifts the scalar right by c.
+template <int N>
+TB_DEV uint32_t pop_window(uint32_t (&s)[N], uint32_t c) {
+  uint32_t bits = s[0] & ((1u << c) - 1u);
+#pragma unroll
+  for (int i = 0; i < N - 1; ++i) s[i] = __funnelshift_r(s[i], s[i + 1], c);
+  s[N - 1] >>= c;
+  return bits;
+}
+
+// Calls f(w, bucket_key, negative) for every non-zero digit.
+template <class Fr, class Fn>
+TB_DEV void for_each_digit(Fp<Fr>& s, const MsmPlan& plan, Fn f) {
+  uint32_t carry = 0;
+  const uint32_t half = plan.B;  // 2^(c-1)
+  for (uint32_t w = 0; w < plan.W; ++w) {
+    uint32_t d = pop_window(s.l, plan.c) + carry;
+    bool neg = d > half;
+    carry = neg ? 1u : 0u;
+    uint32_t mag = neg ? (2u * half - d) : d;
+    f(w, mag, neg);
+  }
+}
+
+// One warp-level atomic per distinct key: lanes holding the same key elect a
+// leader that adds the group size; returns this lane's slot within the group
+// base.  `active` must be the same for the whole warp call site.
+TB_DEV uint32_t warp_aggregated_inc(uint32_t* counter_base, uint32_t key, bool valid) {
+  uint32_t result = 0;
+  uint32_t vote = __ballot_sync(0xffffffffu, valid);
+  if (valid) {
+    uint32_t peers = __match_any_sync(vote, key);
+    uint32_t lane = threadIdx.x & 31;
+    uint32_t leader = __ffs(peers) - 1;
+    uint32_t rank = __popc(peers & ((1u << lane) - 1u));
+    uint32_t base = 0;
+    if (lane == leader) base = atomicAdd(counter_base + key, (uint32_t)__popc(peers));
+    base = __shfl_sync(peers, base, leader);
+    result = base + rank;
+  }
+  return result;
+}
+
+template <class C>
+__global__ void __launch_bounds__(256) digits_hist_kernel(const uint32_t* __restrict__ scalars,
+                                                          MsmPlan plan,
+                                                          uint32_t* __restrict__ count) {
+  using Fr = typename C::Fr;
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  bool in = i < plan.n;
+  Fp<Fr> s;
+  if (in) {
+    load_scalar_canonical<Fr>(s, scalars, i);
+  } else {
+    fp_set_zero<Fr>(s);
+  }
+  for_each_digit<Fr>(s, plan, [&](uint32_t w, uint32_t mag, bool) {
+    bool valid = in && mag != 0;
+    warp_aggregated_inc(count, w * plan.B + mag - 1, valid);
+  });
+}
+
+// cursor[key] starts at offset[key] (a copy of the exclusive scan) and is
+// advanced by the scatter; the value returned by the atomic is the slot.
+template <class C>
+__global__ void __launch_bounds__(256) digits_scatter_kernel(const uint32_t* __restrict__ scalars,
+                                                             MsmPlan plan,
+                                                             uint32_t* __restrict__ cursor,
+                                                             uint32_t* __restrict__ sorted) {
+  using Fr = typename C::Fr;
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  bool in = i < plan.n;
+  Fp<Fr> s;
+  if (in) {
+    load_scalar_canonical<Fr>(s, scalars, i);
+  } else {
+    fp_set_zero<Fr>(s);
+  }
+  for_each_digit<Fr>(s, plan, [&](uint32_t w, uint32_t mag, bool neg) {
+    bool valid = in && mag != 0;
+    uint32_t pos = warp_aggregated_inc(cursor, w * plan.B + mag - 1, valid);
+    if (valid) sorted[pos] = i | (neg ? 0x80000000u : 0u);
+  });
+}
+
+// ---------------------------------------------------------------------------
+// Exclusive scan over TB bucket sizes, carrying two sums at once in a u64:
+// low word = entries (bucket offsets), high word = tasks (ceil(size / seg)).
+// Three passes; kScanItems per block.
+// ---------------------------------------------------------------------------
+constexpr int kScanThreads = 256;
+constexpr int kScanPerThread = 16;
+constexpr int kScanItems = kScanThreads * kScanPerThread;
+
+TB_DEV uint64_t scan_item(uint32_t cnt, uint32_t seg) {
+  uint32_t t = (cnt + seg - 1) / seg;
+  return ((uint64_t)t << 32) | cnt;
+}
+
+TB_DEV uint64_t block_exclusive_scan(uint64_t v, uint64_t* total, uint64_t* smem) {
+  // smem: kScanThreads/32 words
+  uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  uint64_t x = v;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    uint64_t y = __shfl_up_sync(0xffffffffu, x, o);
+    if (lane >= (uint32_t)o) x += y;
+  }
+  if (lane == 31) smem[warp] = x;
+  __syncthreads();
+  if (warp == 0) {
+    uint64_t s = (lane < kScanThreads / 32) ? smem[lane] : 0;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      uint64_t y = __shfl_up_sync(0xffffffffu, s, o);
+      if (lane >= (uint32_t)o) s += y;
+    }
+    if (lane < kScanThreads / 32) smem[lane] = s;
+  }
+  __syncthreads();
+  uint64_t warp_prefix = warp ? smem[warp - 1] : 0;
+  *total = smem[kScanThreads / 32 - 1];
+  __syncthreads();
+  return warp_prefix + x - v;
+}
+
+__global__ void __launch_bounds__(kScanThreads) scan_block_sums_kernel(
+    const uint32_t* __restrict__ count, uint32_t n, uint32_t seg, uint64_t* __restrict__ block_sums) {
+  __shared__ uint64_t smem[kScanThreads / 32];
+  uint32_t base = blockIdx.x * kScanItems + threadIdx.x * kScanPerThread;
+  uint64_t sum = 0;
+#pragma unroll
+  for (int k = 0; k < kScanPerThread; ++k) {
+    uint32_t idx = base + k;
+    if (idx < n) sum += scan_item(count[idx], seg);
+  }
+  uint64_t total;
+  block_exclusive_scan(sum, &total, smem);
+  if (threadIdx.x == 0) block_sums[blockIdx.x] = total;
+}
+
+// single block; nblocks <= kScanItems
+__global__ void __launch_bounds__(kScanThreads) scan_top_kernel(uint64_t* __restrict__ block_sums,
+                                                                uint32_t nblocks,
+                                                                MsmTotals* __restrict__ totals) {
+  __shared__ uint64_t smem[kScanThreads / 32];
+  uint64_t v[kScanPerThread];
+  uint64_t sum = 0;
+  uint32_t base = threadIdx.x * kScanPerThread;
+#pragma unroll
+  for (int k = 0; k < kScanPerThread; ++k) {
+    v[k] = (base + k < nblocks) ? block_sums[base + k] : 0;
+    sum += v[k];
+  }
+  uint64_t total;
+  uint64_t prefix = block_exclusive_scan(sum, &total, smem);
+#pragma unroll
+  for (int k = 0; k < kScanPerThread; ++k) {
+    if (base + k < nblocks) block_sums[base + k] = prefix;
+    prefix += v[k];
+  }
+  if (threadIdx.x == 0) {
+    totals->entries = (uint32_t)total;
+    totals->tasks = (uint32_t)(total >> 32);
+    totals->multi = 0;
+  }
+}
+
+// Writes offset[] (TB+1 entries), cursor[] (= offset, consumed by the scatter)
+// and the tasks of every bucket.  Buckets split into more than one task are
+// appended to multi_keys.
+__global__ void __launch_bounds__(kScanThreads) scan_apply_build_tasks_kernel(
+    const uint32_t* __restrict__ count, uint32_t n, uint32_t seg,
+    const uint64_t* __restrict__ block_prefix, uint32_t* __restrict__ offset,
+    uint32_t* __restrict__ cursor, uint32_t* __restrict__ task_base, uint2* __restrict__ tasks,
+    uint32_t* __restrict__ multi_keys, MsmTotals* __restrict__ totals) {
+  __shared__ uint64_t smem[kScanThreads / 32];
+  uint32_t base = blockIdx.x * kScanItems + threadIdx.x * kScanPerThread;
+  uint32_t cnt[kScanPerThread];
+  uint64_t sum = 0;
+#pragma unroll
+  for (int k = 0; k < kScanPerThread; ++k) {
+    uint32_t idx = base + k;
+    cnt[k] = (idx < n) ? count[idx] : 0;
+    sum += scan_item(cnt[k], seg);
+  }
+  uint64_t total;
+  uint64_t prefix = block_exclusive_scan(sum, &total, smem) + block_prefix[blockIdx.x];
+#pragma unroll
+  for (int k = 0; k < kScanPerThread; ++k) {
+    uint32_t idx = base + k;
+    if (idx < n) {
+      uint32_t off = (uint32_t)prefix;
+      uint32_t tb = (uint32_t)(prefix >> 32);
+      offset[idx] = off;
+      cursor[idx] = off;
+      task_base[idx] = tb;
+      uint32_t t = (cnt[k] + seg - 1) / seg;
+      for (uint32_t s = 0; s < t; ++s) {
+        uint32_t len = min(seg, cnt[k] - s * seg);
+        tasks[tb + s] = make_uint2(off + s * seg, len);
+      }
+      if (t > 1) multi_keys[atomicAdd(&totals->multi, 1u)] = idx;
+      if (idx == n - 1) offset[n] = off + cnt[k];
+    }
+    prefix += scan_item(cnt[k], seg);
+  }
+}
+
+// ---------------------------------------------------------------------------
+// Bucket accumulation — the hot loop (pippenger.h:112-135).  One thread per
+// task; the next point is fetched while the current one is being added.
+// ---------------------------------------------------------------------------
+constexpr int kAccThreads = 128;
+
+template <class C>
+__global__ void __launch_bounds__(kAccThreads) accumulate_kernel(
+    const uint32_t* __restrict__ bases, const uint32_t* __restrict__ sorted,
+    const uint2* __restrict__ tasks, const MsmTotals* __restrict__ totals,
+    uint32_t* __restrict__ task_out) {
+  using Fq = typename C::Fq;
+  constexpr int kAffineWords = 2 * Fp<Fq>::N;
+  constexpr int kXyzzWords = 4 * Fp<Fq>::N;
+  uint32_t g = blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= totals->tasks) return;
+  uint2 task = tasks[g];
+  const uint32_t* ent = sorted + task.x;
+  XYZZ<Fq> acc;
+  xyzz_set_zero<Fq>(acc);
+  uint32_t e = ent[0];
+  Affine<Fq> nxt;
+  affine_load<Fq>(nxt, bases + (size_t)(e & 0x7fffffffu) * kAffineWords);
+  for (uint32_t j = 0; j < task.y; ++j) {
+    Affine<Fq> cur = nxt;
+    bool neg = e >> 31;
+    if (j + 1 < task.y) {
+      e = ent[j + 1];
+      affine_load<Fq>(nxt, bases + (size_t)(e & 0x7fffffffu) * kAffineWords);
+    }
+    xyzz_madd<Fq>(acc, cur, neg);
+  }
+  xyzz_store<Fq>(task_out + (size_t)g * kXyzzWords, acc);
+}
+
+// Buckets split over several tasks: one CTA per bucket sums the partials into
+// the bucket's first task slot.  Grid-stride over the split-bucket list.
+constexpr int kFoldThreads = 128;
+
+template <class C>
+__global__ void __launch_bounds__(kFoldThreads) fold_partials_kernel(
+    const uint32_t* __restrict__ multi_keys, const MsmTotals* __restrict__ totals,
+    const uint32_t* __restrict__ offset, const uint32_t* __restrict__ task_base, uint32_t seg,
+    uint32_t* __restrict__ task_out) {
+  using Fq = typename C::Fq;
+  constexpr int kXyzzWords = 4 * Fp<Fq>::N;
+  __shared__ uint32_t sh[kFoldThreads / 2 * kXyzzWords];
+  for (uint32_t m = blockIdx.x; m < totals->multi; m += gridDim.x) {
+    uint32_t key = multi_keys[m];
+    uint32_t cnt = offset[key + 1] - offset[key];
+    uint32_t t = (cnt + seg - 1) / seg;
+    uint32_t* slots = task_out + (size_t)task_base[key] * kXyzzWords;
+    XYZZ<Fq> acc, tmp;
+    xyzz_set_zero<Fq>(acc);
+    for (uint32_t s = threadIdx.x; s < t; s += kFoldThreads) {
+      xyzz_load<Fq>(tmp, slots + (size_t)s * kXyzzWords);
+      xyzz_add<Fq>(acc, tmp);
+    }
+    __syncthreads();  // all partials read before slot 0 is overwritten
+    for (int stride = kFoldThreads / 2; stride >= 1; stride >>= 1) {
+      if ((int)threadIdx.x >= stride && (int)threadIdx.x < 2 * stride)
+        xyzz_store<Fq>(sh + (threadIdx.x - stride) * kXyzzWords, acc);
+      __syncthreads();
+      if ((int)threadIdx.x < stride) {
+        xyzz_load<Fq>(tmp, sh + threadIdx.x * kXyzzWords);
+        xyzz_add<Fq>(acc, tmp);
+      }
+      __syncthreads();
+    }
+    if (threadIdx.x == 0) xyzz_store<Fq>(slots, acc);
+    __syncthreads();
+  }
+}
+
+// ---------------------------------------------------------------------------
+// Bucket reduction (pippenger_base.h:36-57): S_w = sum_k (k+1) B_k.
+// Blocked running sums: with F(x) = sum_k k x_k and A(x) = sum_k x_k over
+// blocks t of L items,  F(x) = sum_t Wt_t + L * F({A_t}).  Every level maps
+// n items to ceil(n / L) items and carries the already-weighted part in a
+// second series C (scaled by 2^shift = product of the previous Ls), so after
+// the last level S_w = A + C.
+//   level 0: items are buckets (through count/task_base), no C input
+//   level>0: items are the previous level's A and C arrays
+// ---------------------------------------------------------------------------
+constexpr int kReduceThreads = 128;
+
+template <class C, bool kFirst>
+__global__ void __launch_bounds__(kReduceThreads) reduce_level_kernel(
+    const uint32_t* __restrict__ in_a, const uint32_t* __restrict__ in_c,
+    const uint32_t* __restrict__ offset, const uint32_t* __restrict__ task_base, uint32_t n_in,
+    uint32_t n_out, uint32_t L, uint32_t shift, uint32_t windows, uint32_t* __restrict__ out_a,
+    uint32_t* __restrict__ out_c) {
+  using Fq = typename C::Fq;
+  constexpr int kXyzzWords = 4 * Fp<Fq>::N;
+  uint32_t g = blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= n_out * windows) return;
+  uint32_t w = g / n_out, t = g % n_out;
+  uint32_t lo = t * L, hi = min(n_in, lo + L);
+  XYZZ<Fq> run, wt, csum, item;
+  xyzz_set_zero<Fq>(run);
+  xyzz_set_zero<Fq>(wt);
+  xyzz_set_zero<Fq>(csum);
+  for (uint32_t k = hi; k-- > lo;) {
+    uint32_t idx = w * n_in + k;
+    if (kFirst) {
+      if (offset[idx + 1] != offset[idx]) {
+        xyzz_load<Fq>(item, in_a + (size_t)task_base[idx] * kXyzzWords);
+        xyzz_add<Fq>(run, item);
+      }
+    } else {
+      xyzz_load<Fq>(item, in_a + (size_t)idx * kXyzzWords);
+      xyzz_add<Fq>(run, item);
+      xyzz_load<Fq>(item, in_c + (size_t)idx * kXyzzWords);
+      xyzz_add<Fq>(csum, item);
+    }
+    if (k > lo) xyzz_add<Fq>(wt, run);
+  }
+  for (uint32_t s = 0; s < shift; ++s) xyzz_dbl<Fq>(wt);
+  xyzz_add<Fq>(csum, wt);
+  xyzz_store<Fq>(out_a + (size_t)g * kXyzzWords, run);
+  xyzz_store<Fq>(out_c + (size_t)g * kXyzzWords, csum);
+}
+
+// ---------------------------------------------------------------------------
+// Element-wise hooks used by the parity tests (the role of
+// tachyon/math/finite_fields/kernels/prime_field_ops.cu.h:13-51 and
+// short_weierstrass/kernels/elliptic_curve_ops.cu.h:15-79 in the reference's
+// own GPU correctness tests).
+// ---------------------------------------------------------------------------
+template <class F>
+__global__ void field_op_kernel(int op, const uint32_t* a, const uint32_t* b, uint32_t* out,
+                                uint32_t n) {
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  constexpr int N = Fp<F>::N;
+  Fp<F> x, y, r;
+  fp_load<F>(x, a + (size_t)i * N);
+  fp_load<F>(y, b + (size_t)i * N);
+  switch (op) {
+    case 0: fp_add<F>(r, x, y); break;
+    case 1: fp_sub<F>(r, x, y); break;
+    case 2: fp_mul<F>(r, x, y); break;
+    case 3: fp_sqr<F>(r, x); break;
+    case 4: fp_neg<F>(r, x); break;
+    case 5: fp_dbl<F>(r, x); break;
+    case 6: fp_inv<F>(r, x); break;
+    case 7: fp_from_mont<F>(r, x); break;
+    default: fp_to_mont<F>(r, x); break;
+  }
+  fp_store<F>(out + (size_t)i * N, r);
+}
+
+// op 0: out = a + b (XYZZ + XYZZ); 1: out = a + affine b; 2: out = a - affine b;
+// 3: out = 2a.  a, out: XYZZ arrays; b: XYZZ (op 0) or affine (op 1, 2).
+template <class C>
+__global__ void point_op_kernel(int op, const uint32_t* a, const uint32_t* b, uint32_t* out,
+                                uint32_t n) {
+  using Fq = typename C::Fq;
+  constexpr int N = Fp<Fq>::N;
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  XYZZ<Fq> p;
+  xyzz_load<Fq>(p, a + (size_t)i * 4 * N);
+  if (op == 0) {
+    XYZZ<Fq> q;
+    xyzz_load<Fq>(q, b + (size_t)i * 4 * N);
+    xyzz_add<Fq>(p, q);
+  } else if (op == 1 || op == 2) {
+    Affine<Fq> q;
+    affine_load<Fq>(q, b + (size_t)i * 2 * N);
+    xyzz_madd<Fq>(p, q, op == 2);
+  } else {
+    xyzz_dbl<Fq>(p);
+  }
+  xyzz_store<Fq>(out + (size_t)i * 4 * N, p);
+}
+
+// ---------------------------------------------------------------------------
+// Synthetic inputs (mirrors elliptic_curves/test/random.h:11-29
+// and big_int.h:107-116 with a fixed-seed counter-based SplitMix64): chains of
+// 2^12 successive doublings, chain j starting at [h_j] G.
+// ---------------------------------------------------------------------------
+__host__ __device__ inline uint64_t splitmix64_at(uint64_t seed, uint64_t index) {
+  uint64_t z = seed + (index + 1) * 0x9E3779B97F4A7C15ull;
+  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+  z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+  return z ^ (z >> 31);
+}
+
+constexpr uint32_t kChainLog = 12;
+
+// One thread per chain: writes the chain's points as XYZZ.
+template <class C>
+__global__ void generate_chains_kernel(uint64_t seed, uint32_t first_chain, uint32_t n_chains,
+                                       uint32_t n_points, uint32_t* __restrict__ out_xyzz) {
+  using Fq = typename C::Fq;
+  constexpr int N = Fp<Fq>::N;
+  uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n_chains) return;
+  uint64_t h = splitmix64_at(seed ^ 0x7074ull, first_chain + t) | 1ull;
+  Affine<Fq> gen;
+#pragma unroll
+  for (int i = 0; i < N; ++i) {
+    gen.x.l[i] = C::Gen::x32(i);
+    gen.y.l[i] = C::Gen::y32(i);
+  }
+  XYZZ<Fq> p;
+  xyzz_set_zero<Fq>(p);
+  for (int bit = 63; bit >= 0; --bit) {
+    xyzz_dbl<Fq>(p);
+    if ((h >> bit) & 1) xyzz_madd<Fq>(p, gen, false);
+  }
+  uint32_t chain_len = 1u << kChainLog;
+  for (uint32_t d = 0; d < chain_len; ++d) {
+    uint64_t i = (uint64_t)t * chain_len + d;
+    if (i >= n_points) break;
+    xyzz_store<Fq>(out_xyzz + i * 4 * N, p);
+    xyzz_dbl<Fq>(p);
+  }
+}
+
+// XYZZ -> affine (point_xyzz.h:199-213), one thread per point.
+template <class C>
+__global__ void normalize_kernel(const uint32_t* __restrict__ in_xyzz, uint32_t n,
+                                 uint32_t* __restrict__ out_affine) {
+  using Fq = typename C::Fq;
+  constexpr int N = Fp<Fq>::N;
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  XYZZ<Fq> p;
+  xyzz_load<Fq>(p, in_xyzz + (size_t)i * 4 * N);
+  Affine<Fq> a;
+  if (xyzz_is_zero<Fq>(p)) {
+    fp_set_zero<Fq>(a.x);
+    fp_set_zero<Fq>(a.y);
+  } else {
+    Fp<Fq> zi3, zi2;
+    fp_inv<Fq>(zi3, p.zzz);
+    fp_mul<Fq>(zi2, zi3, p.zz);
+    fp_sqr<Fq>(zi2, zi2);
+    fp_mul<Fq>(a.x, p.x, zi2);
+    fp_mul<Fq>(a.y, p.y, zi3);
+  }
+  fp_store<Fq>(out_affine + (size_t)i * 2 * N, a.x);
+  fp_store<Fq>(out_affine + (size_t)i * 2 * N + N, a.y);
+}
+
+// dist: 0 uniform, 1 non_uniform (one scalar repeated), 2 witness
+template <class C>
+__global__ void generate_scalars_kernel(uint64_t seed, int dist, uint64_t first, uint32_t n,
+                                        uint32_t* __restrict__ out) {
+  using Fr = typename C::Fr;
+  constexpr int N = Fp<Fr>::N;
+  uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= n) return;
+  uint64_t i = first + k;
+  Fp<Fr> x;
+  bool random = true;
+  uint64_t src = i;
+  if (dist == 1) src = 0;
+  if (dist == 2) {
+    uint64_t sel = splitmix64_at(seed ^ 0x7769ull, i) % 10;
+    if (sel < 7) {
+      random = false;
+      fp_set_zero<Fr>(x);
+      if (sel >= 4) x.l[0] = 1;
+    } else if (sel < 9) {
+      random = false;
+      fp_set_zero<Fr>(x);
+      x.l[0] = (uint32_t)splitmix64_at(seed ^ 0x7363ull, i * (N / 2));
+    }
+  }
+  if (random) {
+#pragma unroll
+    for (int j = 0; j < N / 2; ++j) {
+      uint64_t v = splitmix64_at(seed ^ 0x7363ull, src * (N / 2) + j);
+      x.l[2 * j] = (uint32_t)v;
+      x.l[2 * j + 1] = (uint32_t)(v >> 32);
+    }
+    // halve until < r   (big_int.h:107-116)
+    for (;;) {
+      uint32_t t = sub_cc(x.l[0], Fr::mod(0));
+#pragma unroll
+      for (int j = 1; j < N; ++j) t = subc_cc(x.l[j], Fr::mod(j));
+      uint32_t borrow = subc(0u, 0u);
+      (void)t;
+      if (borrow) break;
+#pragma unroll
+      for (int j = 0; j < N - 1; ++j) x.l[j] = __funnelshift_r(x.l[j], x.l[j + 1], 1);
+      x.l[N - 1] >>= 1;
+    }
+  }
+  Fp<Fr> m;
+  fp_to_mont<Fr>(m, x);
+  fp_store<Fr>(out + (size_t)k * N, m);
+}
+
+// ---------------------------------------------------------------------------
+// INT32 multiply-pipe peak (the roofline denominator of SURVEY.md §8d):
+// independent chains of 32x32->64 multiply-adds.
+//   variant 0: mad.wide.u32 (IMAD.WIDE.U32), 64-bit accumulate
+//   variant 1: mad.lo.cc / madc.hi.cc pairs (IMAD.WIDE.U32.X, carry in predicate)
+// Each thread issues iters * 16 products.
+// ---------------------------------------------------------------------------
+template <int kVariant>
+__global__ void __launch_bounds__(256) imad_peak_kernel(uint32_t iters, uint32_t seed,
+                                                        uint32_t* __restrict__ out) {
+  uint32_t a = seed + threadIdx.x, b = seed * 2654435761u + blockIdx.x;
+  if (kVariant == 0) {
+    uint64_t acc[16];
+#pragma unroll
+    for (int k = 0; k < 16; ++k) acc[k] = k + a;
+    for (uint32_t it = 0; it < iters; ++it) {
+#pragma unroll
+      for (int k = 0; k < 16; ++k)
+        asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(acc[k]) : "r"(a + k), "r"(b));
+    }
+    uint64_t s = 0;
+#pragma unroll
+    for (int k = 0; k < 16; ++k) s ^= acc[k];
+    if (s == 0x123456789ull) out[0] = (uint32_t)s;
+  } else {
+    uint32_t lo[16], hi[16];
+#pragma unroll
+    for (int k = 0; k < 16; ++k) {
+      lo[k] = k + a;
+      hi[k] = k ^ b;
+    }
+    for (uint32_t it = 0; it < iters; ++it) {
+#pragma unroll
+      for (int g = 0; g < 4; ++g) {
+        lo[4 * g] = mad_lo_cc(a + g, b, lo[4 * g]);
+        hi[4 * g] = madc_hi_cc(a + g, b, hi[4 * g]);
+#pragma unroll
+        for (int k = 1; k < 4; ++k) {
+          lo[4 * g + k] = madc_lo_cc(a + g + k, b, lo[4 * g + k]);
+          hi[4 * g + k] = madc_hi_cc(a + g + k, b, hi[4 * g + k]);
+        }
+      }
+    }
+    uint32_t s = 0;
+#pragma unroll
+    for (int k = 0; k < 16; ++k) s ^= lo[k] ^ hi[k];
+    if (s == 0x12345678u) out[0] = s;
+  }
+}
+
+}  // namespace tb200

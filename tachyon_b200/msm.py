@@ -1,0 +1,178 @@
+"""Host-side mirror of the reference's MSM-GPU interface over the C ABI.
+
+`MSMGpu` corresponds to the object behind `tachyon_<curve>_g1_msm_gpu_ptr`
+(tachyon/c/math/elliptic_curves/msm/msm_gpu.h:22-122): create(degree) ->
+affine_msm / point2_msm(bases, scalars) -> Jacobian point -> destroy.  Inputs are
+numpy uint64 arrays with the byte layout of the C structs (little-endian limbs,
+Montgomery form), or raw device pointers.
+"""
+import ctypes
+
+import numpy as np
+
+from . import _lib
+
+DIST = {"uniform": 0, "non_uniform": 1, "witness": 2}
+FIELD_OPS = {"add": 0, "sub": 1, "mul": 2, "square": 3, "neg": 4, "double": 5, "inverse": 6,
+             "from_mont": 7, "to_mont": 8}
+POINT_OPS = {"add": 0, "madd": 1, "msub": 2, "double": 3}
+
+
+def _ptr(x):
+    """numpy array -> host pointer; int -> raw (device) pointer."""
+    if isinstance(x, (int, np.integer)):
+        return ctypes.c_void_p(int(x))
+    assert x.dtype == np.uint64 and x.flags["C_CONTIGUOUS"]
+    return ctypes.c_void_p(x.ctypes.data)
+
+
+class MSMGpu:
+    def __init__(self, curve="bn254", degree=20, device=None, banner=False):
+        self.curve = curve
+        self.fq_limbs = _lib.CURVES[curve]
+        self.L = _lib.load()
+        self._f = lambda name: getattr(self.L, f"tachyon_{curve}_{name}")
+        self._f("g1_init")()
+        if banner:
+            self.ptr = self._f("g1_create_msm_gpu")(degree)   # reference entry point
+        else:
+            self.ptr = self._f("g1_create_msm_gpu_b200")(degree, 0 if device is None else device)
+        if not self.ptr:
+            raise RuntimeError("create_msm_gpu failed: " + _lib.last_error())
+
+    def close(self):
+        if getattr(self, "ptr", None):
+            self._f("g1_destroy_msm_gpu")(self.ptr)
+            self.ptr = None
+
+    __del__ = close
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def set_option(self, name, value):
+        _lib.check(self._f("g1_msm_gpu_set_option_b200")(self.ptr, name.encode(), int(value)), "set_option")
+
+    def set_stream(self, cuda_stream):
+        _lib.check(self._f("g1_msm_gpu_set_stream_b200")(self.ptr, ctypes.c_void_p(cuda_stream)), "set_stream")
+
+    def _jacobian(self, fn, bases, scalars, size):
+        """Calls the reference-shaped entry point; returns (3, fq_limbs) and frees the result."""
+        p = self._f(fn)(self.ptr, _ptr(bases), _ptr(scalars), size)
+        if not p:
+            raise RuntimeError(fn + " returned NULL")
+        n = 3 * self.fq_limbs
+        out = np.ctypeslib.as_array(ctypes.cast(p, ctypes.POINTER(ctypes.c_uint64)), shape=(n,)).copy()
+        _free_cxx(p)
+        return out.reshape(3, self.fq_limbs)
+
+    def affine_msm(self, bases, scalars, size=None):
+        size = len(scalars) if size is None else size
+        return self._jacobian("g1_affine_msm_gpu", bases, scalars, size)
+
+    def point2_msm(self, bases, scalars, size=None):
+        size = len(scalars) if size is None else size
+        return self._jacobian("g1_point2_msm_gpu", bases, scalars, size)
+
+    def msm_xyzz(self, bases, scalars, size=None):
+        """Un-normalised XYZZ sum (4, fq_limbs); error codes instead of abort."""
+        size = len(scalars) if size is None else size
+        out = np.zeros((4, self.fq_limbs), dtype=np.uint64)
+        _lib.check(self._f("g1_msm_gpu_xyzz_b200")(self.ptr, _ptr(bases), _ptr(scalars), size, _ptr(out)),
+                   "msm_gpu_xyzz")
+        return out
+
+    def last_timing(self):
+        t = _lib.MsmTiming()
+        _lib.check(self._f("g1_msm_gpu_last_timing_b200")(self.ptr, ctypes.byref(t)), "last_timing")
+        return t.as_dict()
+
+
+_libstdcxx = None
+
+
+def _free_cxx(p):
+    """`delete` for the heap Jacobian the C API returns (POD, so operator delete(void*))."""
+    global _libstdcxx
+    if _libstdcxx is None:
+        _libstdcxx = ctypes.CDLL("libstdc++.so.6")
+        _libstdcxx._ZdlPv.argtypes = [ctypes.c_void_p]
+        _libstdcxx._ZdlPv.restype = None
+    _libstdcxx._ZdlPv(ctypes.c_void_p(p))
+
+
+def generate_bases_device(curve, seed, n, device_ptr, first=0):
+    L = _lib.load()
+    _lib.check(getattr(L, f"tachyon_{curve}_g1_generate_bases_b200")(seed, first, n, ctypes.c_void_p(device_ptr)),
+               "generate_bases")
+
+
+def generate_scalars_device(curve, seed, n, device_ptr, dist="uniform", first=0):
+    L = _lib.load()
+    _lib.check(getattr(L, f"tachyon_{curve}_g1_generate_scalars_b200")(
+        seed, DIST[dist], first, n, ctypes.c_void_p(device_ptr)), "generate_scalars")
+
+
+def field_op(curve, field, op, a, b=None):
+    """Element-wise device field op on host arrays (parity hook)."""
+    L = _lib.load()
+    a = np.ascontiguousarray(a, dtype=np.uint64)
+    b = a if b is None else np.ascontiguousarray(b, dtype=np.uint64)
+    out = np.empty_like(a)
+    _lib.check(getattr(L, f"tachyon_{curve}_{field}_op_b200")(FIELD_OPS[op], _ptr(a), _ptr(b), _ptr(out), a.shape[0]),
+               f"{field}_op")
+    return out
+
+
+def point_op(curve, op, a_xyzz, b=None):
+    L = _lib.load()
+    a = np.ascontiguousarray(a_xyzz, dtype=np.uint64)
+    out = np.empty_like(a)
+    bp = _ptr(np.ascontiguousarray(b, dtype=np.uint64)) if b is not None else ctypes.c_void_p(0)
+    _lib.check(getattr(L, f"tachyon_{curve}_g1_point_op_b200")(POINT_OPS[op], _ptr(a), bp, _ptr(out), a.shape[0]),
+               "point_op")
+    return out
+
+
+def imad_peak(device=0, variant=0, repeats=5):
+    v = _lib.load().tachyon_b200_imad_peak(device, variant, repeats)
+    if v < 0:
+        raise RuntimeError("imad_peak failed: " + _lib.last_error())
+    return v
+
+
+def kernel_launch_count():
+    return int(_lib.load().tachyon_b200_kernel_launch_count())
+
+
+def device_count():
+    return int(_lib.load().tachyon_b200_device_count())
+
+
+def xyzz_add(curve, a, b):
+    """Host-side a + b on XYZZ points (4, fq_limbs): combination of per-rank partial sums."""
+    L = _lib.load()
+    a = np.ascontiguousarray(a, dtype=np.uint64)
+    b = np.ascontiguousarray(b, dtype=np.uint64)
+    out = np.empty_like(a)
+    getattr(L, f"tachyon_{curve}_g1_xyzz_add_b200")(_ptr(a), _ptr(b), _ptr(out))
+    return out
+
+
+def xyzz_to_jacobian(curve, a):
+    L = _lib.load()
+    a = np.ascontiguousarray(a, dtype=np.uint64)
+    out = np.zeros((3, a.shape[-1]), dtype=np.uint64)
+    getattr(L, f"tachyon_{curve}_g1_xyzz_to_jacobian_b200")(_ptr(a), _ptr(out))
+    return out
+
+
+def window_bits(n, scalar_bits):
+    return int(_lib.load().tachyon_b200_window_bits(n, scalar_bits))
+
+
+def window_count(scalar_bits, c):
+    return int(_lib.load().tachyon_b200_window_count(scalar_bits, c))

@@ -1,0 +1,84 @@
+"""CPU-only checks of the product library: it loads, exports every symbol the
+public header declares, and its host-only helpers agree with the oracle."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+from oracle import pymodel
+from tachyon_b200 import _lib, msm
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_header_symbols_exported():
+    hdr = open(os.path.join(ROOT, "include", "tachyon_msm_b200.h")).read()
+    # per-curve declarations live in the TACHYON_B200_DECLARE_CURVE macro
+    macro_names = set(re.findall(r"(tachyon_##C##_\w+)\s*\(", hdr))
+    declared = {n.replace("##C##", c) for n in macro_names for c in _lib.CURVES}
+    declared |= set(re.findall(r"\b(tachyon_b200_\w+)\s*\(", hdr))
+    assert declared == set(_lib.all_symbols())
+    L = _lib.load()
+    for name in declared:
+        assert getattr(L, name) is not None
+    # the reference's five entry points per curve (msm_gpu.h.tpl:26-56, point.h.tpl:117)
+    for c in ("bn254", "bls12_381"):
+        for n in ("g1_init", "g1_create_msm_gpu", "g1_destroy_msm_gpu", "g1_point2_msm_gpu",
+                  "g1_affine_msm_gpu"):
+            assert f"tachyon_{c}_{n}" in declared
+
+
+def test_header_compiles_as_c(tmp_path):
+    src = tmp_path / "t.c"
+    src.write_text('#include "tachyon_msm_b200.h"\n'
+                   "_Static_assert(sizeof(struct tachyon_bn254_g1_affine) == 64, \"\");\n"
+                   "_Static_assert(sizeof(struct tachyon_bn254_g1_jacobian) == 96, \"\");\n"
+                   "_Static_assert(sizeof(struct tachyon_bn254_fr) == 32, \"\");\n"
+                   "_Static_assert(sizeof(struct tachyon_bls12_381_g1_affine) == 96, \"\");\n"
+                   "_Static_assert(sizeof(struct tachyon_bls12_381_g1_jacobian) == 144, \"\");\n"
+                   "_Static_assert(sizeof(struct tachyon_bls12_381_g1_xyzz) == 192, \"\");\n"
+                   "int main(void) { return 0; }\n")
+    import subprocess
+    subprocess.check_call(["/usr/bin/gcc", "-std=c11", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"),
+                           "-c", str(src), "-o", str(tmp_path / "t.o")])
+
+
+def test_window_rule_host():
+    # W * c >= bits + 1 so the signed top digit never carries out
+    for bits in (254, 255):
+        for n in (1, 5, 1 << 10, 1 << 16, 1 << 20, 1 << 24):
+            c = msm.window_bits(n, bits)
+            W = msm.window_count(bits, c)
+            assert 2 <= c <= 22 and W * c >= bits + 1 and (W - 1) * c < bits + 1
+            assert W << (c - 1) <= 1 << 24
+    assert msm.window_bits(1 << 24, 254) >= msm.window_bits(1 << 16, 254)
+
+
+@pytest.mark.parametrize("name", ["bn254", "bls12_381"])
+def test_host_point_helpers_vs_oracle(oracles, name):
+    o = oracles[name]
+    pts = o.generate_points(5, 6)
+    ks = o.fr_from_mont(o.generate_scalars(6, 6))
+    xs = [o.scalar_mul(pts[i], ks[i]) for i in range(6)]
+    zero = o.xyzz_zero()
+    for a, b in [(xs[0], xs[1]), (xs[2], xs[2]), (xs[3], zero), (zero, xs[4]), (zero, zero)]:
+        got = msm.xyzz_add(name, a, b)
+        want = o.xyzz_add(a, b)
+        assert (o.xyzz_to_affine(got) == o.xyzz_to_affine(want)).all()
+        assert (msm.xyzz_to_jacobian(name, got) == o.xyzz_to_jacobian(got)).all()
+    # P + (-P) = identity
+    neg = xs[5].copy()
+    neg[1] = o.fq_op("neg", xs[5][1:2])[0]
+    assert (o.xyzz_to_affine(msm.xyzz_add(name, xs[5], neg)) == 0).all()
+
+
+def test_no_gpu_fails_loudly():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    with pytest.raises(RuntimeError):
+        msm.MSMGpu("bn254")
+    with pytest.raises(RuntimeError):
+        msm.field_op("bn254", "fq", "mul", np.zeros((1, 4), dtype=np.uint64))
