@@ -78,12 +78,16 @@ struct MsmOptions {
 // never carries out (see for_each_digit).
 inline uint32_t WindowsFor(uint32_t bits, uint32_t c) { return (bits + 1 + c - 1) / c; }
 
+// c >= 4 keeps W <= 64 (the size of the pinned result buffer).
+constexpr uint32_t kMinWindowBits = 4;
+constexpr uint32_t kMaxWindows = 64;
+
 inline uint32_t ChooseWindowBits(size_t n, uint32_t scalar_bits) {
   constexpr double kReduceInefficiency = 1.5;
   constexpr uint32_t kMaxBuckets = 1u << 24;  // scan_top_kernel capacity
   double best = 1e300;
-  uint32_t best_c = 2;
-  for (uint32_t c = 2; c <= 22; ++c) {
+  uint32_t best_c = kMinWindowBits;
+  for (uint32_t c = kMinWindowBits; c <= 22; ++c) {
     uint32_t W = WindowsFor(scalar_bits, c);
     double buckets = (double)W * (double)(1u << (c - 1));
     if (buckets > kMaxBuckets) break;
@@ -181,7 +185,7 @@ class MsmEngine {
     MsmPlan p{};
     p.n = (uint32_t)n;
     p.c = options_.window_bits ? options_.window_bits : ChooseWindowBits(n, Fr::kBits);
-    if (p.c < 2) p.c = 2;
+    if (p.c < kMinWindowBits) p.c = kMinWindowBits;
     if (p.c > 24) p.c = 24;
     p.W = WindowsFor(Fr::kBits, p.c);
     p.B = 1u << (p.c - 1);
@@ -353,7 +357,7 @@ class MsmEngine {
     return L;
   }
 
-  static constexpr size_t kHostOutBytes = 64 * 2 * 192 + 64;  // <= 64 windows x (A, C) + totals
+  static constexpr size_t kHostOutBytes = kMaxWindows * 2 * kXyzzBytes + 64;  // (A, C) per window + totals
 
   int device_;
   int sm_count_ = 148;

@@ -129,14 +129,13 @@ TB_DEV void xyzz_madd(XYZZ<F>& acc, const Affine<F>& q, bool neg) {
   fp_sub<F>(acc.y, t, ppp);
 }
 
-// acc += b.  add-2008-s.
+// acc += b for acc, b both != identity (add-2008-s).  Straight-line body: the
+// identity cases and the P == R == 0 doubling are dispatched by the inlined
+// wrapper below, so this out-of-line function has no divergent early exit.
+// Returns true when the operands are equal (caller must double instead; acc is
+// left untouched in that case).
 template <class F>
-__device__ __noinline__ void xyzz_add(XYZZ<F>& acc, const XYZZ<F>& b) {
-  if (xyzz_is_zero<F>(b)) return;
-  if (xyzz_is_zero<F>(acc)) {
-    acc = b;
-    return;
-  }
+__device__ __noinline__ bool xyzz_add_nz(XYZZ<F>& acc, const XYZZ<F>& b) {
   Fp<F> u1, s1, p, r, pp, ppp, qq, t;
   fp_mul<F>(u1, acc.x, b.zz);   // U1 = X1 ZZ2
   fp_mul<F>(s1, acc.y, b.zzz);  // S1 = Y1 ZZZ2
@@ -144,25 +143,52 @@ __device__ __noinline__ void xyzz_add(XYZZ<F>& acc, const XYZZ<F>& b) {
   fp_sub<F>(p, p, u1);
   fp_mul<F>(r, b.y, acc.zzz);   // R = Y2 ZZZ1 - S1
   fp_sub<F>(r, r, s1);
-  if (fp_is_zero<F>(p) && fp_is_zero<F>(r)) {
-    xyzz_dbl_nz<F>(acc);
-    return;
-  }
+  bool same = fp_is_zero<F>(p) && fp_is_zero<F>(r);
   fp_sqr<F>(pp, p);
   fp_mul<F>(ppp, p, pp);
   fp_mul<F>(qq, u1, pp);              // Q = U1 PP
-  fp_mul<F>(acc.zz, acc.zz, b.zz);    // ZZ3 = ZZ1 ZZ2 PP
-  fp_mul<F>(acc.zz, acc.zz, pp);
-  fp_mul<F>(acc.zzz, acc.zzz, b.zzz);  // ZZZ3 = ZZZ1 ZZZ2 PPP
-  fp_mul<F>(acc.zzz, acc.zzz, ppp);
-  fp_sqr<F>(acc.x, r);                // X3 = R^2 - PPP - 2Q
-  fp_sub<F>(acc.x, acc.x, ppp);
+  XYZZ<F> o;
+  fp_mul<F>(o.zz, acc.zz, b.zz);      // ZZ3 = ZZ1 ZZ2 PP
+  fp_mul<F>(o.zz, o.zz, pp);
+  fp_mul<F>(o.zzz, acc.zzz, b.zzz);   // ZZZ3 = ZZZ1 ZZZ2 PPP
+  fp_mul<F>(o.zzz, o.zzz, ppp);
+  fp_sqr<F>(o.x, r);                  // X3 = R^2 - PPP - 2Q
+  fp_sub<F>(o.x, o.x, ppp);
   fp_dbl<F>(t, qq);
-  fp_sub<F>(acc.x, acc.x, t);
+  fp_sub<F>(o.x, o.x, t);
   fp_mul<F>(s1, s1, ppp);             // S1 PPP
-  fp_sub<F>(t, qq, acc.x);            // Y3 = R (Q - X3) - S1 PPP
+  fp_sub<F>(t, qq, o.x);              // Y3 = R (Q - X3) - S1 PPP
   fp_mul<F>(t, r, t);
-  fp_sub<F>(acc.y, t, s1);
+  fp_sub<F>(o.y, t, s1);
+#pragma unroll
+  for (int i = 0; i < Fp<F>::N; ++i) {
+    acc.x.l[i] = same ? acc.x.l[i] : o.x.l[i];
+    acc.y.l[i] = same ? acc.y.l[i] : o.y.l[i];
+    acc.zz.l[i] = same ? acc.zz.l[i] : o.zz.l[i];
+    acc.zzz.l[i] = same ? acc.zzz.l[i] : o.zzz.l[i];
+  }
+  return same;
+}
+
+template <class F>
+TB_DEV void xyzz_copy(XYZZ<F>& dst, const XYZZ<F>& src) {
+#pragma unroll
+  for (int i = 0; i < Fp<F>::N; ++i) {
+    dst.x.l[i] = src.x.l[i];
+    dst.y.l[i] = src.y.l[i];
+    dst.zz.l[i] = src.zz.l[i];
+    dst.zzz.l[i] = src.zzz.l[i];
+  }
+}
+
+// acc += b with the reference's case analysis (point_xyzz_impl.h:14-41).
+template <class F>
+TB_DEV void xyzz_add(XYZZ<F>& acc, const XYZZ<F>& b) {
+  bool bz = xyzz_is_zero<F>(b), az = xyzz_is_zero<F>(acc);
+  if (az && !bz) xyzz_copy<F>(acc, b);
+  if (!az && !bz) {
+    if (xyzz_add_nz<F>(acc, b)) xyzz_dbl_nz<F>(acc);
+  }
 }
 
 }  // namespace tb200

@@ -51,7 +51,7 @@ def test_window_rule_host():
         for n in (1, 5, 1 << 10, 1 << 16, 1 << 20, 1 << 24):
             c = msm.window_bits(n, bits)
             W = msm.window_count(bits, c)
-            assert 2 <= c <= 22 and W * c >= bits + 1 and (W - 1) * c < bits + 1
+            assert 4 <= c <= 22 and W <= 64 and W * c >= bits + 1 and (W - 1) * c < bits + 1
             assert W << (c - 1) <= 1 << 24
     assert msm.window_bits(1 << 24, 254) >= msm.window_bits(1 << 16, 254)
 

@@ -5,6 +5,8 @@ import time
 import numpy as np
 import torch
 
+import os
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from tachyon_b200 import msm
 
 curve = sys.argv[1] if len(sys.argv) > 1 else "bn254"
