@@ -1,0 +1,387 @@
+#!/usr/bin/env python3
+"""Benchmark of the hot path: BN254 (or BLS12-381) G1 variable-base MSM.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+                    [--curve bn254|bls12_381] [--log-n 24] [--dist uniform|non_uniform|witness]
+
+One "step" = one whole MSM over synthetic inputs (SURVEY.md §8d generators).
+At N > 1 (launched by torchrun, one rank per GPU) the points are partitioned by
+contiguous range; every rank computes a partial sum on its GPU and the N
+partials (128 B each) are gathered with one NCCL all_gather and added on the
+host — strong scaling, the total stays 2^log_n points.
+
+Rank 0 prints ONE JSON line.  `value` is whole-job points/s with inputs resident
+in HBM; `e2e` is the same through the reference-shaped C-ABI call with pinned
+HOST buffers (H2D inside the timed region).  `--impl reference` times the CPU
+oracle (restatement of Tachyon's OpenMP Pippenger; the reference itself cannot
+be built in this image) on the host cores.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+SEED = 0x7461636879
+SCALAR_BITS = {"bn254": 254, "bls12_381": 255}
+FQ_LIMBS = {"bn254": 4, "bls12_381": 6}
+
+
+def algorithmic_products(curve, n):
+    """W_alg of SURVEY.md §8(d): 32x32->64 products of the reference's own window
+    rule c = max(ceil(log2 n) - 4, 1) (icicle_msm_utils.cc:26-28)."""
+    lam = SCALAR_BITS[curve]
+    limbs = 2 * FQ_LIMBS[curve]
+    c = max((n - 1).bit_length() - 4, 1)
+    W = -(-lam // c)
+    modmuls = n * W * 10 + W * (1 << c) * 14 + W * c * 9 + W * 14
+    per_mul = 2 * limbs * limbs + limbs
+    return dict(c=c, W=W, modmuls=modmuls, products=modmuls * per_mul,
+                accumulate_products=n * W * 10 * per_mul)
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu = gpu_index
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
+                 "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        sm, mx, reasons, power = [], [], set(), []
+        for r in self.rows:
+            try:
+                sm.append(float(r[1]))
+                mx.append(float(r[2]))
+                power.append(float(r[3]))
+            except (ValueError, IndexError):
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[4:8]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "power_w_max": max(power) if power else None, "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def run_reference(args, rank, world):
+    """--impl reference: the CPU path (oracle restatement of Tachyon's OpenMP
+    Pippenger, VariableBaseMSM::Run) on all host threads; a step is an MSM over a
+    bounded prefix of the same workload."""
+    if rank != 0:
+        return
+    from oracle import cpu_oracle
+    cpu_oracle.build()
+    o = cpu_oracle.CurveOracle(args.curve)
+    sample_log = min(args.log_n, args.cpu_sample_log)
+    n = 1 << sample_log
+    threads = cpu_oracle.max_threads()
+    bases = o.generate_points(SEED + 2, n)
+    scalars = o.generate_scalars(SEED + 3, n, args.dist)
+    for _ in range(max(1, min(args.warmup, 1))):
+        o.msm(bases, scalars, threads=threads)
+    steps = max(1, min(args.steps, 5))
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        o.msm(bases, scalars, threads=threads)
+    dt = (time.perf_counter() - t0) / steps
+    value = n / dt
+    sample = f"2^{sample_log}-point prefix of the 2^{args.log_n} workload, {steps} timed MSMs"
+    print(json.dumps({
+        "impl": "reference", "metric": f"{args.curve} G1 MSM throughput", "value": value, "unit": "points/s",
+        "n_gpus": args.gpus, "steps": steps, "warmup": 1, "ms_per_step": dt * 1e3, "higher_is_better": True,
+        "scaling": "strong", "vs_baseline": None, "dtype": "u32 limbs (Montgomery, u64 on CPU)",
+        "data": "synthetic",
+        "config": {"workload": f"{args.curve} G1 MSM 2^{args.log_n} points, {args.dist} scalars", "sample": sample},
+        "cpu_baseline": {"value": value, "unit": "points/s", "cores": threads, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": "points/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--curve", default="bn254", choices=["bn254", "bls12_381"])
+    ap.add_argument("--log-n", type=int, default=24)
+    ap.add_argument("--dist", default="uniform", choices=["uniform", "non_uniform", "witness"])
+    ap.add_argument("--cpu-sample-log", type=int, default=20)
+    ap.add_argument("--no-parity", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extra", action="store_true", help="skip the secondary 2^20 measurement")
+    ap.add_argument("--window-bits", type=int, default=0)
+    args = ap.parse_args()
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+    if world != args.gpus:
+        if world == 1 and args.gpus > 1:
+            raise SystemExit("launch with torchrun --nproc-per-node %d for --gpus %d" % (args.gpus, args.gpus))
+    args.warmup = max(args.warmup, 3)
+
+    import torch
+    import torch.distributed as dist
+    from tachyon_b200 import msm
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (no CPU fallback)")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    curve, fq = args.curve, FQ_LIMBS[args.curve]
+    n_total = 1 << args.log_n
+    lo, hi = n_total * rank // world, n_total * (rank + 1) // world
+    n_local = hi - lo
+
+    def make_inputs(first, count, seed_shift=0):
+        b = torch.empty((count, 2 * fq), dtype=torch.int64, device="cuda")
+        s = torch.empty((count, 4), dtype=torch.int64, device="cuda")
+        msm.generate_bases_device(curve, SEED + 2 + seed_shift, count, b.data_ptr(), first=first)
+        msm.generate_scalars_device(curve, SEED + 3 + seed_shift, count, s.data_ptr(), args.dist, first=first)
+        torch.cuda.synchronize()
+        return b, s
+
+    bases, scalars = make_inputs(lo, n_local)
+    stream = torch.cuda.Stream()
+    ctx = msm.MSMGpu(curve, degree=args.log_n, device=local_rank)
+    ctx.set_stream(stream.cuda_stream)
+    if args.window_bits:
+        ctx.set_option("window_bits", args.window_bits)
+
+    gather_buf = torch.empty((world, 4 * fq), dtype=torch.int64, device="cuda") if world > 1 else None
+
+    def step(b_ptr, s_ptr, count):
+        """One whole MSM: local partial on this GPU, then (N > 1) gather + host add on rank 0."""
+        part = ctx.msm_xyzz(b_ptr, s_ptr, count)
+        if world == 1:
+            return part
+        with torch.cuda.stream(stream):
+            mine = torch.from_numpy(part.view(np.int64).reshape(-1)).to("cuda", non_blocking=True)
+            dist.all_gather_into_tensor(gather_buf.view(-1), mine)
+        stream.synchronize()
+        if rank != 0:
+            return part
+        parts = gather_buf.cpu().numpy().view(np.uint64).reshape(world, 4, fq)
+        total = parts[0]
+        for g in range(1, world):
+            total = msm.xyzz_add(curve, total, parts[g])
+        return total
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        """K steps bracketed by barrier + synchronize, CUDA events on the engine's stream; max over ranks."""
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        t0 = time.perf_counter()
+        e0.record(stream)
+        for _ in range(steps):
+            out = fn()
+        e1.record(stream)
+        barrier()
+        wall_ms = (time.perf_counter() - t0) * 1e3
+        ms = e0.elapsed_time(e1)
+        if world > 1:
+            t = torch.tensor([ms, wall_ms], device="cuda", dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms, wall_ms = t.tolist()
+        return ms / steps, wall_ms / steps, out
+
+    # ---- device-resident measurement ------------------------------------------------
+    resident = lambda: step(bases.data_ptr(), scalars.data_ptr(), n_local)
+    for _ in range(args.warmup):
+        result = resident()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    launches0 = msm.kernel_launch_count()
+    stage = {"sort_ms": 0.0, "accumulate_ms": 0.0, "reduce_ms": 0.0, "host_ms": 0.0, "total_ms": 0.0}
+
+    def resident_with_stages():
+        r = resident()
+        t = ctx.last_timing()
+        for k in stage:
+            stage[k] += t[k]
+        return r
+
+    ms_step, wall_step, result = timed(resident_with_stages, args.steps)
+    launches = (msm.kernel_launch_count() - launches0)
+    clocks = sampler.stop()
+    timing = ctx.last_timing()
+    for k in stage:
+        stage[k] /= args.steps
+    value = n_total / (ms_step * 1e-3)
+
+    # ---- end to end through the reference-shaped C-ABI call, pinned host buffers ----
+    h_bases = torch.empty((n_local, 2 * fq), dtype=torch.int64).pin_memory()
+    h_scalars = torch.empty((n_local, 4), dtype=torch.int64).pin_memory()
+    h_bases.copy_(bases)
+    h_scalars.copy_(scalars)
+    torch.cuda.synchronize()
+
+    def e2e_step():
+        if world == 1:
+            return ctx.affine_msm(h_bases.data_ptr(), h_scalars.data_ptr(), n_local)  # tachyon_*_g1_affine_msm_gpu
+        return step(h_bases.data_ptr(), h_scalars.data_ptr(), n_local)
+
+    e2e_steps = max(2, min(args.steps, 5))
+    e2e_step()
+    e2e_ms, e2e_wall, e2e_out = timed(e2e_step, e2e_steps)
+    e2e_timing = ctx.last_timing()
+    h2d = n_local * (2 * fq * 8 + 32) * world
+    d2h = (2 * e2e_timing["windows"] * 4 * fq * 8 + 16) * world
+    e2e_value = n_total / (max(e2e_ms, e2e_wall) * 1e-3)
+
+    # ---- parity: chain-fold property against the CPU oracle (outside timing) --------
+    parity = "skipped"
+    if not args.no_parity:
+        from oracle import cpu_oracle
+        o = cpu_oracle.CurveOracle(curve)
+        hs = h_scalars.numpy().view(np.uint64)
+        hb = h_bases.numpy().view(np.uint64)
+        folded = o.fold_chain_scalars(hs)
+        want_local = o.msm(hb[::4096], folded)        # this rank's partial sum, CPU
+        mine = ctx.msm_xyzz(bases.data_ptr(), scalars.data_ptr(), n_local)
+        ok = bool((o.xyzz_to_affine(mine) == o.xyzz_to_affine(want_local)).all())
+        if world > 1:
+            flag = torch.tensor([1 if ok else 0], device="cuda")
+            dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+            ok = bool(flag.item())
+            if rank == 0:
+                # and the combined point equals the sum of the CPU partials
+                gathered = [None] * world
+                dist.gather_object(want_local, gathered, dst=0)
+                tot = gathered[0]
+                for g in range(1, world):
+                    tot = o.xyzz_add(tot, gathered[g])
+                ok = ok and bool((o.xyzz_to_affine(result) == o.xyzz_to_affine(tot)).all())
+            else:
+                dist.gather_object(want_local, None, dst=0)
+        else:
+            ok = ok and bool((o.xyzz_to_affine(result) == o.xyzz_to_affine(want_local)).all())
+            jac = np.asarray(e2e_out)
+            ok = ok and bool((o.jacobian_to_affine(jac) == o.xyzz_to_affine(want_local)).all())
+        parity = "bit-exact vs CPU oracle (chain-fold)" if ok else "MISMATCH"
+
+    # ---- IMAD roofline ----------------------------------------------------------------
+    alg = algorithmic_products(curve, n_total)
+    peak = max(msm.imad_peak(local_rank, 0, 3), msm.imad_peak(local_rank, 1, 3)) if rank == 0 else 0.0
+
+    extra = None
+    cpu_baseline = None
+    if rank == 0:
+        # secondary: 2^20 on this one GPU (BASELINE.json configs[1])
+        if not args.no_extra and world == 1 and args.log_n != 20:
+            nb, ns = make_inputs(0, 1 << 20, seed_shift=10)
+            f20 = lambda: ctx.msm_xyzz(nb.data_ptr(), ns.data_ptr(), 1 << 20)
+            for _ in range(3):
+                f20()
+            ms20, _, _ = timed(f20, max(args.steps, 10))
+            a20 = algorithmic_products(curve, 1 << 20)
+            extra = {"workload": f"{curve} G1 MSM 2^20 points, 1 GPU, device-resident", "ms_per_msm": ms20,
+                     "points_per_s": (1 << 20) / (ms20 * 1e-3),
+                     "imad_frac": a20["products"] / (ms20 * 1e-3) / peak if peak else None}
+            del nb, ns
+        if not args.no_cpu_baseline:
+            from oracle import cpu_oracle
+            o = cpu_oracle.CurveOracle(curve)
+            threads = cpu_oracle.max_threads()
+            sl = min(args.log_n, args.cpu_sample_log)
+            cb = o.generate_points(SEED + 2, 1 << sl)
+            cs = o.generate_scalars(SEED + 3, 1 << sl, args.dist)
+            o.msm(cb, cs, threads=threads)
+            reps = 3
+            t0 = time.perf_counter()
+            for _ in range(reps):
+                o.msm(cb, cs, threads=threads)
+            cdt = (time.perf_counter() - t0) / reps
+            cpu_baseline = {"value": (1 << sl) / cdt, "unit": "points/s", "cores": threads, "kind": "port",
+                            "ms_per_msm": cdt * 1e3,
+                            "sample": f"2^{sl}-point prefix of the workload, oracle OpenMP Pippenger "
+                                      f"(kParallelTerm), mean of {reps}"}
+
+    if world > 1:
+        dist.barrier()
+    if rank == 0:
+        acc_ms = stage["accumulate_ms"]
+        line = {
+            "metric": f"{curve} G1 MSM throughput", "value": value, "unit": "points/s",
+            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step,
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "u32 limbs (254/381-bit Montgomery)", "data": "synthetic",
+            "config": {"workload": f"{curve} G1 MSM 2^{args.log_n} points, {args.dist} scalars",
+                       "partition": f"point range over {world} GPU(s), {n_local} points per GPU",
+                       "window_bits": timing["window_bits"], "windows": timing["windows"],
+                       "l2": "inputs + workspace exceed the 126 MB L2 every step"},
+            "wall_ms_per_step": wall_step,
+            "stages_ms": stage,
+            "clocks": clocks,
+            "e2e": {"value": e2e_value, "unit": "points/s", "ms_per_step": max(e2e_ms, e2e_wall),
+                    "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "api": "tachyon_%s_g1_affine_msm_gpu, pinned host buffers" % curve},
+            "gpu_launches": int(launches),
+            "roofline": {"bound": "int32-imad", "kernel": "accumulate_kernel",
+                         "achieved": alg["accumulate_products"] / world / (acc_ms * 1e-3) / 1e9 if acc_ms else None,
+                         "peak": peak / 1e9, "unit": "G products/s (32x32->64)",
+                         "frac": (alg["accumulate_products"] / world / (acc_ms * 1e-3) / peak) if acc_ms and peak else None,
+                         "traffic": None,
+                         "peak_source": "measured live: tachyon_b200_imad_peak (IMAD.WIDE chains)",
+                         "whole_msm_frac": alg["products"] / (ms_step * 1e-3) / (peak * world) if peak else None,
+                         "algorithmic": {"c": alg["c"], "W": alg["W"], "products": alg["products"]}},
+            "hbm": {"algorithmic_bytes": n_total * (2 * fq * 8 + 32),
+                    "achieved_gbs": n_total * (2 * fq * 8 + 32) / (ms_step * 1e-3) / 1e9},
+            "cpu_baseline": cpu_baseline,
+            "parity": parity,
+            "extra_2p20": extra,
+        }
+        print(json.dumps(line), flush=True)
+    ctx.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
