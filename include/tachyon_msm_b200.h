@@ -138,8 +138,8 @@ TACHYON_C_EXPORT int tachyon_b200_device_count(void);
 /* Text of the last error recorded by an extension call on this thread. */
 TACHYON_C_EXPORT const char* tachyon_b200_last_error(void);
 /* Measured INT32 multiply-pipe peak of `device`: 32x32->64 multiply-adds per second
-   (best of `repeats`), variant 0 = IMAD.WIDE chains, 1 = IMAD.WIDE.X carry chains.
-   Negative on error. */
+   (best of `repeats`).  variant 0 = IMAD.WIDE.U32(.X) carry chains, 1 = IMAD.WIDE.U32 with
+   64-bit addend, 2 = IMAD + IMAD.HI pairs.  Negative on error. */
 TACHYON_C_EXPORT double tachyon_b200_imad_peak(int device, int variant, int repeats);
 /* Window size the engine picks for an n-point MSM over a scalar field of `scalar_bits`
    bits, and the matching window count (host-only). */

@@ -379,6 +379,8 @@ struct tachyon_bls12_381_g1_msm_gpu : public MsmGpuContext<Bls381Curve> {
         for (auto& e : ptr->engines) e->options().window_bits = (uint32_t)value;               \
       } else if (k == "segment") {                                                             \
         for (auto& e : ptr->engines) e->options().segment = (uint32_t)value;                   \
+      } else if (k == "aggregate") {                                                           \
+        for (auto& e : ptr->engines) e->options().aggregate = (int)value;                      \
       } else if (k == "devices") {                                                             \
         ptr->SetDevices((int)value);                                                           \
       } else {                                                                                 \
@@ -501,8 +503,10 @@ double tachyon_b200_imad_peak(int device, int variant, int repeats) {
       TB_CUDA(cudaEventRecord(e0));
       if (variant == 0)
         imad_peak_kernel<0><<<blocks, threads>>>(iters, 12345u + r, out);
-      else
+      else if (variant == 1)
         imad_peak_kernel<1><<<blocks, threads>>>(iters, 12345u + r, out);
+      else
+        imad_peak_kernel<2><<<blocks, threads>>>(iters, 12345u + r, out);
       TB_CUDA(cudaEventRecord(e1));
       TB_CUDA(cudaEventSynchronize(e1));
       g_kernel_launches.fetch_add(1);

@@ -68,6 +68,7 @@ struct MsmTiming {
 struct MsmOptions {
   uint32_t window_bits = 0;  // 0 = choose from n
   uint32_t segment = 0;      // 0 = default
+  int aggregate = -1;        // -1 = default
 };
 
 // Window choice.  Cost in units of one mixed addition:
@@ -128,7 +129,7 @@ class MsmEngine {
     cudaSetDevice(device_);
     cudaStreamSynchronize(stream_);
     for (DeviceBuffer* b : {&bases_stage_, &scalars_stage_, &count_, &offset_, &cursor_,
-                            &task_base_, &tasks_, &multi_, &sorted_, &task_out_, &block_sums_,
+                            &task_base_, &tasks_, &multi_, &sorted_, &task_out_, &block_sums_, &order_, &len_hist_,
                             &lvl_a_[0], &lvl_a_[1], &lvl_c_[0], &lvl_c_[1]})
       b->Free();
     if (totals_) cudaFree(totals_);
@@ -191,6 +192,8 @@ class MsmEngine {
     p.B = 1u << (p.c - 1);
     p.TB = p.W * p.B;
     p.seg = options_.segment ? options_.segment : 128;
+    if (p.seg > (uint32_t)kMaxSegment) p.seg = kMaxSegment;
+    p.aggregate = options_.aggregate < 0 ? 1u : (uint32_t)options_.aggregate;
     uint64_t entries = (uint64_t)n * p.W;
     uint64_t nonempty = entries < p.TB ? entries : p.TB;
     p.max_tasks = (uint32_t)(nonempty + entries / p.seg);
@@ -236,6 +239,8 @@ class MsmEngine {
     sorted_.Reserve((size_t)n * plan.W * 4);
     task_out_.Reserve((size_t)plan.max_tasks * kXyzzBytes);
     block_sums_.Reserve((size_t)scan_blocks * 8);
+    order_.Reserve((size_t)plan.max_tasks * 4);
+    len_hist_.Reserve((size_t)(kMaxSegment + 1) * 4);
 
     // ---- sort: histogram, scan, tasks, scatter ----------------------------
     TB_CUDA(cudaMemsetAsync(count_.ptr, 0, (size_t)(plan.TB + 1) * 4, stream_));
@@ -250,12 +255,21 @@ class MsmEngine {
            multi_.as<uint32_t>(), totals_);
     Launch(digits_scatter_kernel<C>, sgrid, 256, d_scalars, plan, cursor_.as<uint32_t>(),
            sorted_.as<uint32_t>());
+    // tasks by descending length
+    TB_CUDA(cudaMemsetAsync(len_hist_.ptr, 0, (size_t)(kMaxSegment + 1) * 4, stream_));
+    uint32_t ogrid = (plan.max_tasks + kOrderThreads * kOrderPerThread - 1) /
+                     (kOrderThreads * kOrderPerThread);
+    Launch(order_hist_kernel, ogrid, kOrderThreads, tasks_.as<uint2>(), totals_,
+           len_hist_.as<uint32_t>());
+    Launch(order_scan_kernel, 1, 1024, len_hist_.as<uint32_t>());
+    Launch(order_scatter_kernel, ogrid, kOrderThreads, tasks_.as<uint2>(), totals_,
+           len_hist_.as<uint32_t>(), order_.as<uint32_t>());
     TB_CUDA(cudaEventRecord(ev_[2], stream_));
 
     // ---- accumulate -------------------------------------------------------
     uint32_t agrid = (plan.max_tasks + kAccThreads - 1) / kAccThreads;
     Launch(accumulate_kernel<C>, agrid, kAccThreads, d_bases, sorted_.as<uint32_t>(),
-           tasks_.as<uint2>(), totals_, task_out_.as<uint32_t>());
+           tasks_.as<uint2>(), order_.as<uint32_t>(), totals_, task_out_.as<uint32_t>());
     Launch(fold_partials_kernel<C>, sm_count_ * 4, kFoldThreads, multi_.as<uint32_t>(), totals_,
            offset_.as<uint32_t>(), task_base_.as<uint32_t>(), plan.seg,
            task_out_.as<uint32_t>());
@@ -370,7 +384,7 @@ class MsmEngine {
   MsmTotals* totals_ = nullptr;
   char* host_out_ = nullptr;
   DeviceBuffer bases_stage_, scalars_stage_, count_, offset_, cursor_, task_base_, tasks_, multi_,
-      sorted_, task_out_, block_sums_, lvl_a_[2], lvl_c_[2];
+      sorted_, task_out_, block_sums_, order_, len_hist_, lvl_a_[2], lvl_c_[2];
 };
 
 }  // namespace tb200

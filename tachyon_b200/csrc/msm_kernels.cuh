@@ -50,6 +50,7 @@ struct MsmPlan {
   uint32_t TB;       // W * B
   uint32_t seg;      // max entries per task
   uint32_t max_tasks;
+  uint32_t aggregate;  // warp-aggregate the bucket atomics (pays off for repeated digits)
 };
 
 // totals written by the scan: [0] = entries (non-zero digits), [1] = tasks,
@@ -101,8 +102,13 @@ TB_DEV void for_each_digit(Fp<Fr>& s, const MsmPlan& plan, Fn f) {
 // One warp-level atomic per distinct key: lanes holding the same key elect a
 // leader that adds the group size; returns this lane's slot within the group
 // base.  `active` must be the same for the whole warp call site.
-TB_DEV uint32_t warp_aggregated_inc(uint32_t* counter_base, uint32_t key, bool valid) {
+TB_DEV uint32_t warp_aggregated_inc(uint32_t* counter_base, uint32_t key, bool valid,
+                                    bool aggregate) {
   uint32_t result = 0;
+  if (!aggregate) {
+    if (valid) result = atomicAdd(counter_base + key, 1u);
+    return result;
+  }
   uint32_t vote = __ballot_sync(0xffffffffu, valid);
   if (valid) {
     uint32_t peers = __match_any_sync(vote, key);
@@ -132,7 +138,7 @@ __global__ void __launch_bounds__(256) digits_hist_kernel(const uint32_t* __rest
   }
   for_each_digit<Fr>(s, plan, [&](uint32_t w, uint32_t mag, bool) {
     bool valid = in && mag != 0;
-    warp_aggregated_inc(count, w * plan.B + mag - 1, valid);
+    warp_aggregated_inc(count, w * plan.B + mag - 1, valid, plan.aggregate != 0);
   });
 }
 
@@ -154,7 +160,7 @@ __global__ void __launch_bounds__(256) digits_scatter_kernel(const uint32_t* __r
   }
   for_each_digit<Fr>(s, plan, [&](uint32_t w, uint32_t mag, bool neg) {
     bool valid = in && mag != 0;
-    uint32_t pos = warp_aggregated_inc(cursor, w * plan.B + mag - 1, valid);
+    uint32_t pos = warp_aggregated_inc(cursor, w * plan.B + mag - 1, valid, plan.aggregate != 0);
     if (valid) sorted[pos] = i | (neg ? 0x80000000u : 0u);
   });
 }
@@ -284,6 +290,98 @@ __global__ void __launch_bounds__(kScanThreads) scan_apply_build_tasks_kernel(
 }
 
 // ---------------------------------------------------------------------------
+// Task ordering: a counting sort of task ids by length, longest first, so that
+// the 32 lanes of a warp of the accumulation kernel run (almost) the same
+// number of mixed additions.  Lengths are <= kMaxSegment.
+//   order_hist     per-CTA shared histogram -> global histogram
+//   order_scan     one CTA: descending exclusive scan -> first slot of every length
+//   order_scatter  per-CTA reservation of a slot range per length, then local ranks
+// ---------------------------------------------------------------------------
+constexpr int kMaxSegment = 1024;
+constexpr int kOrderThreads = 256;
+constexpr int kOrderPerThread = 8;
+
+__global__ void __launch_bounds__(kOrderThreads) order_hist_kernel(
+    const uint2* __restrict__ tasks, const MsmTotals* __restrict__ totals,
+    uint32_t* __restrict__ len_hist) {
+  __shared__ uint32_t sh[kMaxSegment + 1];
+  for (int i = threadIdx.x; i <= kMaxSegment; i += kOrderThreads) sh[i] = 0;
+  __syncthreads();
+  uint32_t T = totals->tasks;
+  uint32_t base = blockIdx.x * (kOrderThreads * kOrderPerThread);
+#pragma unroll
+  for (int k = 0; k < kOrderPerThread; ++k) {
+    uint32_t g = base + k * kOrderThreads + threadIdx.x;
+    if (g < T) atomicAdd(&sh[tasks[g].y], 1u);
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i <= kMaxSegment; i += kOrderThreads)
+    if (sh[i]) atomicAdd(&len_hist[i], sh[i]);
+}
+
+// in: len_hist[0..kMaxSegment] counts; out: len_hist[l] = first slot of length l when
+// lengths are laid out in DEscending order.
+__global__ void __launch_bounds__(1024) order_scan_kernel(uint32_t* __restrict__ len_hist) {
+  __shared__ uint32_t sh[kMaxSegment + 1];
+  __shared__ uint32_t warp_sums[32];
+  // position p = kMaxSegment - l, so ascending p = descending length
+  uint32_t p = threadIdx.x;
+  uint32_t v = len_hist[kMaxSegment - p];
+  uint32_t lane = p & 31, warp = p >> 5;
+  uint32_t x = v;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    uint32_t y = __shfl_up_sync(0xffffffffu, x, o);
+    if (lane >= (uint32_t)o) x += y;
+  }
+  if (lane == 31) warp_sums[warp] = x;
+  __syncthreads();
+  if (warp == 0) {
+    uint32_t s = warp_sums[lane];
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      uint32_t y = __shfl_up_sync(0xffffffffu, s, o);
+      if (lane >= (uint32_t)o) s += y;
+    }
+    warp_sums[lane] = s;
+  }
+  __syncthreads();
+  uint32_t excl = (warp ? warp_sums[warp - 1] : 0) + x - v;
+  sh[kMaxSegment - p] = excl;
+  __syncthreads();
+  len_hist[kMaxSegment - p] = sh[kMaxSegment - p];
+  // length 0 never occurs (tasks are non-empty); its slot is left as the total
+  if (p == 0) len_hist[0] = warp_sums[31];
+}
+
+__global__ void __launch_bounds__(kOrderThreads) order_scatter_kernel(
+    const uint2* __restrict__ tasks, const MsmTotals* __restrict__ totals,
+    uint32_t* __restrict__ len_cursor, uint32_t* __restrict__ order) {
+  __shared__ uint32_t cnt[kMaxSegment + 1];
+  __shared__ uint32_t start[kMaxSegment + 1];
+  for (int i = threadIdx.x; i <= kMaxSegment; i += kOrderThreads) cnt[i] = 0;
+  __syncthreads();
+  uint32_t T = totals->tasks;
+  uint32_t base = blockIdx.x * (kOrderThreads * kOrderPerThread);
+  uint32_t len[kOrderPerThread], rank[kOrderPerThread];
+#pragma unroll
+  for (int k = 0; k < kOrderPerThread; ++k) {
+    uint32_t g = base + k * kOrderThreads + threadIdx.x;
+    len[k] = (g < T) ? tasks[g].y : 0;
+    rank[k] = len[k] ? atomicAdd(&cnt[len[k]], 1u) : 0;
+  }
+  __syncthreads();
+  for (int i = threadIdx.x + 1; i <= kMaxSegment; i += kOrderThreads)
+    if (cnt[i]) start[i] = atomicAdd(&len_cursor[i], cnt[i]);
+  __syncthreads();
+#pragma unroll
+  for (int k = 0; k < kOrderPerThread; ++k) {
+    uint32_t g = base + k * kOrderThreads + threadIdx.x;
+    if (len[k]) order[start[len[k]] + rank[k]] = g;
+  }
+}
+
+// ---------------------------------------------------------------------------
 // Bucket accumulation — the hot loop (pippenger.h:112-135).  One thread per
 // task; the next point is fetched while the current one is being added.
 // ---------------------------------------------------------------------------
@@ -292,13 +390,14 @@ constexpr int kAccThreads = 128;
 template <class C>
 __global__ void __launch_bounds__(kAccThreads) accumulate_kernel(
     const uint32_t* __restrict__ bases, const uint32_t* __restrict__ sorted,
-    const uint2* __restrict__ tasks, const MsmTotals* __restrict__ totals,
-    uint32_t* __restrict__ task_out) {
+    const uint2* __restrict__ tasks, const uint32_t* __restrict__ order,
+    const MsmTotals* __restrict__ totals, uint32_t* __restrict__ task_out) {
   using Fq = typename C::Fq;
   constexpr int kAffineWords = 2 * Fp<Fq>::N;
   constexpr int kXyzzWords = 4 * Fp<Fq>::N;
-  uint32_t g = blockIdx.x * blockDim.x + threadIdx.x;
-  if (g >= totals->tasks) return;
+  uint32_t slot = blockIdx.x * blockDim.x + threadIdx.x;
+  if (slot >= totals->tasks) return;
+  uint32_t g = order[slot];  // tasks in descending length: warps stay convergent
   uint2 task = tasks[g];
   const uint32_t* ent = sorted + task.x;
   XYZZ<Fq> acc;
@@ -581,53 +680,59 @@ __global__ void generate_scalars_kernel(uint64_t seed, int dist, uint64_t first,
 }
 
 // ---------------------------------------------------------------------------
-// INT32 multiply-pipe peak (the roofline denominator of SURVEY.md §8d):
-// independent chains of 32x32->64 multiply-adds.
-//   variant 0: mad.wide.u32 (IMAD.WIDE.U32), 64-bit accumulate
-//   variant 1: mad.lo.cc / madc.hi.cc pairs (IMAD.WIDE.U32.X, carry in predicate)
+// INT32 multiply-pipe peak (the roofline denominator of SURVEY.md §8d): rate of
+// 32x32->64-bit multiply-adds.  Multiplicands are taken from neighbouring
+// accumulators so that ptxas cannot hoist or strength-reduce the products (an
+// earlier version with loop-invariant operands was turned into IADD3s and
+// over-reported the peak by 1.8x; see DESIGN.md "pipe rates").
+//   variant 0: mad.lo.cc / madc.hi.cc chains  -> IMAD.WIDE.U32(.X), carry in predicate
+//   variant 1: mad.wide.u32 with 64-bit addend -> IMAD.WIDE.U32 (+ IADD3 as ptxas sees fit)
+//   variant 2: mad.lo + mad.hi pairs           -> IMAD + IMAD.HI
 // Each thread issues iters * 16 products.
 // ---------------------------------------------------------------------------
 template <int kVariant>
 __global__ void __launch_bounds__(256) imad_peak_kernel(uint32_t iters, uint32_t seed,
                                                         uint32_t* __restrict__ out) {
   uint32_t a = seed + threadIdx.x, b = seed * 2654435761u + blockIdx.x;
-  if (kVariant == 0) {
-    uint64_t acc[16];
+  uint32_t lo[16], hi[16];
 #pragma unroll
-    for (int k = 0; k < 16; ++k) acc[k] = k + a;
-    for (uint32_t it = 0; it < iters; ++it) {
-#pragma unroll
-      for (int k = 0; k < 16; ++k)
-        asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(acc[k]) : "r"(a + k), "r"(b));
-    }
-    uint64_t s = 0;
-#pragma unroll
-    for (int k = 0; k < 16; ++k) s ^= acc[k];
-    if (s == 0x123456789ull) out[0] = (uint32_t)s;
-  } else {
-    uint32_t lo[16], hi[16];
-#pragma unroll
-    for (int k = 0; k < 16; ++k) {
-      lo[k] = k + a;
-      hi[k] = k ^ b;
-    }
-    for (uint32_t it = 0; it < iters; ++it) {
+  for (int k = 0; k < 16; ++k) {
+    lo[k] = k + a;
+    hi[k] = k ^ b;
+  }
+  for (uint32_t it = 0; it < iters; ++it) {
+    if (kVariant == 0) {
 #pragma unroll
       for (int g = 0; g < 4; ++g) {
-        lo[4 * g] = mad_lo_cc(a + g, b, lo[4 * g]);
-        hi[4 * g] = madc_hi_cc(a + g, b, hi[4 * g]);
+        lo[4 * g] = mad_lo_cc(lo[(4 * g + 7) & 15], b, lo[4 * g]);
+        hi[4 * g] = madc_hi_cc(lo[(4 * g + 7) & 15], b, hi[4 * g]);
 #pragma unroll
         for (int k = 1; k < 4; ++k) {
-          lo[4 * g + k] = madc_lo_cc(a + g + k, b, lo[4 * g + k]);
-          hi[4 * g + k] = madc_hi_cc(a + g + k, b, hi[4 * g + k]);
+          uint32_t m = lo[(4 * g + k + 7) & 15];
+          lo[4 * g + k] = madc_lo_cc(m, b, lo[4 * g + k]);
+          hi[4 * g + k] = madc_hi_cc(m, b, hi[4 * g + k]);
         }
       }
-    }
-    uint32_t s = 0;
+    } else if (kVariant == 1) {
 #pragma unroll
-    for (int k = 0; k < 16; ++k) s ^= lo[k] ^ hi[k];
-    if (s == 0x12345678u) out[0] = s;
+      for (int k = 0; k < 16; ++k)
+        asm volatile(
+            "{.reg .u64 t; mov.b64 t, {%0,%1}; mad.wide.u32 t, %2, %3, t; mov.b64 {%0,%1}, t;}"
+            : "+r"(lo[k]), "+r"(hi[k])
+            : "r"(lo[(k + 7) & 15]), "r"(b));
+    } else {
+#pragma unroll
+      for (int k = 0; k < 16; ++k) {
+        uint32_t m = lo[(k + 7) & 15];
+        asm volatile("mad.hi.u32 %0, %1, %2, %0;" : "+r"(hi[k]) : "r"(m), "r"(b));
+        asm volatile("mad.lo.u32 %0, %1, %2, %0;" : "+r"(lo[k]) : "r"(m), "r"(b));
+      }
+    }
   }
+  uint32_t s = 0;
+#pragma unroll
+  for (int k = 0; k < 16; ++k) s ^= lo[k] ^ hi[k];
+  if (s == 0x12345678u) out[0] = s;
 }
 
 }  // namespace tb200
