@@ -161,7 +161,7 @@ def main():
 
     import torch
     import torch.distributed as dist
-    from tachyon_b200 import msm
+    from tachyon_b200 import msm, sharding
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device (no CPU fallback)")
@@ -171,7 +171,7 @@ def main():
 
     curve, fq = args.curve, FQ_LIMBS[args.curve]
     n_total = 1 << args.log_n
-    lo, hi = n_total * rank // world, n_total * (rank + 1) // world
+    lo, hi = sharding.shard_range(n_total, rank, world)
     n_local = hi - lo
 
     def make_inputs(first, count, seed_shift=0):
@@ -197,16 +197,10 @@ def main():
         if world == 1:
             return part
         with torch.cuda.stream(stream):
-            mine = torch.from_numpy(part.view(np.int64).reshape(-1)).to("cuda", non_blocking=True)
-            dist.all_gather_into_tensor(gather_buf.view(-1), mine)
-        stream.synchronize()
+            parts = sharding.gather_partials(part, world, device="cuda", out=gather_buf)
         if rank != 0:
             return part
-        parts = gather_buf.cpu().numpy().view(np.uint64).reshape(world, 4, fq)
-        total = parts[0]
-        for g in range(1, world):
-            total = msm.xyzz_add(curve, total, parts[g])
-        return total
+        return sharding.combine_partials(curve, list(parts))
 
     def barrier():
         if world > 1:
