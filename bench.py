@@ -108,7 +108,7 @@ def run_reference(args, rank, world):
     o = cpu_oracle.CurveOracle(args.curve)
     sample_log = min(args.log_n, args.cpu_sample_log)
     n = 1 << sample_log
-    threads = cpu_oracle.max_threads()
+    threads = os.cpu_count() or cpu_oracle.max_threads()  # torchrun pins OMP_NUM_THREADS=1
     bases = o.generate_points(SEED + 2, n)
     scalars = o.generate_scalars(SEED + 3, n, args.dist)
     for _ in range(max(1, min(args.warmup, 1))):
@@ -322,7 +322,7 @@ def main():
         if not args.no_cpu_baseline:
             from oracle import cpu_oracle
             o = cpu_oracle.CurveOracle(curve)
-            threads = cpu_oracle.max_threads()
+            threads = os.cpu_count() or cpu_oracle.max_threads()  # torchrun pins OMP_NUM_THREADS=1
             sl = min(args.log_n, args.cpu_sample_log)
             cb = o.generate_points(SEED + 2, 1 << sl)
             cs = o.generate_scalars(SEED + 3, 1 << sl, args.dist)

@@ -257,6 +257,86 @@ TB_DEV void fp_mul(Fp<F>& r, const Fp<F>& a, const Fp<F>& b) {
   fp_reduce_once<F>(r, t);
 }
 
+// r = (a * b + a2 * b2) * R^-1 mod p with ONE Montgomery reduction: each row adds two
+// product rows before its reduction row, saving N*N + N of the 2*(2*N*N + N) products of
+// two separate multiplications.  Bounds: V < 4p + 3 * 2^32 p < 2^(32(N+1)) and the result
+// is < p (2p/R + 1) < 2p, so one conditional subtraction still canonicalises it.
+template <class F, int N>
+TB_DEV void mont_mul2_row(uint32_t (&X)[N], uint32_t (&Y)[N], const uint32_t (&a)[N], uint32_t bi,
+                          const uint32_t (&a2)[N], uint32_t b2i) {
+  X[0] = add_cc(X[0], Y[1]);
+#pragma unroll
+  for (int j = 0; j < N; j += 2) {
+    uint32_t c_lo = (j + 2 < N) ? Y[j + 2] : 0u;
+    uint32_t c_hi = (j + 3 < N) ? Y[j + 3] : 0u;
+    Y[j] = madc_lo_cc(a[j + 1], bi, c_lo);
+    Y[j + 1] = madc_hi_cc(a[j + 1], bi, c_hi);
+  }
+  Y[0] = mad_lo_cc(a2[1], b2i, Y[0]);
+  Y[1] = madc_hi_cc(a2[1], b2i, Y[1]);
+#pragma unroll
+  for (int j = 2; j < N; j += 2) {
+    Y[j] = madc_lo_cc(a2[j + 1], b2i, Y[j]);
+    Y[j + 1] = madc_hi_cc(a2[j + 1], b2i, Y[j + 1]);
+  }
+  X[0] = mad_lo_cc(a[0], bi, X[0]);
+  X[1] = madc_hi_cc(a[0], bi, X[1]);
+#pragma unroll
+  for (int j = 2; j < N; j += 2) {
+    X[j] = madc_lo_cc(a[j], bi, X[j]);
+    X[j + 1] = madc_hi_cc(a[j], bi, X[j + 1]);
+  }
+  Y[N - 1] = addc(Y[N - 1], 0u);
+  X[0] = mad_lo_cc(a2[0], b2i, X[0]);
+  X[1] = madc_hi_cc(a2[0], b2i, X[1]);
+#pragma unroll
+  for (int j = 2; j < N; j += 2) {
+    X[j] = madc_lo_cc(a2[j], b2i, X[j]);
+    X[j + 1] = madc_hi_cc(a2[j], b2i, X[j + 1]);
+  }
+  Y[N - 1] = addc(Y[N - 1], 0u);
+  mont_reduce_row<F, N>(X, Y);
+}
+
+template <class F>
+TB_DEV void fp_mul2(Fp<F>& r, const Fp<F>& a, const Fp<F>& b, const Fp<F>& a2, const Fp<F>& b2) {
+  constexpr int N = Fp<F>::N;
+  uint32_t E[N], O[N];
+#pragma unroll
+  for (int j = 0; j < N; j += 2) {
+    mul_wide(E[j], E[j + 1], a.l[j], b.l[0]);
+    mul_wide(O[j], O[j + 1], a.l[j + 1], b.l[0]);
+  }
+  // second product of row 0; carries out of the aligned chain go to O's top limb
+  O[0] = mad_lo_cc(a2.l[1], b2.l[0], O[0]);
+  O[1] = madc_hi_cc(a2.l[1], b2.l[0], O[1]);
+#pragma unroll
+  for (int j = 2; j < N; j += 2) {
+    O[j] = madc_lo_cc(a2.l[j + 1], b2.l[0], O[j]);
+    O[j + 1] = madc_hi_cc(a2.l[j + 1], b2.l[0], O[j + 1]);
+  }
+  E[0] = mad_lo_cc(a2.l[0], b2.l[0], E[0]);
+  E[1] = madc_hi_cc(a2.l[0], b2.l[0], E[1]);
+#pragma unroll
+  for (int j = 2; j < N; j += 2) {
+    E[j] = madc_lo_cc(a2.l[j], b2.l[0], E[j]);
+    E[j + 1] = madc_hi_cc(a2.l[j], b2.l[0], E[j + 1]);
+  }
+  O[N - 1] = addc(O[N - 1], 0u);
+  mont_reduce_row<F, N>(E, O);
+#pragma unroll
+  for (int i = 1; i < N; i += 2) {
+    mont_mul2_row<F, N>(O, E, a.l, b.l[i], a2.l, b2.l[i]);
+    if (i + 1 < N) mont_mul2_row<F, N>(E, O, a.l, b.l[i + 1], a2.l, b2.l[i + 1]);
+  }
+  uint32_t t[N];
+  t[0] = add_cc(E[0], O[1]);
+#pragma unroll
+  for (int j = 1; j < N - 1; ++j) t[j] = addc_cc(E[j], O[j + 1]);
+  t[N - 1] = addc(E[N - 1], 0u);
+  fp_reduce_once<F>(r, t);
+}
+
 template <class F>
 TB_DEV void fp_sqr(Fp<F>& r, const Fp<F>& a) {
   fp_mul<F>(r, a, a);

@@ -72,9 +72,8 @@ struct MsmOptions {
 };
 
 // Window choice.  Cost in units of one mixed addition:
-//   accumulation  n * W
-//   reduction     W * 2^(c-1) * 2 full additions (1.4 madd each), run at lower
-//                 occupancy than the hot kernel (factor kReduceInefficiency)
+//   sort + accumulation  kEntryCost  * n * W
+//   reduction            kBucketCost * W * 2^(c-1)   (2 full additions per bucket)
 // W is the smallest count with W * c >= bits + 1, so the signed top digit
 // never carries out (see for_each_digit).
 inline uint32_t WindowsFor(uint32_t bits, uint32_t c) { return (bits + 1 + c - 1) / c; }
@@ -84,7 +83,9 @@ constexpr uint32_t kMinWindowBits = 4;
 constexpr uint32_t kMaxWindows = 64;
 
 inline uint32_t ChooseWindowBits(size_t n, uint32_t scalar_bits) {
-  constexpr double kReduceInefficiency = 1.5;
+  // measured on B200 (BN254 2^24, c = 20): 0.155 ns per mixed addition, 0.057 ns of
+  // sorting per entry, 0.73 ns of reduction per bucket
+  constexpr double kEntryCost = 1.37, kBucketCost = 4.7;
   constexpr uint32_t kMaxBuckets = 1u << 24;  // scan_top_kernel capacity
   double best = 1e300;
   uint32_t best_c = kMinWindowBits;
@@ -92,7 +93,7 @@ inline uint32_t ChooseWindowBits(size_t n, uint32_t scalar_bits) {
     uint32_t W = WindowsFor(scalar_bits, c);
     double buckets = (double)W * (double)(1u << (c - 1));
     if (buckets > kMaxBuckets) break;
-    double cost = (double)n * W + buckets * 2.0 * 1.4 * kReduceInefficiency;
+    double cost = kEntryCost * (double)n * W + kBucketCost * buckets;
     if (cost < best) {
       best = cost;
       best_c = c;
@@ -129,7 +130,7 @@ class MsmEngine {
     cudaSetDevice(device_);
     cudaStreamSynchronize(stream_);
     for (DeviceBuffer* b : {&bases_stage_, &scalars_stage_, &count_, &offset_, &cursor_,
-                            &task_base_, &tasks_, &multi_, &sorted_, &task_out_, &block_sums_, &order_, &len_hist_,
+                            &task_base_, &tasks_, &multi_, &sorted_, &digits_, &task_out_, &block_sums_, &order_, &len_hist_,
                             &lvl_a_[0], &lvl_a_[1], &lvl_c_[0], &lvl_c_[1]})
       b->Free();
     if (totals_) cudaFree(totals_);
@@ -182,6 +183,14 @@ class MsmEngine {
     g_kernel_launches.fetch_add(1, std::memory_order_relaxed);
   }
 
+  template <class K, class... Args>
+  void LaunchGrid(K kernel, dim3 grid, uint32_t block, Args... args) {
+    kernel<<<grid, block, 0, stream_>>>(args...);
+    TB_CUDA(cudaGetLastError());
+    ++launches_;
+    g_kernel_launches.fetch_add(1, std::memory_order_relaxed);
+  }
+
   MsmPlan MakePlan(size_t n) const {
     MsmPlan p{};
     p.n = (uint32_t)n;
@@ -191,7 +200,11 @@ class MsmEngine {
     p.W = WindowsFor(Fr::kBits, p.c);
     p.B = 1u << (p.c - 1);
     p.TB = p.W * p.B;
-    p.seg = options_.segment ? options_.segment : 128;
+    // Tasks hold up to 4x the mean bucket size, so ordinary buckets are one task and only
+    // genuinely oversized buckets (skewed scalars) are split and folded.
+    uint32_t seg = 128;
+    while (seg < (uint32_t)kMaxSegment && seg < 4 * (n / p.B + 1)) seg <<= 1;
+    p.seg = options_.segment ? options_.segment : seg;
     if (p.seg > (uint32_t)kMaxSegment) p.seg = kMaxSegment;
     p.aggregate = options_.aggregate < 0 ? 1u : (uint32_t)options_.aggregate;
     uint64_t entries = (uint64_t)n * p.W;
@@ -237,6 +250,7 @@ class MsmEngine {
     tasks_.Reserve((size_t)plan.max_tasks * sizeof(uint2));
     multi_.Reserve((size_t)plan.TB * 4);
     sorted_.Reserve((size_t)n * plan.W * 4);
+    digits_.Reserve((size_t)n * plan.W * 4);
     task_out_.Reserve((size_t)plan.max_tasks * kXyzzBytes);
     block_sums_.Reserve((size_t)scan_blocks * 8);
     order_.Reserve((size_t)plan.max_tasks * 4);
@@ -245,7 +259,8 @@ class MsmEngine {
     // ---- sort: histogram, scan, tasks, scatter ----------------------------
     TB_CUDA(cudaMemsetAsync(count_.ptr, 0, (size_t)(plan.TB + 1) * 4, stream_));
     uint32_t sgrid = (plan.n + 255) / 256;
-    Launch(digits_hist_kernel<C>, sgrid, 256, d_scalars, plan, count_.as<uint32_t>());
+    Launch(digits_hist_kernel<C>, sgrid, 256, d_scalars, plan, digits_.as<uint32_t>(),
+           count_.as<uint32_t>());
     Launch(scan_block_sums_kernel, scan_blocks, kScanThreads, count_.as<uint32_t>(), plan.TB,
            plan.seg, block_sums_.as<uint64_t>());
     Launch(scan_top_kernel, 1, kScanThreads, block_sums_.as<uint64_t>(), scan_blocks, totals_);
@@ -253,8 +268,8 @@ class MsmEngine {
            plan.TB, plan.seg, block_sums_.as<uint64_t>(), offset_.as<uint32_t>(),
            cursor_.as<uint32_t>(), task_base_.as<uint32_t>(), tasks_.as<uint2>(),
            multi_.as<uint32_t>(), totals_);
-    Launch(digits_scatter_kernel<C>, sgrid, 256, d_scalars, plan, cursor_.as<uint32_t>(),
-           sorted_.as<uint32_t>());
+    LaunchGrid(digits_scatter_kernel, dim3(sgrid, plan.W), 256, digits_.as<uint32_t>(), plan,
+               cursor_.as<uint32_t>(), sorted_.as<uint32_t>());
     // tasks by descending length
     TB_CUDA(cudaMemsetAsync(len_hist_.ptr, 0, (size_t)(kMaxSegment + 1) * 4, stream_));
     uint32_t ogrid = (plan.max_tasks + kOrderThreads * kOrderPerThread - 1) /
@@ -384,7 +399,7 @@ class MsmEngine {
   MsmTotals* totals_ = nullptr;
   char* host_out_ = nullptr;
   DeviceBuffer bases_stage_, scalars_stage_, count_, offset_, cursor_, task_base_, tasks_, multi_,
-      sorted_, task_out_, block_sums_, order_, len_hist_, lvl_a_[2], lvl_c_[2];
+      sorted_, digits_, task_out_, block_sums_, order_, len_hist_, lvl_a_[2], lvl_c_[2];
 };
 
 }  // namespace tb200

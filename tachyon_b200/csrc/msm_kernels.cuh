@@ -99,13 +99,20 @@ TB_DEV void for_each_digit(Fp<Fr>& s, const MsmPlan& plan, Fn f) {
   }
 }
 
-// One warp-level atomic per distinct key: lanes holding the same key elect a
-// leader that adds the group size; returns this lane's slot within the group
-// base.  `active` must be the same for the whole warp call site.
-TB_DEV uint32_t warp_aggregated_inc(uint32_t* counter_base, uint32_t key, bool valid,
-                                    bool aggregate) {
+// Bucket counter increment for one lane's key; returns the previous value.  Repeated keys
+// inside a warp (small scalars, the reference's "non_uniform" test set, witness vectors full
+// of 0/1) would serialise at one L2 address, so when a cheap neighbour test sees a duplicate
+// the warp switches to one atomic per distinct key (match.any).  The test is a single
+// shuffle + vote; match.any itself saturates the ADU pipe (ncu: 95 %) and is not worth
+// paying on uniformly random digits.
+TB_DEV uint32_t bucket_inc(uint32_t* counter_base, uint32_t key, bool valid, bool aggregate) {
   uint32_t result = 0;
-  if (!aggregate) {
+  bool dup = false;
+  if (aggregate) {
+    uint32_t other = __shfl_xor_sync(0xffffffffu, valid ? key : 0xffffffffu, 1);
+    dup = __any_sync(0xffffffffu, valid && other == key);
+  }
+  if (!dup) {
     if (valid) result = atomicAdd(counter_base + key, 1u);
     return result;
   }
@@ -123,32 +130,14 @@ TB_DEV uint32_t warp_aggregated_inc(uint32_t* counter_base, uint32_t key, bool v
   return result;
 }
 
+// Pass 1 over the scalars: de-Montgomery, recode, write the digit words window-major
+// (digits[w * n + i] = |d| | sign << 31, 0 for a zero digit; coalesced per window) and count
+// bucket sizes.
 template <class C>
 __global__ void __launch_bounds__(256) digits_hist_kernel(const uint32_t* __restrict__ scalars,
                                                           MsmPlan plan,
+                                                          uint32_t* __restrict__ digits,
                                                           uint32_t* __restrict__ count) {
-  using Fr = typename C::Fr;
-  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-  bool in = i < plan.n;
-  Fp<Fr> s;
-  if (in) {
-    load_scalar_canonical<Fr>(s, scalars, i);
-  } else {
-    fp_set_zero<Fr>(s);
-  }
-  for_each_digit<Fr>(s, plan, [&](uint32_t w, uint32_t mag, bool) {
-    bool valid = in && mag != 0;
-    warp_aggregated_inc(count, w * plan.B + mag - 1, valid, plan.aggregate != 0);
-  });
-}
-
-// cursor[key] starts at offset[key] (a copy of the exclusive scan) and is
-// advanced by the scatter; the value returned by the atomic is the slot.
-template <class C>
-__global__ void __launch_bounds__(256) digits_scatter_kernel(const uint32_t* __restrict__ scalars,
-                                                             MsmPlan plan,
-                                                             uint32_t* __restrict__ cursor,
-                                                             uint32_t* __restrict__ sorted) {
   using Fr = typename C::Fr;
   uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   bool in = i < plan.n;
@@ -160,9 +149,29 @@ __global__ void __launch_bounds__(256) digits_scatter_kernel(const uint32_t* __r
   }
   for_each_digit<Fr>(s, plan, [&](uint32_t w, uint32_t mag, bool neg) {
     bool valid = in && mag != 0;
-    uint32_t pos = warp_aggregated_inc(cursor, w * plan.B + mag - 1, valid, plan.aggregate != 0);
-    if (valid) sorted[pos] = i | (neg ? 0x80000000u : 0u);
+    if (in) digits[(size_t)w * plan.n + i] = mag | (neg ? 0x80000000u : 0u);
+    bucket_inc(count, w * plan.B + mag - 1, valid, plan.aggregate != 0);
   });
+}
+
+// Pass 2, window-major (blockIdx.y = window): all CTAs of one window run before the next
+// window's, so the slice of `sorted` being filled (4 n bytes) and the window's cursors
+// (2^(c+1) bytes) stay resident in the 126 MB L2 and every 32-byte sector goes to HBM once.
+// The scalar-major form wrote 4-byte words at random over the whole n*W array: 14.7 GB of
+// DRAM traffic and L2-missing atomics at n = 2^24 (profiles/r1_b_*).
+// cursor[key] starts at offset[key]; the value returned by the atomic is the slot.
+__global__ void __launch_bounds__(256) digits_scatter_kernel(const uint32_t* __restrict__ digits,
+                                                             MsmPlan plan,
+                                                             uint32_t* __restrict__ cursor,
+                                                             uint32_t* __restrict__ sorted) {
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  uint32_t w = blockIdx.y;
+  bool in = i < plan.n;
+  uint32_t d = in ? digits[(size_t)w * plan.n + i] : 0u;
+  uint32_t mag = d & 0x7fffffffu;
+  bool valid = mag != 0;
+  uint32_t pos = bucket_inc(cursor, w * plan.B + mag - 1, valid, plan.aggregate != 0);
+  if (valid) sorted[pos] = i | (d & 0x80000000u);
 }
 
 // ---------------------------------------------------------------------------
@@ -441,7 +450,11 @@ __global__ void __launch_bounds__(kFoldThreads) fold_partials_kernel(
       xyzz_add<Fq>(acc, tmp);
     }
     __syncthreads();  // all partials read before slot 0 is overwritten
-    for (int stride = kFoldThreads / 2; stride >= 1; stride >>= 1) {
+    // tree over the threads that hold something: first power of two >= min(t, threads)
+    int live = t < (uint32_t)kFoldThreads ? (int)t : kFoldThreads;
+    int top = 1;
+    while (top < live) top <<= 1;
+    for (int stride = top / 2; stride >= 1; stride >>= 1) {
       if ((int)threadIdx.x >= stride && (int)threadIdx.x < 2 * stride)
         xyzz_store<Fq>(sh + (threadIdx.x - stride) * kXyzzWords, acc);
       __syncthreads();

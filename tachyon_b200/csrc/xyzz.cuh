@@ -79,13 +79,12 @@ __device__ __noinline__ void xyzz_dbl_nz(XYZZ<F>& p) {
   fp_add<F>(m, m, t);
   fp_mul<F>(p.zz, v, p.zz);    // ZZ3 = V ZZ1
   fp_mul<F>(p.zzz, w, p.zzz);  // ZZZ3 = W ZZZ1
-  fp_mul<F>(w, w, p.y);        // W Y1
   fp_sqr<F>(p.x, m);           // X3 = M^2 - 2 S
   fp_dbl<F>(t, s);
   fp_sub<F>(p.x, p.x, t);
-  fp_sub<F>(t, s, p.x);        // Y3 = M (S - X3) - W Y1
-  fp_mul<F>(t, m, t);
-  fp_sub<F>(p.y, t, w);
+  fp_sub<F>(t, p.x, s);        // Y3 = M (S - X3) - W Y1 = -(W Y1 + M (X3 - S)), one reduction
+  fp_mul2<F>(t, w, p.y, m, t);
+  fp_neg<F>(p.y, t);
 }
 template <class F>
 TB_DEV void xyzz_dbl(XYZZ<F>& p) {
@@ -123,10 +122,9 @@ TB_DEV void xyzz_madd(XYZZ<F>& acc, const Affine<F>& q, bool neg) {
   fp_sub<F>(acc.x, acc.x, ppp);
   fp_dbl<F>(t, qq);
   fp_sub<F>(acc.x, acc.x, t);
-  fp_mul<F>(ppp, acc.y, ppp);        // Y1 PPP
-  fp_sub<F>(t, qq, acc.x);           // Y3 = R (Q - X3) - Y1 PPP
-  fp_mul<F>(t, r, t);
-  fp_sub<F>(acc.y, t, ppp);
+  fp_sub<F>(t, acc.x, qq);           // Y3 = R (Q - X3) - Y1 PPP = -(Y1 PPP + R (X3 - Q)),
+  fp_mul2<F>(t, acc.y, ppp, r, t);   //      one Montgomery reduction for both products
+  fp_neg<F>(acc.y, t);
 }
 
 // acc += b for acc, b both != identity (add-2008-s).  Straight-line body: the
@@ -156,10 +154,9 @@ __device__ __noinline__ bool xyzz_add_nz(XYZZ<F>& acc, const XYZZ<F>& b) {
   fp_sub<F>(o.x, o.x, ppp);
   fp_dbl<F>(t, qq);
   fp_sub<F>(o.x, o.x, t);
-  fp_mul<F>(s1, s1, ppp);             // S1 PPP
-  fp_sub<F>(t, qq, o.x);              // Y3 = R (Q - X3) - S1 PPP
-  fp_mul<F>(t, r, t);
-  fp_sub<F>(o.y, t, s1);
+  fp_sub<F>(t, o.x, qq);              // Y3 = R (Q - X3) - S1 PPP = -(S1 PPP + R (X3 - Q))
+  fp_mul2<F>(t, s1, ppp, r, t);
+  fp_neg<F>(o.y, t);
 #pragma unroll
   for (int i = 0; i < Fp<F>::N; ++i) {
     acc.x.l[i] = same ? acc.x.l[i] : o.x.l[i];
