@@ -131,7 +131,7 @@ class MsmEngine {
     cudaStreamSynchronize(stream_);
     for (DeviceBuffer* b : {&bases_stage_, &scalars_stage_, &count_, &offset_, &cursor_,
                             &task_base_, &tasks_, &multi_, &sorted_, &digits_, &task_out_, &block_sums_, &order_, &len_hist_,
-                            &lvl_a_[0], &lvl_a_[1], &lvl_c_[0], &lvl_c_[1]})
+                            &lvl_a_[0], &lvl_a_[1], &lvl_c_[0], &lvl_c_[1], &tree_[0], &tree_[1]})
       b->Free();
     if (totals_) cudaFree(totals_);
     if (host_out_) cudaFreeHost(host_out_);
@@ -290,62 +290,68 @@ class MsmEngine {
            task_out_.as<uint32_t>());
     TB_CUDA(cudaEventRecord(ev_[3], stream_));
 
-    // ---- bucket reduction levels -------------------------------------------
-    uint32_t n_in = plan.B;
-    uint32_t shift = 0;
-    int level = 0;
-    const uint32_t* in_a = task_out_.as<uint32_t>();
-    const uint32_t* in_c = nullptr;
-    uint32_t* out_a = nullptr;
-    uint32_t* out_c = nullptr;
-    while (true) {
-      uint32_t L = ChooseLevelLength(level, n_in, plan.W);
-      uint32_t n_out = (n_in + L - 1) / L;
-      DeviceBuffer& ba = lvl_a_[level & 1];
-      DeviceBuffer& bc = lvl_c_[level & 1];
-      ba.Reserve((size_t)plan.W * n_out * kXyzzBytes);
-      bc.Reserve((size_t)plan.W * n_out * kXyzzBytes);
-      out_a = ba.as<uint32_t>();
-      out_c = bc.as<uint32_t>();
-      uint32_t threads = plan.W * n_out;
-      uint32_t grid = (threads + kReduceThreads - 1) / kReduceThreads;
-      if (level == 0) {
-        Launch(reduce_level_kernel<C, true>, grid, kReduceThreads, in_a, in_c,
-               offset_.as<uint32_t>(), task_base_.as<uint32_t>(), n_in, n_out, L, shift, plan.W,
-               out_a, out_c);
-      } else {
-        Launch(reduce_level_kernel<C, false>, grid, kReduceThreads, in_a, in_c,
-               (const uint32_t*)nullptr, (const uint32_t*)nullptr, n_in, n_out, L, shift, plan.W,
-               out_a, out_c);
-      }
-      shift += Log2(L);
-      n_in = n_out;
-      in_a = out_a;
-      in_c = out_c;
-      ++level;
-      if (n_out == 1) break;
+    // ---- bucket reduction: one blocked running-sum level, then a merge tree ---------
+    uint32_t L0 = ChooseLevelLength(plan.B, plan.W);
+    uint32_t m = plan.B / L0;  // blocks per window, a power of two
+    lvl_a_[0].Reserve((size_t)plan.W * m * kXyzzBytes);
+    lvl_c_[0].Reserve((size_t)plan.W * m * kXyzzBytes);
+    {
+      uint32_t threads = plan.W * m;
+      Launch(reduce_level_kernel<C, true>, (threads + kReduceThreads - 1) / kReduceThreads,
+             kReduceThreads, task_out_.as<uint32_t>(), (const uint32_t*)nullptr,
+             offset_.as<uint32_t>(), task_base_.as<uint32_t>(), plan.B, m, L0, 0u, plan.W,
+             lvl_a_[0].as<uint32_t>(), lvl_c_[0].as<uint32_t>());
     }
-    // window sums S_w = A_w + C_w, finished on the host
-    size_t win_bytes = (size_t)plan.W * kXyzzBytes;
-    TB_CUDA(cudaMemcpyAsync(host_out_, out_a, win_bytes, cudaMemcpyDeviceToHost, stream_));
-    TB_CUDA(cudaMemcpyAsync(host_out_ + win_bytes, out_c, win_bytes, cudaMemcpyDeviceToHost,
-                            stream_));
-    TB_CUDA(cudaMemcpyAsync(host_out_ + 2 * win_bytes, totals_, sizeof(MsmTotals),
+    uint32_t M = Log2(m);
+    const uint32_t* tin = lvl_a_[0].as<uint32_t>();
+    const uint32_t* tin_p = lvl_c_[0].as<uint32_t>();
+    for (uint32_t s = 0; s < M; ++s) {
+      uint32_t m_out = m >> (s + 1);
+      DeviceBuffer& dst = tree_[s & 1];
+      dst.Reserve((size_t)plan.W * m_out * (s + 3) * kXyzzBytes);
+      uint32_t threads = plan.W * m_out * (s + 3);
+      Launch(reduce_merge_kernel<C>, (threads + kReduceThreads - 1) / kReduceThreads,
+             kReduceThreads, tin, tin_p, s, m_out, plan.W, dst.as<uint32_t>());
+      tin = dst.as<uint32_t>();
+      tin_p = nullptr;
+    }
+    // per window: (A, P, D_0 .. D_(M-1)); finished on the host
+    uint32_t vals = M + 2;
+    size_t win_bytes = (size_t)plan.W * vals * kXyzzBytes;
+    if (M == 0) {
+      TB_CUDA(cudaMemcpy2DAsync(host_out_, 2 * kXyzzBytes, lvl_a_[0].ptr, kXyzzBytes, kXyzzBytes,
+                                plan.W, cudaMemcpyDeviceToHost, stream_));
+      TB_CUDA(cudaMemcpy2DAsync(host_out_ + kXyzzBytes, 2 * kXyzzBytes, lvl_c_[0].ptr, kXyzzBytes,
+                                kXyzzBytes, plan.W, cudaMemcpyDeviceToHost, stream_));
+    } else {
+      TB_CUDA(cudaMemcpyAsync(host_out_, tin, win_bytes, cudaMemcpyDeviceToHost, stream_));
+    }
+    TB_CUDA(cudaMemcpyAsync(host_out_ + win_bytes, totals_, sizeof(MsmTotals),
                             cudaMemcpyDeviceToHost, stream_));
     TB_CUDA(cudaEventRecord(ev_[4], stream_));
     TB_CUDA(cudaStreamSynchronize(stream_));
 
-    // ---- host epilogue (pippenger_base.h:59-77) ----------------------------
+    // ---- host epilogue ------------------------------------------------------------
+    // S_w = A + P + L0 * sum_j 2^j D_j, then Horner over windows (pippenger_base.h:59-77).
     auto host0 = std::chrono::steady_clock::now();
     std::vector<Point> sums(plan.W);
-    const Point* ha = reinterpret_cast<const Point*>(host_out_);
-    const Point* hc = reinterpret_cast<const Point*>(host_out_ + win_bytes);
-    for (uint32_t w = 0; w < plan.W; ++w) sums[w] = ha[w].Add(hc[w]);
+    const Point* hv = reinterpret_cast<const Point*>(host_out_);
+    uint32_t l0 = Log2(L0);
+    for (uint32_t w = 0; w < plan.W; ++w) {
+      const Point* v = hv + (size_t)w * vals;
+      Point q = Point::Zero();
+      for (uint32_t j = M; j-- > 0;) {
+        q = q.Dbl();
+        q = q.Add(v[2 + j]);
+      }
+      for (uint32_t i = 0; i < l0; ++i) q = q.Dbl();
+      sums[w] = v[0].Add(v[1]).Add(q);
+    }
     Point result = CombineWindows<Fq>(sums.data(), plan.W, plan.c);
     auto host1 = std::chrono::steady_clock::now();
 
     MsmTotals tot;
-    memcpy(&tot, host_out_ + 2 * win_bytes, sizeof(tot));
+    memcpy(&tot, host_out_ + win_bytes, sizeof(tot));
     float ms;
     TB_CUDA(cudaEventElapsedTime(&ms, ev_[0], ev_[1]));
     timing_.h2d_ms += ms;
@@ -373,20 +379,19 @@ class MsmEngine {
     return r;
   }
 
-  // Level 0 is throughput-bound (many buckets): blocks as long as the grid
-  // still fills the chip.  Later levels are latency-bound chains of full
-  // additions: keep them short.
-  uint32_t ChooseLevelLength(int level, uint32_t n_in, uint32_t windows) const {
-    if (level > 0) return n_in < 4 ? n_in : 4;
-    uint64_t items = (uint64_t)n_in * windows;
-    uint64_t want_threads = (uint64_t)sm_count_ * 512;
+  // Blocks of the running-sum level: as long as possible while the grid still fills the
+  // chip (a thread costs 2 L full additions, the merge tree ~3 per block).
+  uint32_t ChooseLevelLength(uint32_t buckets_per_window, uint32_t windows) const {
+    uint64_t items = (uint64_t)buckets_per_window * windows;
+    uint64_t want_threads = (uint64_t)sm_count_ * 384;
     uint32_t L = 64;
     while (L > 4 && items / L < want_threads) L >>= 1;
-    if (L > n_in) L = n_in;
+    if (L > buckets_per_window) L = buckets_per_window;
     return L;
   }
 
-  static constexpr size_t kHostOutBytes = kMaxWindows * 2 * kXyzzBytes + 64;  // (A, C) per window + totals
+  // per window (A, P, D_0..D_(M-1)), M <= 22, + totals
+  static constexpr size_t kHostOutBytes = kMaxWindows * 24 * kXyzzBytes + 64;
 
   int device_;
   int sm_count_ = 148;
@@ -399,7 +404,7 @@ class MsmEngine {
   MsmTotals* totals_ = nullptr;
   char* host_out_ = nullptr;
   DeviceBuffer bases_stage_, scalars_stage_, count_, offset_, cursor_, task_base_, tasks_, multi_,
-      sorted_, digits_, task_out_, block_sums_, order_, len_hist_, lvl_a_[2], lvl_c_[2];
+      sorted_, digits_, task_out_, block_sums_, order_, len_hist_, lvl_a_[2], lvl_c_[2], tree_[2];
 };
 
 }  // namespace tb200

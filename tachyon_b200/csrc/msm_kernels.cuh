@@ -518,6 +518,46 @@ __global__ void __launch_bounds__(kReduceThreads) reduce_level_kernel(
   xyzz_store<Fq>(out_c + (size_t)g * kXyzzWords, csum);
 }
 
+// Tail of the bucket reduction.  After level 0 every window has m = 2^M blocks t with
+// (A_t, Wt_t) and  S_w = sum_t A_t + sum_t Wt_t + L * sum_t t A_t.  Writing t in binary,
+// sum_t t A_t = sum_j 2^j D_j with D_j = sum of A_t over the t whose bit j is set, so only
+// PLAIN sums remain and the powers of two are applied once, on the host, inside the window
+// Horner that doubles anyway.  A binary tree carries per node the vector
+// (A, P, D_0 .. D_(s-1)) of its 2^s blocks; a merge is  A = A_l + A_r, P = P_l + P_r,
+// D_i = D_i,l + D_i,r, D_s = A_r — all independent, one thread each — so every level is
+// ONE addition deep (the blocked running sums it replaces were ~27 sequential point
+// operations per level).  Level s input: nodes with s + 2 values; level 0 reads A and P
+// from the two arrays reduce_level_kernel wrote.
+template <class C>
+__global__ void __launch_bounds__(kReduceThreads) reduce_merge_kernel(
+    const uint32_t* __restrict__ in, const uint32_t* __restrict__ in_p0, uint32_t s,
+    uint32_t m_out, uint32_t windows, uint32_t* __restrict__ out) {
+  using Fq = typename C::Fq;
+  constexpr int kXyzzWords = 4 * Fp<Fq>::N;
+  uint32_t vin = s + 2, vout = s + 3;
+  uint32_t g = blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= windows * m_out * vout) return;
+  uint32_t v = g % vout;
+  uint32_t node = (g / vout) % m_out;
+  uint32_t w = g / (vout * m_out);
+  uint32_t m_in = 2 * m_out;
+  size_t left = (size_t)w * m_in + 2 * node, right = left + 1;
+  auto src = [&](size_t nd, uint32_t val) -> const uint32_t* {
+    if (s == 0) return (val == 0 ? in : in_p0) + nd * kXyzzWords;
+    return in + (nd * vin + val) * kXyzzWords;
+  };
+  XYZZ<Fq> a;
+  if (v == s + 2) {
+    xyzz_load<Fq>(a, src(right, 0));  // D_s = A_r
+  } else {
+    XYZZ<Fq> b;
+    xyzz_load<Fq>(a, src(left, v));
+    xyzz_load<Fq>(b, src(right, v));
+    xyzz_add<Fq>(a, b);
+  }
+  xyzz_store<Fq>(out + (size_t)g * kXyzzWords, a);
+}
+
 // ---------------------------------------------------------------------------
 // Element-wise hooks used by the parity tests (the role of
 // tachyon/math/finite_fields/kernels/prime_field_ops.cu.h:13-51 and
