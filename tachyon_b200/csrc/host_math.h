@@ -81,34 +81,35 @@ struct HostFp {
     }
     return r;
   }
+  // CIOS with the product and reduction rows interleaved; both moduli leave the top bit of
+  // the top limb clear, so the two carries of a row fit one word (the "no-carry" variant of
+  // prime_field_fallback.h:331-355).
   HostFp Mul(const HostFp& o) const {
-    uint64_t t[N + 2];
-    for (int i = 0; i < N + 2; ++i) t[i] = 0;
+    typedef unsigned __int128 u128;
+    uint64_t t[N];
+    for (int i = 0; i < N; ++i) t[i] = 0;
+#pragma GCC unroll 8
     for (int i = 0; i < N; ++i) {
-      uint64_t carry = 0;
-      for (int j = 0; j < N; ++j) {
-        unsigned __int128 x = (unsigned __int128)v[j] * o.v[i] + t[j] + carry;
-        t[j] = (uint64_t)x;
-        carry = (uint64_t)(x >> 64);
-      }
-      unsigned __int128 s = (unsigned __int128)t[N] + carry;
-      t[N] = (uint64_t)s;
-      t[N + 1] = (uint64_t)(s >> 64);
-      uint64_t m = t[0] * F::kInv64;
-      unsigned __int128 x = (unsigned __int128)m * F::kMod64[0] + t[0];
-      carry = (uint64_t)(x >> 64);
+      const uint64_t bi = o.v[i];
+      u128 x = (u128)v[0] * bi + t[0];
+      uint64_t lo = (uint64_t)x;
+      uint64_t c1 = (uint64_t)(x >> 64);
+      const uint64_t m = lo * F::kInv64;
+      u128 y = (u128)m * F::kMod64[0] + lo;
+      uint64_t c2 = (uint64_t)(y >> 64);
+#pragma GCC unroll 8
       for (int j = 1; j < N; ++j) {
-        x = (unsigned __int128)m * F::kMod64[j] + t[j] + carry;
-        t[j - 1] = (uint64_t)x;
-        carry = (uint64_t)(x >> 64);
+        x = (u128)v[j] * bi + t[j] + c1;
+        c1 = (uint64_t)(x >> 64);
+        y = (u128)m * F::kMod64[j] + (uint64_t)x + c2;
+        c2 = (uint64_t)(y >> 64);
+        t[j - 1] = (uint64_t)y;
       }
-      s = (unsigned __int128)t[N] + carry;
-      t[N - 1] = (uint64_t)s;
-      t[N] = t[N + 1] + (uint64_t)(s >> 64);
+      t[N - 1] = c1 + c2;
     }
     HostFp r;
     for (int i = 0; i < N; ++i) r.v[i] = t[i];
-    if (t[N] || Geq(r.v, F::kMod64)) SubMod(r.v);
+    if (Geq(r.v, F::kMod64)) SubMod(r.v);
     return r;
   }
   HostFp Sqr() const { return Mul(*this); }

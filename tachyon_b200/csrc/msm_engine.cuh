@@ -332,22 +332,21 @@ class MsmEngine {
     TB_CUDA(cudaStreamSynchronize(stream_));
 
     // ---- host epilogue ------------------------------------------------------------
-    // S_w = A + P + L0 * sum_j 2^j D_j, then Horner over windows (pippenger_base.h:59-77).
+    // total = sum_w 2^(c w) [A_w + P_w + L0 sum_j 2^j D_(w,j)]: one Horner over bit
+    // positions from the top (the c doublings per window of pippenger_base.h:59-77),
+    // adding every term at its own bit, so the bucket-tree weights cost no extra doubling.
     auto host0 = std::chrono::steady_clock::now();
-    std::vector<Point> sums(plan.W);
     const Point* hv = reinterpret_cast<const Point*>(host_out_);
     uint32_t l0 = Log2(L0);
-    for (uint32_t w = 0; w < plan.W; ++w) {
+    Point result = Point::Zero();
+    for (uint32_t w = plan.W; w-- > 0;) {
       const Point* v = hv + (size_t)w * vals;
-      Point q = Point::Zero();
-      for (uint32_t j = M; j-- > 0;) {
-        q = q.Dbl();
-        q = q.Add(v[2 + j]);
+      for (uint32_t bit = plan.c; bit-- > 0;) {
+        if (w + 1 < plan.W || bit + 1 < plan.c) result = result.Dbl();
+        if (bit >= l0 && bit - l0 < M) result = result.Add(v[2 + (bit - l0)]);
+        if (bit == 0) result = result.Add(v[0]).Add(v[1]);
       }
-      for (uint32_t i = 0; i < l0; ++i) q = q.Dbl();
-      sums[w] = v[0].Add(v[1]).Add(q);
     }
-    Point result = CombineWindows<Fq>(sums.data(), plan.W, plan.c);
     auto host1 = std::chrono::steady_clock::now();
 
     MsmTotals tot;
