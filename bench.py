@@ -146,6 +146,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extra", action="store_true", help="skip the secondary 2^20 measurement")
     ap.add_argument("--window-bits", type=int, default=0)
+    ap.add_argument("--ranges", type=int, default=0, help="point ranges per MSM (0 = automatic)")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -188,6 +189,8 @@ def main():
     ctx.set_stream(stream.cuda_stream)
     if args.window_bits:
         ctx.set_option("window_bits", args.window_bits)
+    if args.ranges:
+        ctx.set_option("ranges", args.ranges)
 
     gather_buf = torch.empty((world, 4 * fq), dtype=torch.int64, device="cuda") if world > 1 else None
 
@@ -355,7 +358,9 @@ def main():
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": "points/s", "ms_per_step": max(e2e_ms, e2e_wall),
                     "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "api": "tachyon_%s_g1_affine_msm_gpu, pinned host buffers" % curve},
+                    "ranges": e2e_timing["ranges"], "h2d_ms": e2e_timing["h2d_ms"],
+                    "api": "tachyon_%s_g1_affine_msm_gpu, pinned host buffers; H2D of point range k+1 "
+                           "overlaps sort/accumulate of range k" % curve},
             "gpu_launches": int(launches),
             "roofline": {"bound": "int32-imad", "kernel": "accumulate_kernel",
                          "achieved": alg["accumulate_products"] / world / (acc_ms * 1e-3) / 1e9 if acc_ms else None,

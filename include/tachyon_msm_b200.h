@@ -77,7 +77,8 @@ extern "C" {
   TACHYON_C_EXPORT int tachyon_##C##_g1_msm_gpu_set_stream_b200(                             \
       tachyon_##C##_g1_msm_gpu_ptr ptr, void* cuda_stream);                                  \
   /* name: "window_bits" (0 = automatic), "segment" (max entries per accumulation task),    \
-     "devices" (point-range sharding over the first k devices; 1 = this context's device). */ \
+     "devices" (point-range sharding over the first k devices; 1 = this context's device),  \
+     "ranges" (point ranges one MSM is pipelined over; 0 = automatic). */                    \
   TACHYON_C_EXPORT int tachyon_##C##_g1_msm_gpu_set_option_b200(                             \
       tachyon_##C##_g1_msm_gpu_ptr ptr, const char* name, long value);                       \
   /* MSM returning the un-normalised XYZZ sum by value into *out; returns 0 or a negative   \
@@ -116,7 +117,8 @@ extern "C" {
       const struct tachyon_##C##_g1_xyzz* a, struct tachyon_##C##_g1_jacobian* out);
 
 struct tachyon_b200_msm_timing {
-  float h2d_ms;         /* host->device copies of bases/scalars (0 for device inputs) */
+  float h2d_ms;         /* host->device copies of bases/scalars on the copy stream (0 for device
+                           inputs); overlaps sort/accumulate of the earlier point ranges */
   float sort_ms;        /* recode + histogram + scan + task build + scatter */
   float accumulate_ms;  /* bucket accumulation (+ folding of split buckets) */
   float reduce_ms;      /* bucket reduction levels + device->host of window sums */
@@ -128,6 +130,7 @@ struct tachyon_b200_msm_timing {
   uint32_t entries;     /* non-zero digits = mixed additions performed */
   uint32_t kernel_launches; /* kernels of this library launched by the call */
   uint32_t devices;
+  uint32_t ranges;      /* point ranges the call was pipelined over (1 for device inputs) */
 };
 
 TACHYON_B200_DECLARE_CURVE(bn254, 4)

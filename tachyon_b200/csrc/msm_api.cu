@@ -124,6 +124,7 @@ struct MsmGpuContext {
       timing.tasks += t.tasks;
       timing.entries += t.entries;
       timing.kernel_launches += t.kernel_launches;
+      timing.ranges = std::max(timing.ranges, t.ranges);
     }
     timing.devices = (uint32_t)G;
     TB_CUDA(cudaSetDevice(primary_device));
@@ -381,6 +382,8 @@ struct tachyon_bls12_381_g1_msm_gpu : public MsmGpuContext<Bls381Curve> {
         for (auto& e : ptr->engines) e->options().segment = (uint32_t)value;                   \
       } else if (k == "aggregate") {                                                           \
         for (auto& e : ptr->engines) e->options().aggregate = (int)value;                      \
+      } else if (k == "ranges") {                                                              \
+        for (auto& e : ptr->engines) e->options().ranges = (uint32_t)value;                    \
       } else if (k == "devices") {                                                             \
         ptr->SetDevices((int)value);                                                           \
       } else {                                                                                 \
@@ -422,6 +425,7 @@ struct tachyon_bls12_381_g1_msm_gpu : public MsmGpuContext<Bls381Curve> {
     out->entries = t.entries;                                                                  \
     out->kernel_launches = t.kernel_launches;                                                  \
     out->devices = t.devices;                                                                  \
+    out->ranges = t.ranges;                                                                    \
     return 0;                                                                                  \
   }                                                                                            \
   int tachyon_##CN##_g1_generate_bases_b200(uint64_t seed, size_t first, size_t n,             \

@@ -63,12 +63,14 @@ struct DeviceBuffer {
 struct MsmTiming {
   float h2d_ms = 0, sort_ms = 0, accumulate_ms = 0, reduce_ms = 0, total_ms = 0, host_ms = 0;
   uint32_t window_bits = 0, windows = 0, tasks = 0, entries = 0, kernel_launches = 0, devices = 1;
+  uint32_t ranges = 0;
 };
 
 struct MsmOptions {
   uint32_t window_bits = 0;  // 0 = choose from n
   uint32_t segment = 0;      // 0 = default
   int aggregate = -1;        // -1 = default
+  uint32_t ranges = 0;       // point ranges per MSM; 0 = 1 for device inputs, pipelined for host
 };
 
 // Window choice.  Cost in units of one mixed addition:
@@ -113,13 +115,15 @@ class MsmEngine {
   static constexpr size_t kXyzzBytes = 4 * Fq::kLimbs64 * 8;
   static constexpr int kXyzzWords = 4 * Fq::kLimbs32;
   // n * W must stay below 2^32 (u32 offsets) and n below 2^31 (sign bit)
-  static constexpr size_t kMaxChunk = size_t(1) << 26;
+  static constexpr size_t kMaxPiece = size_t(1) << 26;
+  static constexpr size_t kMaxRanges = 64;   // point ranges per MSM
+  static constexpr size_t kStageSlots = 3;   // H2D staging ring
 
   explicit MsmEngine(int device) : device_(device) {
     TB_CUDA(cudaSetDevice(device_));
     TB_CUDA(cudaStreamCreateWithFlags(&own_stream_, cudaStreamNonBlocking));
     stream_ = own_stream_;
-    for (auto& e : ev_) TB_CUDA(cudaEventCreate(&e));
+    TB_CUDA(cudaStreamCreateWithFlags(&copy_stream_, cudaStreamNonBlocking));
     TB_CUDA(cudaMallocHost(&host_out_, kHostOutBytes));
     TB_CUDA(cudaMalloc(&totals_, sizeof(MsmTotals)));
     int sms = 0;
@@ -129,13 +133,12 @@ class MsmEngine {
   ~MsmEngine() {
     cudaSetDevice(device_);
     cudaStreamSynchronize(stream_);
-    for (DeviceBuffer* b : {&bases_stage_, &scalars_stage_, &count_, &offset_, &cursor_,
-                            &task_base_, &tasks_, &multi_, &sorted_, &digits_, &task_out_, &block_sums_, &order_, &len_hist_,
-                            &lvl_a_[0], &lvl_a_[1], &lvl_c_[0], &lvl_c_[1], &tree_[0], &tree_[1]})
-      b->Free();
+    cudaStreamSynchronize(copy_stream_);
+    for (const DeviceBuffer* b : AllBuffers()) const_cast<DeviceBuffer*>(b)->Free();
     if (totals_) cudaFree(totals_);
     if (host_out_) cudaFreeHost(host_out_);
-    for (auto& e : ev_) cudaEventDestroy(e);
+    for (auto& e : events_) cudaEventDestroy(e);
+    cudaStreamDestroy(copy_stream_);
     cudaStreamDestroy(own_stream_);
   }
   MsmEngine(const MsmEngine&) = delete;
@@ -153,11 +156,11 @@ class MsmEngine {
     timing_ = MsmTiming{};
     Point total = Point::Zero();
     if (n == 0) return total;  // pippenger_adapter.h:62-65
-    // Sequential chunks only when the index arithmetic requires it; unlike
-    // icicle_msm_bn254_g1.cc:56-62 the last chunk keeps its remainder.
-    for (size_t off = 0; off < n; off += kMaxChunk) {
-      size_t len = n - off < kMaxChunk ? n - off : kMaxChunk;
-      Point part = RunChunk(static_cast<const char*>(bases) + off * kAffineBytes,
+    // Independent pieces only when the u32 index arithmetic requires it; unlike
+    // icicle_msm_bn254_g1.cc:56-62 the last piece keeps its remainder.
+    for (size_t off = 0; off < n; off += kMaxPiece) {
+      size_t len = n - off < kMaxPiece ? n - off : kMaxPiece;
+      Point part = RunPiece(static_cast<const char*>(bases) + off * kAffineBytes,
                             static_cast<const char*>(scalars) + off * kScalarBytes, len);
       total = (off == 0) ? part : total.Add(part);
     }
@@ -191,12 +194,11 @@ class MsmEngine {
     g_kernel_launches.fetch_add(1, std::memory_order_relaxed);
   }
 
-  MsmPlan MakePlan(size_t n) const {
+  // Plan of one point range of `n` points inside an MSM whose window size is `c`.
+  MsmPlan MakePlan(size_t n, uint32_t c) const {
     MsmPlan p{};
     p.n = (uint32_t)n;
-    p.c = options_.window_bits ? options_.window_bits : ChooseWindowBits(n, Fr::kBits);
-    if (p.c < kMinWindowBits) p.c = kMinWindowBits;
-    if (p.c > 24) p.c = 24;
+    p.c = c;
     p.W = WindowsFor(Fr::kBits, p.c);
     p.B = 1u << (p.c - 1);
     p.TB = p.W * p.B;
@@ -213,100 +215,199 @@ class MsmEngine {
     return p;
   }
 
-  Point RunChunk(const void* bases, const void* scalars, size_t n) {
-    auto wall0 = std::chrono::steady_clock::now();
-    MsmPlan plan = MakePlan(n);
+  uint32_t WindowBitsFor(size_t n) const {
+    uint32_t c = options_.window_bits ? options_.window_bits : ChooseWindowBits(n, Fr::kBits);
+    if (c < kMinWindowBits) c = kMinWindowBits;
+    if (c > 24) c = 24;
+    return c;
+  }
+
+  // Device bytes one point range of m points needs besides the bucket state (the role of
+  // the footprint model in icicle_msm_utils.cc:10-68, for this pipeline's buffers).
+  size_t RangeFootprint(size_t m, uint32_t c, bool stage_bases, bool stage_scalars,
+                        uint32_t slots) const {
+    MsmPlan p = MakePlan(m, c);
+    size_t b = (size_t)m * p.W * 8;                       // digits + sorted
+    b += (size_t)p.max_tasks * (8 + 4 + 4 + kXyzzBytes);  // tasks, meta, order, task_out
+    b += (size_t)(p.TB + 1) * 4 * 5;                      // count, offset, cursor, task_base, multi
+    if (stage_bases) b += (size_t)m * kAffineBytes * slots;
+    if (stage_scalars) b += (size_t)m * kScalarBytes * slots;
+    return b;
+  }
+
+  cudaEvent_t Event(size_t i) {
+    while (events_.size() <= i) {
+      cudaEvent_t e;
+      TB_CUDA(cudaEventCreate(&e));
+      events_.push_back(e);
+    }
+    return events_[i];
+  }
+
+  // One MSM: bucket values live in `state_` for the whole call; the points are consumed
+  // as K consecutive ranges, each range sorted by bucket and added into the bucket values
+  // (accumulate_kernel starts from the value the earlier ranges left).  With host inputs
+  // the ranges are what gets pipelined: range k+1 crosses PCIe on the copy stream while
+  // range k is sorted and accumulated, so the 1.6 GB of a 2^24 BN254 MSM (~29 ms at PCIe
+  // gen5 rates) hides behind the ~36 ms of bucket work instead of preceding it.  Device
+  // inputs run as one range unless the memory model asks for more.
+  Point RunPiece(const void* bases, const void* scalars, size_t n) {
+    const uint32_t c = WindowBitsFor(n);
+    const bool bases_dev = IsDevicePointer(bases), scalars_dev = IsDevicePointer(scalars);
+    const bool any_host = !bases_dev || !scalars_dev;
+
+    // ---- how many ranges ----------------------------------------------------------
+    size_t K = 1;
+    if (options_.ranges > 0) {
+      K = options_.ranges;
+    } else if (any_host) {
+      K = n >> 20;  // ranges of >= 2^20 points, at most 8
+      if (K > 8) K = 8;
+      if (K < 1) K = 1;
+    }
+    if (K > kMaxRanges) K = kMaxRanges;
+    if (K > n) K = n;
+    MsmPlan whole = MakePlan(n, c);
+    {
+      size_t free_b = 0, total_b = 0;
+      TB_CUDA(cudaMemGetInfo(&free_b, &total_b));
+      size_t budget = (size_t)(0.9 * (double)(free_b + OwnedBytes()));
+      size_t state_b = (size_t)whole.TB * kXyzzBytes;
+      while (K < kMaxRanges && K < n &&
+             state_b + RangeFootprint((n + K - 1) / K, c, !bases_dev, !scalars_dev,
+                                      K < kStageSlots ? K : kStageSlots) > budget)
+        K *= 2;
+      if (K > kMaxRanges) K = kMaxRanges;
+    }
+    const size_t m = (n + K - 1) / K;  // points per range (the last may be shorter)
+    K = (n + m - 1) / m;
+    const size_t slots = K < kStageSlots ? K : kStageSlots;
+    MsmPlan big = MakePlan(m, c);
     launches_ = 0;
-    TB_CUDA(cudaEventRecord(ev_[0], stream_));
 
-    // ---- inputs -----------------------------------------------------------
-    const uint32_t* d_bases;
-    const uint32_t* d_scalars;
-    if (IsDevicePointer(scalars)) {
-      d_scalars = static_cast<const uint32_t*>(scalars);
-    } else {
-      scalars_stage_.Reserve(n * kScalarBytes);
-      TB_CUDA(cudaMemcpyAsync(scalars_stage_.ptr, scalars, n * kScalarBytes,
-                              cudaMemcpyHostToDevice, stream_));
-      d_scalars = scalars_stage_.as<uint32_t>();
-    }
-    if (IsDevicePointer(bases)) {
-      d_bases = static_cast<const uint32_t*>(bases);
-    } else {
-      bases_stage_.Reserve(n * kAffineBytes);
-      TB_CUDA(cudaMemcpyAsync(bases_stage_.ptr, bases, n * kAffineBytes, cudaMemcpyHostToDevice,
-                              stream_));
-      d_bases = bases_stage_.as<uint32_t>();
-    }
-    TB_CUDA(cudaEventRecord(ev_[1], stream_));
-
-    // ---- workspace --------------------------------------------------------
-    uint32_t scan_blocks = (plan.TB + kScanItems - 1) / kScanItems;
-    if (scan_blocks > (uint32_t)kScanItems) throw CudaError{cudaErrorInvalidValue, "too many buckets", __FILE__, __LINE__};
-    count_.Reserve((size_t)(plan.TB + 1) * 4);
-    offset_.Reserve((size_t)(plan.TB + 1) * 4);
-    cursor_.Reserve((size_t)(plan.TB + 1) * 4);
-    task_base_.Reserve((size_t)plan.TB * 4);
-    tasks_.Reserve((size_t)plan.max_tasks * sizeof(uint2));
-    multi_.Reserve((size_t)plan.TB * 4);
-    sorted_.Reserve((size_t)n * plan.W * 4);
-    digits_.Reserve((size_t)n * plan.W * 4);
-    task_out_.Reserve((size_t)plan.max_tasks * kXyzzBytes);
+    // ---- workspace ----------------------------------------------------------------
+    uint32_t scan_blocks = (big.TB + kScanItems - 1) / kScanItems;
+    if (scan_blocks > (uint32_t)kScanItems)
+      throw CudaError{cudaErrorInvalidValue, "too many buckets", __FILE__, __LINE__};
+    state_.Reserve((size_t)big.TB * kXyzzBytes);
+    count_.Reserve((size_t)(big.TB + 1) * 4);
+    offset_.Reserve((size_t)(big.TB + 1) * 4);
+    cursor_.Reserve((size_t)(big.TB + 1) * 4);
+    task_base_.Reserve((size_t)big.TB * 4);
+    multi_.Reserve((size_t)big.TB * 4);
+    tasks_.Reserve((size_t)big.max_tasks * sizeof(uint2));
+    task_meta_.Reserve((size_t)big.max_tasks * 4);
+    order_.Reserve((size_t)big.max_tasks * 4);
+    task_out_.Reserve((size_t)big.max_tasks * kXyzzBytes);
+    sorted_.Reserve((size_t)m * big.W * 4);
+    digits_.Reserve((size_t)m * big.W * 4);
     block_sums_.Reserve((size_t)scan_blocks * 8);
-    order_.Reserve((size_t)plan.max_tasks * 4);
     len_hist_.Reserve((size_t)(kMaxSegment + 1) * 4);
+    if (!bases_dev) bases_stage_.Reserve(m * slots * kAffineBytes);
+    if (!scalars_dev) scalars_stage_.Reserve(m * slots * kScalarBytes);
 
-    // ---- sort: histogram, scan, tasks, scatter ----------------------------
-    TB_CUDA(cudaMemsetAsync(count_.ptr, 0, (size_t)(plan.TB + 1) * 4, stream_));
-    uint32_t sgrid = (plan.n + 255) / 256;
-    Launch(digits_hist_kernel<C>, sgrid, 256, d_scalars, plan, digits_.as<uint32_t>(),
-           count_.as<uint32_t>());
-    Launch(scan_block_sums_kernel, scan_blocks, kScanThreads, count_.as<uint32_t>(), plan.TB,
-           plan.seg, block_sums_.as<uint64_t>());
-    Launch(scan_top_kernel, 1, kScanThreads, block_sums_.as<uint64_t>(), scan_blocks, totals_);
-    Launch(scan_apply_build_tasks_kernel, scan_blocks, kScanThreads, count_.as<uint32_t>(),
-           plan.TB, plan.seg, block_sums_.as<uint64_t>(), offset_.as<uint32_t>(),
-           cursor_.as<uint32_t>(), task_base_.as<uint32_t>(), tasks_.as<uint2>(),
-           multi_.as<uint32_t>(), totals_);
-    LaunchGrid(digits_scatter_kernel, dim3(sgrid, plan.W), 256, digits_.as<uint32_t>(), plan,
-               cursor_.as<uint32_t>(), sorted_.as<uint32_t>());
-    // tasks by descending length
-    TB_CUDA(cudaMemsetAsync(len_hist_.ptr, 0, (size_t)(kMaxSegment + 1) * 4, stream_));
-    uint32_t ogrid = (plan.max_tasks + kOrderThreads * kOrderPerThread - 1) /
-                     (kOrderThreads * kOrderPerThread);
-    Launch(order_hist_kernel, ogrid, kOrderThreads, tasks_.as<uint2>(), totals_,
-           len_hist_.as<uint32_t>());
-    Launch(order_scan_kernel, 1, 1024, len_hist_.as<uint32_t>());
-    Launch(order_scatter_kernel, ogrid, kOrderThreads, tasks_.as<uint2>(), totals_,
-           len_hist_.as<uint32_t>(), order_.as<uint32_t>());
-    TB_CUDA(cudaEventRecord(ev_[2], stream_));
+    // events: 0 begin, 1 end of accumulation, 2 end; per range r: 4r+3 copied, +4 sort
+    // start, +5 sort end, +6 accumulated
+    cudaEvent_t ev_begin = Event(0), ev_acc_end = Event(1), ev_end = Event(2);
+    auto ev = [&](size_t r, int which) { return Event(3 + 4 * r + which); };
+    cudaEvent_t ev_copy_begin = Event(3 + 4 * K);
 
-    // ---- accumulate -------------------------------------------------------
-    uint32_t agrid = (plan.max_tasks + kAccThreads - 1) / kAccThreads;
-    Launch(accumulate_kernel<C>, agrid, kAccThreads, d_bases, sorted_.as<uint32_t>(),
-           tasks_.as<uint2>(), order_.as<uint32_t>(), totals_, task_out_.as<uint32_t>());
-    Launch(fold_partials_kernel<C>, sm_count_ * 4, kFoldThreads, multi_.as<uint32_t>(), totals_,
-           offset_.as<uint32_t>(), task_base_.as<uint32_t>(), plan.seg,
-           task_out_.as<uint32_t>());
-    TB_CUDA(cudaEventRecord(ev_[3], stream_));
+    TB_CUDA(cudaEventRecord(ev_begin, stream_));
+    TB_CUDA(cudaMemsetAsync(state_.ptr, 0, (size_t)big.TB * kXyzzBytes, stream_));
+    if (any_host) {
+      TB_CUDA(cudaStreamWaitEvent(copy_stream_, ev_begin, 0));
+      TB_CUDA(cudaEventRecord(ev_copy_begin, copy_stream_));
+    }
+
+    for (size_t r = 0; r < K; ++r) {
+      const size_t lo = r * m, len = (n - lo < m) ? n - lo : m;
+      MsmPlan plan = MakePlan(len, c);
+      // ---- inputs of this range ---------------------------------------------------
+      const uint32_t* d_bases;
+      const uint32_t* d_scalars;
+      const size_t slot = r % slots;
+      if (any_host && r >= slots)  // the slot's previous tenant must have been consumed
+        TB_CUDA(cudaStreamWaitEvent(copy_stream_, ev(r - slots, 3), 0));
+      if (scalars_dev) {
+        d_scalars = reinterpret_cast<const uint32_t*>(static_cast<const char*>(scalars) +
+                                                      lo * kScalarBytes);
+      } else {
+        char* dst = scalars_stage_.as<char>() + slot * m * kScalarBytes;
+        TB_CUDA(cudaMemcpyAsync(dst, static_cast<const char*>(scalars) + lo * kScalarBytes,
+                                len * kScalarBytes, cudaMemcpyHostToDevice, copy_stream_));
+        d_scalars = reinterpret_cast<const uint32_t*>(dst);
+      }
+      if (bases_dev) {
+        d_bases = reinterpret_cast<const uint32_t*>(static_cast<const char*>(bases) +
+                                                    lo * kAffineBytes);
+      } else {
+        char* dst = bases_stage_.as<char>() + slot * m * kAffineBytes;
+        TB_CUDA(cudaMemcpyAsync(dst, static_cast<const char*>(bases) + lo * kAffineBytes,
+                                len * kAffineBytes, cudaMemcpyHostToDevice, copy_stream_));
+        d_bases = reinterpret_cast<const uint32_t*>(dst);
+      }
+      if (any_host) {
+        TB_CUDA(cudaEventRecord(ev(r, 0), copy_stream_));
+        TB_CUDA(cudaStreamWaitEvent(stream_, ev(r, 0), 0));
+      }
+      TB_CUDA(cudaEventRecord(ev(r, 1), stream_));
+
+      // ---- sort: histogram, scan, tasks, scatter ----------------------------------
+      TB_CUDA(cudaMemsetAsync(count_.ptr, 0, (size_t)(plan.TB + 1) * 4, stream_));
+      uint32_t sgrid = (plan.n + 255) / 256;
+      Launch(digits_hist_kernel<C>, sgrid, 256, d_scalars, plan, digits_.as<uint32_t>(),
+             count_.as<uint32_t>());
+      Launch(scan_block_sums_kernel, scan_blocks, kScanThreads, count_.as<uint32_t>(), plan.TB,
+             plan.seg, block_sums_.as<uint64_t>());
+      Launch(scan_top_kernel, 1, kScanThreads, block_sums_.as<uint64_t>(), scan_blocks, totals_);
+      Launch(scan_apply_build_tasks_kernel, scan_blocks, kScanThreads, count_.as<uint32_t>(),
+             plan.TB, plan.seg, block_sums_.as<uint64_t>(), offset_.as<uint32_t>(),
+             cursor_.as<uint32_t>(), task_base_.as<uint32_t>(), tasks_.as<uint2>(),
+             task_meta_.as<uint32_t>(), multi_.as<uint32_t>(), totals_);
+      LaunchGrid(digits_scatter_kernel, dim3(sgrid, plan.W), 256, digits_.as<uint32_t>(), plan,
+                 cursor_.as<uint32_t>(), sorted_.as<uint32_t>());
+      // tasks by descending length
+      TB_CUDA(cudaMemsetAsync(len_hist_.ptr, 0, (size_t)(kMaxSegment + 1) * 4, stream_));
+      uint32_t ogrid = (plan.max_tasks + kOrderThreads * kOrderPerThread - 1) /
+                       (kOrderThreads * kOrderPerThread);
+      Launch(order_hist_kernel, ogrid, kOrderThreads, tasks_.as<uint2>(), totals_,
+             len_hist_.as<uint32_t>());
+      Launch(order_scan_kernel, 1, 1024, len_hist_.as<uint32_t>());
+      Launch(order_scatter_kernel, ogrid, kOrderThreads, tasks_.as<uint2>(), totals_,
+             len_hist_.as<uint32_t>(), order_.as<uint32_t>());
+      TB_CUDA(cudaEventRecord(ev(r, 2), stream_));
+
+      // ---- accumulate into the bucket values --------------------------------------
+      uint32_t agrid = (plan.max_tasks + kAccThreads - 1) / kAccThreads;
+      Launch(accumulate_kernel<C>, agrid, kAccThreads, d_bases, sorted_.as<uint32_t>(),
+             tasks_.as<uint2>(), task_meta_.as<uint32_t>(), order_.as<uint32_t>(), totals_,
+             state_.as<uint32_t>(), task_out_.as<uint32_t>());
+      Launch(fold_partials_kernel<C>, sm_count_ * 4, kFoldThreads, multi_.as<uint32_t>(), totals_,
+             offset_.as<uint32_t>(), task_base_.as<uint32_t>(), plan.seg,
+             task_out_.as<uint32_t>(), state_.as<uint32_t>());
+      TB_CUDA(cudaMemcpyAsync(host_out_ + kHostWindowBytes + r * sizeof(MsmTotals), totals_,
+                              sizeof(MsmTotals), cudaMemcpyDeviceToHost, stream_));
+      TB_CUDA(cudaEventRecord(ev(r, 3), stream_));
+    }
+    TB_CUDA(cudaEventRecord(ev_acc_end, stream_));
+    const MsmPlan& plan = big;
 
     // ---- bucket reduction: one blocked running-sum level, then a merge tree ---------
     uint32_t L0 = ChooseLevelLength(plan.B, plan.W);
-    uint32_t m = plan.B / L0;  // blocks per window, a power of two
-    lvl_a_[0].Reserve((size_t)plan.W * m * kXyzzBytes);
-    lvl_c_[0].Reserve((size_t)plan.W * m * kXyzzBytes);
+    uint32_t nb = plan.B / L0;  // blocks per window, a power of two
+    lvl_a_[0].Reserve((size_t)plan.W * nb * kXyzzBytes);
+    lvl_c_[0].Reserve((size_t)plan.W * nb * kXyzzBytes);
     {
-      uint32_t threads = plan.W * m;
+      uint32_t threads = plan.W * nb;
       Launch(reduce_level_kernel<C, true>, (threads + kReduceThreads - 1) / kReduceThreads,
-             kReduceThreads, task_out_.as<uint32_t>(), (const uint32_t*)nullptr,
-             offset_.as<uint32_t>(), task_base_.as<uint32_t>(), plan.B, m, L0, 0u, plan.W,
-             lvl_a_[0].as<uint32_t>(), lvl_c_[0].as<uint32_t>());
+             kReduceThreads, state_.as<uint32_t>(), (const uint32_t*)nullptr, plan.B, nb, L0, 0u,
+             plan.W, lvl_a_[0].as<uint32_t>(), lvl_c_[0].as<uint32_t>());
     }
-    uint32_t M = Log2(m);
+    uint32_t M = Log2(nb);
     const uint32_t* tin = lvl_a_[0].as<uint32_t>();
     const uint32_t* tin_p = lvl_c_[0].as<uint32_t>();
     for (uint32_t s = 0; s < M; ++s) {
-      uint32_t m_out = m >> (s + 1);
+      uint32_t m_out = nb >> (s + 1);
       DeviceBuffer& dst = tree_[s & 1];
       dst.Reserve((size_t)plan.W * m_out * (s + 3) * kXyzzBytes);
       uint32_t threads = plan.W * m_out * (s + 3);
@@ -326,9 +427,7 @@ class MsmEngine {
     } else {
       TB_CUDA(cudaMemcpyAsync(host_out_, tin, win_bytes, cudaMemcpyDeviceToHost, stream_));
     }
-    TB_CUDA(cudaMemcpyAsync(host_out_ + win_bytes, totals_, sizeof(MsmTotals),
-                            cudaMemcpyDeviceToHost, stream_));
-    TB_CUDA(cudaEventRecord(ev_[4], stream_));
+    TB_CUDA(cudaEventRecord(ev_end, stream_));
     TB_CUDA(cudaStreamSynchronize(stream_));
 
     // ---- host epilogue ------------------------------------------------------------
@@ -349,27 +448,43 @@ class MsmEngine {
     }
     auto host1 = std::chrono::steady_clock::now();
 
-    MsmTotals tot;
-    memcpy(&tot, host_out_ + win_bytes, sizeof(tot));
     float ms;
-    TB_CUDA(cudaEventElapsedTime(&ms, ev_[0], ev_[1]));
-    timing_.h2d_ms += ms;
-    TB_CUDA(cudaEventElapsedTime(&ms, ev_[1], ev_[2]));
-    timing_.sort_ms += ms;
-    TB_CUDA(cudaEventElapsedTime(&ms, ev_[2], ev_[3]));
-    timing_.accumulate_ms += ms;
-    TB_CUDA(cudaEventElapsedTime(&ms, ev_[3], ev_[4]));
+    for (size_t r = 0; r < K; ++r) {
+      MsmTotals tot;
+      memcpy(&tot, host_out_ + kHostWindowBytes + r * sizeof(MsmTotals), sizeof(tot));
+      timing_.tasks += tot.tasks;
+      timing_.entries += tot.entries;
+      TB_CUDA(cudaEventElapsedTime(&ms, ev(r, 1), ev(r, 2)));
+      timing_.sort_ms += ms;
+      TB_CUDA(cudaEventElapsedTime(&ms, ev(r, 2), ev(r, 3)));
+      timing_.accumulate_ms += ms;
+    }
+    if (any_host) {
+      // time the copy engine was busy or waiting for a free slot; overlaps the bucket work
+      TB_CUDA(cudaEventElapsedTime(&ms, ev_copy_begin, ev(K - 1, 0)));
+      timing_.h2d_ms += ms;
+    }
+    TB_CUDA(cudaEventElapsedTime(&ms, ev_acc_end, ev_end));
     timing_.reduce_ms += ms;
-    TB_CUDA(cudaEventElapsedTime(&ms, ev_[0], ev_[4]));
+    TB_CUDA(cudaEventElapsedTime(&ms, ev_begin, ev_end));
     timing_.total_ms += ms;
     timing_.host_ms += std::chrono::duration<float, std::milli>(host1 - host0).count();
     timing_.window_bits = plan.c;
     timing_.windows = plan.W;
-    timing_.tasks += tot.tasks;
-    timing_.entries += tot.entries;
+    timing_.ranges += (uint32_t)K;
     timing_.kernel_launches += launches_;
-    (void)wall0;
     return result;
+  }
+
+  size_t OwnedBytes() const {
+    size_t b = 0;
+    for (const DeviceBuffer* d : AllBuffers()) b += d->bytes;
+    return b;
+  }
+  std::vector<const DeviceBuffer*> AllBuffers() const {
+    return {&bases_stage_, &scalars_stage_, &state_, &count_, &offset_, &cursor_, &task_base_,
+            &tasks_, &task_meta_, &multi_, &sorted_, &digits_, &task_out_, &block_sums_, &order_,
+            &len_hist_, &lvl_a_[0], &lvl_a_[1], &lvl_c_[0], &lvl_c_[1], &tree_[0], &tree_[1]};
   }
 
   static uint32_t Log2(uint32_t x) {
@@ -389,21 +504,24 @@ class MsmEngine {
     return L;
   }
 
-  // per window (A, P, D_0..D_(M-1)), M <= 22, + totals
-  static constexpr size_t kHostOutBytes = kMaxWindows * 24 * kXyzzBytes + 64;
+  // per window (A, P, D_0..D_(M-1)), M <= 22, then one MsmTotals per range
+  static constexpr size_t kHostWindowBytes = kMaxWindows * 24 * kXyzzBytes;
+  static constexpr size_t kHostOutBytes = kHostWindowBytes + kMaxRanges * sizeof(MsmTotals);
 
   int device_;
   int sm_count_ = 148;
   cudaStream_t own_stream_ = nullptr;
   cudaStream_t stream_ = nullptr;
-  cudaEvent_t ev_[5];
+  cudaStream_t copy_stream_ = nullptr;
+  std::vector<cudaEvent_t> events_;
   MsmOptions options_;
   MsmTiming timing_;
   uint32_t launches_ = 0;
   MsmTotals* totals_ = nullptr;
   char* host_out_ = nullptr;
-  DeviceBuffer bases_stage_, scalars_stage_, count_, offset_, cursor_, task_base_, tasks_, multi_,
-      sorted_, digits_, task_out_, block_sums_, order_, len_hist_, lvl_a_[2], lvl_c_[2], tree_[2];
+  DeviceBuffer bases_stage_, scalars_stage_, state_, count_, offset_, cursor_, task_base_, tasks_,
+      task_meta_, multi_, sorted_, digits_, task_out_, block_sums_, order_, len_hist_, lvl_a_[2],
+      lvl_c_[2], tree_[2];
 };
 
 }  // namespace tb200

@@ -257,6 +257,13 @@ __global__ void __launch_bounds__(kScanThreads) scan_top_kernel(uint64_t* __rest
   }
 }
 
+// task_meta word: bucket key in the low 24 bits; kTaskFirst = first task of its bucket (its
+// accumulator starts from the bucket's running value in `state`), kTaskSingle = the only
+// task of its bucket (its result is the bucket's new value and goes straight to `state`).
+constexpr uint32_t kTaskFirst = 0x80000000u;
+constexpr uint32_t kTaskSingle = 0x40000000u;
+constexpr uint32_t kTaskKeyMask = 0x00ffffffu;
+
 // Writes offset[] (TB+1 entries), cursor[] (= offset, consumed by the scatter)
 // and the tasks of every bucket.  Buckets split into more than one task are
 // appended to multi_keys.
@@ -264,7 +271,8 @@ __global__ void __launch_bounds__(kScanThreads) scan_apply_build_tasks_kernel(
     const uint32_t* __restrict__ count, uint32_t n, uint32_t seg,
     const uint64_t* __restrict__ block_prefix, uint32_t* __restrict__ offset,
     uint32_t* __restrict__ cursor, uint32_t* __restrict__ task_base, uint2* __restrict__ tasks,
-    uint32_t* __restrict__ multi_keys, MsmTotals* __restrict__ totals) {
+    uint32_t* __restrict__ task_meta, uint32_t* __restrict__ multi_keys,
+    MsmTotals* __restrict__ totals) {
   __shared__ uint64_t smem[kScanThreads / 32];
   uint32_t base = blockIdx.x * kScanItems + threadIdx.x * kScanPerThread;
   uint32_t cnt[kScanPerThread];
@@ -290,6 +298,7 @@ __global__ void __launch_bounds__(kScanThreads) scan_apply_build_tasks_kernel(
       for (uint32_t s = 0; s < t; ++s) {
         uint32_t len = min(seg, cnt[k] - s * seg);
         tasks[tb + s] = make_uint2(off + s * seg, len);
+        task_meta[tb + s] = idx | (s == 0 ? kTaskFirst : 0u) | (t == 1 ? kTaskSingle : 0u);
       }
       if (t > 1) multi_keys[atomicAdd(&totals->multi, 1u)] = idx;
       if (idx == n - 1) offset[n] = off + cnt[k];
@@ -395,12 +404,19 @@ __global__ void __launch_bounds__(kOrderThreads) order_scatter_kernel(
 // task; the next point is fetched while the current one is being added.
 // ---------------------------------------------------------------------------
 constexpr int kAccThreads = 128;
+// resident CTAs per SM the register budget is held to: 4 x 128 threads x 128 registers
+// (BN254), 3 x 128 x 168 (BLS12-381)
+template <class C>
+constexpr int AccMinBlocks() {
+  return Fp<typename C::Fq>::N <= 8 ? 4 : 3;
+}
 
 template <class C>
-__global__ void __launch_bounds__(kAccThreads) accumulate_kernel(
+__global__ void __launch_bounds__(kAccThreads, AccMinBlocks<C>()) accumulate_kernel(
     const uint32_t* __restrict__ bases, const uint32_t* __restrict__ sorted,
-    const uint2* __restrict__ tasks, const uint32_t* __restrict__ order,
-    const MsmTotals* __restrict__ totals, uint32_t* __restrict__ task_out) {
+    const uint2* __restrict__ tasks, const uint32_t* __restrict__ task_meta,
+    const uint32_t* __restrict__ order, const MsmTotals* __restrict__ totals,
+    uint32_t* __restrict__ state, uint32_t* __restrict__ task_out) {
   using Fq = typename C::Fq;
   constexpr int kAffineWords = 2 * Fp<Fq>::N;
   constexpr int kXyzzWords = 4 * Fp<Fq>::N;
@@ -408,12 +424,18 @@ __global__ void __launch_bounds__(kAccThreads) accumulate_kernel(
   if (slot >= totals->tasks) return;
   uint32_t g = order[slot];  // tasks in descending length: warps stay convergent
   uint2 task = tasks[g];
+  uint32_t meta = task_meta[g];
+  uint32_t* bucket = state + (size_t)(meta & kTaskKeyMask) * kXyzzWords;
   const uint32_t* ent = sorted + task.x;
-  XYZZ<Fq> acc;
-  xyzz_set_zero<Fq>(acc);
   uint32_t e = ent[0];
   Affine<Fq> nxt;
   affine_load<Fq>(nxt, bases + (size_t)(e & 0x7fffffffu) * kAffineWords);
+  XYZZ<Fq> acc;
+  if (meta & kTaskFirst) {
+    xyzz_load<Fq>(acc, bucket);  // value left by the earlier point ranges (zz == 0: none)
+  } else {
+    xyzz_set_zero<Fq>(acc);
+  }
   for (uint32_t j = 0; j < task.y; ++j) {
     Affine<Fq> cur = nxt;
     bool neg = e >> 31;
@@ -423,18 +445,19 @@ __global__ void __launch_bounds__(kAccThreads) accumulate_kernel(
     }
     xyzz_madd<Fq>(acc, cur, neg);
   }
-  xyzz_store<Fq>(task_out + (size_t)g * kXyzzWords, acc);
+  xyzz_store<Fq>((meta & kTaskSingle) ? bucket : task_out + (size_t)g * kXyzzWords, acc);
 }
 
-// Buckets split over several tasks: one CTA per bucket sums the partials into
-// the bucket's first task slot.  Grid-stride over the split-bucket list.
+// Buckets split over several tasks: one CTA per bucket sums the partials (the first of
+// which already carries the bucket's previous value) into `state`.  Grid-stride over the
+// split-bucket list.
 constexpr int kFoldThreads = 128;
 
 template <class C>
 __global__ void __launch_bounds__(kFoldThreads) fold_partials_kernel(
     const uint32_t* __restrict__ multi_keys, const MsmTotals* __restrict__ totals,
     const uint32_t* __restrict__ offset, const uint32_t* __restrict__ task_base, uint32_t seg,
-    uint32_t* __restrict__ task_out) {
+    const uint32_t* __restrict__ task_out, uint32_t* __restrict__ state) {
   using Fq = typename C::Fq;
   constexpr int kXyzzWords = 4 * Fp<Fq>::N;
   __shared__ uint32_t sh[kFoldThreads / 2 * kXyzzWords];
@@ -442,14 +465,13 @@ __global__ void __launch_bounds__(kFoldThreads) fold_partials_kernel(
     uint32_t key = multi_keys[m];
     uint32_t cnt = offset[key + 1] - offset[key];
     uint32_t t = (cnt + seg - 1) / seg;
-    uint32_t* slots = task_out + (size_t)task_base[key] * kXyzzWords;
+    const uint32_t* slots = task_out + (size_t)task_base[key] * kXyzzWords;
     XYZZ<Fq> acc, tmp;
     xyzz_set_zero<Fq>(acc);
     for (uint32_t s = threadIdx.x; s < t; s += kFoldThreads) {
       xyzz_load<Fq>(tmp, slots + (size_t)s * kXyzzWords);
       xyzz_add<Fq>(acc, tmp);
     }
-    __syncthreads();  // all partials read before slot 0 is overwritten
     // tree over the threads that hold something: first power of two >= min(t, threads)
     int live = t < (uint32_t)kFoldThreads ? (int)t : kFoldThreads;
     int top = 1;
@@ -464,7 +486,7 @@ __global__ void __launch_bounds__(kFoldThreads) fold_partials_kernel(
       }
       __syncthreads();
     }
-    if (threadIdx.x == 0) xyzz_store<Fq>(slots, acc);
+    if (threadIdx.x == 0) xyzz_store<Fq>(state + (size_t)key * kXyzzWords, acc);
     __syncthreads();
   }
 }
@@ -476,15 +498,14 @@ __global__ void __launch_bounds__(kFoldThreads) fold_partials_kernel(
 // n items to ceil(n / L) items and carries the already-weighted part in a
 // second series C (scaled by 2^shift = product of the previous Ls), so after
 // the last level S_w = A + C.
-//   level 0: items are buckets (through count/task_base), no C input
+//   level 0: items are the bucket values in `state` (zz == 0: empty), no C input
 //   level>0: items are the previous level's A and C arrays
 // ---------------------------------------------------------------------------
 constexpr int kReduceThreads = 128;
 
 template <class C, bool kFirst>
 __global__ void __launch_bounds__(kReduceThreads) reduce_level_kernel(
-    const uint32_t* __restrict__ in_a, const uint32_t* __restrict__ in_c,
-    const uint32_t* __restrict__ offset, const uint32_t* __restrict__ task_base, uint32_t n_in,
+    const uint32_t* __restrict__ in_a, const uint32_t* __restrict__ in_c, uint32_t n_in,
     uint32_t n_out, uint32_t L, uint32_t shift, uint32_t windows, uint32_t* __restrict__ out_a,
     uint32_t* __restrict__ out_c) {
   using Fq = typename C::Fq;
@@ -500,10 +521,8 @@ __global__ void __launch_bounds__(kReduceThreads) reduce_level_kernel(
   for (uint32_t k = hi; k-- > lo;) {
     uint32_t idx = w * n_in + k;
     if (kFirst) {
-      if (offset[idx + 1] != offset[idx]) {
-        xyzz_load<Fq>(item, in_a + (size_t)task_base[idx] * kXyzzWords);
-        xyzz_add<Fq>(run, item);
-      }
+      xyzz_load<Fq>(item, in_a + (size_t)idx * kXyzzWords);
+      xyzz_add<Fq>(run, item);
     } else {
       xyzz_load<Fq>(item, in_a + (size_t)idx * kXyzzWords);
       xyzz_add<Fq>(run, item);

@@ -202,6 +202,38 @@ def test_msm_device_resident_inputs(oracles, torch_cuda, name):
         assert ctx.last_timing()["kernel_launches"] >= 8
 
 
+# One MSM consumed as several point ranges that share the bucket values (what the engine
+# does with host inputs so that H2D overlaps the bucket work, and when memory is short;
+# the analogue of the chunk loop of icicle_msm_bn254_g1.cc:56-73): every split must give
+# the same group element, with ragged last ranges, more ranges than staging slots, skewed
+# scalars whose buckets are split into several tasks in every range, and device inputs.
+@pytest.mark.parametrize("name", CURVES)
+def test_msm_point_ranges(oracles, torch_cuda, name):
+    o = oracles[name]
+    n = 6001
+    bases, scalars = o.generate_points(81, n), o.generate_scalars(82, n)
+    skew = o.generate_scalars(83, n, "witness")
+    want, want_skew = o.msm_affine(bases, scalars), o.msm_affine(bases, skew)
+    import torch
+    db = torch.from_numpy(bases.view(np.int64)).cuda()
+    ds = torch.from_numpy(scalars.view(np.int64)).cuda()
+    with msm.MSMGpu(name) as ctx:
+        for ranges in (1, 2, 3, 4, 7, 64):
+            ctx.set_option("ranges", ranges)
+            assert (o.jacobian_to_affine(ctx.affine_msm(bases, scalars)) == want).all(), ranges
+            assert ctx.last_timing()["ranges"] == ranges
+            assert (o.jacobian_to_affine(ctx.affine_msm(db.data_ptr(), ds.data_ptr(), n)) == want).all(), ranges
+            assert (o.jacobian_to_affine(ctx.affine_msm(db.data_ptr(), scalars, n)) == want).all(), ranges
+        ctx.set_option("ranges", 5)
+        ctx.set_option("segment", 16)
+        ctx.set_option("window_bits", 6)
+        assert (o.jacobian_to_affine(ctx.affine_msm(bases, skew)) == want_skew).all()
+        ctx.set_option("ranges", 0)       # automatic again
+        ctx.set_option("segment", 0)
+        ctx.set_option("window_bits", 0)
+        assert (o.jacobian_to_affine(ctx.affine_msm(bases, skew)) == want_skew).all()
+
+
 # Full benchmark sizes through a size-independent property: the synthetic bases
 # are chains P_(j,d) = 2^d H_j, so MSM(P, s) == MSM(H, fold(s)) with
 # fold(s)_j = sum_d s_(j,d) 2^d mod r — a 2^12-times smaller MSM the oracle does in
