@@ -49,52 +49,69 @@ def algorithmic_products(curve, n):
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons during the timed region."""
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
-         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
-         "clocks_event_reasons.sw_power_cap")
+    """SM clock, power and throttle reasons of one GPU DURING the timed region: NVML polled
+    every 5 ms from a thread (an MSM step is tens of ms, too short for `nvidia-smi -lms`);
+    falls back to one nvidia-smi query if NVML is unavailable."""
+    REASONS = (("hw_slowdown", 0x8), ("hw_thermal_slowdown", 0x40), ("sw_thermal_slowdown", 0x20),
+               ("sw_power_cap", 0x4))
 
-    def __init__(self, gpu_index):
-        self.gpu = gpu_index
-        self.rows = []
-        self.proc = None
+    def __init__(self, uuid, gpu_index):
+        self.uuid, self.gpu = uuid, gpu_index
+        self.sm, self.power, self.bits = [], [], 0
+        self.max_sm = None
+        self.stop_flag = threading.Event()
+        self.thread = None
+        self.nvml = None
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(
-                ["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
-                 "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            self.thread = threading.Thread(target=self._read, daemon=True)
+            import pynvml
+            pynvml.nvmlInit()
+            try:
+                h = pynvml.nvmlDeviceGetHandleByUUID(("GPU-" + self.uuid).encode() if self.uuid else b"")
+            except Exception:
+                h = pynvml.nvmlDeviceGetHandleByIndex(self.gpu)
+            self.max_sm = float(pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM))
+            self.nvml, self.handle = pynvml, h
+            self.thread = threading.Thread(target=self._poll, daemon=True)
             self.thread.start()
-        except OSError:
-            self.proc = None
+        except Exception:
+            self.nvml = None
 
-    def _read(self):
-        for line in self.proc.stdout:
-            self.rows.append([x.strip() for x in line.split(",")])
+    def _poll(self):
+        n, h = self.nvml, self.handle
+        while not self.stop_flag.is_set():
+            try:
+                self.sm.append(float(n.nvmlDeviceGetClockInfo(h, n.NVML_CLOCK_SM)))
+                self.power.append(n.nvmlDeviceGetPowerUsage(h) / 1000.0)
+                self.bits |= int(n.nvmlDeviceGetCurrentClocksThrottleReasons(h))
+            except Exception:
+                pass
+            time.sleep(0.005)
 
     def stop(self):
-        if not self.proc:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
-        self.proc.terminate()
+        if self.nvml is None:
+            return self._smi_once()
+        self.stop_flag.set()
+        self.thread.join(timeout=1)
+        return {"sm_mhz": statistics.median(self.sm) if self.sm else None, "sm_max_mhz": self.max_sm,
+                "power_w_max": max(self.power) if self.power else None, "samples": len(self.sm),
+                "reasons": [name for name, bit in self.REASONS if self.bits & bit], "source": "nvml, 5 ms poll"}
+
+    def _smi_once(self):
+        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
         try:
-            self.proc.wait(timeout=2)
-        except subprocess.TimeoutExpired:
-            self.proc.kill()
-        sm, mx, reasons, power = [], [], set(), []
-        for r in self.rows:
-            try:
-                sm.append(float(r[1]))
-                mx.append(float(r[2]))
-                power.append(float(r[3]))
-            except (ValueError, IndexError):
-                continue
-            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[4:8]):
-                if v.lower().startswith("active"):
-                    reasons.add(name)
-        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "power_w_max": max(power) if power else None, "samples": len(sm), "reasons": sorted(reasons)}
+            out = subprocess.run(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + q,
+                                  "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=10).stdout
+            r = [x.strip() for x in out.strip().split(",")]
+            names = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")
+            return {"sm_mhz": float(r[0]), "sm_max_mhz": float(r[1]), "power_w_max": float(r[2]), "samples": 1,
+                    "reasons": [n for n, v in zip(names, r[3:7]) if v.lower().startswith("active")],
+                    "source": "nvidia-smi, one query after the timed region"}
+        except Exception as e:  # noqa: BLE001
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["clock query unavailable: %s" % e], "samples": 0}
 
 
 def run_reference(args, rank, world):
@@ -232,7 +249,11 @@ def main():
     resident = lambda: step(bases.data_ptr(), scalars.data_ptr(), n_local)
     for _ in range(args.warmup):
         result = resident()
-    sampler = ClockSampler(local_rank)
+    try:
+        gpu_uuid = str(torch.cuda.get_device_properties(local_rank).uuid)
+    except Exception:  # noqa: BLE001
+        gpu_uuid = ""
+    sampler = ClockSampler(gpu_uuid, local_rank)
     sampler.start()
     launches0 = msm.kernel_launch_count()
     stage = {"sort_ms": 0.0, "accumulate_ms": 0.0, "reduce_ms": 0.0, "host_ms": 0.0, "total_ms": 0.0}
@@ -344,6 +365,13 @@ def main():
         dist.barrier()
     if rank == 0:
         acc_ms = stage["accumulate_ms"]
+        # DRAM bytes of the dominant kernel per launch, from the committed ncu --set full capture
+        traffic = {}
+        try:
+            with open(os.path.join(ROOT, "profiles", "roofline_traffic.json")) as f:
+                traffic = json.load(f).get(f"{curve}:{args.log_n}:{world}", {})
+        except OSError:
+            pass
         line = {
             "metric": f"{curve} G1 MSM throughput", "value": value, "unit": "points/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step,
@@ -366,7 +394,7 @@ def main():
                          "achieved": alg["accumulate_products"] / world / (acc_ms * 1e-3) / 1e9 if acc_ms else None,
                          "peak": peak / 1e9, "unit": "G products/s (32x32->64)",
                          "frac": (alg["accumulate_products"] / world / (acc_ms * 1e-3) / peak) if acc_ms and peak else None,
-                         "traffic": None,
+                         "traffic": traffic.get("bytes"), "traffic_source": traffic.get("source"),
                          "peak_source": "measured live: tachyon_b200_imad_peak, best of IMAD.WIDE.X chains / IMAD.WIDE acc64 / IMAD+IMAD.HI",
                          "whole_msm_frac": alg["products"] / (ms_step * 1e-3) / (peak * world) if peak else None,
                          "algorithmic": {"c": alg["c"], "W": alg["W"], "products": alg["products"]}},

@@ -86,6 +86,24 @@ extern "C" {
   TACHYON_C_EXPORT int tachyon_##C##_g1_msm_gpu_xyzz_b200(                                   \
       tachyon_##C##_g1_msm_gpu_ptr ptr, const struct tachyon_##C##_g1_affine* bases,         \
       const struct tachyon_##C##_fr* scalars, size_t size, struct tachyon_##C##_g1_xyzz* out); \
+  /* Device-resident bases + batched commitments (the SRS handling of           \
+     tachyon/crypto/commitments/kzg/kzg.h:91-113 and the commit loop of :217-313).           \
+     register_bases copies `size` bases (host or device source) into memory the context      \
+     owns, on every device of the context; it replaces an earlier registration.              \
+     commit_batch runs `count` MSMs, MSM i over the first sizes[i] registered bases and       \
+     scalars[i] (host or device), and writes the un-normalised sums to out[i]; consecutive    \
+     MSMs are pipelined (scalars of the next one cross PCIe while the current one runs) and   \
+     with "devices" = k they are dealt out over k GPUs.  0 or a negative error code. */       \
+  TACHYON_C_EXPORT int tachyon_##C##_g1_msm_gpu_register_bases_b200(                         \
+      tachyon_##C##_g1_msm_gpu_ptr ptr, const struct tachyon_##C##_g1_affine* bases,         \
+      size_t size);                                                                          \
+  TACHYON_C_EXPORT int tachyon_##C##_g1_msm_gpu_commit_batch_b200(                           \
+      tachyon_##C##_g1_msm_gpu_ptr ptr, const struct tachyon_##C##_fr* const* scalars,       \
+      const size_t* sizes, size_t count, struct tachyon_##C##_g1_xyzz* out);                 \
+  /* Host-only: n XYZZ points -> affine with one field inversion (point_xyzz.h:109-163       \
+     BatchNormalize); the identity becomes (0, 0). */                                        \
+  TACHYON_C_EXPORT void tachyon_##C##_g1_xyzz_batch_normalize_b200(                          \
+      const struct tachyon_##C##_g1_xyzz* in, size_t n, struct tachyon_##C##_g1_affine* out); \
   /* Stage timings of the last call on this context (CUDA events on its stream). */         \
   TACHYON_C_EXPORT int tachyon_##C##_g1_msm_gpu_last_timing_b200(                            \
       tachyon_##C##_g1_msm_gpu_ptr ptr, struct tachyon_b200_msm_timing* out);                \

@@ -113,6 +113,21 @@ struct HostFp {
     return r;
   }
   HostFp Sqr() const { return Mul(*this); }
+  // a^(p-2); zero maps to zero
+  HostFp Inv() const {
+    uint64_t e[N];
+    uint64_t borrow = 2;
+    for (int i = 0; i < N; ++i) {
+      e[i] = F::kMod64[i] - borrow;
+      borrow = F::kMod64[i] < borrow ? 1 : 0;
+    }
+    HostFp acc = One();
+    for (int i = 64 * N - 1; i >= 0; --i) {
+      acc = acc.Sqr();
+      if ((e[i >> 6] >> (i & 63)) & 1) acc = acc.Mul(*this);
+    }
+    return acc;
+  }
 };
 
 template <class F>
@@ -164,6 +179,39 @@ HostJacobian<F> ToJacobian(const HostXYZZ<F>& p) {
   if (p.zz.IsOne()) return HostJacobian<F>{p.x, p.y, HostFp<F>::One()};
   HostFp<F> z = p.zz.Mul(p.zzz);
   return HostJacobian<F>{p.x.Mul(p.zzz).Mul(z), p.y.Mul(p.zz).Mul(z.Sqr()), z};
+}
+
+template <class F>
+struct HostAffine {
+  HostFp<F> x, y;
+};
+
+// XYZZ -> affine for n points with ONE field inversion (Montgomery's trick), the
+// BatchNormalize of short_weierstrass/point_xyzz.h:109-163: x / zz, y / zzz; the identity
+// maps to (0, 0).
+template <class F>
+void BatchNormalize(const HostXYZZ<F>* in, size_t n, HostAffine<F>* out) {
+  if (n == 0) return;
+  HostFp<F>* prefix = new HostFp<F>[n];
+  HostFp<F> acc = HostFp<F>::One();
+  for (size_t i = 0; i < n; ++i) {
+    prefix[i] = acc;
+    if (!in[i].IsZero()) acc = acc.Mul(in[i].zzz);
+  }
+  HostFp<F> inv = acc.Inv();
+  for (size_t i = n; i-- > 0;) {
+    if (in[i].IsZero()) {
+      out[i].x = HostFp<F>::Zero();
+      out[i].y = HostFp<F>::Zero();
+      continue;
+    }
+    HostFp<F> zi3 = inv.Mul(prefix[i]);   // 1 / zzz_i
+    inv = inv.Mul(in[i].zzz);
+    HostFp<F> zi2 = zi3.Mul(in[i].zz).Sqr();  // (zz / zzz)^2 = 1 / zz
+    out[i].x = in[i].x.Mul(zi2);
+    out[i].y = in[i].y.Mul(zi3);
+  }
+  delete[] prefix;
 }
 
 // pippenger_base.h:59-77: Horner over window sums, c doublings per window.

@@ -66,6 +66,72 @@ struct MsmGpuContext {
     }
   }
 
+  // The same bases on every engine's device (kzg.h:91-113: the SRS is uploaded once).
+  void RegisterBases(const void* bases, size_t n) {
+    for (auto& e : engines) e->RegisterBases(bases, n);
+    TB_CUDA(cudaSetDevice(primary_device));
+  }
+
+  // `count` MSMs over the registered bases (the commit loop of kzg.h:217-313; the four
+  // G1 queries of groth16/prove.h:100-131 when called with one set of bases each).  With k
+  // devices MSM i runs on device i mod k — whole MSMs are independent, so they are dealt
+  // out rather than sharded; each device keeps two of its MSMs in flight.
+  void RunBatch(const void* const* scalars, const size_t* sizes, size_t count, Point* out) {
+    size_t G = engines.size();
+    for (size_t i = 0; i < count; ++i)
+      if (sizes[i] > engines[0]->registered_size())
+        throw CudaError{cudaErrorInvalidValue, "batch MSM larger than the registered bases", __FILE__, __LINE__};
+    if (G == 1 || count == 1) {
+      engines[0]->RunBatch(engines[0]->registered_bases(), scalars, sizes, count, out);
+      timing = engines[0]->timing();
+      return;
+    }
+    std::vector<CudaError> errs(G, CudaError{cudaSuccess, "", "", 0});
+    std::vector<std::thread> threads;
+    auto wall0 = std::chrono::steady_clock::now();
+    for (size_t g = 0; g < G; ++g) {
+      threads.emplace_back([&, g] {
+        std::vector<const void*> sc;
+        std::vector<size_t> sz, idx;
+        for (size_t i = g; i < count; i += G) {
+          sc.push_back(scalars[i]);
+          sz.push_back(sizes[i]);
+          idx.push_back(i);
+        }
+        std::vector<Point> res(sc.size());
+        try {
+          engines[g]->RunBatch(engines[g]->registered_bases(), sc.data(), sz.data(), sc.size(),
+                               res.data());
+          for (size_t k = 0; k < idx.size(); ++k) out[idx[k]] = res[k];
+        } catch (const CudaError& e) {
+          errs[g] = e;
+        }
+      });
+    }
+    for (auto& t : threads) t.join();
+    for (auto& e : errs)
+      if (e.code != cudaSuccess) throw e;
+    timing = MsmTiming{};
+    for (size_t g = 0; g < G; ++g) {
+      const MsmTiming& t = engines[g]->timing();
+      timing.sort_ms = std::max(timing.sort_ms, t.sort_ms);
+      timing.accumulate_ms = std::max(timing.accumulate_ms, t.accumulate_ms);
+      timing.reduce_ms = std::max(timing.reduce_ms, t.reduce_ms);
+      timing.h2d_ms = std::max(timing.h2d_ms, t.h2d_ms);
+      timing.host_ms = std::max(timing.host_ms, t.host_ms);
+      timing.window_bits = t.window_bits;
+      timing.windows = t.windows;
+      timing.tasks += t.tasks;
+      timing.entries += t.entries;
+      timing.kernel_launches += t.kernel_launches;
+      timing.ranges = std::max(timing.ranges, t.ranges);
+    }
+    timing.total_ms =
+        std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - wall0).count();
+    timing.devices = (uint32_t)G;
+    TB_CUDA(cudaSetDevice(primary_device));
+  }
+
   // Point-range sharding (the split of pippenger_adapter.h:82-113 across GPUs
   // instead of threads): device g takes [g*n/G, (g+1)*n/G); partial sums are
   // added on the host.  Device-resident inputs stay on the primary device.
@@ -408,6 +474,35 @@ struct tachyon_bls12_381_g1_msm_gpu : public MsmGpuContext<Bls381Curve> {
     } catch (const CudaError& e) {                                                             \
       return Fail(e);                                                                          \
     }                                                                                          \
+  }                                                                                            \
+  int tachyon_##CN##_g1_msm_gpu_register_bases_b200(tachyon_##CN##_g1_msm_gpu_ptr ptr,         \
+                                                    const tachyon_##CN##_g1_affine* bases,     \
+                                                    size_t size) {                             \
+    if (!ptr || (!bases && size)) return -1;                                                   \
+    try {                                                                                      \
+      ptr->RegisterBases(bases, size);                                                         \
+      return 0;                                                                                \
+    } catch (const CudaError& e) {                                                             \
+      return Fail(e);                                                                          \
+    }                                                                                          \
+  }                                                                                            \
+  int tachyon_##CN##_g1_msm_gpu_commit_batch_b200(                                             \
+      tachyon_##CN##_g1_msm_gpu_ptr ptr, const tachyon_##CN##_fr* const* scalars,              \
+      const size_t* sizes, size_t count, tachyon_##CN##_g1_xyzz* out) {                        \
+    if (!ptr || (count && (!scalars || !sizes || !out))) return -1;                            \
+    try {                                                                                      \
+      static_assert(sizeof(*out) == sizeof(MsmGpuContext<CURVE>::Point), "layout");            \
+      ptr->RunBatch(reinterpret_cast<const void* const*>(scalars), sizes, count,               \
+                    reinterpret_cast<MsmGpuContext<CURVE>::Point*>(out));                      \
+      return 0;                                                                                \
+    } catch (const CudaError& e) {                                                             \
+      return Fail(e);                                                                          \
+    }                                                                                          \
+  }                                                                                            \
+  void tachyon_##CN##_g1_xyzz_batch_normalize_b200(const tachyon_##CN##_g1_xyzz* in, size_t n, \
+                                                   tachyon_##CN##_g1_affine* out) {            \
+    BatchNormalize<CURVE::Fq>(reinterpret_cast<const HostXYZZ<CURVE::Fq>*>(in), n,             \
+                              reinterpret_cast<HostAffine<CURVE::Fq>*>(out));                  \
   }                                                                                            \
   int tachyon_##CN##_g1_msm_gpu_last_timing_b200(tachyon_##CN##_g1_msm_gpu_ptr ptr,            \
                                                  tachyon_b200_msm_timing* out) {               \

@@ -11,7 +11,9 @@
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
+#include <initializer_list>
 #include <string>
+#include <utility>
 #include <vector>
 
 #include "host_math.h"
@@ -124,7 +126,7 @@ class MsmEngine {
     TB_CUDA(cudaStreamCreateWithFlags(&own_stream_, cudaStreamNonBlocking));
     stream_ = own_stream_;
     TB_CUDA(cudaStreamCreateWithFlags(&copy_stream_, cudaStreamNonBlocking));
-    TB_CUDA(cudaMallocHost(&host_out_, kHostOutBytes));
+    TB_CUDA(cudaMallocHost(&host_out_, 2 * kHostOutBytes));
     TB_CUDA(cudaMalloc(&totals_, sizeof(MsmTotals)));
     int sms = 0;
     TB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device_));
@@ -160,14 +162,86 @@ class MsmEngine {
     // icicle_msm_bn254_g1.cc:56-62 the last piece keeps its remainder.
     for (size_t off = 0; off < n; off += kMaxPiece) {
       size_t len = n - off < kMaxPiece ? n - off : kMaxPiece;
-      Point part = RunPiece(static_cast<const char*>(bases) + off * kAffineBytes,
-                            static_cast<const char*>(scalars) + off * kScalarBytes, len);
+      Pending p = Enqueue(static_cast<const char*>(bases) + off * kAffineBytes,
+                          static_cast<const char*>(scalars) + off * kScalarBytes, len, 0);
+      Point part = Finish(p);
       total = (off == 0) ? part : total.Add(part);
     }
     return total;
   }
 
+  // Keeps a private device copy of `n` bases (host or device source) for later MSMs — the
+  // SRS of kzg.h:91-113, uploaded once instead of once per commitment.
+  void RegisterBases(const void* bases, size_t n) {
+    TB_CUDA(cudaSetDevice(device_));
+    TB_CUDA(cudaStreamSynchronize(stream_));
+    TB_CUDA(cudaStreamSynchronize(copy_stream_));
+    registered_.Reserve(n * kAffineBytes);
+    if (n) TB_CUDA(cudaMemcpy(registered_.ptr, bases, n * kAffineBytes, cudaMemcpyDefault));
+    registered_n_ = n;
+  }
+  const void* registered_bases() const { return registered_.ptr; }
+  size_t registered_size() const { return registered_n_; }
+
+  // `count` MSMs over the same bases (bases: max(sizes) points; MSM i uses the first
+  // sizes[i] of them with scalars[i]) — the commit loop of
+  // tachyon/crypto/commitments/kzg/kzg.h:217-313.  Two MSMs are kept in flight: the
+  // scalars of MSM i+1 cross PCIe and its kernels are queued while MSM i runs, and the
+  // host epilogue of MSM i overlaps the device work of MSM i+1.
+  void RunBatch(const void* bases, const void* const* scalars, const size_t* sizes, size_t count,
+                Point* out) {
+    TB_CUDA(cudaSetDevice(device_));
+    timing_ = MsmTiming{};
+    size_t biggest = 0;
+    for (size_t i = 0; i < count; ++i) biggest = sizes[i] > biggest ? sizes[i] : biggest;
+    if (biggest > kMaxPiece) {  // rare: fall back to one blocking call each
+      MsmTiming sum{};
+      for (size_t i = 0; i < count; ++i) {
+        out[i] = Run(bases, scalars[i], sizes[i]);
+        sum.total_ms += timing_.total_ms;
+        sum.kernel_launches += timing_.kernel_launches;
+      }
+      timing_ = sum;
+      return;
+    }
+    auto wall0 = std::chrono::steady_clock::now();
+    Pending pend[2];
+    bool live[2] = {false, false};
+    for (size_t i = 0; i < count + 1; ++i) {
+      int slot = (int)(i & 1);
+      if (i < count) {
+        if (sizes[i] == 0) {
+          out[i] = Point::Zero();
+        } else {
+          // the other slot's MSM is still in flight: growing a buffer would wait for it,
+          // which is correct (cudaFree synchronises) but serialises; sizes are usually equal
+          pend[slot] = Enqueue(bases, scalars[i], sizes[i], slot);
+          pend[slot].index = i;
+          live[slot] = true;
+        }
+      }
+      int prev = slot ^ 1;
+      if (i >= 1 && live[prev]) {
+        out[pend[prev].index] = Finish(pend[prev]);
+        live[prev] = false;
+      }
+    }
+    timing_.total_ms =
+        std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - wall0).count();
+  }
+
  private:
+  // One enqueued MSM: everything the host epilogue needs once the device is done.
+  struct Pending {
+    MsmPlan plan{};
+    uint32_t L0 = 0, M = 0;
+    size_t K = 0;
+    bool any_host = false;
+    int slot = 0;       // host result buffer / event set
+    uint32_t launches = 0;
+    size_t index = 0;
+  };
+
   static bool IsDevicePointer(const void* p) {
     cudaPointerAttributes attr;
     cudaError_t e = cudaPointerGetAttributes(&attr, p);
@@ -222,16 +296,15 @@ class MsmEngine {
     return c;
   }
 
-  // Device bytes one point range of m points needs besides the bucket state (the role of
+  // Device bytes one point range of m points needs besides the bucket values (the role of
   // the footprint model in icicle_msm_utils.cc:10-68, for this pipeline's buffers).
-  size_t RangeFootprint(size_t m, uint32_t c, bool stage_bases, bool stage_scalars,
-                        uint32_t slots) const {
+  size_t RangeFootprint(size_t m, uint32_t c, bool stage_bases, bool stage_scalars) const {
     MsmPlan p = MakePlan(m, c);
     size_t b = (size_t)m * p.W * 8;                       // digits + sorted
     b += (size_t)p.max_tasks * (8 + 4 + 4 + kXyzzBytes);  // tasks, meta, order, task_out
     b += (size_t)(p.TB + 1) * 4 * 5;                      // count, offset, cursor, task_base, multi
-    if (stage_bases) b += (size_t)m * kAffineBytes * slots;
-    if (stage_scalars) b += (size_t)m * kScalarBytes * slots;
+    if (stage_bases) b += (size_t)m * kAffineBytes * kStageSlots;
+    if (stage_scalars) b += (size_t)m * kScalarBytes * kStageSlots;
     return b;
   }
 
@@ -243,6 +316,23 @@ class MsmEngine {
     }
     return events_[i];
   }
+  // event sets: per Pending slot, 0 begin, 1 end of accumulation, 2 end, 3 copy begin, then
+  // per range r: 4 + 4r copied, +1 sort start, +2 sort end, +3 accumulated
+  static constexpr size_t kEventsPerSlot = 4 + 4 * kMaxRanges;
+  cudaEvent_t SlotEvent(int slot, size_t i) { return Event((size_t)slot * kEventsPerSlot + i); }
+  cudaEvent_t StageFreeEvent(size_t stage) { return Event(2 * kEventsPerSlot + stage); }
+
+  // Grow-only workspace.  A buffer that has to grow is freed and reallocated, which is only
+  // safe once nothing in flight uses it: drain both streams first.
+  void ReserveAll(std::initializer_list<std::pair<DeviceBuffer*, size_t>> wants) {
+    bool grow = false;
+    for (auto& w : wants) grow = grow || w.second > w.first->bytes;
+    if (!grow) return;
+    TB_CUDA(cudaStreamSynchronize(copy_stream_));
+    TB_CUDA(cudaStreamSynchronize(stream_));
+    for (auto& w : wants) w.first->Reserve(w.second);
+    for (auto& u : stage_used_) u = false;
+  }
 
   // One MSM: bucket values live in `state_` for the whole call; the points are consumed
   // as K consecutive ranges, each range sorted by bucket and added into the bucket values
@@ -251,16 +341,23 @@ class MsmEngine {
   // range k is sorted and accumulated, so the 1.6 GB of a 2^24 BN254 MSM (~29 ms at PCIe
   // gen5 rates) hides behind the ~36 ms of bucket work instead of preceding it.  Device
   // inputs run as one range unless the memory model asks for more.
-  Point RunPiece(const void* bases, const void* scalars, size_t n) {
+  //
+  // Enqueue() only queues work (copies on the copy stream through a ring of staging slots,
+  // kernels and the final D2H on the compute stream); Finish() waits and runs the host
+  // epilogue.  All device buffers except the staging ring are shared by consecutive MSMs,
+  // which is safe because their kernels are ordered on the one compute stream.
+  Pending Enqueue(const void* bases, const void* scalars, size_t n, int slot) {
     const uint32_t c = WindowBitsFor(n);
     const bool bases_dev = IsDevicePointer(bases), scalars_dev = IsDevicePointer(scalars);
-    const bool any_host = !bases_dev || !scalars_dev;
+    Pending pd;
+    pd.any_host = !bases_dev || !scalars_dev;
+    pd.slot = slot;
 
     // ---- how many ranges ----------------------------------------------------------
     size_t K = 1;
     if (options_.ranges > 0) {
       K = options_.ranges;
-    } else if (any_host) {
+    } else if (pd.any_host) {
       K = n >> 20;  // ranges of >= 2^20 points, at most 8
       if (K > 8) K = 8;
       if (K < 1) K = 1;
@@ -274,65 +371,78 @@ class MsmEngine {
       size_t budget = (size_t)(0.9 * (double)(free_b + OwnedBytes()));
       size_t state_b = (size_t)whole.TB * kXyzzBytes;
       while (K < kMaxRanges && K < n &&
-             state_b + RangeFootprint((n + K - 1) / K, c, !bases_dev, !scalars_dev,
-                                      K < kStageSlots ? K : kStageSlots) > budget)
+             state_b + RangeFootprint((n + K - 1) / K, c, !bases_dev, !scalars_dev) > budget)
         K *= 2;
       if (K > kMaxRanges) K = kMaxRanges;
     }
     const size_t m = (n + K - 1) / K;  // points per range (the last may be shorter)
     K = (n + m - 1) / m;
-    const size_t slots = K < kStageSlots ? K : kStageSlots;
     MsmPlan big = MakePlan(m, c);
+    pd.plan = big;
+    pd.K = K;
     launches_ = 0;
 
     // ---- workspace ----------------------------------------------------------------
     uint32_t scan_blocks = (big.TB + kScanItems - 1) / kScanItems;
     if (scan_blocks > (uint32_t)kScanItems)
       throw CudaError{cudaErrorInvalidValue, "too many buckets", __FILE__, __LINE__};
-    state_.Reserve((size_t)big.TB * kXyzzBytes);
-    count_.Reserve((size_t)(big.TB + 1) * 4);
-    offset_.Reserve((size_t)(big.TB + 1) * 4);
-    cursor_.Reserve((size_t)(big.TB + 1) * 4);
-    task_base_.Reserve((size_t)big.TB * 4);
-    multi_.Reserve((size_t)big.TB * 4);
-    tasks_.Reserve((size_t)big.max_tasks * sizeof(uint2));
-    task_meta_.Reserve((size_t)big.max_tasks * 4);
-    order_.Reserve((size_t)big.max_tasks * 4);
-    task_out_.Reserve((size_t)big.max_tasks * kXyzzBytes);
-    sorted_.Reserve((size_t)m * big.W * 4);
-    digits_.Reserve((size_t)m * big.W * 4);
-    block_sums_.Reserve((size_t)scan_blocks * 8);
-    len_hist_.Reserve((size_t)(kMaxSegment + 1) * 4);
-    if (!bases_dev) bases_stage_.Reserve(m * slots * kAffineBytes);
-    if (!scalars_dev) scalars_stage_.Reserve(m * slots * kScalarBytes);
+    pd.L0 = ChooseLevelLength(big.B, big.W);
+    const uint32_t nb = big.B / pd.L0;  // blocks per window, a power of two
+    pd.M = Log2(nb);
+    size_t tree_b[2] = {0, 0};
+    for (uint32_t s = 0; s < pd.M; ++s) {
+      size_t need = (size_t)big.W * (nb >> (s + 1)) * (s + 3) * kXyzzBytes;
+      if (need > tree_b[s & 1]) tree_b[s & 1] = need;
+    }
+    ReserveAll({{&state_, (size_t)big.TB * kXyzzBytes},
+                {&count_, (size_t)(big.TB + 1) * 4},
+                {&offset_, (size_t)(big.TB + 1) * 4},
+                {&cursor_, (size_t)(big.TB + 1) * 4},
+                {&task_base_, (size_t)big.TB * 4},
+                {&multi_, (size_t)big.TB * 4},
+                {&tasks_, (size_t)big.max_tasks * sizeof(uint2)},
+                {&task_meta_, (size_t)big.max_tasks * 4},
+                {&order_, (size_t)big.max_tasks * 4},
+                {&task_out_, (size_t)big.max_tasks * kXyzzBytes},
+                {&sorted_, (size_t)m * big.W * 4},
+                {&digits_, (size_t)m * big.W * 4},
+                {&block_sums_, (size_t)scan_blocks * 8},
+                {&len_hist_, (size_t)(kMaxSegment + 1) * 4},
+                {&lvl_a_[0], (size_t)big.W * nb * kXyzzBytes},
+                {&lvl_c_[0], (size_t)big.W * nb * kXyzzBytes},
+                {&tree_[0], tree_b[0]},
+                {&tree_[1], tree_b[1]},
+                {&bases_stage_, bases_dev ? 0 : m * kStageSlots * kAffineBytes},
+                {&scalars_stage_, scalars_dev ? 0 : m * kStageSlots * kScalarBytes}});
+    const size_t bases_slot_bytes = bases_stage_.bytes / kStageSlots / 256 * 256;
+    const size_t scalars_slot_bytes = scalars_stage_.bytes / kStageSlots / 256 * 256;
 
-    // events: 0 begin, 1 end of accumulation, 2 end; per range r: 4r+3 copied, +4 sort
-    // start, +5 sort end, +6 accumulated
-    cudaEvent_t ev_begin = Event(0), ev_acc_end = Event(1), ev_end = Event(2);
-    auto ev = [&](size_t r, int which) { return Event(3 + 4 * r + which); };
-    cudaEvent_t ev_copy_begin = Event(3 + 4 * K);
+    cudaEvent_t ev_begin = SlotEvent(slot, 0), ev_acc_end = SlotEvent(slot, 1),
+                ev_end = SlotEvent(slot, 2), ev_copy_begin = SlotEvent(slot, 3);
+    auto ev = [&](size_t r, int which) { return SlotEvent(slot, 4 + 4 * r + which); };
 
     TB_CUDA(cudaEventRecord(ev_begin, stream_));
     TB_CUDA(cudaMemsetAsync(state_.ptr, 0, (size_t)big.TB * kXyzzBytes, stream_));
-    if (any_host) {
-      TB_CUDA(cudaStreamWaitEvent(copy_stream_, ev_begin, 0));
-      TB_CUDA(cudaEventRecord(ev_copy_begin, copy_stream_));
-    }
+    if (pd.any_host) TB_CUDA(cudaEventRecord(ev_copy_begin, copy_stream_));
 
+    char* host_out = host_out_ + (size_t)slot * kHostOutBytes;
     for (size_t r = 0; r < K; ++r) {
       const size_t lo = r * m, len = (n - lo < m) ? n - lo : m;
       MsmPlan plan = MakePlan(len, c);
       // ---- inputs of this range ---------------------------------------------------
       const uint32_t* d_bases;
       const uint32_t* d_scalars;
-      const size_t slot = r % slots;
-      if (any_host && r >= slots)  // the slot's previous tenant must have been consumed
-        TB_CUDA(cudaStreamWaitEvent(copy_stream_, ev(r - slots, 3), 0));
+      size_t stage = 0;
+      if (pd.any_host) {
+        stage = stage_seq_++ % kStageSlots;
+        // the slot's previous tenant must have been consumed
+        if (stage_used_[stage]) TB_CUDA(cudaStreamWaitEvent(copy_stream_, StageFreeEvent(stage), 0));
+      }
       if (scalars_dev) {
         d_scalars = reinterpret_cast<const uint32_t*>(static_cast<const char*>(scalars) +
                                                       lo * kScalarBytes);
       } else {
-        char* dst = scalars_stage_.as<char>() + slot * m * kScalarBytes;
+        char* dst = scalars_stage_.as<char>() + stage * scalars_slot_bytes;
         TB_CUDA(cudaMemcpyAsync(dst, static_cast<const char*>(scalars) + lo * kScalarBytes,
                                 len * kScalarBytes, cudaMemcpyHostToDevice, copy_stream_));
         d_scalars = reinterpret_cast<const uint32_t*>(dst);
@@ -341,12 +451,12 @@ class MsmEngine {
         d_bases = reinterpret_cast<const uint32_t*>(static_cast<const char*>(bases) +
                                                     lo * kAffineBytes);
       } else {
-        char* dst = bases_stage_.as<char>() + slot * m * kAffineBytes;
+        char* dst = bases_stage_.as<char>() + stage * bases_slot_bytes;
         TB_CUDA(cudaMemcpyAsync(dst, static_cast<const char*>(bases) + lo * kAffineBytes,
                                 len * kAffineBytes, cudaMemcpyHostToDevice, copy_stream_));
         d_bases = reinterpret_cast<const uint32_t*>(dst);
       }
-      if (any_host) {
+      if (pd.any_host) {
         TB_CUDA(cudaEventRecord(ev(r, 0), copy_stream_));
         TB_CUDA(cudaStreamWaitEvent(stream_, ev(r, 0), 0));
       }
@@ -385,31 +495,29 @@ class MsmEngine {
       Launch(fold_partials_kernel<C>, sm_count_ * 4, kFoldThreads, multi_.as<uint32_t>(), totals_,
              offset_.as<uint32_t>(), task_base_.as<uint32_t>(), plan.seg,
              task_out_.as<uint32_t>(), state_.as<uint32_t>());
-      TB_CUDA(cudaMemcpyAsync(host_out_ + kHostWindowBytes + r * sizeof(MsmTotals), totals_,
+      TB_CUDA(cudaMemcpyAsync(host_out + kHostWindowBytes + r * sizeof(MsmTotals), totals_,
                               sizeof(MsmTotals), cudaMemcpyDeviceToHost, stream_));
       TB_CUDA(cudaEventRecord(ev(r, 3), stream_));
+      if (pd.any_host) {
+        TB_CUDA(cudaEventRecord(StageFreeEvent(stage), stream_));
+        stage_used_[stage] = true;
+      }
     }
     TB_CUDA(cudaEventRecord(ev_acc_end, stream_));
     const MsmPlan& plan = big;
 
     // ---- bucket reduction: one blocked running-sum level, then a merge tree ---------
-    uint32_t L0 = ChooseLevelLength(plan.B, plan.W);
-    uint32_t nb = plan.B / L0;  // blocks per window, a power of two
-    lvl_a_[0].Reserve((size_t)plan.W * nb * kXyzzBytes);
-    lvl_c_[0].Reserve((size_t)plan.W * nb * kXyzzBytes);
     {
       uint32_t threads = plan.W * nb;
       Launch(reduce_level_kernel<C, true>, (threads + kReduceThreads - 1) / kReduceThreads,
-             kReduceThreads, state_.as<uint32_t>(), (const uint32_t*)nullptr, plan.B, nb, L0, 0u,
-             plan.W, lvl_a_[0].as<uint32_t>(), lvl_c_[0].as<uint32_t>());
+             kReduceThreads, state_.as<uint32_t>(), (const uint32_t*)nullptr, plan.B, nb, pd.L0,
+             0u, plan.W, lvl_a_[0].as<uint32_t>(), lvl_c_[0].as<uint32_t>());
     }
-    uint32_t M = Log2(nb);
     const uint32_t* tin = lvl_a_[0].as<uint32_t>();
     const uint32_t* tin_p = lvl_c_[0].as<uint32_t>();
-    for (uint32_t s = 0; s < M; ++s) {
+    for (uint32_t s = 0; s < pd.M; ++s) {
       uint32_t m_out = nb >> (s + 1);
       DeviceBuffer& dst = tree_[s & 1];
-      dst.Reserve((size_t)plan.W * m_out * (s + 3) * kXyzzBytes);
       uint32_t threads = plan.W * m_out * (s + 3);
       Launch(reduce_merge_kernel<C>, (threads + kReduceThreads - 1) / kReduceThreads,
              kReduceThreads, tin, tin_p, s, m_out, plan.W, dst.as<uint32_t>());
@@ -417,26 +525,35 @@ class MsmEngine {
       tin_p = nullptr;
     }
     // per window: (A, P, D_0 .. D_(M-1)); finished on the host
-    uint32_t vals = M + 2;
+    uint32_t vals = pd.M + 2;
     size_t win_bytes = (size_t)plan.W * vals * kXyzzBytes;
-    if (M == 0) {
-      TB_CUDA(cudaMemcpy2DAsync(host_out_, 2 * kXyzzBytes, lvl_a_[0].ptr, kXyzzBytes, kXyzzBytes,
+    if (pd.M == 0) {
+      TB_CUDA(cudaMemcpy2DAsync(host_out, 2 * kXyzzBytes, lvl_a_[0].ptr, kXyzzBytes, kXyzzBytes,
                                 plan.W, cudaMemcpyDeviceToHost, stream_));
-      TB_CUDA(cudaMemcpy2DAsync(host_out_ + kXyzzBytes, 2 * kXyzzBytes, lvl_c_[0].ptr, kXyzzBytes,
+      TB_CUDA(cudaMemcpy2DAsync(host_out + kXyzzBytes, 2 * kXyzzBytes, lvl_c_[0].ptr, kXyzzBytes,
                                 kXyzzBytes, plan.W, cudaMemcpyDeviceToHost, stream_));
     } else {
-      TB_CUDA(cudaMemcpyAsync(host_out_, tin, win_bytes, cudaMemcpyDeviceToHost, stream_));
+      TB_CUDA(cudaMemcpyAsync(host_out, tin, win_bytes, cudaMemcpyDeviceToHost, stream_));
     }
     TB_CUDA(cudaEventRecord(ev_end, stream_));
-    TB_CUDA(cudaStreamSynchronize(stream_));
+    pd.launches = launches_;
+    return pd;
+  }
+
+  Point Finish(const Pending& pd) {
+    const MsmPlan& plan = pd.plan;
+    const int slot = pd.slot;
+    auto ev = [&](size_t r, int which) { return SlotEvent(slot, 4 + 4 * r + which); };
+    TB_CUDA(cudaEventSynchronize(SlotEvent(slot, 2)));
+    const char* host_out = host_out_ + (size_t)slot * kHostOutBytes;
 
     // ---- host epilogue ------------------------------------------------------------
     // total = sum_w 2^(c w) [A_w + P_w + L0 sum_j 2^j D_(w,j)]: one Horner over bit
     // positions from the top (the c doublings per window of pippenger_base.h:59-77),
     // adding every term at its own bit, so the bucket-tree weights cost no extra doubling.
     auto host0 = std::chrono::steady_clock::now();
-    const Point* hv = reinterpret_cast<const Point*>(host_out_);
-    uint32_t l0 = Log2(L0);
+    const Point* hv = reinterpret_cast<const Point*>(host_out);
+    const uint32_t l0 = Log2(pd.L0), M = pd.M, vals = M + 2;
     Point result = Point::Zero();
     for (uint32_t w = plan.W; w-- > 0;) {
       const Point* v = hv + (size_t)w * vals;
@@ -449,9 +566,9 @@ class MsmEngine {
     auto host1 = std::chrono::steady_clock::now();
 
     float ms;
-    for (size_t r = 0; r < K; ++r) {
+    for (size_t r = 0; r < pd.K; ++r) {
       MsmTotals tot;
-      memcpy(&tot, host_out_ + kHostWindowBytes + r * sizeof(MsmTotals), sizeof(tot));
+      memcpy(&tot, host_out + kHostWindowBytes + r * sizeof(MsmTotals), sizeof(tot));
       timing_.tasks += tot.tasks;
       timing_.entries += tot.entries;
       TB_CUDA(cudaEventElapsedTime(&ms, ev(r, 1), ev(r, 2)));
@@ -459,20 +576,20 @@ class MsmEngine {
       TB_CUDA(cudaEventElapsedTime(&ms, ev(r, 2), ev(r, 3)));
       timing_.accumulate_ms += ms;
     }
-    if (any_host) {
+    if (pd.any_host) {
       // time the copy engine was busy or waiting for a free slot; overlaps the bucket work
-      TB_CUDA(cudaEventElapsedTime(&ms, ev_copy_begin, ev(K - 1, 0)));
+      TB_CUDA(cudaEventElapsedTime(&ms, SlotEvent(slot, 3), ev(pd.K - 1, 0)));
       timing_.h2d_ms += ms;
     }
-    TB_CUDA(cudaEventElapsedTime(&ms, ev_acc_end, ev_end));
+    TB_CUDA(cudaEventElapsedTime(&ms, SlotEvent(slot, 1), SlotEvent(slot, 2)));
     timing_.reduce_ms += ms;
-    TB_CUDA(cudaEventElapsedTime(&ms, ev_begin, ev_end));
+    TB_CUDA(cudaEventElapsedTime(&ms, SlotEvent(slot, 0), SlotEvent(slot, 2)));
     timing_.total_ms += ms;
     timing_.host_ms += std::chrono::duration<float, std::milli>(host1 - host0).count();
     timing_.window_bits = plan.c;
     timing_.windows = plan.W;
-    timing_.ranges += (uint32_t)K;
-    timing_.kernel_launches += launches_;
+    timing_.ranges += (uint32_t)pd.K;
+    timing_.kernel_launches += pd.launches;
     return result;
   }
 
@@ -482,7 +599,7 @@ class MsmEngine {
     return b;
   }
   std::vector<const DeviceBuffer*> AllBuffers() const {
-    return {&bases_stage_, &scalars_stage_, &state_, &count_, &offset_, &cursor_, &task_base_,
+    return {&registered_, &bases_stage_, &scalars_stage_, &state_, &count_, &offset_, &cursor_, &task_base_,
             &tasks_, &task_meta_, &multi_, &sorted_, &digits_, &task_out_, &block_sums_, &order_,
             &len_hist_, &lvl_a_[0], &lvl_a_[1], &lvl_c_[0], &lvl_c_[1], &tree_[0], &tree_[1]};
   }
@@ -514,12 +631,15 @@ class MsmEngine {
   cudaStream_t stream_ = nullptr;
   cudaStream_t copy_stream_ = nullptr;
   std::vector<cudaEvent_t> events_;
+  size_t stage_seq_ = 0;
+  bool stage_used_[kStageSlots] = {};
   MsmOptions options_;
   MsmTiming timing_;
   uint32_t launches_ = 0;
   MsmTotals* totals_ = nullptr;
   char* host_out_ = nullptr;
-  DeviceBuffer bases_stage_, scalars_stage_, state_, count_, offset_, cursor_, task_base_, tasks_,
+  size_t registered_n_ = 0;
+  DeviceBuffer registered_, bases_stage_, scalars_stage_, state_, count_, offset_, cursor_, task_base_, tasks_,
       task_meta_, multi_, sorted_, digits_, task_out_, block_sums_, order_, len_hist_, lvl_a_[2],
       lvl_c_[2], tree_[2];
 };

@@ -85,6 +85,22 @@ class MSMGpu:
                    "msm_gpu_xyzz")
         return out
 
+    def register_bases(self, bases, size=None):
+        """Upload (or copy, for a device pointer) the bases once; later commit_batch calls use them."""
+        size = len(bases) if size is None else size
+        self._registered_keepalive = None
+        _lib.check(self._f("g1_msm_gpu_register_bases_b200")(self.ptr, _ptr(bases), size), "register_bases")
+
+    def commit_batch(self, scalars_list, sizes=None):
+        """One MSM per entry of scalars_list over the registered bases -> (count, 4, fq_limbs) XYZZ."""
+        count = len(scalars_list)
+        sizes = [len(s) for s in scalars_list] if sizes is None else list(sizes)
+        ptrs = (ctypes.c_void_p * count)(*[_ptr(s) for s in scalars_list])
+        szs = (ctypes.c_size_t * count)(*sizes)
+        out = np.zeros((count, 4, self.fq_limbs), dtype=np.uint64)
+        _lib.check(self._f("g1_msm_gpu_commit_batch_b200")(self.ptr, ptrs, szs, count, _ptr(out)), "commit_batch")
+        return out
+
     def last_timing(self):
         t = _lib.MsmTiming()
         _lib.check(self._f("g1_msm_gpu_last_timing_b200")(self.ptr, ctypes.byref(t)), "last_timing")
@@ -167,6 +183,16 @@ def xyzz_to_jacobian(curve, a):
     a = np.ascontiguousarray(a, dtype=np.uint64)
     out = np.zeros((3, a.shape[-1]), dtype=np.uint64)
     getattr(L, f"tachyon_{curve}_g1_xyzz_to_jacobian_b200")(_ptr(a), _ptr(out))
+    return out
+
+
+def batch_normalize(curve, xyzz):
+    """(n, 4, fq_limbs) XYZZ -> (n, 2 * fq_limbs) affine with one inversion (host)."""
+    L = _lib.load()
+    a = np.ascontiguousarray(xyzz, dtype=np.uint64)
+    n = a.shape[0]
+    out = np.zeros((n, 2 * a.shape[-1]), dtype=np.uint64)
+    getattr(L, f"tachyon_{curve}_g1_xyzz_batch_normalize_b200")(_ptr(a), n, _ptr(out))
     return out
 
 

@@ -234,6 +234,43 @@ def test_msm_point_ranges(oracles, torch_cuda, name):
         assert (o.jacobian_to_affine(ctx.affine_msm(bases, skew)) == want_skew).all()
 
 
+# bases registered once (the SRS of kzg.h:91-113), then a batch of
+# commitments with fresh scalars (kzg.h:217-313), results batch-normalised (point_xyzz.h:109-163).
+@pytest.mark.parametrize("name", CURVES)
+def test_registered_bases_commit_batch(oracles, torch_cuda, name):
+    o = oracles[name]
+    n = 3000
+    bases = o.generate_points(91, n)
+    sizes = [n, 1, 0, 2500, n, 17, n]
+    scal = [o.generate_scalars(92 + i, s, "witness" if i % 3 == 2 else "uniform") for i, s in enumerate(sizes)]
+    want = [o.msm_affine(bases[:s], scal[i]) if s else np.zeros_like(bases[0]).reshape(2, -1)
+            for i, s in enumerate(sizes)]
+    with msm.MSMGpu(name) as ctx:
+        ctx.register_bases(bases)
+        got = msm.batch_normalize(name, ctx.commit_batch(scal, sizes))
+        for i in range(len(sizes)):
+            assert (got[i] == np.asarray(want[i]).reshape(-1)).all(), i
+        # device-resident scalars, and a re-registration from a device pointer with fewer bases
+        import torch
+        dsc = [torch.from_numpy(s.view(np.int64)).cuda() for s in scal]
+        got = msm.batch_normalize(name, ctx.commit_batch([d.data_ptr() if s else 0 for d, s in zip(dsc, sizes)], sizes))
+        for i in range(len(sizes)):
+            assert (got[i] == np.asarray(want[i]).reshape(-1)).all(), i
+        db = torch.from_numpy(bases[:2500].view(np.int64)).cuda()
+        ctx.register_bases(db.data_ptr(), 2500)
+        got = msm.batch_normalize(name, ctx.commit_batch([scal[3]], [2500]))
+        assert (got[0] == np.asarray(want[3]).reshape(-1)).all()
+        with pytest.raises(RuntimeError):
+            ctx.commit_batch([scal[0]], [n])      # larger than what is registered now
+        ndev = msm.device_count()
+        if ndev > 1:
+            ctx.set_option("devices", min(ndev, 4))
+            ctx.register_bases(bases)
+            got = msm.batch_normalize(name, ctx.commit_batch(scal, sizes))
+            for i in range(len(sizes)):
+                assert (got[i] == np.asarray(want[i]).reshape(-1)).all(), i
+
+
 # Full benchmark sizes through a size-independent property: the synthetic bases
 # are chains P_(j,d) = 2^d H_j, so MSM(P, s) == MSM(H, fold(s)) with
 # fold(s)_j = sum_d s_(j,d) 2^d mod r — a 2^12-times smaller MSM the oracle does in

@@ -74,6 +74,23 @@ def test_host_point_helpers_vs_oracle(oracles, name):
     assert (o.xyzz_to_affine(msm.xyzz_add(name, xs[5], neg)) == 0).all()
 
 
+@pytest.mark.parametrize("name", ["bn254", "bls12_381"])
+def test_batch_normalize_vs_oracle(oracles, name):
+    # point_xyzz.h:109-163 BatchNormalize: one inversion for the whole batch, identity -> (0, 0)
+    o = oracles[name]
+    pts = o.generate_points(15, 9)
+    ks = o.fr_from_mont(o.generate_scalars(16, 9))
+    xs = np.stack([o.scalar_mul(pts[i], ks[i]) for i in range(9)])
+    xs[0] = o.xyzz_zero()
+    xs[4] = o.xyzz_zero()
+    xs[8] = o.xyzz_zero()
+    got = msm.batch_normalize(name, xs)
+    for i in range(9):
+        assert (got[i] == o.xyzz_to_affine(xs[i]).reshape(-1)).all(), i
+    assert msm.batch_normalize(name, xs[:0]).shape[0] == 0
+    assert (msm.batch_normalize(name, xs[:1]) == 0).all()
+
+
 def test_no_gpu_fails_loudly():
     import torch
     if torch.cuda.is_available():
