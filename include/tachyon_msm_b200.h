@@ -149,6 +149,8 @@ struct tachyon_b200_msm_timing {
   uint32_t kernel_launches; /* kernels of this library launched by the call */
   uint32_t devices;
   uint32_t ranges;      /* point ranges the call was pipelined over (1 for device inputs) */
+  float enqueue_ms;     /* host wall clock spent queueing copies and kernels */
+  float wait_ms;        /* host wall clock blocked waiting for the device */
 };
 
 TACHYON_B200_DECLARE_CURVE(bn254, 4)

@@ -14,6 +14,8 @@ CSRC = os.path.join(HERE, "csrc")
 LIB_DIR = os.path.join(HERE, "lib")
 LIB = os.path.join(LIB_DIR, "libtachyon_msm_b200.so")
 SOURCES = ["msm_api.cu"]
+REPLAY = os.path.join(LIB_DIR, "msm_gpu_replay")
+REPLAY_SRC = os.path.join(CSRC, "tools", "msm_gpu_replay.cc")
 HEADERS = ["fp.cuh", "xyzz.cuh", "msm_kernels.cuh", "msm_engine.cuh", "host_math.h",
            "field_constants.h", os.path.join("..", "..", "include", "tachyon_msm_b200.h")]
 
@@ -39,7 +41,9 @@ def up_to_date():
         return False
     t = os.path.getmtime(LIB)
     deps = [os.path.join(CSRC, f) for f in SOURCES + HEADERS] + [os.path.abspath(__file__)]
-    return all(os.path.getmtime(d) <= t for d in deps)
+    if not all(os.path.getmtime(d) <= t for d in deps):
+        return False
+    return os.path.exists(REPLAY) and os.path.getmtime(REPLAY_SRC) <= os.path.getmtime(REPLAY)
 
 
 def build(force=False, verbose=False):
@@ -57,6 +61,13 @@ def build(force=False, verbose=False):
         sys.stderr.write(res.stdout)
     if res.returncode != 0:
         raise RuntimeError("nvcc failed building libtachyon_msm_b200.so")
+    # the replay CLI: plain C++ over the C ABI
+    cmd = ["/usr/bin/g++", "-O2", "-std=c++17", "-march=x86-64-v3", "-o", REPLAY, REPLAY_SRC,
+           "-L" + LIB_DIR, "-ltachyon_msm_b200", "-Wl,-rpath,$ORIGIN"]
+    res = subprocess.run(cmd, env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    if res.returncode != 0:
+        sys.stderr.write(res.stdout)
+        raise RuntimeError("g++ failed building msm_gpu_replay")
     return LIB
 
 

@@ -204,13 +204,14 @@ static std::string FpHex(const HostFp<F>& montgomery) {
   HostFp<F> one = HostFp<F>::Zero();
   one.v[0] = 1;
   HostFp<F> c = montgomery.Mul(one);
-  std::string s = "0x";
+  std::string s;
   char buf[17];
   for (int i = HostFp<F>::N; i-- > 0;) {
     snprintf(buf, sizeof(buf), "%016llx", (unsigned long long)c.v[i]);
     s += buf;
   }
-  return s;
+  size_t nz = s.find_first_not_of('0');  // ToHexString(pad_zero = false), big_int.cc:55-58
+  return "0x" + (nz == std::string::npos ? std::string("0") : s.substr(nz));
 }
 
 // Dump format of msm_gpu.h:99-119 / msm_gpu_replay.cc:19-37: u64 count, then
@@ -521,6 +522,8 @@ struct tachyon_bls12_381_g1_msm_gpu : public MsmGpuContext<Bls381Curve> {
     out->kernel_launches = t.kernel_launches;                                                  \
     out->devices = t.devices;                                                                  \
     out->ranges = t.ranges;                                                                    \
+    out->enqueue_ms = t.enqueue_ms;                                                            \
+    out->wait_ms = t.wait_ms;                                                                  \
     return 0;                                                                                  \
   }                                                                                            \
   int tachyon_##CN##_g1_generate_bases_b200(uint64_t seed, size_t first, size_t n,             \

@@ -66,6 +66,7 @@ struct MsmTiming {
   float h2d_ms = 0, sort_ms = 0, accumulate_ms = 0, reduce_ms = 0, total_ms = 0, host_ms = 0;
   uint32_t window_bits = 0, windows = 0, tasks = 0, entries = 0, kernel_launches = 0, devices = 1;
   uint32_t ranges = 0;
+  float enqueue_ms = 0, wait_ms = 0;  // host wall clock: queueing the work / blocked on the device
 };
 
 struct MsmOptions {
@@ -347,6 +348,7 @@ class MsmEngine {
   // epilogue.  All device buffers except the staging ring are shared by consecutive MSMs,
   // which is safe because their kernels are ordered on the one compute stream.
   Pending Enqueue(const void* bases, const void* scalars, size_t n, int slot) {
+    auto wall0 = std::chrono::steady_clock::now();
     const uint32_t c = WindowBitsFor(n);
     const bool bases_dev = IsDevicePointer(bases), scalars_dev = IsDevicePointer(scalars);
     Pending pd;
@@ -366,14 +368,20 @@ class MsmEngine {
     if (K > n) K = n;
     MsmPlan whole = MakePlan(n, c);
     {
-      size_t free_b = 0, total_b = 0;
-      TB_CUDA(cudaMemGetInfo(&free_b, &total_b));
-      size_t budget = (size_t)(0.9 * (double)(free_b + OwnedBytes()));
-      size_t state_b = (size_t)whole.TB * kXyzzBytes;
-      while (K < kMaxRanges && K < n &&
-             state_b + RangeFootprint((n + K - 1) / K, c, !bases_dev, !scalars_dev) > budget)
-        K *= 2;
-      if (K > kMaxRanges) K = kMaxRanges;
+      // Memory model (icicle_msm_utils.cc:10-68 analogue): more ranges when one range's
+      // buffers would not fit.  cudaMemGetInfo costs milliseconds, so the driver is asked
+      // only when this call needs more than the engine already owns.
+      const size_t state_b = (size_t)whole.TB * kXyzzBytes;
+      auto need = [&](size_t k) {
+        return state_b + RangeFootprint((n + k - 1) / k, c, !bases_dev, !scalars_dev);
+      };
+      if (need(K) > OwnedBytes()) {
+        size_t free_b = 0, total_b = 0;
+        TB_CUDA(cudaMemGetInfo(&free_b, &total_b));
+        size_t budget = (size_t)(0.9 * (double)(free_b + OwnedBytes()));
+        while (K < kMaxRanges && K < n && need(K) > budget) K *= 2;
+        if (K > kMaxRanges) K = kMaxRanges;
+      }
     }
     const size_t m = (n + K - 1) / K;  // points per range (the last may be shorter)
     K = (n + m - 1) / m;
@@ -537,6 +545,8 @@ class MsmEngine {
     }
     TB_CUDA(cudaEventRecord(ev_end, stream_));
     pd.launches = launches_;
+    timing_.enqueue_ms +=
+        std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - wall0).count();
     return pd;
   }
 
@@ -544,7 +554,10 @@ class MsmEngine {
     const MsmPlan& plan = pd.plan;
     const int slot = pd.slot;
     auto ev = [&](size_t r, int which) { return SlotEvent(slot, 4 + 4 * r + which); };
+    auto wait0 = std::chrono::steady_clock::now();
     TB_CUDA(cudaEventSynchronize(SlotEvent(slot, 2)));
+    timing_.wait_ms +=
+        std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - wait0).count();
     const char* host_out = host_out_ + (size_t)slot * kHostOutBytes;
 
     // ---- host epilogue ------------------------------------------------------------

@@ -271,6 +271,44 @@ def test_registered_bases_commit_batch(oracles, torch_cuda, name):
                 assert (got[i] == np.asarray(want[i]).reshape(-1)).all(), i
 
 
+# the dump written under TACHYON_MSM_GPU_INPUT_DIR (msm_gpu.h:99-119: u64 count,
+# canonical little-endian limbs) and the replay CLI (msm_gpu_replay.cc:40-88: --idx --degree
+# --input_dir, prints the time and the affine point as hex without leading zeros).
+@pytest.mark.parametrize("name", CURVES)
+def test_dump_and_replay_cli(oracles, torch_cuda, name, tmp_path, monkeypatch):
+    import os
+    import subprocess
+    o, c = oracles[name], pymodel.CURVES[name]
+    n = 700
+    bases, scalars = o.generate_points(95, n), o.generate_scalars(96, n)
+    bases[5] = 0
+    monkeypatch.setenv("TACHYON_MSM_GPU_INPUT_DIR", str(tmp_path))
+    with msm.MSMGpu(name) as ctx:
+        ctx.affine_msm(bases, scalars)
+        ctx.point2_msm(bases[:40], scalars[:40])
+    monkeypatch.delenv("TACHYON_MSM_GPU_INPUT_DIR")
+    raw = np.fromfile(tmp_path / "bases0.txt", dtype=np.uint64)
+    assert raw[0] == n and raw.size == 1 + n * 2 * c.fq_limbs
+    assert (raw[1:].reshape(n, -1) == np.concatenate(
+        [o.fq_from_mont(bases[:, :c.fq_limbs]), o.fq_from_mont(bases[:, c.fq_limbs:])], axis=1)).all()
+    raw = np.fromfile(tmp_path / "scalars1.txt", dtype=np.uint64)
+    assert raw[0] == 40 and (raw[1:].reshape(40, 4) == o.fr_from_mont(scalars[:40])).all()
+    exe = os.path.join(os.path.dirname(msm._lib.LIB_PATH), "msm_gpu_replay")
+    env = {k: v for k, v in os.environ.items() if k != "TACHYON_MSM_GPU_INPUT_DIR"}
+    out = subprocess.run([exe, "--idx", "0,1", "--degree", "10", "--input_dir", str(tmp_path), "--curve", name],
+                         capture_output=True, text=True, env=env, check=True).stdout.splitlines()
+    points = [ln for ln in out if ln.startswith("(0x")]
+    assert len(points) == 2
+    for line, k in zip(points, (n, 40)):
+        want = o.fq_from_mont(o.msm_affine(bases[:k], scalars[:k]))
+        hx = ["0x%x" % pymodel.from_limbs([int(v) for v in want[i]]) for i in range(2)]
+        assert line == "(%s, %s)" % tuple(hx)
+    # the reference refuses to run with the dump variable set (msm_gpu_replay.cc:41-44)
+    bad = subprocess.run([exe, "--idx", "0", "--degree", "10", "--input_dir", str(tmp_path)],
+                         capture_output=True, text=True, env=dict(env, TACHYON_MSM_GPU_INPUT_DIR=str(tmp_path)))
+    assert bad.returncode == 1
+
+
 # Full benchmark sizes through a size-independent property: the synthetic bases
 # are chains P_(j,d) = 2^d H_j, so MSM(P, s) == MSM(H, fold(s)) with
 # fold(s)_j = sum_d s_(j,d) 2^d mod r — a 2^12-times smaller MSM the oracle does in
