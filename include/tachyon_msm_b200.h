@@ -100,6 +100,14 @@ extern "C" {
   TACHYON_C_EXPORT int tachyon_##C##_g1_msm_gpu_commit_batch_b200(                           \
       tachyon_##C##_g1_msm_gpu_ptr ptr, const struct tachyon_##C##_fr* const* scalars,       \
       const size_t* sizes, size_t count, struct tachyon_##C##_g1_xyzz* out);                 \
+  /* The general batch: MSM i over bases[i] (NULL = the registered bases) and scalars[i],    \
+     sizes[i] elements each, host or device memory — e.g. the A, B1, L and H queries of a    \
+     Groth16 proof (zk/r1cs/groth16/prove.h:100-131) in one call.  Pipelined and dealt out   \
+     like commit_batch (explicit device pointers keep the batch on the context's device). */ \
+  TACHYON_C_EXPORT int tachyon_##C##_g1_msm_gpu_batch_b200(                                  \
+      tachyon_##C##_g1_msm_gpu_ptr ptr, const struct tachyon_##C##_g1_affine* const* bases,  \
+      const struct tachyon_##C##_fr* const* scalars, const size_t* sizes, size_t count,      \
+      struct tachyon_##C##_g1_xyzz* out);                                                    \
   /* Host-only: n XYZZ points -> affine with one field inversion (point_xyzz.h:109-163       \
      BatchNormalize); the identity becomes (0, 0). */                                        \
   TACHYON_C_EXPORT void tachyon_##C##_g1_xyzz_batch_normalize_b200(                          \

@@ -35,6 +35,7 @@ CURVE_SYMBOLS = [
     "tachyon_{c}_g1_point_op_b200", "tachyon_{c}_g1_xyzz_add_b200",
     "tachyon_{c}_g1_xyzz_to_jacobian_b200", "tachyon_{c}_g1_msm_gpu_register_bases_b200",
     "tachyon_{c}_g1_msm_gpu_commit_batch_b200", "tachyon_{c}_g1_xyzz_batch_normalize_b200",
+    "tachyon_{c}_g1_msm_gpu_batch_b200",
 ]
 GLOBAL_SYMBOLS = ["tachyon_b200_device_count", "tachyon_b200_last_error", "tachyon_b200_imad_peak",
                   "tachyon_b200_kernel_launch_count", "tachyon_b200_window_bits",
@@ -83,6 +84,8 @@ def load():
         f("tachyon_{c}_g1_xyzz_add_b200").argtypes = [vp, vp, vp]
         f("tachyon_{c}_g1_msm_gpu_register_bases_b200").argtypes = [vp, vp, sz]
         f("tachyon_{c}_g1_msm_gpu_commit_batch_b200").argtypes = [vp, ctypes.POINTER(vp), ctypes.POINTER(sz), sz, vp]
+        f("tachyon_{c}_g1_msm_gpu_batch_b200").argtypes = [vp, ctypes.POINTER(vp), ctypes.POINTER(vp),
+                                                           ctypes.POINTER(sz), sz, vp]
         f("tachyon_{c}_g1_xyzz_batch_normalize_b200").restype = None
         f("tachyon_{c}_g1_xyzz_batch_normalize_b200").argtypes = [vp, sz, vp]
         f("tachyon_{c}_g1_xyzz_to_jacobian_b200").restype = None

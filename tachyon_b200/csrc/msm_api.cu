@@ -72,17 +72,24 @@ struct MsmGpuContext {
     TB_CUDA(cudaSetDevice(primary_device));
   }
 
-  // `count` MSMs over the registered bases (the commit loop of kzg.h:217-313; the four
-  // G1 queries of groth16/prove.h:100-131 when called with one set of bases each).  With k
-  // devices MSM i runs on device i mod k — whole MSMs are independent, so they are dealt
-  // out rather than sharded; each device keeps two of its MSMs in flight.
-  void RunBatch(const void* const* scalars, const size_t* sizes, size_t count, Point* out) {
+  // `count` MSMs, MSM i over bases[i] (nullptr: the registered bases) — the commit loop of
+  // kzg.h:217-313, or the four G1 queries of groth16/prove.h:100-131 with one base set each.
+  // With k devices MSM i runs on device i mod k — whole MSMs are independent, so they are
+  // dealt out rather than sharded; each device keeps two of its MSMs in flight.  Explicit
+  // device pointers belong to the primary device, so they confine the batch to it.
+  void RunBatch(const void* const* bases, const void* const* scalars, const size_t* sizes,
+                size_t count, Point* out) {
     size_t G = engines.size();
-    for (size_t i = 0; i < count; ++i)
-      if (sizes[i] > engines[0]->registered_size())
-        throw CudaError{cudaErrorInvalidValue, "batch MSM larger than the registered bases", __FILE__, __LINE__};
+    for (size_t i = 0; i < count && G > 1; ++i) {
+      cudaPointerAttributes a;
+      for (const void* p : {bases[i], scalars[i]}) {
+        if (p && cudaPointerGetAttributes(&a, p) == cudaSuccess && a.type == cudaMemoryTypeDevice)
+          G = 1;
+        cudaGetLastError();
+      }
+    }
     if (G == 1 || count == 1) {
-      engines[0]->RunBatch(engines[0]->registered_bases(), scalars, sizes, count, out);
+      engines[0]->RunBatch(bases, scalars, sizes, count, out);
       timing = engines[0]->timing();
       return;
     }
@@ -91,17 +98,17 @@ struct MsmGpuContext {
     auto wall0 = std::chrono::steady_clock::now();
     for (size_t g = 0; g < G; ++g) {
       threads.emplace_back([&, g] {
-        std::vector<const void*> sc;
+        std::vector<const void*> bs, sc;
         std::vector<size_t> sz, idx;
         for (size_t i = g; i < count; i += G) {
+          bs.push_back(bases[i]);
           sc.push_back(scalars[i]);
           sz.push_back(sizes[i]);
           idx.push_back(i);
         }
         std::vector<Point> res(sc.size());
         try {
-          engines[g]->RunBatch(engines[g]->registered_bases(), sc.data(), sz.data(), sc.size(),
-                               res.data());
+          engines[g]->RunBatch(bs.data(), sc.data(), sz.data(), sc.size(), res.data());
           for (size_t k = 0; k < idx.size(); ++k) out[idx[k]] = res[k];
         } catch (const CudaError& e) {
           errs[g] = e;
@@ -493,7 +500,22 @@ struct tachyon_bls12_381_g1_msm_gpu : public MsmGpuContext<Bls381Curve> {
     if (!ptr || (count && (!scalars || !sizes || !out))) return -1;                            \
     try {                                                                                      \
       static_assert(sizeof(*out) == sizeof(MsmGpuContext<CURVE>::Point), "layout");            \
-      ptr->RunBatch(reinterpret_cast<const void* const*>(scalars), sizes, count,               \
+      std::vector<const void*> none(count, nullptr);                                           \
+      ptr->RunBatch(none.data(), reinterpret_cast<const void* const*>(scalars), sizes, count,  \
+                    reinterpret_cast<MsmGpuContext<CURVE>::Point*>(out));                      \
+      return 0;                                                                                \
+    } catch (const CudaError& e) {                                                             \
+      return Fail(e);                                                                          \
+    }                                                                                          \
+  }                                                                                            \
+  int tachyon_##CN##_g1_msm_gpu_batch_b200(                                                    \
+      tachyon_##CN##_g1_msm_gpu_ptr ptr, const tachyon_##CN##_g1_affine* const* bases,         \
+      const tachyon_##CN##_fr* const* scalars, const size_t* sizes, size_t count,              \
+      tachyon_##CN##_g1_xyzz* out) {                                                           \
+    if (!ptr || (count && (!bases || !scalars || !sizes || !out))) return -1;                  \
+    try {                                                                                      \
+      ptr->RunBatch(reinterpret_cast<const void* const*>(bases),                               \
+                    reinterpret_cast<const void* const*>(scalars), sizes, count,               \
                     reinterpret_cast<MsmGpuContext<CURVE>::Point*>(out));                      \
       return 0;                                                                                \
     } catch (const CudaError& e) {                                                             \

@@ -184,21 +184,27 @@ class MsmEngine {
   const void* registered_bases() const { return registered_.ptr; }
   size_t registered_size() const { return registered_n_; }
 
-  // `count` MSMs over the same bases (bases: max(sizes) points; MSM i uses the first
-  // sizes[i] of them with scalars[i]) — the commit loop of
-  // tachyon/crypto/commitments/kzg/kzg.h:217-313.  Two MSMs are kept in flight: the
-  // scalars of MSM i+1 cross PCIe and its kernels are queued while MSM i runs, and the
-  // host epilogue of MSM i overlaps the device work of MSM i+1.
-  void RunBatch(const void* bases, const void* const* scalars, const size_t* sizes, size_t count,
-                Point* out) {
+  // `count` MSMs, MSM i over bases[i] (nullptr: the registered bases) and scalars[i], both
+  // sizes[i] long — the commit loop of tachyon/crypto/commitments/kzg/kzg.h:217-313 and the
+  // G1 queries of zk/r1cs/groth16/prove.h:100-131.  Two MSMs are kept in flight: the inputs
+  // of MSM i+1 cross PCIe and its kernels are queued while MSM i runs, and the host
+  // epilogue of MSM i overlaps the device work of MSM i+1.
+  void RunBatch(const void* const* bases, const void* const* scalars, const size_t* sizes,
+                size_t count, Point* out) {
     TB_CUDA(cudaSetDevice(device_));
     timing_ = MsmTiming{};
     size_t biggest = 0;
-    for (size_t i = 0; i < count; ++i) biggest = sizes[i] > biggest ? sizes[i] : biggest;
+    for (size_t i = 0; i < count; ++i) {
+      biggest = sizes[i] > biggest ? sizes[i] : biggest;
+      if (!bases[i] && sizes[i] > registered_n_)
+        throw CudaError{cudaErrorInvalidValue, "MSM larger than the registered bases", __FILE__,
+                        __LINE__};
+    }
+    auto bases_of = [&](size_t i) { return bases[i] ? bases[i] : registered_.ptr; };
     if (biggest > kMaxPiece) {  // rare: fall back to one blocking call each
       MsmTiming sum{};
       for (size_t i = 0; i < count; ++i) {
-        out[i] = Run(bases, scalars[i], sizes[i]);
+        out[i] = Run(bases_of(i), scalars[i], sizes[i]);
         sum.total_ms += timing_.total_ms;
         sum.kernel_launches += timing_.kernel_launches;
       }
@@ -216,7 +222,7 @@ class MsmEngine {
         } else {
           // the other slot's MSM is still in flight: growing a buffer would wait for it,
           // which is correct (cudaFree synchronises) but serialises; sizes are usually equal
-          pend[slot] = Enqueue(bases, scalars[i], sizes[i], slot);
+          pend[slot] = Enqueue(bases_of(i), scalars[i], sizes[i], slot);
           pend[slot].index = i;
           live[slot] = true;
         }

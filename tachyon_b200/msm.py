@@ -101,6 +101,17 @@ class MSMGpu:
         _lib.check(self._f("g1_msm_gpu_commit_batch_b200")(self.ptr, ptrs, szs, count, _ptr(out)), "commit_batch")
         return out
 
+    def msm_batch(self, bases_list, scalars_list, sizes=None):
+        """MSM i over bases_list[i] (None = registered bases) and scalars_list[i] -> (count, 4, fq_limbs)."""
+        count = len(scalars_list)
+        sizes = [len(s) for s in scalars_list] if sizes is None else list(sizes)
+        bptr = (ctypes.c_void_p * count)(*[ctypes.c_void_p(0) if b is None else _ptr(b) for b in bases_list])
+        sptr = (ctypes.c_void_p * count)(*[_ptr(s) for s in scalars_list])
+        szs = (ctypes.c_size_t * count)(*sizes)
+        out = np.zeros((count, 4, self.fq_limbs), dtype=np.uint64)
+        _lib.check(self._f("g1_msm_gpu_batch_b200")(self.ptr, bptr, sptr, szs, count, _ptr(out)), "msm_batch")
+        return out
+
     def last_timing(self):
         t = _lib.MsmTiming()
         _lib.check(self._f("g1_msm_gpu_last_timing_b200")(self.ptr, ctypes.byref(t)), "last_timing")

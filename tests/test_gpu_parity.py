@@ -271,6 +271,38 @@ def test_registered_bases_commit_batch(oracles, torch_cuda, name):
                 assert (got[i] == np.asarray(want[i]).reshape(-1)).all(), i
 
 
+# BASELINE.json configs[4] in miniature: the four G1 MSMs of a Groth16 proof (A, B1 over the
+# full assignment, L over its witness part, H over uniform coefficients; prove.h:100-131),
+# each with its own bases, through the general batch call.
+@pytest.mark.parametrize("name", CURVES)
+def test_groth16_msm_set_batch(oracles, torch_cuda, name):
+    import torch
+    o = oracles[name]
+    m, n_pub = 1 << 12, 10
+    full = o.generate_scalars(131, m, "witness")
+    hco = o.generate_scalars(132, m, "uniform")
+    sizes = [m, m, m - n_pub, m]
+    bases = [o.generate_points(140 + j, n) for j, n in enumerate(sizes)]
+    scal = [full, full, full[n_pub:].copy(), hco]
+    want = [o.msm_affine(b, s) for b, s in zip(bases, scal)]
+    with msm.MSMGpu(name) as ctx:
+        got = msm.batch_normalize(name, ctx.msm_batch(bases, scal))
+        for j in range(4):
+            assert (got[j] == np.asarray(want[j]).reshape(-1)).all(), j
+        # resident proving key, host scalars; one MSM falls back to the registered bases
+        db = [torch.from_numpy(b.view(np.int64)).cuda() for b in bases]
+        ctx.register_bases(bases[3])
+        got = msm.batch_normalize(name, ctx.msm_batch([db[0].data_ptr(), db[1].data_ptr(), db[2].data_ptr(), None],
+                                                      scal, sizes))
+        for j in range(4):
+            assert (got[j] == np.asarray(want[j]).reshape(-1)).all(), j
+        if msm.device_count() > 1:
+            ctx.set_option("devices", min(msm.device_count(), 4))
+            got = msm.batch_normalize(name, ctx.msm_batch(bases, scal))
+            for j in range(4):
+                assert (got[j] == np.asarray(want[j]).reshape(-1)).all(), j
+
+
 # the dump written under TACHYON_MSM_GPU_INPUT_DIR (msm_gpu.h:99-119: u64 count,
 # canonical little-endian limbs) and the replay CLI (msm_gpu_replay.cc:40-88: --idx --degree
 # --input_dir, prints the time and the affine point as hex without leading zeros).
