@@ -78,7 +78,9 @@ extern "C" {
       tachyon_##C##_g1_msm_gpu_ptr ptr, void* cuda_stream);                                  \
   /* name: "window_bits" (0 = automatic), "segment" (max entries per accumulation task),    \
      "devices" (point-range sharding over the first k devices; 1 = this context's device),  \
-     "ranges" (point ranges one MSM is pipelined over; 0 = automatic). */                    \
+     "ranges" (point ranges one MSM is pipelined over; 0 = automatic), "pair_rounds"        \
+     (experimental batched-affine rounds before the XYZZ accumulation; -1 = none, the       \
+     default; -2 = chosen from the bucket occupancy; 0..4 = forced). */                       \
   TACHYON_C_EXPORT int tachyon_##C##_g1_msm_gpu_set_option_b200(                             \
       tachyon_##C##_g1_msm_gpu_ptr ptr, const char* name, long value);                       \
   /* MSM returning the un-normalised XYZZ sum by value into *out; returns 0 or a negative   \
@@ -159,6 +161,7 @@ struct tachyon_b200_msm_timing {
   uint32_t ranges;      /* point ranges the call was pipelined over (1 for device inputs) */
   float enqueue_ms;     /* host wall clock spent queueing copies and kernels */
   float wait_ms;        /* host wall clock blocked waiting for the device */
+  uint32_t pair_rounds; /* batched-affine pair rounds run before the XYZZ accumulation */
 };
 
 TACHYON_B200_DECLARE_CURVE(bn254, 4)

@@ -18,6 +18,7 @@ class MsmTiming(ctypes.Structure):
         ("window_bits", ctypes.c_uint32), ("windows", ctypes.c_uint32), ("tasks", ctypes.c_uint32),
         ("entries", ctypes.c_uint32), ("kernel_launches", ctypes.c_uint32), ("devices", ctypes.c_uint32),
         ("ranges", ctypes.c_uint32), ("enqueue_ms", ctypes.c_float), ("wait_ms", ctypes.c_float),
+        ("pair_rounds", ctypes.c_uint32),
     ]
 
     def as_dict(self):

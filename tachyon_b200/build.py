@@ -16,7 +16,7 @@ LIB = os.path.join(LIB_DIR, "libtachyon_msm_b200.so")
 SOURCES = ["msm_api.cu"]
 REPLAY = os.path.join(LIB_DIR, "msm_gpu_replay")
 REPLAY_SRC = os.path.join(CSRC, "tools", "msm_gpu_replay.cc")
-HEADERS = ["fp.cuh", "xyzz.cuh", "msm_kernels.cuh", "msm_engine.cuh", "host_math.h",
+HEADERS = ["fp.cuh", "xyzz.cuh", "msm_kernels.cuh", "msm_engine.cuh", "host_math.h", "parallel_memcpy.h",
            "field_constants.h", os.path.join("..", "..", "include", "tachyon_msm_b200.h")]
 
 NVCC_FLAGS = [

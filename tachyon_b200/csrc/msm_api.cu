@@ -456,6 +456,8 @@ struct tachyon_bls12_381_g1_msm_gpu : public MsmGpuContext<Bls381Curve> {
         for (auto& e : ptr->engines) e->options().segment = (uint32_t)value;                   \
       } else if (k == "aggregate") {                                                           \
         for (auto& e : ptr->engines) e->options().aggregate = (int)value;                      \
+      } else if (k == "pair_rounds") {                                                         \
+        for (auto& e : ptr->engines) e->options().pair_rounds = (int)value;                    \
       } else if (k == "ranges") {                                                              \
         for (auto& e : ptr->engines) e->options().ranges = (uint32_t)value;                    \
       } else if (k == "devices") {                                                             \
@@ -546,6 +548,7 @@ struct tachyon_bls12_381_g1_msm_gpu : public MsmGpuContext<Bls381Curve> {
     out->ranges = t.ranges;                                                                    \
     out->enqueue_ms = t.enqueue_ms;                                                            \
     out->wait_ms = t.wait_ms;                                                                  \
+    out->pair_rounds = t.pair_rounds;                                                          \
     return 0;                                                                                  \
   }                                                                                            \
   int tachyon_##CN##_g1_generate_bases_b200(uint64_t seed, size_t first, size_t n,             \

@@ -12,11 +12,14 @@
 #include <cstdio>
 #include <cstdlib>
 #include <initializer_list>
+#include <memory>
 #include <string>
+#include <thread>
 #include <utility>
 #include <vector>
 
 #include "host_math.h"
+#include "parallel_memcpy.h"
 #include "msm_kernels.cuh"
 
 namespace tb200 {
@@ -67,6 +70,7 @@ struct MsmTiming {
   uint32_t window_bits = 0, windows = 0, tasks = 0, entries = 0, kernel_launches = 0, devices = 1;
   uint32_t ranges = 0;
   float enqueue_ms = 0, wait_ms = 0;  // host wall clock: queueing the work / blocked on the device
+  uint32_t pair_rounds = 0;
 };
 
 struct MsmOptions {
@@ -74,6 +78,8 @@ struct MsmOptions {
   uint32_t segment = 0;      // 0 = default
   int aggregate = -1;        // -1 = default
   uint32_t ranges = 0;       // point ranges per MSM; 0 = 1 for device inputs, pipelined for host
+  int pair_rounds = -1;      // batched-affine pair rounds before the XYZZ accumulation:
+                             // -1 = none (default), -2 = from bucket occupancy, >= 0 = forced
 };
 
 // Window choice.  Cost in units of one mixed addition:
@@ -121,6 +127,10 @@ class MsmEngine {
   static constexpr size_t kMaxPiece = size_t(1) << 26;
   static constexpr size_t kMaxRanges = 64;   // point ranges per MSM
   static constexpr size_t kStageSlots = 3;   // H2D staging ring
+  static constexpr size_t kBounceSlots = 4;  // pinned bounce buffers for pageable sources
+  static constexpr size_t kBounceBytes = size_t(16) << 20;
+  static constexpr uint32_t kMaxPairRounds = 4;
+  static constexpr uint32_t kMinPairBatch = 96;  // pairs per thread below which a round is skipped
 
   explicit MsmEngine(int device) : device_(device) {
     TB_CUDA(cudaSetDevice(device_));
@@ -140,6 +150,7 @@ class MsmEngine {
     for (const DeviceBuffer* b : AllBuffers()) const_cast<DeviceBuffer*>(b)->Free();
     if (totals_) cudaFree(totals_);
     if (host_out_) cudaFreeHost(host_out_);
+    if (bounce_) cudaFreeHost(bounce_);
     for (auto& e : events_) cudaEventDestroy(e);
     cudaStreamDestroy(copy_stream_);
     cudaStreamDestroy(own_stream_);
@@ -259,6 +270,45 @@ class MsmEngine {
     return attr.type == cudaMemoryTypeDevice || attr.type == cudaMemoryTypeManaged;
   }
 
+  static bool IsPageable(const void* p) {
+    cudaPointerAttributes attr;
+    cudaError_t e = cudaPointerGetAttributes(&attr, p);
+    if (e != cudaSuccess) {
+      cudaGetLastError();
+      return true;
+    }
+    return attr.type == cudaMemoryTypeUnregistered;
+  }
+
+  // Host -> device on the copy stream.  Pinned sources go straight to the DMA engine;
+  // pageable ones are copied by a few host threads into a ring of pinned bounce buffers
+  // first (a pageable cudaMemcpyAsync runs at ~11 GB/s on this platform, PCIe at ~55).
+  void CopyToDevice(void* dst, const void* src, size_t bytes, bool pageable) {
+    if (!pageable || bytes < (size_t(8) << 20)) {  // small copies: the driver's own staging wins
+      TB_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, copy_stream_));
+      return;
+    }
+    if (!bounce_) {
+      TB_CUDA(cudaMallocHost(&bounce_, kBounceSlots * kBounceBytes));
+      int hw = (int)std::thread::hardware_concurrency();
+      int want = hw >= 4 ? (hw * 3 / 4 > 16 ? 16 : hw * 3 / 4) : 1;
+      if (const char* e = getenv("TACHYON_B200_COPY_THREADS")) want = atoi(e);
+      copier_.reset(new ParallelMemcpy(want));
+    }
+    for (size_t off = 0; off < bytes; off += kBounceBytes) {
+      size_t len = bytes - off < kBounceBytes ? bytes - off : kBounceBytes;
+      size_t slot = bounce_seq_++ % kBounceSlots;
+      cudaEvent_t ev = Event(2 * kEventsPerSlot + kStageSlots + slot);
+      if (bounce_used_[slot]) TB_CUDA(cudaEventSynchronize(ev));  // its last DMA has drained
+      char* b = bounce_ + slot * kBounceBytes;
+      copier_->Copy(b, static_cast<const char*>(src) + off, len);
+      TB_CUDA(cudaMemcpyAsync(static_cast<char*>(dst) + off, b, len, cudaMemcpyHostToDevice,
+                              copy_stream_));
+      TB_CUDA(cudaEventRecord(ev, copy_stream_));
+      bounce_used_[slot] = true;
+    }
+  }
+
   template <class K, class... Args>
   void Launch(K kernel, uint32_t grid, uint32_t block, Args... args) {
     kernel<<<grid, block, 0, stream_>>>(args...);
@@ -293,7 +343,31 @@ class MsmEngine {
     uint64_t entries = (uint64_t)n * p.W;
     uint64_t nonempty = entries < p.TB ? entries : p.TB;
     p.max_tasks = (uint32_t)(nonempty + entries / p.seg);
+    // Pair rounds (batched-affine pre-reduction) are OFF unless asked for: measured on B200
+    // they lose to the XYZZ path at every size (BN254 2^24: accumulate 31.4 ms -> 37.7 ms at
+    // R = 3).  "pair_rounds" = -2 picks R from the bucket occupancy:
+    // leave ~4-8 points per bucket for the XYZZ stage and stop while a round still has enough
+    // pairs for every thread of a full grid to amortise its inversion.
+    uint32_t R = 0;
+    if (options_.pair_rounds >= 0) {
+      R = (uint32_t)options_.pair_rounds;
+    } else if (options_.pair_rounds == -2) {
+      uint64_t mean = n / p.B;
+      while (R < kMaxPairRounds && (mean >> (R + 3)) >= 1 &&
+             (entries >> (R + 1)) >= (uint64_t)sm_count_ * 512 * kMinPairBatch)
+        ++R;
+    }
+    if (R > kMaxPairRounds) R = kMaxPairRounds;
+    p.R = R;
     return p;
+  }
+
+  // Upper bound of the padded entry count of a range (what totals->entries can reach).
+  static uint64_t PaddedBound(const MsmPlan& p) {
+    uint64_t entries = (uint64_t)p.n * p.W;
+    uint64_t nonempty = entries < p.TB ? entries : p.TB;
+    uint64_t a = (uint64_t(1) << p.R) - 1;
+    return ((entries + a * nonempty) + a) & ~a;
   }
 
   uint32_t WindowBitsFor(size_t n) const {
@@ -307,7 +381,8 @@ class MsmEngine {
   // the footprint model in icicle_msm_utils.cc:10-68, for this pipeline's buffers).
   size_t RangeFootprint(size_t m, uint32_t c, bool stage_bases, bool stage_scalars) const {
     MsmPlan p = MakePlan(m, c);
-    size_t b = (size_t)m * p.W * 8;                       // digits + sorted
+    size_t b = (size_t)m * p.W * 4 + PaddedBound(p) * 4;  // digits + sorted
+    if (p.R) b += PaddedBound(p) * (kAffineBytes + kAffineBytes / 4);  // pair outputs + prefixes
     b += (size_t)p.max_tasks * (8 + 4 + 4 + kXyzzBytes);  // tasks, meta, order, task_out
     b += (size_t)(p.TB + 1) * 4 * 5;                      // count, offset, cursor, task_base, multi
     if (stage_bases) b += (size_t)m * kAffineBytes * kStageSlots;
@@ -339,6 +414,7 @@ class MsmEngine {
     TB_CUDA(cudaStreamSynchronize(stream_));
     for (auto& w : wants) w.first->Reserve(w.second);
     for (auto& u : stage_used_) u = false;
+    budget_ = 0;
   }
 
   // One MSM: bucket values live in `state_` for the whole call; the points are consumed
@@ -357,6 +433,8 @@ class MsmEngine {
     auto wall0 = std::chrono::steady_clock::now();
     const uint32_t c = WindowBitsFor(n);
     const bool bases_dev = IsDevicePointer(bases), scalars_dev = IsDevicePointer(scalars);
+    const bool bases_pageable = !bases_dev && IsPageable(bases);
+    const bool scalars_pageable = !scalars_dev && IsPageable(scalars);
     Pending pd;
     pd.any_host = !bases_dev || !scalars_dev;
     pd.slot = slot;
@@ -366,13 +444,14 @@ class MsmEngine {
     if (options_.ranges > 0) {
       K = options_.ranges;
     } else if (pd.any_host) {
-      K = n >> 20;  // ranges of >= 2^20 points, at most 8
+      K = n >> 18;  // ranges of >= 2^18 points on average, at most 8
       if (K > 8) K = 8;
       if (K < 1) K = 1;
     }
     if (K > kMaxRanges) K = kMaxRanges;
     if (K > n) K = n;
     MsmPlan whole = MakePlan(n, c);
+    bool memory_bound = false;
     {
       // Memory model (icicle_msm_utils.cc:10-68 analogue): more ranges when one range's
       // buffers would not fit.  cudaMemGetInfo costs milliseconds, so the driver is asked
@@ -382,15 +461,40 @@ class MsmEngine {
         return state_b + RangeFootprint((n + k - 1) / k, c, !bases_dev, !scalars_dev);
       };
       if (need(K) > OwnedBytes()) {
-        size_t free_b = 0, total_b = 0;
-        TB_CUDA(cudaMemGetInfo(&free_b, &total_b));
-        size_t budget = (size_t)(0.9 * (double)(free_b + OwnedBytes()));
-        while (K < kMaxRanges && K < n && need(K) > budget) K *= 2;
+        if (budget_ == 0) {  // refreshed whenever the workspace grows (ReserveAll)
+          size_t free_b = 0, total_b = 0;
+          TB_CUDA(cudaMemGetInfo(&free_b, &total_b));
+          budget_ = (size_t)(0.9 * (double)(free_b + OwnedBytes()));
+        }
+        while (K < kMaxRanges && K < n && need(K) > budget_) {
+          K *= 2;
+          memory_bound = true;
+        }
         if (K > kMaxRanges) K = kMaxRanges;
       }
     }
-    const size_t m = (n + K - 1) / K;  // points per range (the last may be shorter)
-    K = (n + m - 1) / m;
+    // Range boundaries.  Equal ranges when the split is forced or memory-driven.  For the
+    // automatic host-input pipeline the ranges GROW geometrically: nothing can start before
+    // range 0 has crossed PCIe, so it is small, and range k+1 may be as much larger than
+    // range k as the copy is faster than the bucket work (ratio q), so the copy engine still
+    // stays ahead of the kernels.
+    std::vector<size_t> bound(K + 1, n);
+    bound[0] = 0;
+    if (K > 1 && pd.any_host && options_.ranges == 0 && !memory_bound) {
+      const double q = C::kRangeGrowth;
+      double f = (q - 1.0) / (std::pow(q, (double)K) - 1.0), acc = 0;
+      for (size_t r = 1; r < K; ++r) {
+        acc += f;
+        f *= q;
+        size_t b = (size_t)(acc * (double)n) & ~size_t(255);
+        bound[r] = b > bound[r - 1] ? b : bound[r - 1];
+      }
+    } else {
+      const size_t eq = (n + K - 1) / K;
+      for (size_t r = 1; r < K; ++r) bound[r] = r * eq < n ? r * eq : n;
+    }
+    size_t m = 0;  // the largest range: what the per-range workspace is sized for
+    for (size_t r = 0; r < K; ++r) m = bound[r + 1] - bound[r] > m ? bound[r + 1] - bound[r] : m;
     MsmPlan big = MakePlan(m, c);
     pd.plan = big;
     pd.K = K;
@@ -418,7 +522,14 @@ class MsmEngine {
                 {&task_meta_, (size_t)big.max_tasks * 4},
                 {&order_, (size_t)big.max_tasks * 4},
                 {&task_out_, (size_t)big.max_tasks * kXyzzBytes},
-                {&sorted_, (size_t)m * big.W * 4},
+                {&sorted_, (size_t)PaddedBound(big) * 4},
+                {&pair_prefix_, big.R ? (size_t)((PaddedBound(big) >> 1) + PairThreads(big, 0)) *
+                                            (kAffineBytes / 2)
+                                      : 0},
+                {&pair_out_[0], big.R > 0 ? (size_t)(PaddedBound(big) >> 1) * kAffineBytes : 0},
+                {&pair_out_[1], big.R > 1 ? (size_t)(PaddedBound(big) >> 2) * kAffineBytes : 0},
+                {&pair_out_[2], big.R > 2 ? (size_t)(PaddedBound(big) >> 3) * kAffineBytes : 0},
+                {&pair_out_[3], big.R > 3 ? (size_t)(PaddedBound(big) >> 4) * kAffineBytes : 0},
                 {&digits_, (size_t)m * big.W * 4},
                 {&block_sums_, (size_t)scan_blocks * 8},
                 {&len_hist_, (size_t)(kMaxSegment + 1) * 4},
@@ -441,7 +552,13 @@ class MsmEngine {
 
     char* host_out = host_out_ + (size_t)slot * kHostOutBytes;
     for (size_t r = 0; r < K; ++r) {
-      const size_t lo = r * m, len = (n - lo < m) ? n - lo : m;
+      const size_t lo = bound[r], len = bound[r + 1] - bound[r];
+      if (len == 0) {  // degenerate split: keep the event bookkeeping of Finish() simple
+        TB_CUDA(cudaEventRecord(ev(r, 0), copy_stream_));
+        for (int w = 1; w <= 3; ++w) TB_CUDA(cudaEventRecord(ev(r, w), stream_));
+        memset(host_out + kHostWindowBytes + r * sizeof(MsmTotals), 0, sizeof(MsmTotals));
+        continue;
+      }
       MsmPlan plan = MakePlan(len, c);
       // ---- inputs of this range ---------------------------------------------------
       const uint32_t* d_bases;
@@ -457,8 +574,8 @@ class MsmEngine {
                                                       lo * kScalarBytes);
       } else {
         char* dst = scalars_stage_.as<char>() + stage * scalars_slot_bytes;
-        TB_CUDA(cudaMemcpyAsync(dst, static_cast<const char*>(scalars) + lo * kScalarBytes,
-                                len * kScalarBytes, cudaMemcpyHostToDevice, copy_stream_));
+        CopyToDevice(dst, static_cast<const char*>(scalars) + lo * kScalarBytes,
+                     len * kScalarBytes, scalars_pageable);
         d_scalars = reinterpret_cast<const uint32_t*>(dst);
       }
       if (bases_dev) {
@@ -466,8 +583,8 @@ class MsmEngine {
                                                     lo * kAffineBytes);
       } else {
         char* dst = bases_stage_.as<char>() + stage * bases_slot_bytes;
-        TB_CUDA(cudaMemcpyAsync(dst, static_cast<const char*>(bases) + lo * kAffineBytes,
-                                len * kAffineBytes, cudaMemcpyHostToDevice, copy_stream_));
+        CopyToDevice(dst, static_cast<const char*>(bases) + lo * kAffineBytes, len * kAffineBytes,
+                     bases_pageable);
         d_bases = reinterpret_cast<const uint32_t*>(dst);
       }
       if (pd.any_host) {
@@ -482,12 +599,12 @@ class MsmEngine {
       Launch(digits_hist_kernel<C>, sgrid, 256, d_scalars, plan, digits_.as<uint32_t>(),
              count_.as<uint32_t>());
       Launch(scan_block_sums_kernel, scan_blocks, kScanThreads, count_.as<uint32_t>(), plan.TB,
-             plan.seg, block_sums_.as<uint64_t>());
+             plan.seg, plan.R, block_sums_.as<uint64_t>());
       Launch(scan_top_kernel, 1, kScanThreads, block_sums_.as<uint64_t>(), scan_blocks, totals_);
       Launch(scan_apply_build_tasks_kernel, scan_blocks, kScanThreads, count_.as<uint32_t>(),
-             plan.TB, plan.seg, block_sums_.as<uint64_t>(), offset_.as<uint32_t>(),
+             plan.TB, plan.seg, plan.R, block_sums_.as<uint64_t>(), offset_.as<uint32_t>(),
              cursor_.as<uint32_t>(), task_base_.as<uint32_t>(), tasks_.as<uint2>(),
-             task_meta_.as<uint32_t>(), multi_.as<uint32_t>(), totals_);
+             task_meta_.as<uint32_t>(), multi_.as<uint32_t>(), sorted_.as<uint32_t>(), totals_);
       LaunchGrid(digits_scatter_kernel, dim3(sgrid, plan.W), 256, digits_.as<uint32_t>(), plan,
                  cursor_.as<uint32_t>(), sorted_.as<uint32_t>());
       // tasks by descending length
@@ -501,13 +618,28 @@ class MsmEngine {
              len_hist_.as<uint32_t>(), order_.as<uint32_t>());
       TB_CUDA(cudaEventRecord(ev(r, 2), stream_));
 
-      // ---- accumulate into the bucket values --------------------------------------
+      // ---- batched-affine pair rounds, then XYZZ accumulation into the bucket values ----
+      for (uint32_t r = 0; r < plan.R; ++r) {
+        uint32_t grid = PairThreads(plan, r) / kPairThreads;
+        if (r == 0)
+          Launch(pair_round_kernel<C, true>, grid, kPairThreads, d_bases, sorted_.as<uint32_t>(),
+                 totals_, r, pair_prefix_.as<uint32_t>(), pair_out_[0].as<uint32_t>());
+        else
+          Launch(pair_round_kernel<C, false>, grid, kPairThreads, (const uint32_t*)nullptr,
+                 pair_out_[r - 1].as<uint32_t>(), totals_, r, pair_prefix_.as<uint32_t>(),
+                 pair_out_[r].as<uint32_t>());
+      }
       uint32_t agrid = (plan.max_tasks + kAccThreads - 1) / kAccThreads;
-      Launch(accumulate_kernel<C>, agrid, kAccThreads, d_bases, sorted_.as<uint32_t>(),
-             tasks_.as<uint2>(), task_meta_.as<uint32_t>(), order_.as<uint32_t>(), totals_,
-             state_.as<uint32_t>(), task_out_.as<uint32_t>());
+      if (plan.R)
+        Launch(accumulate_kernel<C, true>, agrid, kAccThreads, pair_out_[plan.R - 1].as<uint32_t>(),
+               (const uint32_t*)nullptr, tasks_.as<uint2>(), task_meta_.as<uint32_t>(),
+               order_.as<uint32_t>(), totals_, state_.as<uint32_t>(), task_out_.as<uint32_t>());
+      else
+        Launch(accumulate_kernel<C, false>, agrid, kAccThreads, d_bases, sorted_.as<uint32_t>(),
+               tasks_.as<uint2>(), task_meta_.as<uint32_t>(), order_.as<uint32_t>(), totals_,
+               state_.as<uint32_t>(), task_out_.as<uint32_t>());
       Launch(fold_partials_kernel<C>, sm_count_ * 4, kFoldThreads, multi_.as<uint32_t>(), totals_,
-             offset_.as<uint32_t>(), task_base_.as<uint32_t>(), plan.seg,
+             offset_.as<uint32_t>(), task_base_.as<uint32_t>(), plan.seg, plan.R,
              task_out_.as<uint32_t>(), state_.as<uint32_t>());
       TB_CUDA(cudaMemcpyAsync(host_out + kHostWindowBytes + r * sizeof(MsmTotals), totals_,
                               sizeof(MsmTotals), cudaMemcpyDeviceToHost, stream_));
@@ -608,8 +740,19 @@ class MsmEngine {
     timing_.window_bits = plan.c;
     timing_.windows = plan.W;
     timing_.ranges += (uint32_t)pd.K;
+    timing_.pair_rounds = plan.R;
     timing_.kernel_launches += pd.launches;
     return result;
+  }
+
+  // Threads of pair round r: kPairBatch pairs each, but never fewer than a full grid.
+  uint32_t PairThreads(const MsmPlan& p, uint32_t r) const {
+    uint64_t pairs = (PaddedBound(p) >> r) >> 1;
+    uint64_t t = (pairs + kPairBatch - 1) / kPairBatch;
+    uint64_t full = (uint64_t)sm_count_ * AccMinBlocks<C>() * kPairThreads;
+    if (t < full) t = full;
+    if (t > pairs) t = pairs ? pairs : 1;
+    return (uint32_t)((t + kPairThreads - 1) / kPairThreads * kPairThreads);
   }
 
   size_t OwnedBytes() const {
@@ -620,7 +763,8 @@ class MsmEngine {
   std::vector<const DeviceBuffer*> AllBuffers() const {
     return {&registered_, &bases_stage_, &scalars_stage_, &state_, &count_, &offset_, &cursor_, &task_base_,
             &tasks_, &task_meta_, &multi_, &sorted_, &digits_, &task_out_, &block_sums_, &order_,
-            &len_hist_, &lvl_a_[0], &lvl_a_[1], &lvl_c_[0], &lvl_c_[1], &tree_[0], &tree_[1]};
+            &len_hist_, &lvl_a_[0], &lvl_a_[1], &lvl_c_[0], &lvl_c_[1], &tree_[0], &tree_[1],
+            &pair_prefix_, &pair_out_[0], &pair_out_[1], &pair_out_[2], &pair_out_[3]};
   }
 
   static uint32_t Log2(uint32_t x) {
@@ -651,6 +795,11 @@ class MsmEngine {
   cudaStream_t copy_stream_ = nullptr;
   std::vector<cudaEvent_t> events_;
   size_t stage_seq_ = 0;
+  char* bounce_ = nullptr;
+  size_t bounce_seq_ = 0;
+  bool bounce_used_[kBounceSlots] = {};
+  std::unique_ptr<ParallelMemcpy> copier_;
+  size_t budget_ = 0;  // device bytes this engine may use; 0 = ask the driver
   bool stage_used_[kStageSlots] = {};
   MsmOptions options_;
   MsmTiming timing_;
@@ -660,7 +809,7 @@ class MsmEngine {
   size_t registered_n_ = 0;
   DeviceBuffer registered_, bases_stage_, scalars_stage_, state_, count_, offset_, cursor_, task_base_, tasks_,
       task_meta_, multi_, sorted_, digits_, task_out_, block_sums_, order_, len_hist_, lvl_a_[2],
-      lvl_c_[2], tree_[2];
+      lvl_c_[2], tree_[2], pair_prefix_, pair_out_[4];
 };
 
 }  // namespace tb200

@@ -34,12 +34,16 @@ struct Bn254Curve {
   using Fr = Bn254FrParams;
   using Gen = Bn254G1Generator;
   static constexpr const char* kName = "bn254";
+  // how much larger the next pipelined host range may be: bucket work per point / PCIe time
+  // per point (2.4 ns vs 1.75 ns for 96 B at ~55 GB/s), with a margin
+  static constexpr double kRangeGrowth = 1.3;
 };
 struct Bls381Curve {
   using Fq = Bls381FqParams;
   using Fr = Bls381FrParams;
   using Gen = Bls381G1Generator;
   static constexpr const char* kName = "bls12_381";
+  static constexpr double kRangeGrowth = 2.0;  // 6.3 ns of bucket work vs 2.3 ns of PCIe per point
 };
 
 struct MsmPlan {
@@ -51,7 +55,11 @@ struct MsmPlan {
   uint32_t seg;      // max entries per task
   uint32_t max_tasks;
   uint32_t aggregate;  // warp-aggregate the bucket atomics (pays off for repeated digits)
+  uint32_t R;          // pair rounds of the batched-affine pre-reduction; bucket runs in
+                       // `sorted` start at multiples of 2^R and are padded with kNoEntry
 };
+
+constexpr uint32_t kNoEntry = 0xffffffffu;  // padding slot in `sorted`: the identity
 
 // totals written by the scan: [0] = entries (non-zero digits), [1] = tasks,
 // [2] = number of split buckets (filled by build_tasks)
@@ -183,9 +191,16 @@ constexpr int kScanThreads = 256;
 constexpr int kScanPerThread = 16;
 constexpr int kScanItems = kScanThreads * kScanPerThread;
 
-TB_DEV uint64_t scan_item(uint32_t cnt, uint32_t seg) {
-  uint32_t t = (cnt + seg - 1) / seg;
-  return ((uint64_t)t << 32) | cnt;
+// cnt entries occupy cntp = cnt rounded up to 2^R slots; after the R pair rounds the bucket
+// is a run of cntp >> R affine points, cut into tasks of <= seg.
+TB_DEV uint32_t padded_count(uint32_t cnt, uint32_t R) {
+  uint32_t a = (1u << R) - 1u;
+  return (cnt + a) & ~a;
+}
+TB_DEV uint64_t scan_item(uint32_t cnt, uint32_t seg, uint32_t R) {
+  uint32_t cntp = padded_count(cnt, R);
+  uint32_t t = ((cntp >> R) + seg - 1) / seg;
+  return ((uint64_t)t << 32) | cntp;
 }
 
 TB_DEV uint64_t block_exclusive_scan(uint64_t v, uint64_t* total, uint64_t* smem) {
@@ -216,14 +231,15 @@ TB_DEV uint64_t block_exclusive_scan(uint64_t v, uint64_t* total, uint64_t* smem
 }
 
 __global__ void __launch_bounds__(kScanThreads) scan_block_sums_kernel(
-    const uint32_t* __restrict__ count, uint32_t n, uint32_t seg, uint64_t* __restrict__ block_sums) {
+    const uint32_t* __restrict__ count, uint32_t n, uint32_t seg, uint32_t R,
+    uint64_t* __restrict__ block_sums) {
   __shared__ uint64_t smem[kScanThreads / 32];
   uint32_t base = blockIdx.x * kScanItems + threadIdx.x * kScanPerThread;
   uint64_t sum = 0;
 #pragma unroll
   for (int k = 0; k < kScanPerThread; ++k) {
     uint32_t idx = base + k;
-    if (idx < n) sum += scan_item(count[idx], seg);
+    if (idx < n) sum += scan_item(count[idx], seg, R);
   }
   uint64_t total;
   block_exclusive_scan(sum, &total, smem);
@@ -268,11 +284,11 @@ constexpr uint32_t kTaskKeyMask = 0x00ffffffu;
 // and the tasks of every bucket.  Buckets split into more than one task are
 // appended to multi_keys.
 __global__ void __launch_bounds__(kScanThreads) scan_apply_build_tasks_kernel(
-    const uint32_t* __restrict__ count, uint32_t n, uint32_t seg,
+    const uint32_t* __restrict__ count, uint32_t n, uint32_t seg, uint32_t R,
     const uint64_t* __restrict__ block_prefix, uint32_t* __restrict__ offset,
     uint32_t* __restrict__ cursor, uint32_t* __restrict__ task_base, uint2* __restrict__ tasks,
     uint32_t* __restrict__ task_meta, uint32_t* __restrict__ multi_keys,
-    MsmTotals* __restrict__ totals) {
+    uint32_t* __restrict__ sorted, MsmTotals* __restrict__ totals) {
   __shared__ uint64_t smem[kScanThreads / 32];
   uint32_t base = blockIdx.x * kScanItems + threadIdx.x * kScanPerThread;
   uint32_t cnt[kScanPerThread];
@@ -281,7 +297,7 @@ __global__ void __launch_bounds__(kScanThreads) scan_apply_build_tasks_kernel(
   for (int k = 0; k < kScanPerThread; ++k) {
     uint32_t idx = base + k;
     cnt[k] = (idx < n) ? count[idx] : 0;
-    sum += scan_item(cnt[k], seg);
+    sum += scan_item(cnt[k], seg, R);
   }
   uint64_t total;
   uint64_t prefix = block_exclusive_scan(sum, &total, smem) + block_prefix[blockIdx.x];
@@ -294,16 +310,19 @@ __global__ void __launch_bounds__(kScanThreads) scan_apply_build_tasks_kernel(
       offset[idx] = off;
       cursor[idx] = off;
       task_base[idx] = tb;
-      uint32_t t = (cnt[k] + seg - 1) / seg;
+      uint32_t cntp = padded_count(cnt[k], R);
+      uint32_t run = cntp >> R;  // points left after the pair rounds
+      uint32_t t = (run + seg - 1) / seg;
       for (uint32_t s = 0; s < t; ++s) {
-        uint32_t len = min(seg, cnt[k] - s * seg);
-        tasks[tb + s] = make_uint2(off + s * seg, len);
+        uint32_t len = min(seg, run - s * seg);
+        tasks[tb + s] = make_uint2((off >> R) + s * seg, len);
         task_meta[tb + s] = idx | (s == 0 ? kTaskFirst : 0u) | (t == 1 ? kTaskSingle : 0u);
       }
+      for (uint32_t q = cnt[k]; q < cntp; ++q) sorted[off + q] = kNoEntry;
       if (t > 1) multi_keys[atomicAdd(&totals->multi, 1u)] = idx;
-      if (idx == n - 1) offset[n] = off + cnt[k];
+      if (idx == n - 1) offset[n] = off + cntp;
     }
-    prefix += scan_item(cnt[k], seg);
+    prefix += scan_item(cnt[k], seg, R);
   }
 }
 
@@ -411,7 +430,9 @@ constexpr int AccMinBlocks() {
   return Fp<typename C::Fq>::N <= 8 ? 4 : 3;
 }
 
-template <class C>
+// kReduced: the task's points are a run of affine points left by the pair rounds (read in
+// order, no index or sign); otherwise they are gathered from `bases` through `sorted`.
+template <class C, bool kReduced>
 __global__ void __launch_bounds__(kAccThreads, AccMinBlocks<C>()) accumulate_kernel(
     const uint32_t* __restrict__ bases, const uint32_t* __restrict__ sorted,
     const uint2* __restrict__ tasks, const uint32_t* __restrict__ task_meta,
@@ -427,9 +448,14 @@ __global__ void __launch_bounds__(kAccThreads, AccMinBlocks<C>()) accumulate_ker
   uint32_t meta = task_meta[g];
   uint32_t* bucket = state + (size_t)(meta & kTaskKeyMask) * kXyzzWords;
   const uint32_t* ent = sorted + task.x;
-  uint32_t e = ent[0];
+  const uint32_t* run = bases + (size_t)task.x * kAffineWords;
+  uint32_t e = kReduced ? 0u : ent[0];
   Affine<Fq> nxt;
-  affine_load<Fq>(nxt, bases + (size_t)(e & 0x7fffffffu) * kAffineWords);
+  if (kReduced) {
+    affine_load<Fq>(nxt, run);
+  } else {
+    affine_load<Fq>(nxt, bases + (size_t)(e & 0x7fffffffu) * kAffineWords);
+  }
   XYZZ<Fq> acc;
   if (meta & kTaskFirst) {
     xyzz_load<Fq>(acc, bucket);  // value left by the earlier point ranges (zz == 0: none)
@@ -440,12 +466,165 @@ __global__ void __launch_bounds__(kAccThreads, AccMinBlocks<C>()) accumulate_ker
     Affine<Fq> cur = nxt;
     bool neg = e >> 31;
     if (j + 1 < task.y) {
-      e = ent[j + 1];
-      affine_load<Fq>(nxt, bases + (size_t)(e & 0x7fffffffu) * kAffineWords);
+      if (kReduced) {
+        affine_load<Fq>(nxt, run + (size_t)(j + 1) * kAffineWords);
+      } else {
+        e = ent[j + 1];
+        affine_load<Fq>(nxt, bases + (size_t)(e & 0x7fffffffu) * kAffineWords);
+      }
     }
     xyzz_madd<Fq>(acc, cur, neg);
   }
   xyzz_store<Fq>((meta & kTaskSingle) ? bucket : task_out + (size_t)g * kXyzzWords, acc);
+}
+
+// ---------------------------------------------------------------------------
+// Batched-affine pre-reduction ("pair rounds").  A mixed XYZZ addition costs 10 field
+// multiplications; an affine + affine addition costs 3 (lambda, lambda^2, y3) plus one
+// inversion, and Montgomery's trick shares ONE inversion among a whole batch at 3 more
+// multiplications per addition — 6 + (inversion / batch) instead of 10.  Round r replaces
+// slots (2p, 2p+1) of its input array by their sum in slot p of its output array.  Bucket
+// runs start at multiples of 2^R and are padded with the identity, so after R rounds every
+// bucket is a run of (padded count >> R) affine points at (offset >> R), which
+// accumulate_kernel<kReduced> then finishes in XYZZ.  No bucket structure is needed inside
+// a round: pairs never straddle buckets by construction.
+//
+// One thread owns the batch {t, t + T, t + 2T, ...} (T = threads of the grid; neighbouring
+// lanes touch neighbouring slots, so all streaming accesses are coalesced):
+//   forward   prefix_j = d_0 ... d_(j-1) stored to scratch, d_j = the pair's denominator
+//   invert    1 / (d_0 ... d_(B-1)) by Fermat, once per thread
+//   backward  1/d_j = inv * prefix_j, inv *= d_j, then the addition itself
+// Denominators: x2 - x1 (addition), 2 y1 (doubling, x1 == x2 and y1 == y2 != 0), 1 when
+// there is nothing to divide (an operand is the identity, or P + (-P)).  Same group results
+// as the XYZZ path's case analysis (point_xyzz_impl.h:114-176); the affine identity is (0, 0)
+// (affine_point.h:125).
+// ---------------------------------------------------------------------------
+constexpr int kPairThreads = 128;
+constexpr uint32_t kPairBatch = 512;  // pairs per thread the grid is sized for
+
+enum : uint32_t { kPairAdd = 0, kPairDouble = 1, kPairCopy1 = 2, kPairCopy2 = 3, kPairZero = 4 };
+
+// Loads pair p.  kFirst: slots hold point index | sign << 31 into `bases` (kNoEntry: identity).
+template <class C, bool kFirst>
+TB_DEV void pair_load(Affine<typename C::Fq>& p1, Affine<typename C::Fq>& p2, uint32_t p,
+                      const uint32_t* __restrict__ bases, const uint32_t* __restrict__ in) {
+  using Fq = typename C::Fq;
+  constexpr int kAffineWords = 2 * Fp<Fq>::N;
+  if (kFirst) {
+    uint2 e = reinterpret_cast<const uint2*>(in)[p];
+    if (e.x == kNoEntry) {
+      fp_set_zero<Fq>(p1.x);
+      fp_set_zero<Fq>(p1.y);
+    } else {
+      affine_load<Fq>(p1, bases + (size_t)(e.x & 0x7fffffffu) * kAffineWords);
+      fp_cneg<Fq>(p1.y, p1.y, e.x >> 31);
+    }
+    if (e.y == kNoEntry) {
+      fp_set_zero<Fq>(p2.x);
+      fp_set_zero<Fq>(p2.y);
+    } else {
+      affine_load<Fq>(p2, bases + (size_t)(e.y & 0x7fffffffu) * kAffineWords);
+      fp_cneg<Fq>(p2.y, p2.y, e.y >> 31);
+    }
+  } else {
+    affine_load<Fq>(p1, in + (size_t)(2 * (size_t)p) * kAffineWords);
+    affine_load<Fq>(p2, in + (size_t)(2 * (size_t)p + 1) * kAffineWords);
+  }
+}
+
+// Case of the pair and its denominator d (never zero).
+template <class F>
+TB_DEV uint32_t pair_denominator(Fp<F>& d, const Affine<F>& p1, const Affine<F>& p2) {
+  bool z1 = affine_is_zero<F>(p1), z2 = affine_is_zero<F>(p2);
+  fp_sub<F>(d, p2.x, p1.x);
+  uint32_t kind = kPairAdd;
+  if (z1 || z2) {
+    kind = z1 ? (z2 ? kPairZero : kPairCopy2) : kPairCopy1;
+  } else if (fp_is_zero<F>(d)) {
+    if (fp_eq<F>(p1.y, p2.y) && !fp_is_zero<F>(p1.y)) {
+      kind = kPairDouble;
+      fp_dbl<F>(d, p1.y);
+    } else {
+      kind = kPairZero;
+    }
+  }
+  if (kind >= kPairCopy1) fp_set_one<F>(d);
+  return kind;
+}
+
+template <class C, bool kFirst>
+__global__ void __launch_bounds__(kPairThreads, AccMinBlocks<C>()) pair_round_kernel(
+    const uint32_t* __restrict__ bases, const uint32_t* __restrict__ in,
+    const MsmTotals* __restrict__ totals, uint32_t round, uint32_t* __restrict__ prefix,
+    uint32_t* __restrict__ out) {
+  using Fq = typename C::Fq;
+  constexpr int N = Fp<Fq>::N;
+  constexpr int kAffineWords = 2 * N;
+  const uint32_t pairs = (totals->entries >> round) >> 1;  // entries is a multiple of 2^R
+  const uint32_t T = gridDim.x * blockDim.x;
+  const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= pairs) return;
+  const uint32_t B = (pairs - t + T - 1) / T;  // this thread's batch
+
+  // ---- forward: prefix products of the denominators ---------------------------------
+  Fp<Fq> acc;
+  fp_set_one<Fq>(acc);
+  {
+    Affine<Fq> n1, n2;
+    pair_load<C, kFirst>(n1, n2, t, bases, in);
+    for (uint32_t j = 0; j < B; ++j) {
+      Affine<Fq> p1 = n1, p2 = n2;
+      if (j + 1 < B) pair_load<C, kFirst>(n1, n2, t + (j + 1) * T, bases, in);
+      Fp<Fq> d;
+      pair_denominator<Fq>(d, p1, p2);
+      fp_store<Fq>(prefix + ((size_t)j * T + t) * N, acc);
+      fp_mul<Fq>(acc, acc, d);
+    }
+  }
+  Fp<Fq> inv;
+  fp_inv<Fq>(inv, acc);
+
+  // ---- backward: the additions --------------------------------------------------------
+  Affine<Fq> n1, n2;
+  Fp<Fq> npre;
+  pair_load<C, kFirst>(n1, n2, t + (B - 1) * T, bases, in);
+  fp_load_rw<Fq>(npre, prefix + ((size_t)(B - 1) * T + t) * N);
+  for (uint32_t j = B; j-- > 0;) {
+    Affine<Fq> p1 = n1, p2 = n2;
+    Fp<Fq> pre = npre;
+    if (j > 0) {
+      pair_load<C, kFirst>(n1, n2, t + (j - 1) * T, bases, in);
+      fp_load_rw<Fq>(npre, prefix + ((size_t)(j - 1) * T + t) * N);
+    }
+    Fp<Fq> d, dinv, num, lam, x3, y3, tt;
+    uint32_t kind = pair_denominator<Fq>(d, p1, p2);
+    fp_mul<Fq>(dinv, inv, pre);  // 1 / d_j
+    fp_mul<Fq>(inv, inv, d);     // inverse of the remaining prefix
+    fp_sub<Fq>(num, p2.y, p1.y);
+    if (kind == kPairDouble) {   // lambda = 3 x1^2 / (2 y1)
+      fp_sqr<Fq>(tt, p1.x);
+      fp_dbl<Fq>(num, tt);
+      fp_add<Fq>(num, num, tt);
+    }
+    fp_mul<Fq>(lam, num, dinv);
+    fp_sqr<Fq>(x3, lam);         // x3 = lambda^2 - x1 - x2
+    fp_sub<Fq>(x3, x3, p1.x);
+    fp_sub<Fq>(x3, x3, p2.x);
+    fp_sub<Fq>(tt, p1.x, x3);    // y3 = lambda (x1 - x3) - y1
+    fp_mul<Fq>(y3, lam, tt);
+    fp_sub<Fq>(y3, y3, p1.y);
+    Affine<Fq> r;
+#pragma unroll
+    for (int i = 0; i < N; ++i) {
+      uint32_t cx = kind == kPairCopy1 ? p1.x.l[i] : (kind == kPairCopy2 ? p2.x.l[i] : 0u);
+      uint32_t cy = kind == kPairCopy1 ? p1.y.l[i] : (kind == kPairCopy2 ? p2.y.l[i] : 0u);
+      r.x.l[i] = kind <= kPairDouble ? x3.l[i] : cx;
+      r.y.l[i] = kind <= kPairDouble ? y3.l[i] : cy;
+    }
+    uint32_t* dst = out + (size_t)(t + j * T) * kAffineWords;
+    fp_store<Fq>(dst, r.x);
+    fp_store<Fq>(dst + N, r.y);
+  }
 }
 
 // Buckets split over several tasks: one CTA per bucket sums the partials (the first of
@@ -457,13 +636,13 @@ template <class C>
 __global__ void __launch_bounds__(kFoldThreads) fold_partials_kernel(
     const uint32_t* __restrict__ multi_keys, const MsmTotals* __restrict__ totals,
     const uint32_t* __restrict__ offset, const uint32_t* __restrict__ task_base, uint32_t seg,
-    const uint32_t* __restrict__ task_out, uint32_t* __restrict__ state) {
+    uint32_t R, const uint32_t* __restrict__ task_out, uint32_t* __restrict__ state) {
   using Fq = typename C::Fq;
   constexpr int kXyzzWords = 4 * Fp<Fq>::N;
   __shared__ uint32_t sh[kFoldThreads / 2 * kXyzzWords];
   for (uint32_t m = blockIdx.x; m < totals->multi; m += gridDim.x) {
     uint32_t key = multi_keys[m];
-    uint32_t cnt = offset[key + 1] - offset[key];
+    uint32_t cnt = (offset[key + 1] - offset[key]) >> R;  // padded run after the pair rounds
     uint32_t t = (cnt + seg - 1) / seg;
     const uint32_t* slots = task_out + (size_t)task_base[key] * kXyzzWords;
     XYZZ<Fq> acc, tmp;

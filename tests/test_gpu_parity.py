@@ -234,6 +234,37 @@ def test_msm_point_ranges(oracles, torch_cuda, name):
         assert (o.jacobian_to_affine(ctx.affine_msm(bases, skew)) == want_skew).all()
 
 
+# The experimental batched-affine pre-reduction (pair rounds: affine + affine additions sharing
+# one inversion per thread batch) must give the same group element for
+# every round count, including the doubling / cancelling / identity cases inside a pair.
+@pytest.mark.parametrize("name", CURVES)
+def test_msm_pair_rounds(oracles, torch_cuda, name):
+    o, c = oracles[name], pymodel.CURVES[name]
+    n = 5000
+    bases, scalars = o.generate_points(111, n), o.generate_scalars(112, n)
+    bases[3] = 0
+    bases[9] = bases[8]
+    scalars[9] = scalars[8]                                   # P + P inside one bucket
+    neg_y = o.fq_op("neg", bases[10].reshape(2, -1)[1:2])
+    bases[11] = np.concatenate([bases[10][:c.fq_limbs], neg_y[0]])
+    scalars[11] = scalars[10]                                 # P + (-P)
+    bases[100:164] = bases[100]
+    scalars[100:164] = scalars[100]                           # 64 copies: doubling chain through every round
+    skew = o.generate_scalars(113, n, "witness")
+    want, want_skew = o.msm_affine(bases, scalars), o.msm_affine(bases, skew)
+    with msm.MSMGpu(name) as ctx:
+        ctx.set_option("window_bits", 7)                      # ~78 entries per bucket
+        for rounds in (1, 2, 3, 4, -2):
+            ctx.set_option("pair_rounds", rounds)
+            assert (o.jacobian_to_affine(ctx.affine_msm(bases, scalars)) == want).all(), rounds
+            if rounds > 0:
+                assert ctx.last_timing()["pair_rounds"] == rounds
+            assert (o.jacobian_to_affine(ctx.affine_msm(bases, skew)) == want_skew).all(), rounds
+        ctx.set_option("ranges", 3)
+        ctx.set_option("pair_rounds", 2)
+        assert (o.jacobian_to_affine(ctx.affine_msm(bases, scalars)) == want).all()
+
+
 # bases registered once (the SRS of kzg.h:91-113), then a batch of
 # commitments with fresh scalars (kzg.h:217-313), results batch-normalised (point_xyzz.h:109-163).
 @pytest.mark.parametrize("name", CURVES)

@@ -23,11 +23,14 @@ hs = torch.empty((n, 4), dtype=torch.int64).pin_memory()
 hb.copy_(bases)
 hs.copy_(scalars)
 torch.cuda.synchronize()
+pb = hb.numpy().copy()   # pageable copies
+ps = hs.numpy().copy()
 ctx = msm.MSMGpu(curve)
 ref = ctx.msm_xyzz(bases.data_ptr(), scalars.data_ptr(), n)
 for r in ranges:
     ctx.set_option("ranges", r)
-    for kind, b, s in (("host", hb.data_ptr(), hs.data_ptr()), ("dev", bases.data_ptr(), scalars.data_ptr())):
+    for kind, b, s in (("pinned", hb.data_ptr(), hs.data_ptr()), ("pageable", pb.ctypes.data, ps.ctypes.data),
+                       ("dev", bases.data_ptr(), scalars.data_ptr())):
         best = 1e9
         for it in range(4):
             t0 = time.perf_counter()
