@@ -31,19 +31,22 @@ sys.path.insert(0, ROOT)
 import numpy as np  # noqa: E402
 
 SEED = 0x7461636879
-SCALAR_BITS = {"bn254": 254, "bls12_381": 255}
-FQ_LIMBS = {"bn254": 4, "bls12_381": 6}
+SCALAR_BITS = {"bn254": 254, "bls12_381": 255, "bn254_g2": 254, "bls12_381_g2": 255}
+FQ_LIMBS = {"bn254": 4, "bls12_381": 6, "bn254_g2": 8, "bls12_381_g2": 12}   # u64 limbs of one coordinate
+BASE_LIMBS = {"bn254": 4, "bls12_381": 6, "bn254_g2": 4, "bls12_381_g2": 6}  # u64 limbs of Fq
 
 
 def algorithmic_products(curve, n):
     """W_alg of SURVEY.md §8(d): 32x32->64 products of the reference's own window
     rule c = max(ceil(log2 n) - 4, 1) (icicle_msm_utils.cc:26-28)."""
     lam = SCALAR_BITS[curve]
-    limbs = 2 * FQ_LIMBS[curve]
+    limbs = 2 * BASE_LIMBS[curve]
     c = max((n - 1).bit_length() - 4, 1)
     W = -(-lam // c)
     modmuls = n * W * 10 + W * (1 << c) * 14 + W * c * 9 + W * 14
     per_mul = 2 * limbs * limbs + limbs
+    if curve.endswith("_g2"):
+        per_mul *= 3        # one Fq2 multiplication = 3 Fq multiplications (Karatsuba count)
     return dict(c=c, W=W, modmuls=modmuls, products=modmuls * per_mul,
                 accumulate_products=n * W * 10 * per_mul)
 
@@ -286,7 +289,7 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--curve", default="bn254", choices=["bn254", "bls12_381"])
+    ap.add_argument("--curve", default="bn254", choices=["bn254", "bls12_381", "bn254_g2", "bls12_381_g2"])
     ap.add_argument("--log-n", type=int, default=24)
     ap.add_argument("--dist", default="uniform", choices=["uniform", "non_uniform", "witness"])
     ap.add_argument("--cpu-sample-log", type=int, default=20)
@@ -524,8 +527,9 @@ def main():
             "e2e": {"value": e2e_value, "unit": "points/s", "ms_per_step": max(e2e_ms, e2e_wall),
                     "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ranges": e2e_timing["ranges"], "h2d_ms": e2e_timing["h2d_ms"],
-                    "api": "tachyon_%s_g1_affine_msm_gpu, pinned host buffers; H2D of point range k+1 "
-                           "overlaps sort/accumulate of range k" % curve},
+                    "api": "tachyon_%s_%s_affine_msm_gpu, pinned host buffers; H2D of point range k+1 "
+                           "overlaps sort/accumulate of range k" % (curve.replace("_g2", ""),
+                                                                    "g2" if curve.endswith("_g2") else "g1")},
             "gpu_launches": int(launches),
             "roofline": {"bound": "int32-imad", "kernel": "accumulate_kernel",
                          "achieved": alg["accumulate_products"] / world / (acc_ms * 1e-3) / 1e9 if acc_ms else None,

@@ -39,55 +39,68 @@ extern "C" {
 /* Part 1 — the reference's MSM-GPU C API                                     */
 /* ------------------------------------------------------------------------- */
 
-#define TACHYON_B200_DECLARE_CURVE(C, FQ_LIMBS)                                              \
-  struct tachyon_##C##_fr { uint64_t limbs[4]; };              /* prime_field.h.tpl:36-38 */ \
+/* Field element structs of one curve (prime_field.h.tpl:36-38; Fq2 = Fq[u]/(u^2 + 1) as in   \
+   ext_field.h.tpl, c0 first) and the element-wise parity hooks on HOST arrays (copied to the  \
+   current device and back).  op: 0 add 1 sub 2 mul 3 square 4 neg 5 double 6 inverse          \
+   7 from_mont 8 to_mont (fq2: 0..6). */
+#define TACHYON_B200_DECLARE_FIELDS(C, FQ_LIMBS)                                             \
+  struct tachyon_##C##_fr { uint64_t limbs[4]; };                                            \
   struct tachyon_##C##_fq { uint64_t limbs[FQ_LIMBS]; };                                     \
-  struct tachyon_##C##_g1_affine { struct tachyon_##C##_fq x, y; };     /* point.h.tpl:22-25 */ \
-  struct tachyon_##C##_g1_point2 { struct tachyon_##C##_fq x, y; };     /* point.h.tpl:78-81 */ \
-  struct tachyon_##C##_g1_jacobian { struct tachyon_##C##_fq x, y, z; };/* point.h.tpl:50-54 */ \
-  struct tachyon_##C##_g1_xyzz { struct tachyon_##C##_fq x, y, zz, zzz; };/* point.h.tpl:64-69 */ \
-  typedef struct tachyon_##C##_g1_msm_gpu* tachyon_##C##_g1_msm_gpu_ptr; /* msm_gpu.h.tpl:17 */ \
+  struct tachyon_##C##_fq2 { struct tachyon_##C##_fq c0, c1; };                              \
+  TACHYON_C_EXPORT int tachyon_##C##_fq_op_b200(int op, const uint64_t* a, const uint64_t* b, \
+                                                uint64_t* out, size_t n);                    \
+  TACHYON_C_EXPORT int tachyon_##C##_fr_op_b200(int op, const uint64_t* a, const uint64_t* b, \
+                                                uint64_t* out, size_t n);                    \
+  TACHYON_C_EXPORT int tachyon_##C##_fq2_op_b200(int op, const uint64_t* a, const uint64_t* b, \
+                                                 uint64_t* out, size_t n);
+
+#define TACHYON_B200_DECLARE_GROUP(C, G, FE)                                              \
+  struct tachyon_##C##_##G##_affine { struct FE x, y; };     /* point.h.tpl:22-25 */ \
+  struct tachyon_##C##_##G##_point2 { struct FE x, y; };     /* point.h.tpl:78-81 */ \
+  struct tachyon_##C##_##G##_jacobian { struct FE x, y, z; };/* point.h.tpl:50-54 */ \
+  struct tachyon_##C##_##G##_xyzz { struct FE x, y, zz, zzz; };/* point.h.tpl:64-69 */ \
+  typedef struct tachyon_##C##_##G##_msm_gpu* tachyon_##C##_##G##_msm_gpu_ptr; /* msm_gpu.h.tpl:17 */ \
                                                                                              \
   /* point.h.tpl:117 — idempotent, cheap; callers invoke it before anything else */         \
-  TACHYON_C_EXPORT void tachyon_##C##_g1_init(void);                                         \
+  TACHYON_C_EXPORT void tachyon_##C##_##G##_init(void);                                         \
   /* msm_gpu.h.tpl:26 — degree = log2(max size), advisory (reference never reads it,        \
      c/math/elliptic_curves/msm/msm_gpu.h:35).  Prints "CreateMSMGpuApi()" and honours      \
      TACHYON_MSM_GPU_INPUT_DIR / TACHYON_LOG_MSM like msm_gpu.h:36-52.  Aborts on CUDA       \
      failure (msm_gpu.h:59-62). */                                                           \
-  TACHYON_C_EXPORT tachyon_##C##_g1_msm_gpu_ptr tachyon_##C##_g1_create_msm_gpu(uint8_t degree); \
+  TACHYON_C_EXPORT tachyon_##C##_##G##_msm_gpu_ptr tachyon_##C##_##G##_create_msm_gpu(uint8_t degree); \
   /* msm_gpu.h.tpl:32 */                                                                     \
-  TACHYON_C_EXPORT void tachyon_##C##_g1_destroy_msm_gpu(tachyon_##C##_g1_msm_gpu_ptr ptr);  \
+  TACHYON_C_EXPORT void tachyon_##C##_##G##_destroy_msm_gpu(tachyon_##C##_##G##_msm_gpu_ptr ptr);  \
   /* msm_gpu.h.tpl:42-44.  bases/scalars: `size` elements each, host memory (pageable or    \
      pinned) or device memory (icicle_msm_bn254_g1.cc:38-45).  Returns a heap object made   \
      with C++ `new`, owned by the caller (msm_gpu.h:81).  Any failure aborts (msm_gpu.h:79). */ \
-  TACHYON_C_EXPORT struct tachyon_##C##_g1_jacobian* tachyon_##C##_g1_point2_msm_gpu(        \
-      tachyon_##C##_g1_msm_gpu_ptr ptr, const struct tachyon_##C##_g1_point2* bases,         \
+  TACHYON_C_EXPORT struct tachyon_##C##_##G##_jacobian* tachyon_##C##_##G##_point2_msm_gpu(        \
+      tachyon_##C##_##G##_msm_gpu_ptr ptr, const struct tachyon_##C##_##G##_point2* bases,         \
       const struct tachyon_##C##_fr* scalars, size_t size);                                  \
   /* msm_gpu.h.tpl:54-56 — same code path as point2 (msm_input_provider.h:23-29) */          \
-  TACHYON_C_EXPORT struct tachyon_##C##_g1_jacobian* tachyon_##C##_g1_affine_msm_gpu(        \
-      tachyon_##C##_g1_msm_gpu_ptr ptr, const struct tachyon_##C##_g1_affine* bases,         \
+  TACHYON_C_EXPORT struct tachyon_##C##_##G##_jacobian* tachyon_##C##_##G##_affine_msm_gpu(        \
+      tachyon_##C##_##G##_msm_gpu_ptr ptr, const struct tachyon_##C##_##G##_affine* bases,         \
       const struct tachyon_##C##_fr* scalars, size_t size);                                  \
                                                                                              \
   /* ---- Part 2: extensions ---------------------------------------------------------- */  \
   /* Context on a given CUDA device, silent (no banner).  NULL on failure. */               \
-  TACHYON_C_EXPORT tachyon_##C##_g1_msm_gpu_ptr tachyon_##C##_g1_create_msm_gpu_b200(        \
+  TACHYON_C_EXPORT tachyon_##C##_##G##_msm_gpu_ptr tachyon_##C##_##G##_create_msm_gpu_b200(        \
       uint8_t degree, int device);                                                           \
   /* Run all work of this context on an existing CUDA stream (a cudaStream_t) of the        \
      context's device instead of its own stream.  0 on success. */                           \
-  TACHYON_C_EXPORT int tachyon_##C##_g1_msm_gpu_set_stream_b200(                             \
-      tachyon_##C##_g1_msm_gpu_ptr ptr, void* cuda_stream);                                  \
+  TACHYON_C_EXPORT int tachyon_##C##_##G##_msm_gpu_set_stream_b200(                             \
+      tachyon_##C##_##G##_msm_gpu_ptr ptr, void* cuda_stream);                                  \
   /* name: "window_bits" (0 = automatic), "segment" (max entries per accumulation task),    \
      "devices" (point-range sharding over the first k devices; 1 = this context's device),  \
      "ranges" (point ranges one MSM is pipelined over; 0 = automatic), "pair_rounds"        \
      (experimental batched-affine rounds before the XYZZ accumulation; -1 = none, the       \
      default; -2 = chosen from the bucket occupancy; 0..4 = forced). */                       \
-  TACHYON_C_EXPORT int tachyon_##C##_g1_msm_gpu_set_option_b200(                             \
-      tachyon_##C##_g1_msm_gpu_ptr ptr, const char* name, long value);                       \
+  TACHYON_C_EXPORT int tachyon_##C##_##G##_msm_gpu_set_option_b200(                             \
+      tachyon_##C##_##G##_msm_gpu_ptr ptr, const char* name, long value);                       \
   /* MSM returning the un-normalised XYZZ sum by value into *out; returns 0 or a negative   \
      error code instead of aborting.  Pointers as for *_affine_msm_gpu. */                   \
-  TACHYON_C_EXPORT int tachyon_##C##_g1_msm_gpu_xyzz_b200(                                   \
-      tachyon_##C##_g1_msm_gpu_ptr ptr, const struct tachyon_##C##_g1_affine* bases,         \
-      const struct tachyon_##C##_fr* scalars, size_t size, struct tachyon_##C##_g1_xyzz* out); \
+  TACHYON_C_EXPORT int tachyon_##C##_##G##_msm_gpu_xyzz_b200(                                   \
+      tachyon_##C##_##G##_msm_gpu_ptr ptr, const struct tachyon_##C##_##G##_affine* bases,         \
+      const struct tachyon_##C##_fr* scalars, size_t size, struct tachyon_##C##_##G##_xyzz* out); \
   /* Device-resident bases + batched commitments (the SRS handling of           \
      tachyon/crypto/commitments/kzg/kzg.h:91-113 and the commit loop of :217-313).           \
      register_bases copies `size` bases (host or device source) into memory the context      \
@@ -96,53 +109,47 @@ extern "C" {
      scalars[i] (host or device), and writes the un-normalised sums to out[i]; consecutive    \
      MSMs are pipelined (scalars of the next one cross PCIe while the current one runs) and   \
      with "devices" = k they are dealt out over k GPUs.  0 or a negative error code. */       \
-  TACHYON_C_EXPORT int tachyon_##C##_g1_msm_gpu_register_bases_b200(                         \
-      tachyon_##C##_g1_msm_gpu_ptr ptr, const struct tachyon_##C##_g1_affine* bases,         \
+  TACHYON_C_EXPORT int tachyon_##C##_##G##_msm_gpu_register_bases_b200(                         \
+      tachyon_##C##_##G##_msm_gpu_ptr ptr, const struct tachyon_##C##_##G##_affine* bases,         \
       size_t size);                                                                          \
-  TACHYON_C_EXPORT int tachyon_##C##_g1_msm_gpu_commit_batch_b200(                           \
-      tachyon_##C##_g1_msm_gpu_ptr ptr, const struct tachyon_##C##_fr* const* scalars,       \
-      const size_t* sizes, size_t count, struct tachyon_##C##_g1_xyzz* out);                 \
+  TACHYON_C_EXPORT int tachyon_##C##_##G##_msm_gpu_commit_batch_b200(                           \
+      tachyon_##C##_##G##_msm_gpu_ptr ptr, const struct tachyon_##C##_fr* const* scalars,       \
+      const size_t* sizes, size_t count, struct tachyon_##C##_##G##_xyzz* out);                 \
   /* The general batch: MSM i over bases[i] (NULL = the registered bases) and scalars[i],    \
      sizes[i] elements each, host or device memory — e.g. the A, B1, L and H queries of a    \
      Groth16 proof (zk/r1cs/groth16/prove.h:100-131) in one call.  Pipelined and dealt out   \
      like commit_batch (explicit device pointers keep the batch on the context's device). */ \
-  TACHYON_C_EXPORT int tachyon_##C##_g1_msm_gpu_batch_b200(                                  \
-      tachyon_##C##_g1_msm_gpu_ptr ptr, const struct tachyon_##C##_g1_affine* const* bases,  \
+  TACHYON_C_EXPORT int tachyon_##C##_##G##_msm_gpu_batch_b200(                                  \
+      tachyon_##C##_##G##_msm_gpu_ptr ptr, const struct tachyon_##C##_##G##_affine* const* bases,  \
       const struct tachyon_##C##_fr* const* scalars, const size_t* sizes, size_t count,      \
-      struct tachyon_##C##_g1_xyzz* out);                                                    \
+      struct tachyon_##C##_##G##_xyzz* out);                                                    \
   /* Host-only: n XYZZ points -> affine with one field inversion (point_xyzz.h:109-163       \
      BatchNormalize); the identity becomes (0, 0). */                                        \
-  TACHYON_C_EXPORT void tachyon_##C##_g1_xyzz_batch_normalize_b200(                          \
-      const struct tachyon_##C##_g1_xyzz* in, size_t n, struct tachyon_##C##_g1_affine* out); \
+  TACHYON_C_EXPORT void tachyon_##C##_##G##_xyzz_batch_normalize_b200(                          \
+      const struct tachyon_##C##_##G##_xyzz* in, size_t n, struct tachyon_##C##_##G##_affine* out); \
   /* Stage timings of the last call on this context (CUDA events on its stream). */         \
-  TACHYON_C_EXPORT int tachyon_##C##_g1_msm_gpu_last_timing_b200(                            \
-      tachyon_##C##_g1_msm_gpu_ptr ptr, struct tachyon_b200_msm_timing* out);                \
+  TACHYON_C_EXPORT int tachyon_##C##_##G##_msm_gpu_last_timing_b200(                            \
+      tachyon_##C##_##G##_msm_gpu_ptr ptr, struct tachyon_b200_msm_timing* out);                \
   /* Deterministic synthetic test set written to DEVICE memory of the current device:       \
      points first..first+n of the doubling-chain stream, scalars of distribution dist       \
      (0 uniform, 1 non_uniform, 2 witness).  Mirrors msm/test/variable_base_msm_test_set.h. */ \
-  TACHYON_C_EXPORT int tachyon_##C##_g1_generate_bases_b200(uint64_t seed, size_t first,     \
+  TACHYON_C_EXPORT int tachyon_##C##_##G##_generate_bases_b200(uint64_t seed, size_t first,     \
                                                             size_t n, void* device_out);     \
-  TACHYON_C_EXPORT int tachyon_##C##_g1_generate_scalars_b200(uint64_t seed, int dist,       \
+  TACHYON_C_EXPORT int tachyon_##C##_##G##_generate_scalars_b200(uint64_t seed, int dist,       \
                                                               size_t first, size_t n,        \
                                                               void* device_out);             \
-  /* Element-wise parity hooks on HOST arrays (copied to the current device and back).      \
-     fq/fr op: 0 add 1 sub 2 mul 3 square 4 neg 5 double 6 inverse 7 from_mont 8 to_mont.   \
-     point op: 0 xyzz+xyzz 1 xyzz+affine 2 xyzz-affine 3 double. */                          \
-  TACHYON_C_EXPORT int tachyon_##C##_fq_op_b200(int op, const uint64_t* a, const uint64_t* b, \
-                                                uint64_t* out, size_t n);                    \
-  TACHYON_C_EXPORT int tachyon_##C##_fr_op_b200(int op, const uint64_t* a, const uint64_t* b, \
-                                                uint64_t* out, size_t n);                    \
-  TACHYON_C_EXPORT int tachyon_##C##_g1_point_op_b200(int op, const uint64_t* a,             \
+  /* Point-op parity hook on HOST arrays: 0 xyzz+xyzz 1 xyzz+affine 2 xyzz-affine 3 double. */ \
+  TACHYON_C_EXPORT int tachyon_##C##_##G##_point_op_b200(int op, const uint64_t* a,             \
                                                       const uint64_t* b, uint64_t* out,      \
                                                       size_t n);                             \
   /* Host-only helpers (no GPU needed): out = a + b on XYZZ points — how per-GPU / per-rank  \
      partial sums are combined (pippenger_adapter.h:110-113) — and XYZZ -> Jacobian           \
      (point_xyzz.h:228-237), the conversion applied to every MSM result. */                  \
-  TACHYON_C_EXPORT void tachyon_##C##_g1_xyzz_add_b200(const struct tachyon_##C##_g1_xyzz* a, \
-                                                       const struct tachyon_##C##_g1_xyzz* b, \
-                                                       struct tachyon_##C##_g1_xyzz* out);   \
-  TACHYON_C_EXPORT void tachyon_##C##_g1_xyzz_to_jacobian_b200(                              \
-      const struct tachyon_##C##_g1_xyzz* a, struct tachyon_##C##_g1_jacobian* out);
+  TACHYON_C_EXPORT void tachyon_##C##_##G##_xyzz_add_b200(const struct tachyon_##C##_##G##_xyzz* a, \
+                                                       const struct tachyon_##C##_##G##_xyzz* b, \
+                                                       struct tachyon_##C##_##G##_xyzz* out);   \
+  TACHYON_C_EXPORT void tachyon_##C##_##G##_xyzz_to_jacobian_b200(                              \
+      const struct tachyon_##C##_##G##_xyzz* a, struct tachyon_##C##_##G##_jacobian* out);
 
 struct tachyon_b200_msm_timing {
   float h2d_ms;         /* host->device copies of bases/scalars on the copy stream (0 for device
@@ -164,8 +171,16 @@ struct tachyon_b200_msm_timing {
   uint32_t pair_rounds; /* batched-affine pair rounds run before the XYZZ accumulation */
 };
 
-TACHYON_B200_DECLARE_CURVE(bn254, 4)
-TACHYON_B200_DECLARE_CURVE(bls12_381, 6)
+TACHYON_B200_DECLARE_FIELDS(bn254, 4)
+TACHYON_B200_DECLARE_FIELDS(bls12_381, 6)
+TACHYON_B200_DECLARE_GROUP(bn254, g1, tachyon_bn254_fq)
+TACHYON_B200_DECLARE_GROUP(bls12_381, g1, tachyon_bls12_381_fq)
+/* G2: the reference has the g2 point structs (point.h.tpl instantiated for g2,
+   build_defs.bzl:93-170) but reaches its G2 MSM only through C++
+   (VariableBaseMSMGpu<G2AffinePoint>, zk/r1cs/groth16/prove.h:129-131 ->
+   icicle_msm_bn254_g2.cc); the entry points below give it the same C shape as G1. */
+TACHYON_B200_DECLARE_GROUP(bn254, g2, tachyon_bn254_fq2)
+TACHYON_B200_DECLARE_GROUP(bls12_381, g2, tachyon_bls12_381_fq2)
 
 /* Number of CUDA devices visible, or a negative error. */
 TACHYON_C_EXPORT int tachyon_b200_device_count(void);

@@ -140,3 +140,100 @@ def fill_digits(k, c_bits, num_digits):
         digits.append(coeff - (carry << c_bits))
     digits[-1] += carry << c_bits
     return digits
+
+
+# --- G2: the same curves over Fq2 = Fq[u] / (u^2 + 1) --------------------------------------
+# Constants from bn/bn254/BUILD.bazel:150-200 (b = 3 / (9 + u)) and
+# bls12/bls12_381/BUILD.bazel:153-200 (b = 4 + 4u).  Elements are (c0, c1) tuples of ints.
+@dataclass(frozen=True)
+class CurveG2:
+    name: str
+    p: int
+    r: int
+    b: tuple
+    gx: tuple
+    gy: tuple
+    fq_limbs: int   # u64 limbs of ONE Fq component
+    fr_limbs: int
+
+
+BN254_G2 = CurveG2(
+    "bn254_g2", BN254.p, BN254.r,
+    (19485874751759354771024239261021720505790618469301721065564631296452457478373,
+     266929791119991161246907387137283842545076965332900288569378510910307636690),
+    (10857046999023057135944570762232829481370756359578518086990519993285655852781,
+     11559732032986387107991004021392285783925812861821192530917403151452391805634),
+    (8495653923123431417604973247489272438418190587263600148770280649306958101930,
+     4082367875863433681332203403145435568316851327593401208105741076214120093531),
+    4, 4)
+
+BLS12_381_G2 = CurveG2(
+    "bls12_381_g2", BLS12_381.p, BLS12_381.r, (4, 4),
+    (352701069587466618187139116011060144890029952792775240219908644239793785735715026873347600343865175952761926303160,
+     3059144344244213709971259814753781636986470325476647558659373206291635324768958432433509563104347017837885763365758),
+    (1985150602287291935568054521177171638300868978215655730859378665066344726373823718423869104263333984641494340347905,
+     927553665492332455747201965776037880757740193453592970025027978793976877002675564980949289727957565575433344219582),
+    6, 4)
+
+CURVES_G2 = {"bn254_g2": BN254_G2, "bls12_381_g2": BLS12_381_G2}
+
+
+def f2_add(p, a, b):
+    return ((a[0] + b[0]) % p, (a[1] + b[1]) % p)
+
+
+def f2_sub(p, a, b):
+    return ((a[0] - b[0]) % p, (a[1] - b[1]) % p)
+
+
+def f2_mul(p, a, b):
+    return ((a[0] * b[0] - a[1] * b[1]) % p, (a[0] * b[1] + a[1] * b[0]) % p)
+
+
+def f2_inv(p, a):
+    n = pow(a[0] * a[0] + a[1] * a[1], -1, p)
+    return (a[0] * n % p, (-a[1] * n) % p)
+
+
+def g2_is_on_curve(c, pt):
+    if pt is INF:
+        return True
+    x, y = pt
+    return f2_sub(c.p, f2_mul(c.p, y, y), f2_add(c.p, f2_mul(c.p, f2_mul(c.p, x, x), x), c.b)) == (0, 0)
+
+
+def g2_add(c, p1, p2):
+    p = c.p
+    if p1 is INF:
+        return p2
+    if p2 is INF:
+        return p1
+    x1, y1 = p1
+    x2, y2 = p2
+    if x1 == x2:
+        if f2_add(p, y1, y2) == (0, 0):
+            return INF
+        x1sq = f2_mul(p, x1, x1)
+        lam = f2_mul(p, f2_add(p, f2_add(p, x1sq, x1sq), x1sq), f2_inv(p, f2_add(p, y1, y1)))
+    else:
+        lam = f2_mul(p, f2_sub(p, y2, y1), f2_inv(p, f2_sub(p, x2, x1)))
+    x3 = f2_sub(p, f2_sub(p, f2_mul(p, lam, lam), x1), x2)
+    y3 = f2_sub(p, f2_mul(p, lam, f2_sub(p, x1, x3)), y1)
+    return (x3, y3)
+
+
+def g2_mul(c, k, pt):
+    acc = INF
+    while k > 0:
+        if k & 1:
+            acc = g2_add(c, acc, pt)
+        pt = g2_add(c, pt, pt)
+        k >>= 1
+    return acc
+
+
+def g2_msm(c, points, scalars):
+    acc = INF
+    for pt, k in zip(points, scalars):
+        acc = g2_add(c, acc, g2_mul(c, k % c.r, pt))
+    return acc

@@ -295,6 +295,80 @@ struct Fp {
 template <typename Tag, size_t N_>
 FieldParams<N_> Fp<Tag, N_>::P;
 
+
+// ---------------------------------------------------------------------------
+// Fq2 = Fq[u] / (u^2 - q) with q = -1 for both curves
+// (bn/bn254/BUILD.bazel:62-71, bls12/bls12_381/BUILD.bazel fq2: non_residue = ["-1"]).
+// tachyon/math/finite_fields/quadratic_extension_field.h: DoMul :315-338 (degree 2:
+// c0 = a0 b0 + q a1 b1, c1 = a0 b1 + a1 b0), DoSquareImpl :361-385 (q = -1:
+// c0 = (a0 - a1)(a0 + a1), c1 = 2 a0 a1), DoInverse :407-427 (norm), additive ops
+// component-wise.  Same interface as Fp so the point and MSM templates above/below
+// instantiate unchanged for G2.
+// ---------------------------------------------------------------------------
+template <typename Base>
+struct Fp2 {
+  static constexpr size_t N = 2 * Base::N;
+  Base c0, c1;
+
+  static Fp2 Zero() { return Fp2{Base::Zero(), Base::Zero()}; }
+  static Fp2 One() { return Fp2{Base::One(), Base::Zero()}; }
+  bool IsZero() const { return c0.IsZero() && c1.IsZero(); }
+  bool IsOne() const { return c0.IsOne() && c1.IsZero(); }
+  bool operator==(const Fp2& o) const { return c0 == o.c0 && c1 == o.c1; }
+  bool operator!=(const Fp2& o) const { return !(*this == o); }
+  Fp2 Add(const Fp2& o) const { return Fp2{c0.Add(o.c0), c1.Add(o.c1)}; }
+  Fp2 Sub(const Fp2& o) const { return Fp2{c0.Sub(o.c0), c1.Sub(o.c1)}; }
+  Fp2 Double() const { return Fp2{c0.Double(), c1.Double()}; }
+  Fp2 Neg() const { return Fp2{c0.Neg(), c1.Neg()}; }
+  Fp2 Mul(const Fp2& o) const {
+    return Fp2{c0.Mul(o.c0).Sub(c1.Mul(o.c1)), c0.Mul(o.c1).Add(c1.Mul(o.c0))};
+  }
+  Fp2 Square() const {
+    Base v0 = c0.Sub(c1).Mul(c0.Add(c1));
+    return Fp2{v0, c0.Mul(c1).Double()};
+  }
+  Fp2 Inverse() const {
+    Base v0 = c0.Square().Add(c1.Square());  // c0^2 - q c1^2
+    Base inv = v0.Inverse();
+    return Fp2{c0.Mul(inv), c1.Mul(inv).Neg()};
+  }
+};
+
+// helpers the C ABI uses so that one macro serves prime and quadratic fields
+template <typename Tag, size_t N_>
+void StoreConstants(const Fp<Tag, N_>*, u64* mod, u64* one, u64* r2, u64* inv) {
+  memcpy(mod, &Fp<Tag, N_>::P.modulus, sizeof(u64) * N_);
+  memcpy(one, &Fp<Tag, N_>::P.r, sizeof(u64) * N_);
+  memcpy(r2, &Fp<Tag, N_>::P.r2, sizeof(u64) * N_);
+  *inv = Fp<Tag, N_>::P.inv64;
+}
+template <typename Base>
+void StoreConstants(const Fp2<Base>*, u64* mod, u64* one, u64* r2, u64* inv) {
+  // (modulus, 0), (R, 0) = One, (R^2, 0): what the Python side needs to build XYZZ zero
+  memset(mod, 0, sizeof(u64) * 2 * Base::N);
+  memset(one, 0, sizeof(u64) * 2 * Base::N);
+  memset(r2, 0, sizeof(u64) * 2 * Base::N);
+  StoreConstants((const Base*)nullptr, mod, one, r2, inv);
+}
+template <typename Tag, size_t N_>
+Fp<Tag, N_> FromCanonical(const Fp<Tag, N_>*, const u64* a) {
+  return Fp<Tag, N_>::FromBigInt(*(const BigInt<N_>*)a);
+}
+template <typename Base>
+Fp2<Base> FromCanonical(const Fp2<Base>*, const u64* a) {
+  return Fp2<Base>{FromCanonical((const Base*)nullptr, a), FromCanonical((const Base*)nullptr, a + Base::N)};
+}
+template <typename Tag, size_t N_>
+void ToCanonical(const Fp<Tag, N_>& x, u64* out) {
+  BigInt<N_> b = x.ToBigInt();
+  memcpy(out, &b, sizeof(b));
+}
+template <typename Base>
+void ToCanonical(const Fp2<Base>& x, u64* out) {
+  ToCanonical(x.c0, out);
+  ToCanonical(x.c1, out + Base::N);
+}
+
 // ---------------------------------------------------------------------------
 // Short-Weierstrass points, a = 0
 // (tachyon/math/elliptic_curves/short_weierstrass/*)
@@ -662,9 +736,13 @@ using Bn254Fr = Fp<Bn254FrTag, 4>;
 using Bls381Fq = Fp<Bls381FqTag, 6>;
 using Bls381Fr = Fp<Bls381FrTag, 4>;
 using Gf7 = Fp<Gf7Tag, 1>;
+using Bn254Fq2 = Fp2<Bn254Fq>;
+using Bls381Fq2 = Fp2<Bls381Fq>;
 
 Affine<Bn254Fq> g_bn254_gen;
 Affine<Bls381Fq> g_bls381_gen;
+Affine<Bn254Fq2> g_bn254_g2_gen;
+Affine<Bls381Fq2> g_bls381_g2_gen;
 
 struct Init {
   Init() {
@@ -692,6 +770,27 @@ struct Init {
     BigInt<6> gy{{0x0caa232946c5e7e1ull, 0xd03cc744a2888ae4ull, 0x00db18cb2c04b3edull,
                   0xfcf5e095d5d00af6ull, 0xa09e30ed741d8ae4ull, 0x08b3f481e3aaa0f1ull}};
     g_bls381_gen = Affine<Bls381Fq>{Bls381Fq::FromBigInt(gx), Bls381Fq::FromBigInt(gy)};
+
+    // G2 generators, coordinates (c0, c1): bn/bn254/BUILD.bazel:188-199 (hex in the comments
+    // there), bls12/bls12_381/BUILD.bazel:187-198
+    auto bn = [](u64 a, u64 b, u64 c, u64 d) { return Bn254Fq::FromBigInt(BigInt<4>{{d, c, b, a}}); };
+    g_bn254_g2_gen = Affine<Bn254Fq2>{
+        Bn254Fq2{bn(0x1800deef121f1e76ull, 0x426a00665e5c4479ull, 0x674322d4f75edaddull, 0x46debd5cd992f6edull),
+                 bn(0x198e9393920d483aull, 0x7260bfb731fb5d25ull, 0xf1aa493335a9e712ull, 0x97e485b7aef312c2ull)},
+        Bn254Fq2{bn(0x12c85ea5db8c6debull, 0x4aab71808dcb408full, 0xe3d1e7690c43d37bull, 0x4ce6cc0166fa7daaull),
+                 bn(0x090689d0585ff075ull, 0xec9e99ad690c3395ull, 0xbc4b313370b38ef3ull, 0x55acdadcd122975bull)}};
+    auto bl = [](u64 a, u64 b, u64 c, u64 d, u64 e, u64 f) {
+      return Bls381Fq::FromBigInt(BigInt<6>{{f, e, d, c, b, a}});
+    };
+    g_bls381_g2_gen = Affine<Bls381Fq2>{
+        Bls381Fq2{bl(0x024aa2b2f08f0a91ull, 0x260805272dc51051ull, 0xc6e47ad4fa403b02ull,
+                     0xb4510b647ae3d177ull, 0x0bac0326a805bbefull, 0xd48056c8c121bdb8ull),
+                  bl(0x13e02b6052719f60ull, 0x7dacd3a088274f65ull, 0x596bd0d09920b61aull,
+                     0xb5da61bbdc7f5049ull, 0x334cf11213945d57ull, 0xe5ac7d055d042b7eull)},
+        Bls381Fq2{bl(0x0ce5d527727d6e11ull, 0x8cc9cdc6da2e351aull, 0xadfd9baa8cbdd3a7ull,
+                     0x6d429a695160d12cull, 0x923ac9cc3baca289ull, 0xe193548608b82801ull),
+                  bl(0x0606c4a02ea734ccull, 0x32acd2b02bc28b99ull, 0xcb3e287e85a763afull,
+                     0x267492ab572e99abull, 0x3f370d275cec1da1ull, 0xaaa9075ff05f79beull)}};
   }
 } g_init;
 
@@ -712,10 +811,7 @@ void StoreXYZZ(const XYZZ<Fq>& p, u64* out) {
   int oracle_##PFX##_fr_limbs() { return (int)FR::N; }                                       \
   void oracle_##PFX##_constants(u64* fq_mod, u64* fq_r, u64* fq_r2, u64* fq_inv, u64* fr_mod, \
                                 u64* fr_r, u64* fr_r2, u64* fr_inv, u64* gen_xy) {            \
-    memcpy(fq_mod, &FQ::P.modulus, sizeof(u64) * FQ::N);                                      \
-    memcpy(fq_r, &FQ::P.r, sizeof(u64) * FQ::N);                                              \
-    memcpy(fq_r2, &FQ::P.r2, sizeof(u64) * FQ::N);                                            \
-    *fq_inv = FQ::P.inv64;                                                                    \
+    StoreConstants((const FQ*)nullptr, fq_mod, fq_r, fq_r2, fq_inv);                          \
     memcpy(fr_mod, &FR::P.modulus, sizeof(u64) * FR::N);                                      \
     memcpy(fr_r, &FR::P.r, sizeof(u64) * FR::N);                                              \
     memcpy(fr_r2, &FR::P.r2, sizeof(u64) * FR::N);                                            \
@@ -741,11 +837,10 @@ void StoreXYZZ(const XYZZ<Fq>& p, u64* out) {
   }                                                                                          \
   void oracle_##PFX##_fq_to_mont(const u64* a, u64* out, size_t n) {                          \
     for (size_t i = 0; i < n; ++i)                                                            \
-      ((FQ*)out)[i] = FQ::FromBigInt(((const BigInt<FQ::N>*)a)[i]);                           \
+      ((FQ*)out)[i] = FromCanonical((const FQ*)nullptr, a + i * FQ::N);                       \
   }                                                                                          \
   void oracle_##PFX##_fq_from_mont(const u64* a, u64* out, size_t n) {                        \
-    for (size_t i = 0; i < n; ++i)                                                            \
-      ((BigInt<FQ::N>*)out)[i] = ((const FQ*)a)[i].ToBigInt();                                \
+    for (size_t i = 0; i < n; ++i) ToCanonical(((const FQ*)a)[i], out + i * FQ::N);            \
   }                                                                                          \
   void oracle_##PFX##_fr_to_mont(const u64* a, u64* out, size_t n) {                          \
     for (size_t i = 0; i < n; ++i)                                                            \
@@ -824,6 +919,9 @@ void StoreXYZZ(const XYZZ<Fq>& p, u64* out) {
 
 ORACLE_CURVE_API(bn254, Bn254Fq, Bn254Fr, g_bn254_gen)
 ORACLE_CURVE_API(bls12_381, Bls381Fq, Bls381Fr, g_bls381_gen)
+// G2: the same templates over Fq2 (VariableBaseMSM<G2AffinePoint>, groth16/prove.h:129-131)
+ORACLE_CURVE_API(bn254_g2, Bn254Fq2, Bn254Fr, g_bn254_g2_gen)
+ORACLE_CURVE_API(bls12_381_g2, Bls381Fq2, Bls381Fr, g_bls381_g2_gen)
 
 // GF(7) toy curve y^2 = x^3 + 5 (short_weierstrass/test/sw_curve_config.h:31-45):
 // the same XYZZ/Jacobian templates run over a 1-limb Montgomery field so that

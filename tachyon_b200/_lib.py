@@ -9,6 +9,21 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "lib", "libtachyon_msm_b200.so")
 
 CURVES = {"bn254": 4, "bls12_381": 6}  # curve -> Fq u64 limbs (Fr is 4 for both)
+GROUPS = ("g1", "g2")                  # g2: coordinates in Fq2, twice the limbs
+
+
+def split_name(name):
+    """"bn254" / "bn254_g2" -> (curve, group)."""
+    if name.endswith("_g2"):
+        return name[:-3], "g2"
+    if name.endswith("_g1"):
+        return name[:-3], "g1"
+    return name, "g1"
+
+
+def element_limbs(name):
+    curve, group = split_name(name)
+    return CURVES[curve] * (2 if group == "g2" else 1)
 
 
 class MsmTiming(ctypes.Structure):
@@ -25,26 +40,27 @@ class MsmTiming(ctypes.Structure):
         return {k: getattr(self, k) for k, _ in self._fields_}
 
 
-# every symbol include/tachyon_msm_b200.h declares, per curve
-CURVE_SYMBOLS = [
-    "tachyon_{c}_g1_init", "tachyon_{c}_g1_create_msm_gpu", "tachyon_{c}_g1_destroy_msm_gpu",
-    "tachyon_{c}_g1_point2_msm_gpu", "tachyon_{c}_g1_affine_msm_gpu",
-    "tachyon_{c}_g1_create_msm_gpu_b200", "tachyon_{c}_g1_msm_gpu_set_stream_b200",
-    "tachyon_{c}_g1_msm_gpu_set_option_b200", "tachyon_{c}_g1_msm_gpu_xyzz_b200",
-    "tachyon_{c}_g1_msm_gpu_last_timing_b200", "tachyon_{c}_g1_generate_bases_b200",
-    "tachyon_{c}_g1_generate_scalars_b200", "tachyon_{c}_fq_op_b200", "tachyon_{c}_fr_op_b200",
-    "tachyon_{c}_g1_point_op_b200", "tachyon_{c}_g1_xyzz_add_b200",
-    "tachyon_{c}_g1_xyzz_to_jacobian_b200", "tachyon_{c}_g1_msm_gpu_register_bases_b200",
-    "tachyon_{c}_g1_msm_gpu_commit_batch_b200", "tachyon_{c}_g1_xyzz_batch_normalize_b200",
-    "tachyon_{c}_g1_msm_gpu_batch_b200",
+# every symbol include/tachyon_msm_b200.h declares: per curve and group, per curve, global
+GROUP_SYMBOLS = [
+    "tachyon_{c}_{g}_init", "tachyon_{c}_{g}_create_msm_gpu", "tachyon_{c}_{g}_destroy_msm_gpu",
+    "tachyon_{c}_{g}_point2_msm_gpu", "tachyon_{c}_{g}_affine_msm_gpu",
+    "tachyon_{c}_{g}_create_msm_gpu_b200", "tachyon_{c}_{g}_msm_gpu_set_stream_b200",
+    "tachyon_{c}_{g}_msm_gpu_set_option_b200", "tachyon_{c}_{g}_msm_gpu_xyzz_b200",
+    "tachyon_{c}_{g}_msm_gpu_last_timing_b200", "tachyon_{c}_{g}_generate_bases_b200",
+    "tachyon_{c}_{g}_generate_scalars_b200", "tachyon_{c}_{g}_point_op_b200",
+    "tachyon_{c}_{g}_xyzz_add_b200", "tachyon_{c}_{g}_xyzz_to_jacobian_b200",
+    "tachyon_{c}_{g}_msm_gpu_register_bases_b200", "tachyon_{c}_{g}_msm_gpu_commit_batch_b200",
+    "tachyon_{c}_{g}_xyzz_batch_normalize_b200", "tachyon_{c}_{g}_msm_gpu_batch_b200",
 ]
+FIELD_SYMBOLS = ["tachyon_{c}_fq_op_b200", "tachyon_{c}_fr_op_b200", "tachyon_{c}_fq2_op_b200"]
 GLOBAL_SYMBOLS = ["tachyon_b200_device_count", "tachyon_b200_last_error", "tachyon_b200_imad_peak",
                   "tachyon_b200_kernel_launch_count", "tachyon_b200_window_bits",
                   "tachyon_b200_window_count"]
 
 
 def all_symbols():
-    return [s.format(c=c) for c in CURVES for s in CURVE_SYMBOLS] + GLOBAL_SYMBOLS
+    return ([s.format(c=c, g=g) for c in CURVES for g in GROUPS for s in GROUP_SYMBOLS] +
+            [s.format(c=c) for c in CURVES for s in FIELD_SYMBOLS] + GLOBAL_SYMBOLS)
 
 
 _lib = None
@@ -62,7 +78,10 @@ def load():
     lib = ctypes.CDLL(LIB_PATH)
     vp, sz, u64, i32 = ctypes.c_void_p, ctypes.c_size_t, ctypes.c_uint64, ctypes.c_int
     for c in CURVES:
-        f = lambda name: getattr(lib, name.format(c=c))
+        for n in FIELD_SYMBOLS:
+            getattr(lib, n.format(c=c)).argtypes = [i32, vp, vp, vp, sz]
+    for c, g in [(c, g) for c in CURVES for g in GROUPS]:
+        f = lambda name: getattr(lib, name.format(c=c).replace("_g1_", "_%s_" % g))
         f("tachyon_{c}_g1_init").restype = None
         f("tachyon_{c}_g1_create_msm_gpu").restype = vp
         f("tachyon_{c}_g1_create_msm_gpu").argtypes = [ctypes.c_uint8]
@@ -79,8 +98,7 @@ def load():
         f("tachyon_{c}_g1_msm_gpu_last_timing_b200").argtypes = [vp, ctypes.POINTER(MsmTiming)]
         f("tachyon_{c}_g1_generate_bases_b200").argtypes = [u64, sz, sz, vp]
         f("tachyon_{c}_g1_generate_scalars_b200").argtypes = [u64, i32, sz, sz, vp]
-        for n in ("tachyon_{c}_fq_op_b200", "tachyon_{c}_fr_op_b200", "tachyon_{c}_g1_point_op_b200"):
-            f(n).argtypes = [i32, vp, vp, vp, sz]
+        f("tachyon_{c}_g1_point_op_b200").argtypes = [i32, vp, vp, vp, sz]
         f("tachyon_{c}_g1_xyzz_add_b200").restype = None
         f("tachyon_{c}_g1_xyzz_add_b200").argtypes = [vp, vp, vp]
         f("tachyon_{c}_g1_msm_gpu_register_bases_b200").argtypes = [vp, vp, sz]

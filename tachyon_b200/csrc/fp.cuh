@@ -412,4 +412,157 @@ TB_DEV void fp_store(void* p, const Fp<F>& a) {
     q[i] = make_uint4(a.l[4 * i], a.l[4 * i + 1], a.l[4 * i + 2], a.l[4 * i + 3]);
 }
 
+// ---------------------------------------------------------------------------
+// Coordinate fields of the point code.  A "field kind" K names an element type
+// K::El (kWords u32 words, stored contiguously) and the operations the XYZZ
+// formulas need; the point and MSM kernels are written once against K and
+// instantiated for the base field (G1) and its quadratic extension (G2).
+// ---------------------------------------------------------------------------
+template <class F>
+struct FpField {
+  using Params = F;
+  using El = Fp<F>;
+  static constexpr int kWords = Fp<F>::N;
+  static constexpr int kDegree = 1;
+  static TB_DEV void set_zero(El& r) { fp_set_zero<F>(r); }
+  static TB_DEV void set_one(El& r) { fp_set_one<F>(r); }
+  static TB_DEV bool is_zero(const El& a) { return fp_is_zero<F>(a); }
+  static TB_DEV bool eq(const El& a, const El& b) { return fp_eq<F>(a, b); }
+  static TB_DEV void add(El& r, const El& a, const El& b) { fp_add<F>(r, a, b); }
+  static TB_DEV void sub(El& r, const El& a, const El& b) { fp_sub<F>(r, a, b); }
+  static TB_DEV void dbl(El& r, const El& a) { fp_dbl<F>(r, a); }
+  static TB_DEV void neg(El& r, const El& a) { fp_neg<F>(r, a); }
+  static TB_DEV void cneg(El& r, const El& a, bool n) { fp_cneg<F>(r, a, n); }
+  static TB_DEV void mul(El& r, const El& a, const El& b) { fp_mul<F>(r, a, b); }
+  static TB_DEV void sqr(El& r, const El& a) { fp_sqr<F>(r, a); }
+  // r = a * b + a2 * b2
+  static TB_DEV void mul2(El& r, const El& a, const El& b, const El& a2, const El& b2) {
+    fp_mul2<F>(r, a, b, a2, b2);
+  }
+  static TB_DEV void inv(El& r, const El& a) { fp_inv<F>(r, a); }
+  static TB_DEV void select(El& r, bool take_a, const El& a, const El& b) {
+#pragma unroll
+    for (int i = 0; i < kWords; ++i) r.l[i] = take_a ? a.l[i] : b.l[i];
+  }
+  // element from the constant words G::aff32(base), G::aff32(base + 1), ...
+  template <class G>
+  static TB_DEV void set_words(El& r, int base) {
+#pragma unroll
+    for (int i = 0; i < kWords; ++i) r.l[i] = G::aff32(base + i);
+  }
+  static TB_DEV void load(El& r, const void* p) { fp_load<F>(r, p); }
+  static TB_DEV void load_rw(El& r, const void* p) { fp_load_rw<F>(r, p); }
+  static TB_DEV void store(void* p, const El& a) { fp_store<F>(p, a); }
+};
+
+// Fq2 = Fq[u] / (u^2 + 1): both curves use the non-residue -1
+// (bn/bn254/BUILD.bazel:62-71, bls12/bls12_381/BUILD.bazel fq2).  Formulas of
+// tachyon/math/finite_fields/quadratic_extension_field.h: multiplication as two sums of
+// two products (:326-338, SumOfProductsSerial — here one Montgomery reduction each via
+// fp_mul2), complex squaring for q = -1 (:371-385), norm inverse (:407-427).
+template <class F>
+struct Fp2 {
+  Fp<F> c0, c1;
+};
+
+template <class F>
+struct Fp2Field {
+  using Params = F;
+  using El = Fp2<F>;
+  static constexpr int kWords = 2 * Fp<F>::N;
+  static constexpr int kDegree = 2;
+  static TB_DEV void set_zero(El& r) {
+    fp_set_zero<F>(r.c0);
+    fp_set_zero<F>(r.c1);
+  }
+  static TB_DEV void set_one(El& r) {
+    fp_set_one<F>(r.c0);
+    fp_set_zero<F>(r.c1);
+  }
+  static TB_DEV bool is_zero(const El& a) { return fp_is_zero<F>(a.c0) && fp_is_zero<F>(a.c1); }
+  static TB_DEV bool eq(const El& a, const El& b) {
+    return fp_eq<F>(a.c0, b.c0) && fp_eq<F>(a.c1, b.c1);
+  }
+  static TB_DEV void add(El& r, const El& a, const El& b) {
+    fp_add<F>(r.c0, a.c0, b.c0);
+    fp_add<F>(r.c1, a.c1, b.c1);
+  }
+  static TB_DEV void sub(El& r, const El& a, const El& b) {
+    fp_sub<F>(r.c0, a.c0, b.c0);
+    fp_sub<F>(r.c1, a.c1, b.c1);
+  }
+  static TB_DEV void dbl(El& r, const El& a) {
+    fp_dbl<F>(r.c0, a.c0);
+    fp_dbl<F>(r.c1, a.c1);
+  }
+  static TB_DEV void neg(El& r, const El& a) {
+    fp_neg<F>(r.c0, a.c0);
+    fp_neg<F>(r.c1, a.c1);
+  }
+  static TB_DEV void cneg(El& r, const El& a, bool n) {
+    fp_cneg<F>(r.c0, a.c0, n);
+    fp_cneg<F>(r.c1, a.c1, n);
+  }
+  static __device__ __noinline__ void mul(El& r, const El& a, const El& b) {
+    Fp<F> nb1, t0;
+    fp_neg<F>(nb1, b.c1);
+    fp_mul2<F>(t0, a.c0, b.c0, a.c1, nb1);    // c0 = a0 b0 - a1 b1
+    fp_mul2<F>(r.c1, a.c0, b.c1, a.c1, b.c0);  // c1 = a0 b1 + a1 b0
+    r.c0 = t0;
+  }
+  static __device__ __noinline__ void sqr(El& r, const El& a) {
+    Fp<F> s, d, m;
+    fp_add<F>(s, a.c0, a.c1);
+    fp_sub<F>(d, a.c0, a.c1);
+    fp_mul<F>(m, a.c0, a.c1);
+    fp_mul<F>(r.c0, s, d);  // c0^2 - c1^2
+    fp_dbl<F>(r.c1, m);     // 2 c0 c1
+  }
+  // r = a * b + a2 * b2: four products per component, still one reduction each
+  static __device__ __noinline__ void mul2(El& r, const El& a, const El& b, const El& a2,
+                                           const El& b2) {
+    El t, u;
+    mul(t, a, b);
+    mul(u, a2, b2);
+    add(r, t, u);
+  }
+  static __device__ __noinline__ void inv(El& r, const El& a) {
+    Fp<F> n, t;
+    fp_sqr<F>(n, a.c0);
+    fp_sqr<F>(t, a.c1);
+    fp_add<F>(n, n, t);  // norm = c0^2 + c1^2
+    fp_inv<F>(t, n);
+    fp_mul<F>(r.c0, a.c0, t);
+    fp_mul<F>(n, a.c1, t);
+    fp_neg<F>(r.c1, n);
+  }
+  static TB_DEV void select(El& r, bool take_a, const El& a, const El& b) {
+#pragma unroll
+    for (int i = 0; i < Fp<F>::N; ++i) {
+      r.c0.l[i] = take_a ? a.c0.l[i] : b.c0.l[i];
+      r.c1.l[i] = take_a ? a.c1.l[i] : b.c1.l[i];
+    }
+  }
+  template <class G>
+  static TB_DEV void set_words(El& r, int base) {
+#pragma unroll
+    for (int i = 0; i < Fp<F>::N; ++i) {
+      r.c0.l[i] = G::aff32(base + i);
+      r.c1.l[i] = G::aff32(base + Fp<F>::N + i);
+    }
+  }
+  static TB_DEV void load(El& r, const void* p) {
+    fp_load<F>(r.c0, p);
+    fp_load<F>(r.c1, static_cast<const char*>(p) + 4 * Fp<F>::N);
+  }
+  static TB_DEV void load_rw(El& r, const void* p) {
+    fp_load_rw<F>(r.c0, p);
+    fp_load_rw<F>(r.c1, static_cast<const char*>(p) + 4 * Fp<F>::N);
+  }
+  static TB_DEV void store(void* p, const El& a) {
+    fp_store<F>(p, a.c0);
+    fp_store<F>(static_cast<char*>(p) + 4 * Fp<F>::N, a.c1);
+  }
+};
+
 }  // namespace tb200

@@ -130,35 +130,56 @@ struct HostFp {
   }
 };
 
+// Fq2 = Fq[u] / (u^2 + 1) on the host (quadratic_extension_field.h:315-427 for q = -1).
 template <class F>
-struct HostXYZZ {
-  HostFp<F> x, y, zz, zzz;
+struct HostFp2 {
+  HostFp<F> c0, c1;
 
-  static HostXYZZ Zero() {
-    return HostXYZZ{HostFp<F>::One(), HostFp<F>::One(), HostFp<F>::Zero(), HostFp<F>::Zero()};
+  static HostFp2 Zero() { return HostFp2{HostFp<F>::Zero(), HostFp<F>::Zero()}; }
+  static HostFp2 One() { return HostFp2{HostFp<F>::One(), HostFp<F>::Zero()}; }
+  bool IsZero() const { return c0.IsZero() && c1.IsZero(); }
+  bool IsOne() const { return c0.IsOne() && c1.IsZero(); }
+  HostFp2 Add(const HostFp2& o) const { return HostFp2{c0.Add(o.c0), c1.Add(o.c1)}; }
+  HostFp2 Sub(const HostFp2& o) const { return HostFp2{c0.Sub(o.c0), c1.Sub(o.c1)}; }
+  HostFp2 Dbl() const { return HostFp2{c0.Dbl(), c1.Dbl()}; }
+  HostFp2 Mul(const HostFp2& o) const {
+    return HostFp2{c0.Mul(o.c0).Sub(c1.Mul(o.c1)), c0.Mul(o.c1).Add(c1.Mul(o.c0))};
   }
+  HostFp2 Sqr() const { return HostFp2{c0.Add(c1).Mul(c0.Sub(c1)), c0.Mul(c1).Dbl()}; }
+  HostFp2 Inv() const {
+    HostFp<F> t = c0.Sqr().Add(c1.Sqr()).Inv();
+    return HostFp2{c0.Mul(t), HostFp<F>::Zero().Sub(c1.Mul(t))};
+  }
+};
+
+// Points over an element type E (HostFp<F> for G1, HostFp2<F> for G2).
+template <class E>
+struct HostPointXYZZ {
+  E x, y, zz, zzz;
+
+  static HostPointXYZZ Zero() { return HostPointXYZZ{E::One(), E::One(), E::Zero(), E::Zero()}; }
   bool IsZero() const { return zz.IsZero(); }
 
-  HostXYZZ Dbl() const {
+  HostPointXYZZ Dbl() const {
     if (IsZero()) return *this;
-    HostFp<F> u = y.Dbl(), v = u.Sqr(), w = u.Mul(v), s = x.Mul(v);
-    HostFp<F> m = x.Sqr();
+    E u = y.Dbl(), v = u.Sqr(), w = u.Mul(v), s = x.Mul(v);
+    E m = x.Sqr();
     m = m.Add(m.Dbl());
-    HostXYZZ r;
+    HostPointXYZZ r;
     r.x = m.Sqr().Sub(s.Dbl());
     r.y = m.Mul(s.Sub(r.x)).Sub(w.Mul(y));
     r.zz = v.Mul(zz);
     r.zzz = w.Mul(zzz);
     return r;
   }
-  HostXYZZ Add(const HostXYZZ& b) const {
+  HostPointXYZZ Add(const HostPointXYZZ& b) const {
     if (IsZero()) return b;
     if (b.IsZero()) return *this;
-    HostFp<F> u1 = x.Mul(b.zz), s1 = y.Mul(b.zzz);
-    HostFp<F> p = b.x.Mul(zz).Sub(u1), r = b.y.Mul(zzz).Sub(s1);
+    E u1 = x.Mul(b.zz), s1 = y.Mul(b.zzz);
+    E p = b.x.Mul(zz).Sub(u1), r = b.y.Mul(zzz).Sub(s1);
     if (p.IsZero() && r.IsZero()) return Dbl();
-    HostFp<F> pp = p.Sqr(), ppp = p.Mul(pp), q = u1.Mul(pp);
-    HostXYZZ c;
+    E pp = p.Sqr(), ppp = p.Mul(pp), q = u1.Mul(pp);
+    HostPointXYZZ c;
     c.x = r.Sqr().Sub(ppp).Sub(q.Dbl());
     c.y = r.Mul(q.Sub(c.x)).Sub(s1.Mul(ppp));
     c.zz = zz.Mul(b.zz).Mul(pp);
@@ -167,47 +188,54 @@ struct HostXYZZ {
   }
 };
 
-template <class F>
-struct HostJacobian {
-  HostFp<F> x, y, z;
+template <class E>
+struct HostPointJacobian {
+  E x, y, z;
 };
+
+template <class E>
+struct HostPointAffine {
+  E x, y;
+};
+
+template <class F>
+using HostXYZZ = HostPointXYZZ<HostFp<F>>;
+template <class F>
+using HostJacobian = HostPointJacobian<HostFp<F>>;
+template <class F>
+using HostAffine = HostPointAffine<HostFp<F>>;
 
 // point_xyzz.h:228-237
-template <class F>
-HostJacobian<F> ToJacobian(const HostXYZZ<F>& p) {
-  if (p.IsZero()) return HostJacobian<F>{HostFp<F>::One(), HostFp<F>::One(), HostFp<F>::Zero()};
-  if (p.zz.IsOne()) return HostJacobian<F>{p.x, p.y, HostFp<F>::One()};
-  HostFp<F> z = p.zz.Mul(p.zzz);
-  return HostJacobian<F>{p.x.Mul(p.zzz).Mul(z), p.y.Mul(p.zz).Mul(z.Sqr()), z};
+template <class E>
+HostPointJacobian<E> ToJacobian(const HostPointXYZZ<E>& p) {
+  if (p.IsZero()) return HostPointJacobian<E>{E::One(), E::One(), E::Zero()};
+  if (p.zz.IsOne()) return HostPointJacobian<E>{p.x, p.y, E::One()};
+  E z = p.zz.Mul(p.zzz);
+  return HostPointJacobian<E>{p.x.Mul(p.zzz).Mul(z), p.y.Mul(p.zz).Mul(z.Sqr()), z};
 }
-
-template <class F>
-struct HostAffine {
-  HostFp<F> x, y;
-};
 
 // XYZZ -> affine for n points with ONE field inversion (Montgomery's trick), the
 // BatchNormalize of short_weierstrass/point_xyzz.h:109-163: x / zz, y / zzz; the identity
 // maps to (0, 0).
-template <class F>
-void BatchNormalize(const HostXYZZ<F>* in, size_t n, HostAffine<F>* out) {
+template <class E>
+void BatchNormalize(const HostPointXYZZ<E>* in, size_t n, HostPointAffine<E>* out) {
   if (n == 0) return;
-  HostFp<F>* prefix = new HostFp<F>[n];
-  HostFp<F> acc = HostFp<F>::One();
+  E* prefix = new E[n];
+  E acc = E::One();
   for (size_t i = 0; i < n; ++i) {
     prefix[i] = acc;
     if (!in[i].IsZero()) acc = acc.Mul(in[i].zzz);
   }
-  HostFp<F> inv = acc.Inv();
+  E inv = acc.Inv();
   for (size_t i = n; i-- > 0;) {
     if (in[i].IsZero()) {
-      out[i].x = HostFp<F>::Zero();
-      out[i].y = HostFp<F>::Zero();
+      out[i].x = E::Zero();
+      out[i].y = E::Zero();
       continue;
     }
-    HostFp<F> zi3 = inv.Mul(prefix[i]);   // 1 / zzz_i
+    E zi3 = inv.Mul(prefix[i]);   // 1 / zzz_i
     inv = inv.Mul(in[i].zzz);
-    HostFp<F> zi2 = zi3.Mul(in[i].zz).Sqr();  // (zz / zzz)^2 = 1 / zz
+    E zi2 = zi3.Mul(in[i].zz).Sqr();  // (zz / zzz)^2 = 1 / zz
     out[i].x = in[i].x.Mul(zi2);
     out[i].y = in[i].y.Mul(zi3);
   }
@@ -215,9 +243,9 @@ void BatchNormalize(const HostXYZZ<F>* in, size_t n, HostAffine<F>* out) {
 }
 
 // pippenger_base.h:59-77: Horner over window sums, c doublings per window.
-template <class F>
-HostXYZZ<F> CombineWindows(const HostXYZZ<F>* sums, uint32_t windows, uint32_t c) {
-  HostXYZZ<F> total = HostXYZZ<F>::Zero();
+template <class E>
+HostPointXYZZ<E> CombineWindows(const HostPointXYZZ<E>* sums, uint32_t windows, uint32_t c) {
+  HostPointXYZZ<E> total = HostPointXYZZ<E>::Zero();
   for (uint32_t w = windows; w-- > 1;) {
     total = total.Add(sums[w]);
     for (uint32_t i = 0; i < c; ++i) total = total.Dbl();

@@ -223,15 +223,24 @@ static std::string FpHex(const HostFp<F>& montgomery) {
 
 // Dump format of msm_gpu.h:99-119 / msm_gpu_replay.cc:19-37: u64 count, then
 // every field element as canonical little-endian u64 limbs.
+template <class F>
+static std::string ElHex(const HostFp<F>& e) {
+  return FpHex<F>(e);
+}
+template <class F>
+static std::string ElHex(const HostFp2<F>& e) {
+  return "(" + FpHex<F>(e.c0) + ", " + FpHex<F>(e.c1) + ")";
+}
+
 template <class C>
 static void MaybeLogAndDump(MsmGpuContext<C>& ctx, const void* bases, const void* scalars,
-                            size_t size, const HostJacobian<typename C::Fq>& jac) {
+                            size_t size, const HostPointJacobian<HostElT<C>>& jac) {
   using Fq = typename C::Fq;
   using Fr = typename C::Fr;
   if (ctx.log_msm) {
     std::cout << "\033[33mDoMSMGpu()" << ctx.idx << "\033[0m" << std::endl;
-    std::cout << "(" << FpHex<Fq>(jac.x) << ", " << FpHex<Fq>(jac.y) << ", " << FpHex<Fq>(jac.z)
-              << ")" << std::endl;
+    std::cout << "(" << ElHex(jac.x) << ", " << ElHex(jac.y) << ", " << ElHex(jac.z) << ")"
+              << std::endl;
   }
   ctx.idx++;
   if (!ctx.input_dir.empty()) {
@@ -258,7 +267,7 @@ static void MaybeLogAndDump(MsmGpuContext<C>& ctx, const void* bases, const void
         f.write(reinterpret_cast<const char*>(c.v), sizeof(c.v));
       }
     };
-    write("bases", Fq{}, bases, 2);
+    write("bases", Fq{}, bases, 2 * C::Field::kDegree);
     write("scalars", Fr{}, scalars, 1);
   }
 }
@@ -266,10 +275,9 @@ static void MaybeLogAndDump(MsmGpuContext<C>& ctx, const void* bases, const void
 template <class C, class CJacobian>
 static CJacobian* DoMsmGpu(MsmGpuContext<C>* ctx, const void* bases, const void* scalars,
                            size_t size) {
-  using Fq = typename C::Fq;
   try {
     auto sum = ctx->Run(bases, scalars, size);
-    HostJacobian<Fq> jac = ToJacobian<Fq>(sum);
+    HostPointJacobian<HostElT<C>> jac = ToJacobian(sum);
     static_assert(sizeof(CJacobian) == sizeof(jac), "layout");
     CJacobian* ret = new CJacobian();  // caller deletes (msm_gpu.h:81)
     memcpy(ret, &jac, sizeof(jac));
@@ -320,12 +328,36 @@ static int FieldOpGpu(int op, const uint64_t* a, const uint64_t* b, uint64_t* ou
   }
 }
 
-template <class C>
-static int PointOpGpu(int op, const uint64_t* a, const uint64_t* b, uint64_t* out, size_t n) {
-  using Fq = typename C::Fq;
+template <class K>
+static int ExtFieldOpGpu(int op, const uint64_t* a, const uint64_t* b, uint64_t* out, size_t n) {
   try {
     if (n == 0) return 0;
-    size_t fe = Fq::kLimbs64 * 8;
+    if (op < 0 || op > 6) throw CudaError{cudaErrorInvalidValue, "fq2 op", __FILE__, __LINE__};
+    size_t bytes = n * K::kWords * 4;
+    uint32_t *da, *db, *dout;
+    TB_CUDA(cudaMalloc(&da, bytes));
+    TB_CUDA(cudaMalloc(&db, bytes));
+    TB_CUDA(cudaMalloc(&dout, bytes));
+    TB_CUDA(cudaMemcpy(da, a, bytes, cudaMemcpyHostToDevice));
+    TB_CUDA(cudaMemcpy(db, b ? b : a, bytes, cudaMemcpyHostToDevice));
+    ext_field_op_kernel<K><<<(uint32_t)((n + 63) / 64), 64>>>(op, da, db, dout, (uint32_t)n);
+    g_kernel_launches.fetch_add(1);
+    TB_CUDA(cudaGetLastError());
+    TB_CUDA(cudaMemcpy(out, dout, bytes, cudaMemcpyDeviceToHost));
+    cudaFree(da);
+    cudaFree(db);
+    cudaFree(dout);
+    return 0;
+  } catch (const CudaError& e) {
+    return Fail(e);
+  }
+}
+
+template <class C>
+static int PointOpGpu(int op, const uint64_t* a, const uint64_t* b, uint64_t* out, size_t n) {
+  try {
+    if (n == 0) return 0;
+    size_t fe = C::Field::kWords * 4;
     size_t abytes = n * 4 * fe, bbytes = n * (op == 0 ? 4 : 2) * fe;
     uint32_t *da, *db, *dout;
     TB_CUDA(cudaMalloc(&da, abytes));
@@ -348,7 +380,6 @@ static int PointOpGpu(int op, const uint64_t* a, const uint64_t* b, uint64_t* ou
 
 template <class C>
 static int GenerateBases(uint64_t seed, size_t first, size_t n, void* device_out) {
-  using Fq = typename C::Fq;
   try {
     if (n == 0) return 0;
     const size_t chain = size_t(1) << kChainLog;
@@ -357,7 +388,7 @@ static int GenerateBases(uint64_t seed, size_t first, size_t n, void* device_out
     const size_t slab = size_t(1) << 22;
     uint32_t* scratch;
     size_t scratch_pts = n < slab ? n : slab;
-    TB_CUDA(cudaMalloc(&scratch, scratch_pts * 4 * Fq::kLimbs64 * 8));
+    TB_CUDA(cudaMalloc(&scratch, scratch_pts * 4 * C::Field::kWords * 4));
     for (size_t off = 0; off < n; off += slab) {
       size_t len = n - off < slab ? n - off : slab;
       uint32_t chains = (uint32_t)((len + chain - 1) / chain);
@@ -366,7 +397,7 @@ static int GenerateBases(uint64_t seed, size_t first, size_t n, void* device_out
       TB_CUDA(cudaGetLastError());
       normalize_kernel<C><<<(uint32_t)((len + 127) / 128), 128>>>(
           scratch, (uint32_t)len,
-          reinterpret_cast<uint32_t*>(static_cast<char*>(device_out) + off * 2 * Fq::kLimbs64 * 8));
+          reinterpret_cast<uint32_t*>(static_cast<char*>(device_out) + off * 2 * C::Field::kWords * 4));
       TB_CUDA(cudaGetLastError());
       g_kernel_launches.fetch_add(2);
     }
@@ -403,49 +434,69 @@ struct tachyon_bn254_g1_msm_gpu : public MsmGpuContext<Bn254Curve> {
 struct tachyon_bls12_381_g1_msm_gpu : public MsmGpuContext<Bls381Curve> {
   using MsmGpuContext<Bls381Curve>::MsmGpuContext;
 };
+struct tachyon_bn254_g2_msm_gpu : public MsmGpuContext<Bn254G2Curve> {
+  using MsmGpuContext<Bn254G2Curve>::MsmGpuContext;
+};
+struct tachyon_bls12_381_g2_msm_gpu : public MsmGpuContext<Bls381G2Curve> {
+  using MsmGpuContext<Bls381G2Curve>::MsmGpuContext;
+};
 
-#define TB200_DEFINE_CURVE_API(CN, CURVE)                                                      \
-  void tachyon_##CN##_g1_init(void) {}                                                         \
-  tachyon_##CN##_g1_msm_gpu_ptr tachyon_##CN##_g1_create_msm_gpu(uint8_t degree) {             \
+#define TB200_DEFINE_FIELD_API(CN, CURVE)                                                      \
+  int tachyon_##CN##_fq_op_b200(int op, const uint64_t* a, const uint64_t* b, uint64_t* out,   \
+                                size_t n) {                                                    \
+    return FieldOpGpu<CURVE::Fq>(op, a, b, out, n);                                            \
+  }                                                                                            \
+  int tachyon_##CN##_fr_op_b200(int op, const uint64_t* a, const uint64_t* b, uint64_t* out,   \
+                                size_t n) {                                                    \
+    return FieldOpGpu<CURVE::Fr>(op, a, b, out, n);                                            \
+  }                                                                                            \
+  int tachyon_##CN##_fq2_op_b200(int op, const uint64_t* a, const uint64_t* b, uint64_t* out,  \
+                                 size_t n) {                                                   \
+    return ExtFieldOpGpu<Fp2Field<CURVE::Fq>>(op, a, b, out, n);                               \
+  }
+
+#define TB200_DEFINE_GROUP_API(CN, G, CURVE)                                                      \
+  void tachyon_##CN##_##G##_init(void) {}                                                         \
+  tachyon_##CN##_##G##_msm_gpu_ptr tachyon_##CN##_##G##_create_msm_gpu(uint8_t degree) {             \
     (void)degree; /* advisory, unread by the reference too (msm_gpu.h:35) */                   \
     try {                                                                                      \
       int dev = 0;                                                                             \
       if (cudaGetDevice(&dev) != cudaSuccess) dev = 0;                                         \
-      return CreateContext<tachyon_##CN##_g1_msm_gpu>(dev, true);      \
+      return CreateContext<tachyon_##CN##_##G##_msm_gpu>(dev, true);      \
     } catch (const CudaError& e) {                                                             \
       Die(e);                                                                                  \
     }                                                                                          \
   }                                                                                            \
-  tachyon_##CN##_g1_msm_gpu_ptr tachyon_##CN##_g1_create_msm_gpu_b200(uint8_t degree,          \
+  tachyon_##CN##_##G##_msm_gpu_ptr tachyon_##CN##_##G##_create_msm_gpu_b200(uint8_t degree,          \
                                                                      int device) {             \
     (void)degree;                                                                              \
     try {                                                                                      \
-      return CreateContext<tachyon_##CN##_g1_msm_gpu>(device, false);  \
+      return CreateContext<tachyon_##CN##_##G##_msm_gpu>(device, false);  \
     } catch (const CudaError& e) {                                                             \
       Fail(e);                                                                                 \
       return nullptr;                                                                          \
     }                                                                                          \
   }                                                                                            \
-  void tachyon_##CN##_g1_destroy_msm_gpu(tachyon_##CN##_g1_msm_gpu_ptr ptr) {                  \
+  void tachyon_##CN##_##G##_destroy_msm_gpu(tachyon_##CN##_##G##_msm_gpu_ptr ptr) {                  \
     delete ptr;                                            \
   }                                                                                            \
-  tachyon_##CN##_g1_jacobian* tachyon_##CN##_g1_point2_msm_gpu(                                \
-      tachyon_##CN##_g1_msm_gpu_ptr ptr, const tachyon_##CN##_g1_point2* bases,                \
+  tachyon_##CN##_##G##_jacobian* tachyon_##CN##_##G##_point2_msm_gpu(                                \
+      tachyon_##CN##_##G##_msm_gpu_ptr ptr, const tachyon_##CN##_##G##_point2* bases,                \
       const tachyon_##CN##_fr* scalars, size_t size) {                                         \
-    return DoMsmGpu<CURVE, tachyon_##CN##_g1_jacobian>(ptr, bases, scalars, size);             \
+    return DoMsmGpu<CURVE, tachyon_##CN##_##G##_jacobian>(ptr, bases, scalars, size);             \
   }                                                                                            \
-  tachyon_##CN##_g1_jacobian* tachyon_##CN##_g1_affine_msm_gpu(                                \
-      tachyon_##CN##_g1_msm_gpu_ptr ptr, const tachyon_##CN##_g1_affine* bases,                \
+  tachyon_##CN##_##G##_jacobian* tachyon_##CN##_##G##_affine_msm_gpu(                                \
+      tachyon_##CN##_##G##_msm_gpu_ptr ptr, const tachyon_##CN##_##G##_affine* bases,                \
       const tachyon_##CN##_fr* scalars, size_t size) {                                         \
-    return DoMsmGpu<CURVE, tachyon_##CN##_g1_jacobian>(ptr, bases, scalars, size);             \
+    return DoMsmGpu<CURVE, tachyon_##CN##_##G##_jacobian>(ptr, bases, scalars, size);             \
   }                                                                                            \
-  int tachyon_##CN##_g1_msm_gpu_set_stream_b200(tachyon_##CN##_g1_msm_gpu_ptr ptr,             \
+  int tachyon_##CN##_##G##_msm_gpu_set_stream_b200(tachyon_##CN##_##G##_msm_gpu_ptr ptr,             \
                                                 void* cuda_stream) {                           \
     if (!ptr || ptr->engines.size() != 1) return -1;                                           \
     ptr->engines[0]->SetStream(static_cast<cudaStream_t>(cuda_stream));                        \
     return 0;                                                                                  \
   }                                                                                            \
-  int tachyon_##CN##_g1_msm_gpu_set_option_b200(tachyon_##CN##_g1_msm_gpu_ptr ptr,             \
+  int tachyon_##CN##_##G##_msm_gpu_set_option_b200(tachyon_##CN##_##G##_msm_gpu_ptr ptr,             \
                                                 const char* name, long value) {                \
     if (!ptr || !name) return -1;                                                              \
     try {                                                                                      \
@@ -471,10 +522,10 @@ struct tachyon_bls12_381_g1_msm_gpu : public MsmGpuContext<Bls381Curve> {
       return Fail(e);                                                                          \
     }                                                                                          \
   }                                                                                            \
-  int tachyon_##CN##_g1_msm_gpu_xyzz_b200(tachyon_##CN##_g1_msm_gpu_ptr ptr,                   \
-                                          const tachyon_##CN##_g1_affine* bases,               \
+  int tachyon_##CN##_##G##_msm_gpu_xyzz_b200(tachyon_##CN##_##G##_msm_gpu_ptr ptr,                   \
+                                          const tachyon_##CN##_##G##_affine* bases,               \
                                           const tachyon_##CN##_fr* scalars, size_t size,       \
-                                          tachyon_##CN##_g1_xyzz* out) {                       \
+                                          tachyon_##CN##_##G##_xyzz* out) {                       \
     if (!ptr || !out) return -1;                                                               \
     try {                                                                                      \
       auto sum = ptr->Run(bases, scalars, size);                                               \
@@ -485,8 +536,8 @@ struct tachyon_bls12_381_g1_msm_gpu : public MsmGpuContext<Bls381Curve> {
       return Fail(e);                                                                          \
     }                                                                                          \
   }                                                                                            \
-  int tachyon_##CN##_g1_msm_gpu_register_bases_b200(tachyon_##CN##_g1_msm_gpu_ptr ptr,         \
-                                                    const tachyon_##CN##_g1_affine* bases,     \
+  int tachyon_##CN##_##G##_msm_gpu_register_bases_b200(tachyon_##CN##_##G##_msm_gpu_ptr ptr,         \
+                                                    const tachyon_##CN##_##G##_affine* bases,     \
                                                     size_t size) {                             \
     if (!ptr || (!bases && size)) return -1;                                                   \
     try {                                                                                      \
@@ -496,9 +547,9 @@ struct tachyon_bls12_381_g1_msm_gpu : public MsmGpuContext<Bls381Curve> {
       return Fail(e);                                                                          \
     }                                                                                          \
   }                                                                                            \
-  int tachyon_##CN##_g1_msm_gpu_commit_batch_b200(                                             \
-      tachyon_##CN##_g1_msm_gpu_ptr ptr, const tachyon_##CN##_fr* const* scalars,              \
-      const size_t* sizes, size_t count, tachyon_##CN##_g1_xyzz* out) {                        \
+  int tachyon_##CN##_##G##_msm_gpu_commit_batch_b200(                                             \
+      tachyon_##CN##_##G##_msm_gpu_ptr ptr, const tachyon_##CN##_fr* const* scalars,              \
+      const size_t* sizes, size_t count, tachyon_##CN##_##G##_xyzz* out) {                        \
     if (!ptr || (count && (!scalars || !sizes || !out))) return -1;                            \
     try {                                                                                      \
       static_assert(sizeof(*out) == sizeof(MsmGpuContext<CURVE>::Point), "layout");            \
@@ -510,10 +561,10 @@ struct tachyon_bls12_381_g1_msm_gpu : public MsmGpuContext<Bls381Curve> {
       return Fail(e);                                                                          \
     }                                                                                          \
   }                                                                                            \
-  int tachyon_##CN##_g1_msm_gpu_batch_b200(                                                    \
-      tachyon_##CN##_g1_msm_gpu_ptr ptr, const tachyon_##CN##_g1_affine* const* bases,         \
+  int tachyon_##CN##_##G##_msm_gpu_batch_b200(                                                    \
+      tachyon_##CN##_##G##_msm_gpu_ptr ptr, const tachyon_##CN##_##G##_affine* const* bases,         \
       const tachyon_##CN##_fr* const* scalars, const size_t* sizes, size_t count,              \
-      tachyon_##CN##_g1_xyzz* out) {                                                           \
+      tachyon_##CN##_##G##_xyzz* out) {                                                           \
     if (!ptr || (count && (!bases || !scalars || !sizes || !out))) return -1;                  \
     try {                                                                                      \
       ptr->RunBatch(reinterpret_cast<const void* const*>(bases),                               \
@@ -524,12 +575,12 @@ struct tachyon_bls12_381_g1_msm_gpu : public MsmGpuContext<Bls381Curve> {
       return Fail(e);                                                                          \
     }                                                                                          \
   }                                                                                            \
-  void tachyon_##CN##_g1_xyzz_batch_normalize_b200(const tachyon_##CN##_g1_xyzz* in, size_t n, \
-                                                   tachyon_##CN##_g1_affine* out) {            \
-    BatchNormalize<CURVE::Fq>(reinterpret_cast<const HostXYZZ<CURVE::Fq>*>(in), n,             \
-                              reinterpret_cast<HostAffine<CURVE::Fq>*>(out));                  \
+  void tachyon_##CN##_##G##_xyzz_batch_normalize_b200(const tachyon_##CN##_##G##_xyzz* in, size_t n, \
+                                                   tachyon_##CN##_##G##_affine* out) {            \
+    BatchNormalize(reinterpret_cast<const HostPointXYZZ<HostElT<CURVE>>*>(in), n,             \
+                              reinterpret_cast<HostPointAffine<HostElT<CURVE>>*>(out));                  \
   }                                                                                            \
-  int tachyon_##CN##_g1_msm_gpu_last_timing_b200(tachyon_##CN##_g1_msm_gpu_ptr ptr,            \
+  int tachyon_##CN##_##G##_msm_gpu_last_timing_b200(tachyon_##CN##_##G##_msm_gpu_ptr ptr,            \
                                                  tachyon_b200_msm_timing* out) {               \
     if (!ptr || !out) return -1;                                                               \
     const MsmTiming& t = ptr->timing;                                                          \
@@ -551,47 +602,43 @@ struct tachyon_bls12_381_g1_msm_gpu : public MsmGpuContext<Bls381Curve> {
     out->pair_rounds = t.pair_rounds;                                                          \
     return 0;                                                                                  \
   }                                                                                            \
-  int tachyon_##CN##_g1_generate_bases_b200(uint64_t seed, size_t first, size_t n,             \
+  int tachyon_##CN##_##G##_generate_bases_b200(uint64_t seed, size_t first, size_t n,             \
                                             void* device_out) {                                \
     return GenerateBases<CURVE>(seed, first, n, device_out);                                   \
   }                                                                                            \
-  int tachyon_##CN##_g1_generate_scalars_b200(uint64_t seed, int dist, size_t first, size_t n, \
+  int tachyon_##CN##_##G##_generate_scalars_b200(uint64_t seed, int dist, size_t first, size_t n, \
                                               void* device_out) {                              \
     return GenerateScalars<CURVE>(seed, dist, first, n, device_out);                           \
   }                                                                                            \
-  int tachyon_##CN##_fq_op_b200(int op, const uint64_t* a, const uint64_t* b, uint64_t* out,   \
-                                size_t n) {                                                    \
-    return FieldOpGpu<CURVE::Fq>(op, a, b, out, n);                                            \
-  }                                                                                            \
-  int tachyon_##CN##_fr_op_b200(int op, const uint64_t* a, const uint64_t* b, uint64_t* out,   \
-                                size_t n) {                                                    \
-    return FieldOpGpu<CURVE::Fr>(op, a, b, out, n);                                            \
-  }                                                                                            \
-  int tachyon_##CN##_g1_point_op_b200(int op, const uint64_t* a, const uint64_t* b,            \
+  int tachyon_##CN##_##G##_point_op_b200(int op, const uint64_t* a, const uint64_t* b,            \
                                       uint64_t* out, size_t n) {                               \
     return PointOpGpu<CURVE>(op, a, b, out, n);                                                \
   }                                                                                            \
-  void tachyon_##CN##_g1_xyzz_add_b200(const tachyon_##CN##_g1_xyzz* a,                        \
-                                       const tachyon_##CN##_g1_xyzz* b,                        \
-                                       tachyon_##CN##_g1_xyzz* out) {                          \
-    HostXYZZ<CURVE::Fq> x, y;                                                                  \
+  void tachyon_##CN##_##G##_xyzz_add_b200(const tachyon_##CN##_##G##_xyzz* a,                        \
+                                       const tachyon_##CN##_##G##_xyzz* b,                        \
+                                       tachyon_##CN##_##G##_xyzz* out) {                          \
+    HostPointXYZZ<HostElT<CURVE>> x, y;                                                                  \
     memcpy(&x, a, sizeof(x));                                                                  \
     memcpy(&y, b, sizeof(y));                                                                  \
-    HostXYZZ<CURVE::Fq> r = x.Add(y);                                                          \
+    HostPointXYZZ<HostElT<CURVE>> r = x.Add(y);                                                          \
     memcpy(out, &r, sizeof(r));                                                                \
   }                                                                                            \
-  void tachyon_##CN##_g1_xyzz_to_jacobian_b200(const tachyon_##CN##_g1_xyzz* a,                \
-                                               tachyon_##CN##_g1_jacobian* out) {              \
-    HostXYZZ<CURVE::Fq> x;                                                                     \
+  void tachyon_##CN##_##G##_xyzz_to_jacobian_b200(const tachyon_##CN##_##G##_xyzz* a,                \
+                                               tachyon_##CN##_##G##_jacobian* out) {              \
+    HostPointXYZZ<HostElT<CURVE>> x;                                                                     \
     memcpy(&x, a, sizeof(x));                                                                  \
-    HostJacobian<CURVE::Fq> j = ToJacobian<CURVE::Fq>(x);                                      \
+    HostPointJacobian<HostElT<CURVE>> j = ToJacobian(x);                                      \
     memcpy(out, &j, sizeof(j));                                                                \
   }
 
 extern "C" {
 
-TB200_DEFINE_CURVE_API(bn254, Bn254Curve)
-TB200_DEFINE_CURVE_API(bls12_381, Bls381Curve)
+TB200_DEFINE_FIELD_API(bn254, Bn254Curve)
+TB200_DEFINE_FIELD_API(bls12_381, Bls381Curve)
+TB200_DEFINE_GROUP_API(bn254, g1, Bn254Curve)
+TB200_DEFINE_GROUP_API(bls12_381, g1, Bls381Curve)
+TB200_DEFINE_GROUP_API(bn254, g2, Bn254G2Curve)
+TB200_DEFINE_GROUP_API(bls12_381, g2, Bls381G2Curve)
 
 int tachyon_b200_device_count(void) {
   int n = 0;

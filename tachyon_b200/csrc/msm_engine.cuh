@@ -113,16 +113,30 @@ inline uint32_t ChooseWindowBits(size_t n, uint32_t scalar_bits) {
   return best_c;
 }
 
+// Host element type of a device field kind.
+template <class K>
+struct HostElOf;
+template <class F>
+struct HostElOf<FpField<F>> {
+  using type = HostFp<F>;
+};
+template <class F>
+struct HostElOf<Fp2Field<F>> {
+  using type = HostFp2<F>;
+};
+template <class C>
+using HostElT = typename HostElOf<typename C::Field>::type;
+
 template <class C>
 class MsmEngine {
  public:
-  using Fq = typename C::Fq;
   using Fr = typename C::Fr;
-  using Point = HostXYZZ<Fq>;
-  static constexpr size_t kAffineBytes = 2 * Fq::kLimbs64 * 8;
+  using Point = HostPointXYZZ<HostElT<C>>;
+  static constexpr size_t kElBytes = C::Field::kWords * 4;
+  static constexpr size_t kAffineBytes = 2 * kElBytes;
   static constexpr size_t kScalarBytes = Fr::kLimbs64 * 8;
-  static constexpr size_t kXyzzBytes = 4 * Fq::kLimbs64 * 8;
-  static constexpr int kXyzzWords = 4 * Fq::kLimbs32;
+  static constexpr size_t kXyzzBytes = 4 * kElBytes;
+  static constexpr int kXyzzWords = 4 * C::Field::kWords;
   // n * W must stay below 2^32 (u32 offsets) and n below 2^31 (sign bit)
   static constexpr size_t kMaxPiece = size_t(1) << 26;
   static constexpr size_t kMaxRanges = 64;   // point ranges per MSM

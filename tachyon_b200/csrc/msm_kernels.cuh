@@ -31,6 +31,7 @@ namespace tb200 {
 
 struct Bn254Curve {
   using Fq = Bn254FqParams;
+  using Field = FpField<Bn254FqParams>;  // coordinate field of the group
   using Fr = Bn254FrParams;
   using Gen = Bn254G1Generator;
   static constexpr const char* kName = "bn254";
@@ -40,10 +41,30 @@ struct Bn254Curve {
 };
 struct Bls381Curve {
   using Fq = Bls381FqParams;
+  using Field = FpField<Bls381FqParams>;
   using Fr = Bls381FrParams;
   using Gen = Bls381G1Generator;
   static constexpr const char* kName = "bls12_381";
   static constexpr double kRangeGrowth = 2.0;  // 6.3 ns of bucket work vs 2.3 ns of PCIe per point
+};
+
+// G2: the same curves over Fq2 (bn254/BUILD.bazel:150-200, bls12_381/BUILD.bazel:153-200);
+// SURVEY 8f-2, the B2 query of a Groth16 proof (zk/r1cs/groth16/prove.h:129-131).
+struct Bn254G2Curve {
+  using Fq = Bn254FqParams;
+  using Field = Fp2Field<Bn254FqParams>;
+  using Fr = Bn254FrParams;
+  using Gen = Bn254G2Generator;
+  static constexpr const char* kName = "bn254_g2";
+  static constexpr double kRangeGrowth = 2.0;
+};
+struct Bls381G2Curve {
+  using Fq = Bls381FqParams;
+  using Field = Fp2Field<Bls381FqParams>;
+  using Fr = Bls381FrParams;
+  using Gen = Bls381G2Generator;
+  static constexpr const char* kName = "bls12_381_g2";
+  static constexpr double kRangeGrowth = 2.5;
 };
 
 struct MsmPlan {
@@ -424,10 +445,10 @@ __global__ void __launch_bounds__(kOrderThreads) order_scatter_kernel(
 // ---------------------------------------------------------------------------
 constexpr int kAccThreads = 128;
 // resident CTAs per SM the register budget is held to: 4 x 128 threads x 128 registers
-// (BN254), 3 x 128 x 168 (BLS12-381)
+// (BN254 G1), 3 x 128 x 168 (BLS12-381 G1), 2 x 128 x 255 (BN254 G2), 1 (BLS12-381 G2)
 template <class C>
 constexpr int AccMinBlocks() {
-  return Fp<typename C::Fq>::N <= 8 ? 4 : 3;
+  return C::Field::kWords <= 8 ? 4 : (C::Field::kWords <= 12 ? 3 : (C::Field::kWords <= 16 ? 2 : 1));
 }
 
 // kReduced: the task's points are a run of affine points left by the pair rounds (read in
@@ -438,9 +459,9 @@ __global__ void __launch_bounds__(kAccThreads, AccMinBlocks<C>()) accumulate_ker
     const uint2* __restrict__ tasks, const uint32_t* __restrict__ task_meta,
     const uint32_t* __restrict__ order, const MsmTotals* __restrict__ totals,
     uint32_t* __restrict__ state, uint32_t* __restrict__ task_out) {
-  using Fq = typename C::Fq;
-  constexpr int kAffineWords = 2 * Fp<Fq>::N;
-  constexpr int kXyzzWords = 4 * Fp<Fq>::N;
+  using K = typename C::Field;
+  constexpr int kAffineWords = 2 * K::kWords;
+  constexpr int kXyzzWords = 4 * K::kWords;
   uint32_t slot = blockIdx.x * blockDim.x + threadIdx.x;
   if (slot >= totals->tasks) return;
   uint32_t g = order[slot];  // tasks in descending length: warps stay convergent
@@ -450,32 +471,32 @@ __global__ void __launch_bounds__(kAccThreads, AccMinBlocks<C>()) accumulate_ker
   const uint32_t* ent = sorted + task.x;
   const uint32_t* run = bases + (size_t)task.x * kAffineWords;
   uint32_t e = kReduced ? 0u : ent[0];
-  Affine<Fq> nxt;
+  Affine<K> nxt;
   if (kReduced) {
-    affine_load<Fq>(nxt, run);
+    affine_load<K>(nxt, run);
   } else {
-    affine_load<Fq>(nxt, bases + (size_t)(e & 0x7fffffffu) * kAffineWords);
+    affine_load<K>(nxt, bases + (size_t)(e & 0x7fffffffu) * kAffineWords);
   }
-  XYZZ<Fq> acc;
+  XYZZ<K> acc;
   if (meta & kTaskFirst) {
-    xyzz_load<Fq>(acc, bucket);  // value left by the earlier point ranges (zz == 0: none)
+    xyzz_load<K>(acc, bucket);  // value left by the earlier point ranges (zz == 0: none)
   } else {
-    xyzz_set_zero<Fq>(acc);
+    xyzz_set_zero<K>(acc);
   }
   for (uint32_t j = 0; j < task.y; ++j) {
-    Affine<Fq> cur = nxt;
+    Affine<K> cur = nxt;
     bool neg = e >> 31;
     if (j + 1 < task.y) {
       if (kReduced) {
-        affine_load<Fq>(nxt, run + (size_t)(j + 1) * kAffineWords);
+        affine_load<K>(nxt, run + (size_t)(j + 1) * kAffineWords);
       } else {
         e = ent[j + 1];
-        affine_load<Fq>(nxt, bases + (size_t)(e & 0x7fffffffu) * kAffineWords);
+        affine_load<K>(nxt, bases + (size_t)(e & 0x7fffffffu) * kAffineWords);
       }
     }
-    xyzz_madd<Fq>(acc, cur, neg);
+    xyzz_madd<K>(acc, cur, neg);
   }
-  xyzz_store<Fq>((meta & kTaskSingle) ? bucket : task_out + (size_t)g * kXyzzWords, acc);
+  xyzz_store<K>((meta & kTaskSingle) ? bucket : task_out + (size_t)g * kXyzzWords, acc);
 }
 
 // ---------------------------------------------------------------------------
@@ -506,49 +527,49 @@ enum : uint32_t { kPairAdd = 0, kPairDouble = 1, kPairCopy1 = 2, kPairCopy2 = 3,
 
 // Loads pair p.  kFirst: slots hold point index | sign << 31 into `bases` (kNoEntry: identity).
 template <class C, bool kFirst>
-TB_DEV void pair_load(Affine<typename C::Fq>& p1, Affine<typename C::Fq>& p2, uint32_t p,
+TB_DEV void pair_load(Affine<typename C::Field>& p1, Affine<typename C::Field>& p2, uint32_t p,
                       const uint32_t* __restrict__ bases, const uint32_t* __restrict__ in) {
-  using Fq = typename C::Fq;
-  constexpr int kAffineWords = 2 * Fp<Fq>::N;
+  using K = typename C::Field;
+  constexpr int kAffineWords = 2 * K::kWords;
   if (kFirst) {
     uint2 e = reinterpret_cast<const uint2*>(in)[p];
     if (e.x == kNoEntry) {
-      fp_set_zero<Fq>(p1.x);
-      fp_set_zero<Fq>(p1.y);
+      K::set_zero(p1.x);
+      K::set_zero(p1.y);
     } else {
-      affine_load<Fq>(p1, bases + (size_t)(e.x & 0x7fffffffu) * kAffineWords);
-      fp_cneg<Fq>(p1.y, p1.y, e.x >> 31);
+      affine_load<K>(p1, bases + (size_t)(e.x & 0x7fffffffu) * kAffineWords);
+      K::cneg(p1.y, p1.y, e.x >> 31);
     }
     if (e.y == kNoEntry) {
-      fp_set_zero<Fq>(p2.x);
-      fp_set_zero<Fq>(p2.y);
+      K::set_zero(p2.x);
+      K::set_zero(p2.y);
     } else {
-      affine_load<Fq>(p2, bases + (size_t)(e.y & 0x7fffffffu) * kAffineWords);
-      fp_cneg<Fq>(p2.y, p2.y, e.y >> 31);
+      affine_load<K>(p2, bases + (size_t)(e.y & 0x7fffffffu) * kAffineWords);
+      K::cneg(p2.y, p2.y, e.y >> 31);
     }
   } else {
-    affine_load<Fq>(p1, in + (size_t)(2 * (size_t)p) * kAffineWords);
-    affine_load<Fq>(p2, in + (size_t)(2 * (size_t)p + 1) * kAffineWords);
+    affine_load<K>(p1, in + (size_t)(2 * (size_t)p) * kAffineWords);
+    affine_load<K>(p2, in + (size_t)(2 * (size_t)p + 1) * kAffineWords);
   }
 }
 
 // Case of the pair and its denominator d (never zero).
-template <class F>
-TB_DEV uint32_t pair_denominator(Fp<F>& d, const Affine<F>& p1, const Affine<F>& p2) {
-  bool z1 = affine_is_zero<F>(p1), z2 = affine_is_zero<F>(p2);
-  fp_sub<F>(d, p2.x, p1.x);
+template <class K>
+TB_DEV uint32_t pair_denominator(typename K::El& d, const Affine<K>& p1, const Affine<K>& p2) {
+  bool z1 = affine_is_zero<K>(p1), z2 = affine_is_zero<K>(p2);
+  K::sub(d, p2.x, p1.x);
   uint32_t kind = kPairAdd;
   if (z1 || z2) {
     kind = z1 ? (z2 ? kPairZero : kPairCopy2) : kPairCopy1;
-  } else if (fp_is_zero<F>(d)) {
-    if (fp_eq<F>(p1.y, p2.y) && !fp_is_zero<F>(p1.y)) {
+  } else if (K::is_zero(d)) {
+    if (K::eq(p1.y, p2.y) && !K::is_zero(p1.y)) {
       kind = kPairDouble;
-      fp_dbl<F>(d, p1.y);
+      K::dbl(d, p1.y);
     } else {
       kind = kPairZero;
     }
   }
-  if (kind >= kPairCopy1) fp_set_one<F>(d);
+  if (kind >= kPairCopy1) K::set_one(d);
   return kind;
 }
 
@@ -557,8 +578,8 @@ __global__ void __launch_bounds__(kPairThreads, AccMinBlocks<C>()) pair_round_ke
     const uint32_t* __restrict__ bases, const uint32_t* __restrict__ in,
     const MsmTotals* __restrict__ totals, uint32_t round, uint32_t* __restrict__ prefix,
     uint32_t* __restrict__ out) {
-  using Fq = typename C::Fq;
-  constexpr int N = Fp<Fq>::N;
+  using K = typename C::Field;
+  constexpr int N = K::kWords;
   constexpr int kAffineWords = 2 * N;
   const uint32_t pairs = (totals->entries >> round) >> 1;  // entries is a multiple of 2^R
   const uint32_t T = gridDim.x * blockDim.x;
@@ -567,63 +588,64 @@ __global__ void __launch_bounds__(kPairThreads, AccMinBlocks<C>()) pair_round_ke
   const uint32_t B = (pairs - t + T - 1) / T;  // this thread's batch
 
   // ---- forward: prefix products of the denominators ---------------------------------
-  Fp<Fq> acc;
-  fp_set_one<Fq>(acc);
+  typename K::El acc;
+  K::set_one(acc);
   {
-    Affine<Fq> n1, n2;
+    Affine<K> n1, n2;
     pair_load<C, kFirst>(n1, n2, t, bases, in);
     for (uint32_t j = 0; j < B; ++j) {
-      Affine<Fq> p1 = n1, p2 = n2;
+      Affine<K> p1 = n1, p2 = n2;
       if (j + 1 < B) pair_load<C, kFirst>(n1, n2, t + (j + 1) * T, bases, in);
-      Fp<Fq> d;
-      pair_denominator<Fq>(d, p1, p2);
-      fp_store<Fq>(prefix + ((size_t)j * T + t) * N, acc);
-      fp_mul<Fq>(acc, acc, d);
+      typename K::El d;
+      pair_denominator<K>(d, p1, p2);
+      K::store(prefix + ((size_t)j * T + t) * N, acc);
+      K::mul(acc, acc, d);
     }
   }
-  Fp<Fq> inv;
-  fp_inv<Fq>(inv, acc);
+  typename K::El inv;
+  K::inv(inv, acc);
 
   // ---- backward: the additions --------------------------------------------------------
-  Affine<Fq> n1, n2;
-  Fp<Fq> npre;
+  Affine<K> n1, n2;
+  typename K::El npre;
   pair_load<C, kFirst>(n1, n2, t + (B - 1) * T, bases, in);
-  fp_load_rw<Fq>(npre, prefix + ((size_t)(B - 1) * T + t) * N);
+  K::load_rw(npre, prefix + ((size_t)(B - 1) * T + t) * N);
   for (uint32_t j = B; j-- > 0;) {
-    Affine<Fq> p1 = n1, p2 = n2;
-    Fp<Fq> pre = npre;
+    Affine<K> p1 = n1, p2 = n2;
+    typename K::El pre = npre;
     if (j > 0) {
       pair_load<C, kFirst>(n1, n2, t + (j - 1) * T, bases, in);
-      fp_load_rw<Fq>(npre, prefix + ((size_t)(j - 1) * T + t) * N);
+      K::load_rw(npre, prefix + ((size_t)(j - 1) * T + t) * N);
     }
-    Fp<Fq> d, dinv, num, lam, x3, y3, tt;
-    uint32_t kind = pair_denominator<Fq>(d, p1, p2);
-    fp_mul<Fq>(dinv, inv, pre);  // 1 / d_j
-    fp_mul<Fq>(inv, inv, d);     // inverse of the remaining prefix
-    fp_sub<Fq>(num, p2.y, p1.y);
+    typename K::El d, dinv, num, lam, x3, y3, tt;
+    uint32_t kind = pair_denominator<K>(d, p1, p2);
+    K::mul(dinv, inv, pre);  // 1 / d_j
+    K::mul(inv, inv, d);     // inverse of the remaining prefix
+    K::sub(num, p2.y, p1.y);
     if (kind == kPairDouble) {   // lambda = 3 x1^2 / (2 y1)
-      fp_sqr<Fq>(tt, p1.x);
-      fp_dbl<Fq>(num, tt);
-      fp_add<Fq>(num, num, tt);
+      K::sqr(tt, p1.x);
+      K::dbl(num, tt);
+      K::add(num, num, tt);
     }
-    fp_mul<Fq>(lam, num, dinv);
-    fp_sqr<Fq>(x3, lam);         // x3 = lambda^2 - x1 - x2
-    fp_sub<Fq>(x3, x3, p1.x);
-    fp_sub<Fq>(x3, x3, p2.x);
-    fp_sub<Fq>(tt, p1.x, x3);    // y3 = lambda (x1 - x3) - y1
-    fp_mul<Fq>(y3, lam, tt);
-    fp_sub<Fq>(y3, y3, p1.y);
-    Affine<Fq> r;
-#pragma unroll
-    for (int i = 0; i < N; ++i) {
-      uint32_t cx = kind == kPairCopy1 ? p1.x.l[i] : (kind == kPairCopy2 ? p2.x.l[i] : 0u);
-      uint32_t cy = kind == kPairCopy1 ? p1.y.l[i] : (kind == kPairCopy2 ? p2.y.l[i] : 0u);
-      r.x.l[i] = kind <= kPairDouble ? x3.l[i] : cx;
-      r.y.l[i] = kind <= kPairDouble ? y3.l[i] : cy;
-    }
+    K::mul(lam, num, dinv);
+    K::sqr(x3, lam);         // x3 = lambda^2 - x1 - x2
+    K::sub(x3, x3, p1.x);
+    K::sub(x3, x3, p2.x);
+    K::sub(tt, p1.x, x3);    // y3 = lambda (x1 - x3) - y1
+    K::mul(y3, lam, tt);
+    K::sub(y3, y3, p1.y);
+    Affine<K> r, cp;
+    typename K::El zero;
+    K::set_zero(zero);
+    K::select(cp.x, kind == kPairCopy1, p1.x, p2.x);  // the operand that is not the identity
+    K::select(cp.y, kind == kPairCopy1, p1.y, p2.y);
+    K::select(cp.x, kind == kPairZero, zero, cp.x);
+    K::select(cp.y, kind == kPairZero, zero, cp.y);
+    K::select(r.x, kind <= kPairDouble, x3, cp.x);
+    K::select(r.y, kind <= kPairDouble, y3, cp.y);
     uint32_t* dst = out + (size_t)(t + j * T) * kAffineWords;
-    fp_store<Fq>(dst, r.x);
-    fp_store<Fq>(dst + N, r.y);
+    K::store(dst, r.x);
+    K::store(dst + N, r.y);
   }
 }
 
@@ -637,19 +659,19 @@ __global__ void __launch_bounds__(kFoldThreads) fold_partials_kernel(
     const uint32_t* __restrict__ multi_keys, const MsmTotals* __restrict__ totals,
     const uint32_t* __restrict__ offset, const uint32_t* __restrict__ task_base, uint32_t seg,
     uint32_t R, const uint32_t* __restrict__ task_out, uint32_t* __restrict__ state) {
-  using Fq = typename C::Fq;
-  constexpr int kXyzzWords = 4 * Fp<Fq>::N;
+  using K = typename C::Field;
+  constexpr int kXyzzWords = 4 * K::kWords;
   __shared__ uint32_t sh[kFoldThreads / 2 * kXyzzWords];
   for (uint32_t m = blockIdx.x; m < totals->multi; m += gridDim.x) {
     uint32_t key = multi_keys[m];
     uint32_t cnt = (offset[key + 1] - offset[key]) >> R;  // padded run after the pair rounds
     uint32_t t = (cnt + seg - 1) / seg;
     const uint32_t* slots = task_out + (size_t)task_base[key] * kXyzzWords;
-    XYZZ<Fq> acc, tmp;
-    xyzz_set_zero<Fq>(acc);
+    XYZZ<K> acc, tmp;
+    xyzz_set_zero<K>(acc);
     for (uint32_t s = threadIdx.x; s < t; s += kFoldThreads) {
-      xyzz_load<Fq>(tmp, slots + (size_t)s * kXyzzWords);
-      xyzz_add<Fq>(acc, tmp);
+      xyzz_load<K>(tmp, slots + (size_t)s * kXyzzWords);
+      xyzz_add<K>(acc, tmp);
     }
     // tree over the threads that hold something: first power of two >= min(t, threads)
     int live = t < (uint32_t)kFoldThreads ? (int)t : kFoldThreads;
@@ -657,15 +679,15 @@ __global__ void __launch_bounds__(kFoldThreads) fold_partials_kernel(
     while (top < live) top <<= 1;
     for (int stride = top / 2; stride >= 1; stride >>= 1) {
       if ((int)threadIdx.x >= stride && (int)threadIdx.x < 2 * stride)
-        xyzz_store<Fq>(sh + (threadIdx.x - stride) * kXyzzWords, acc);
+        xyzz_store<K>(sh + (threadIdx.x - stride) * kXyzzWords, acc);
       __syncthreads();
       if ((int)threadIdx.x < stride) {
-        xyzz_load<Fq>(tmp, sh + threadIdx.x * kXyzzWords);
-        xyzz_add<Fq>(acc, tmp);
+        xyzz_load<K>(tmp, sh + threadIdx.x * kXyzzWords);
+        xyzz_add<K>(acc, tmp);
       }
       __syncthreads();
     }
-    if (threadIdx.x == 0) xyzz_store<Fq>(state + (size_t)key * kXyzzWords, acc);
+    if (threadIdx.x == 0) xyzz_store<K>(state + (size_t)key * kXyzzWords, acc);
     __syncthreads();
   }
 }
@@ -687,33 +709,33 @@ __global__ void __launch_bounds__(kReduceThreads) reduce_level_kernel(
     const uint32_t* __restrict__ in_a, const uint32_t* __restrict__ in_c, uint32_t n_in,
     uint32_t n_out, uint32_t L, uint32_t shift, uint32_t windows, uint32_t* __restrict__ out_a,
     uint32_t* __restrict__ out_c) {
-  using Fq = typename C::Fq;
-  constexpr int kXyzzWords = 4 * Fp<Fq>::N;
+  using K = typename C::Field;
+  constexpr int kXyzzWords = 4 * K::kWords;
   uint32_t g = blockIdx.x * blockDim.x + threadIdx.x;
   if (g >= n_out * windows) return;
   uint32_t w = g / n_out, t = g % n_out;
   uint32_t lo = t * L, hi = min(n_in, lo + L);
-  XYZZ<Fq> run, wt, csum, item;
-  xyzz_set_zero<Fq>(run);
-  xyzz_set_zero<Fq>(wt);
-  xyzz_set_zero<Fq>(csum);
+  XYZZ<K> run, wt, csum, item;
+  xyzz_set_zero<K>(run);
+  xyzz_set_zero<K>(wt);
+  xyzz_set_zero<K>(csum);
   for (uint32_t k = hi; k-- > lo;) {
     uint32_t idx = w * n_in + k;
     if (kFirst) {
-      xyzz_load<Fq>(item, in_a + (size_t)idx * kXyzzWords);
-      xyzz_add<Fq>(run, item);
+      xyzz_load<K>(item, in_a + (size_t)idx * kXyzzWords);
+      xyzz_add<K>(run, item);
     } else {
-      xyzz_load<Fq>(item, in_a + (size_t)idx * kXyzzWords);
-      xyzz_add<Fq>(run, item);
-      xyzz_load<Fq>(item, in_c + (size_t)idx * kXyzzWords);
-      xyzz_add<Fq>(csum, item);
+      xyzz_load<K>(item, in_a + (size_t)idx * kXyzzWords);
+      xyzz_add<K>(run, item);
+      xyzz_load<K>(item, in_c + (size_t)idx * kXyzzWords);
+      xyzz_add<K>(csum, item);
     }
-    if (k > lo) xyzz_add<Fq>(wt, run);
+    if (k > lo) xyzz_add<K>(wt, run);
   }
-  for (uint32_t s = 0; s < shift; ++s) xyzz_dbl<Fq>(wt);
-  xyzz_add<Fq>(csum, wt);
-  xyzz_store<Fq>(out_a + (size_t)g * kXyzzWords, run);
-  xyzz_store<Fq>(out_c + (size_t)g * kXyzzWords, csum);
+  for (uint32_t s = 0; s < shift; ++s) xyzz_dbl<K>(wt);
+  xyzz_add<K>(csum, wt);
+  xyzz_store<K>(out_a + (size_t)g * kXyzzWords, run);
+  xyzz_store<K>(out_c + (size_t)g * kXyzzWords, csum);
 }
 
 // Tail of the bucket reduction.  After level 0 every window has m = 2^M blocks t with
@@ -730,8 +752,8 @@ template <class C>
 __global__ void __launch_bounds__(kReduceThreads) reduce_merge_kernel(
     const uint32_t* __restrict__ in, const uint32_t* __restrict__ in_p0, uint32_t s,
     uint32_t m_out, uint32_t windows, uint32_t* __restrict__ out) {
-  using Fq = typename C::Fq;
-  constexpr int kXyzzWords = 4 * Fp<Fq>::N;
+  using K = typename C::Field;
+  constexpr int kXyzzWords = 4 * K::kWords;
   uint32_t vin = s + 2, vout = s + 3;
   uint32_t g = blockIdx.x * blockDim.x + threadIdx.x;
   if (g >= windows * m_out * vout) return;
@@ -744,16 +766,16 @@ __global__ void __launch_bounds__(kReduceThreads) reduce_merge_kernel(
     if (s == 0) return (val == 0 ? in : in_p0) + nd * kXyzzWords;
     return in + (nd * vin + val) * kXyzzWords;
   };
-  XYZZ<Fq> a;
+  XYZZ<K> a;
   if (v == s + 2) {
-    xyzz_load<Fq>(a, src(right, 0));  // D_s = A_r
+    xyzz_load<K>(a, src(right, 0));  // D_s = A_r
   } else {
-    XYZZ<Fq> b;
-    xyzz_load<Fq>(a, src(left, v));
-    xyzz_load<Fq>(b, src(right, v));
-    xyzz_add<Fq>(a, b);
+    XYZZ<K> b;
+    xyzz_load<K>(a, src(left, v));
+    xyzz_load<K>(b, src(right, v));
+    xyzz_add<K>(a, b);
   }
-  xyzz_store<Fq>(out + (size_t)g * kXyzzWords, a);
+  xyzz_store<K>(out + (size_t)g * kXyzzWords, a);
 }
 
 // ---------------------------------------------------------------------------
@@ -785,29 +807,51 @@ __global__ void field_op_kernel(int op, const uint32_t* a, const uint32_t* b, ui
   fp_store<F>(out + (size_t)i * N, r);
 }
 
+// The same hook for an extension field kind (Fq2): ops 0..6 as above.
+template <class K>
+__global__ void ext_field_op_kernel(int op, const uint32_t* a, const uint32_t* b, uint32_t* out,
+                                    uint32_t n) {
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  constexpr int N = K::kWords;
+  typename K::El x, y, r;
+  K::load(x, a + (size_t)i * N);
+  K::load(y, b + (size_t)i * N);
+  switch (op) {
+    case 0: K::add(r, x, y); break;
+    case 1: K::sub(r, x, y); break;
+    case 2: K::mul(r, x, y); break;
+    case 3: K::sqr(r, x); break;
+    case 4: K::neg(r, x); break;
+    case 5: K::dbl(r, x); break;
+    default: K::inv(r, x); break;
+  }
+  K::store(out + (size_t)i * N, r);
+}
+
 // op 0: out = a + b (XYZZ + XYZZ); 1: out = a + affine b; 2: out = a - affine b;
 // 3: out = 2a.  a, out: XYZZ arrays; b: XYZZ (op 0) or affine (op 1, 2).
 template <class C>
 __global__ void point_op_kernel(int op, const uint32_t* a, const uint32_t* b, uint32_t* out,
                                 uint32_t n) {
-  using Fq = typename C::Fq;
-  constexpr int N = Fp<Fq>::N;
+  using K = typename C::Field;
+  constexpr int N = K::kWords;
   uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
-  XYZZ<Fq> p;
-  xyzz_load<Fq>(p, a + (size_t)i * 4 * N);
+  XYZZ<K> p;
+  xyzz_load<K>(p, a + (size_t)i * 4 * N);
   if (op == 0) {
-    XYZZ<Fq> q;
-    xyzz_load<Fq>(q, b + (size_t)i * 4 * N);
-    xyzz_add<Fq>(p, q);
+    XYZZ<K> q;
+    xyzz_load<K>(q, b + (size_t)i * 4 * N);
+    xyzz_add<K>(p, q);
   } else if (op == 1 || op == 2) {
-    Affine<Fq> q;
-    affine_load<Fq>(q, b + (size_t)i * 2 * N);
-    xyzz_madd<Fq>(p, q, op == 2);
+    Affine<K> q;
+    affine_load<K>(q, b + (size_t)i * 2 * N);
+    xyzz_madd<K>(p, q, op == 2);
   } else {
-    xyzz_dbl<Fq>(p);
+    xyzz_dbl<K>(p);
   }
-  xyzz_store<Fq>(out + (size_t)i * 4 * N, p);
+  xyzz_store<K>(out + (size_t)i * 4 * N, p);
 }
 
 // ---------------------------------------------------------------------------
@@ -828,29 +872,26 @@ constexpr uint32_t kChainLog = 12;
 template <class C>
 __global__ void generate_chains_kernel(uint64_t seed, uint32_t first_chain, uint32_t n_chains,
                                        uint32_t n_points, uint32_t* __restrict__ out_xyzz) {
-  using Fq = typename C::Fq;
-  constexpr int N = Fp<Fq>::N;
+  using K = typename C::Field;
+  constexpr int N = K::kWords;
   uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= n_chains) return;
   uint64_t h = splitmix64_at(seed ^ 0x7074ull, first_chain + t) | 1ull;
-  Affine<Fq> gen;
-#pragma unroll
-  for (int i = 0; i < N; ++i) {
-    gen.x.l[i] = C::Gen::x32(i);
-    gen.y.l[i] = C::Gen::y32(i);
-  }
-  XYZZ<Fq> p;
-  xyzz_set_zero<Fq>(p);
+  Affine<K> gen;
+  K::template set_words<typename C::Gen>(gen.x, 0);
+  K::template set_words<typename C::Gen>(gen.y, N);
+  XYZZ<K> p;
+  xyzz_set_zero<K>(p);
   for (int bit = 63; bit >= 0; --bit) {
-    xyzz_dbl<Fq>(p);
-    if ((h >> bit) & 1) xyzz_madd<Fq>(p, gen, false);
+    xyzz_dbl<K>(p);
+    if ((h >> bit) & 1) xyzz_madd<K>(p, gen, false);
   }
   uint32_t chain_len = 1u << kChainLog;
   for (uint32_t d = 0; d < chain_len; ++d) {
     uint64_t i = (uint64_t)t * chain_len + d;
     if (i >= n_points) break;
-    xyzz_store<Fq>(out_xyzz + i * 4 * N, p);
-    xyzz_dbl<Fq>(p);
+    xyzz_store<K>(out_xyzz + i * 4 * N, p);
+    xyzz_dbl<K>(p);
   }
 }
 
@@ -858,26 +899,26 @@ __global__ void generate_chains_kernel(uint64_t seed, uint32_t first_chain, uint
 template <class C>
 __global__ void normalize_kernel(const uint32_t* __restrict__ in_xyzz, uint32_t n,
                                  uint32_t* __restrict__ out_affine) {
-  using Fq = typename C::Fq;
-  constexpr int N = Fp<Fq>::N;
+  using K = typename C::Field;
+  constexpr int N = K::kWords;
   uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
-  XYZZ<Fq> p;
-  xyzz_load<Fq>(p, in_xyzz + (size_t)i * 4 * N);
-  Affine<Fq> a;
-  if (xyzz_is_zero<Fq>(p)) {
-    fp_set_zero<Fq>(a.x);
-    fp_set_zero<Fq>(a.y);
+  XYZZ<K> p;
+  xyzz_load<K>(p, in_xyzz + (size_t)i * 4 * N);
+  Affine<K> a;
+  if (xyzz_is_zero<K>(p)) {
+    K::set_zero(a.x);
+    K::set_zero(a.y);
   } else {
-    Fp<Fq> zi3, zi2;
-    fp_inv<Fq>(zi3, p.zzz);
-    fp_mul<Fq>(zi2, zi3, p.zz);
-    fp_sqr<Fq>(zi2, zi2);
-    fp_mul<Fq>(a.x, p.x, zi2);
-    fp_mul<Fq>(a.y, p.y, zi3);
+    typename K::El zi3, zi2;
+    K::inv(zi3, p.zzz);
+    K::mul(zi2, zi3, p.zz);
+    K::sqr(zi2, zi2);
+    K::mul(a.x, p.x, zi2);
+    K::mul(a.y, p.y, zi3);
   }
-  fp_store<Fq>(out_affine + (size_t)i * 2 * N, a.x);
-  fp_store<Fq>(out_affine + (size_t)i * 2 * N + N, a.y);
+  K::store(out_affine + (size_t)i * 2 * N, a.x);
+  K::store(out_affine + (size_t)i * 2 * N + N, a.y);
 }
 
 // dist: 0 uniform, 1 non_uniform (one scalar repeated), 2 witness

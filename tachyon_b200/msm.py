@@ -28,10 +28,13 @@ def _ptr(x):
 
 class MSMGpu:
     def __init__(self, curve="bn254", degree=20, device=None, banner=False):
-        self.curve = curve
-        self.fq_limbs = _lib.CURVES[curve]
+        """curve: "bn254", "bls12_381" (G1) or "bn254_g2", "bls12_381_g2" (G2)."""
+        self.name = curve
+        curve, group = _lib.split_name(curve)
+        self.curve, self.group = curve, group
+        self.fq_limbs = _lib.element_limbs(self.name)   # u64 limbs of one point coordinate
         self.L = _lib.load()
-        self._f = lambda name: getattr(self.L, f"tachyon_{curve}_{name}")
+        self._f = lambda name: getattr(self.L, f"tachyon_{curve}_" + name.replace("g1_", group + "_", 1))
         self._f("g1_init")()
         if banner:
             self.ptr = self._f("g1_create_msm_gpu")(degree)   # reference entry point
@@ -118,6 +121,12 @@ class MSMGpu:
         return t.as_dict()
 
 
+def _sym(name, fn):
+    """C symbol of a per-group function for a curve name such as "bn254" or "bn254_g2"."""
+    curve, group = _lib.split_name(name)
+    return getattr(_lib.load(), f"tachyon_{curve}_{group}_{fn}")
+
+
 _libstdcxx = None
 
 
@@ -132,14 +141,11 @@ def _free_cxx(p):
 
 
 def generate_bases_device(curve, seed, n, device_ptr, first=0):
-    L = _lib.load()
-    _lib.check(getattr(L, f"tachyon_{curve}_g1_generate_bases_b200")(seed, first, n, ctypes.c_void_p(device_ptr)),
-               "generate_bases")
+    _lib.check(_sym(curve, "generate_bases_b200")(seed, first, n, ctypes.c_void_p(device_ptr)), "generate_bases")
 
 
 def generate_scalars_device(curve, seed, n, device_ptr, dist="uniform", first=0):
-    L = _lib.load()
-    _lib.check(getattr(L, f"tachyon_{curve}_g1_generate_scalars_b200")(
+    _lib.check(_sym(curve, "generate_scalars_b200")(
         seed, DIST[dist], first, n, ctypes.c_void_p(device_ptr)), "generate_scalars")
 
 
@@ -149,6 +155,7 @@ def field_op(curve, field, op, a, b=None):
     a = np.ascontiguousarray(a, dtype=np.uint64)
     b = a if b is None else np.ascontiguousarray(b, dtype=np.uint64)
     out = np.empty_like(a)
+    curve = _lib.split_name(curve)[0]
     _lib.check(getattr(L, f"tachyon_{curve}_{field}_op_b200")(FIELD_OPS[op], _ptr(a), _ptr(b), _ptr(out), a.shape[0]),
                f"{field}_op")
     return out
@@ -159,8 +166,7 @@ def point_op(curve, op, a_xyzz, b=None):
     a = np.ascontiguousarray(a_xyzz, dtype=np.uint64)
     out = np.empty_like(a)
     bp = _ptr(np.ascontiguousarray(b, dtype=np.uint64)) if b is not None else ctypes.c_void_p(0)
-    _lib.check(getattr(L, f"tachyon_{curve}_g1_point_op_b200")(POINT_OPS[op], _ptr(a), bp, _ptr(out), a.shape[0]),
-               "point_op")
+    _lib.check(_sym(curve, "point_op_b200")(POINT_OPS[op], _ptr(a), bp, _ptr(out), a.shape[0]), "point_op")
     return out
 
 
@@ -185,7 +191,7 @@ def xyzz_add(curve, a, b):
     a = np.ascontiguousarray(a, dtype=np.uint64)
     b = np.ascontiguousarray(b, dtype=np.uint64)
     out = np.empty_like(a)
-    getattr(L, f"tachyon_{curve}_g1_xyzz_add_b200")(_ptr(a), _ptr(b), _ptr(out))
+    _sym(curve, "xyzz_add_b200")(_ptr(a), _ptr(b), _ptr(out))
     return out
 
 
@@ -193,7 +199,7 @@ def xyzz_to_jacobian(curve, a):
     L = _lib.load()
     a = np.ascontiguousarray(a, dtype=np.uint64)
     out = np.zeros((3, a.shape[-1]), dtype=np.uint64)
-    getattr(L, f"tachyon_{curve}_g1_xyzz_to_jacobian_b200")(_ptr(a), _ptr(out))
+    _sym(curve, "xyzz_to_jacobian_b200")(_ptr(a), _ptr(out))
     return out
 
 
@@ -203,7 +209,7 @@ def batch_normalize(curve, xyzz):
     a = np.ascontiguousarray(xyzz, dtype=np.uint64)
     n = a.shape[0]
     out = np.zeros((n, 2 * a.shape[-1]), dtype=np.uint64)
-    getattr(L, f"tachyon_{curve}_g1_xyzz_batch_normalize_b200")(_ptr(a), n, _ptr(out))
+    _sym(curve, "xyzz_batch_normalize_b200")(_ptr(a), n, _ptr(out))
     return out
 
 

@@ -16,4 +16,4 @@ def pytest_configure(config):
 def oracles():
     from oracle import cpu_oracle
     cpu_oracle.build()
-    return {n: cpu_oracle.CurveOracle(n) for n in ("bn254", "bls12_381")}
+    return {n: cpu_oracle.CurveOracle(n) for n in ("bn254", "bls12_381", "bn254_g2", "bls12_381_g2")}

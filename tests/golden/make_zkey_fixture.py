@@ -41,15 +41,21 @@ def main():
     pts = {}
     pts["alpha_g1"] = hdr[off:off + 2 * n8q].hex(); off += 2 * n8q
     pts["beta_g1"] = hdr[off:off + 2 * n8q].hex(); off += 2 * n8q
-    off += 4 * n8q  # beta2
-    off += 4 * n8q  # gamma2
+    pts["beta_g2"] = hdr[off:off + 4 * n8q].hex(); off += 4 * n8q
+    pts["gamma_g2"] = hdr[off:off + 4 * n8q].hex(); off += 4 * n8q
     pts["delta_g1"] = hdr[off:off + 2 * n8q].hex(); off += 2 * n8q
+    pts["delta_g2"] = hdr[off:off + 4 * n8q].hex(); off += 4 * n8q
 
     test_src = open(f"{REF}/circomlib/zkey/zkey_unittest.cc").read()
     expected = {}
     for name in ("alpha_g1", "beta_g1", "delta_g1"):
         m = re.search(name + r"_str\[2\]\s*=\s*\{\s*\"(\d+)\",\s*\"(\d+)\"", test_src)
         expected[name] = [m.group(1), m.group(2)]
+    # G2 points: x = (c0, c1), y = (c0, c1), stored c0 first (zkey_unittest.cc:84-119)
+    for name in ("beta_g2", "gamma_g2", "delta_g2"):
+        m = re.search(name + r"_str\[2\]\[2\]\s*=\s*\{\s*\{\s*\"(\d+)\",\s*\"(\d+)\",?\s*\},\s*\{\s*\"(\d+)\",\s*\"(\d+)\"",
+                      test_src)
+        expected[name] = [m.group(1), m.group(2), m.group(3), m.group(4)]
     out = {
         "source": "vendors/circom/examples/multiplier_3.zkey + circomlib/zkey/zkey_unittest.cc:66-101",
         "q": str(q), "r": str(r), "n8q": n8q,

@@ -14,6 +14,17 @@ from tachyon_b200 import msm
 pytestmark = pytest.mark.gpu
 
 CURVES = ["bn254", "bls12_381"]
+G2 = ["bn254_g2", "bls12_381_g2"]          # the same pipeline over Fq2 coordinates
+ALL = CURVES + G2
+
+
+def _consts(name):
+    """(r, u64 limbs of one point coordinate) for a G1 or G2 name."""
+    if name in pymodel.CURVES:
+        c = pymodel.CURVES[name]
+        return c.r, c.fq_limbs
+    c = pymodel.CURVES_G2[name]
+    return c.r, 2 * c.fq_limbs
 
 
 @pytest.fixture(scope="module")
@@ -54,9 +65,24 @@ def test_fr_montgomery_conversion(oracles, torch_cuda, name):
     assert (msm.field_op(name, "fr", "to_mont", a) == o.fr_to_mont(a)).all()
 
 
-@pytest.mark.parametrize("name", CURVES)
+@pytest.mark.parametrize("name", G2)
+def test_fq2_ops(oracles, torch_cuda, name):
+    """Fq2 = Fq[u]/(u^2 + 1) on the device against the oracle (quadratic_extension_field.h)."""
+    o = oracles[name]
+    c = pymodel.CURVES_G2[name]
+    a = np.concatenate([_rand_elems(c.p, c.fq_limbs, 2000, 5), _rand_elems(c.p, c.fq_limbs, 2000, 6)[::-1]], axis=1)
+    b = np.concatenate([_rand_elems(c.p, c.fq_limbs, 2000, 7)[::-1], _rand_elems(c.p, c.fq_limbs, 2000, 8)], axis=1)
+    for op in ("add", "sub", "mul"):
+        assert (msm.field_op(name, "fq2", op, a, b) == o.fq_op(op, a, b)).all(), op
+    for op in ("square", "neg", "double"):
+        assert (msm.field_op(name, "fq2", op, a) == o.fq_op(op, a)).all(), op
+    nz = a[6:200]
+    assert (msm.field_op(name, "fq2", "inverse", nz) == o.fq_op("inverse", nz)).all()
+
+
+@pytest.mark.parametrize("name", ALL)
 def test_point_ops(oracles, torch_cuda, name):
-    o, c = oracles[name], pymodel.CURVES[name]
+    o = oracles[name]
     n = 96
     aff = o.generate_points(11, n)
     ks = o.fr_from_mont(o.generate_scalars(12, n))
@@ -106,7 +132,7 @@ def _to_np(t):
     return t.cpu().numpy().view(np.uint64)
 
 
-@pytest.mark.parametrize("name", CURVES)
+@pytest.mark.parametrize("name", ALL)
 def test_generators_match_oracle(oracles, torch_cuda, name):
     o = oracles[name]
     n = 4096 + 300
@@ -137,7 +163,18 @@ def test_msm_host_inputs(oracles, torch_cuda, name, n):
         _check_msm(o, name, ctx, bases, scalars, entry="point2")
 
 
-@pytest.mark.parametrize("name", CURVES)
+@pytest.mark.parametrize("name", G2)
+@pytest.mark.parametrize("n", [0, 1, 2, 5, 33, 1000, 5000])
+def test_g2_msm_host_inputs(oracles, torch_cuda, name, n):
+    # VariableBaseMSMGpu<G2AffinePoint> (groth16/prove.h:129-131) vs the CPU path
+    o = oracles[name]
+    bases, scalars = o.generate_points(100 + n, n), o.generate_scalars(200 + n, n)
+    with msm.MSMGpu(name) as ctx:
+        _check_msm(o, name, ctx, bases, scalars, entry="affine")
+        _check_msm(o, name, ctx, bases, scalars, entry="point2")
+
+
+@pytest.mark.parametrize("name", ALL)
 @pytest.mark.parametrize("dist", ["non_uniform", "witness"])
 def test_msm_skewed_scalars(oracles, torch_cuda, name, dist):
     o = oracles[name]
@@ -151,19 +188,20 @@ def test_msm_skewed_scalars(oracles, torch_cuda, name, dist):
         assert t["tasks"] > 0 and t["entries"] > 0
 
 
-@pytest.mark.parametrize("name", CURVES)
+@pytest.mark.parametrize("name", ALL)
 def test_msm_edge_cases(oracles, torch_cuda, name):
-    o, c = oracles[name], pymodel.CURVES[name]
+    o = oracles[name]
+    r_mod, el = _consts(name)
     n = 600
     bases, scalars = o.generate_points(41, n), o.generate_scalars(42, n, "witness")
     bases[3] = 0                                    # identity base (0, 0)
     bases[9] = bases[8]                             # duplicate point, equal scalar -> doubling branch
     scalars[9] = scalars[8]
     neg_y = o.fq_op("neg", bases[10].reshape(2, -1)[1:2])
-    bases[11] = np.concatenate([bases[10][:c.fq_limbs], neg_y[0]])   # P and -P with equal scalars
+    bases[11] = np.concatenate([bases[10][:el], neg_y[0]])   # P and -P with equal scalars
     scalars[11] = scalars[10]
-    for i, v in enumerate((c.r - 1, 1, 0, (1 << 253) + 12345, c.r - 2)):
-        scalars[20 + i] = np.array(pymodel.to_limbs(pymodel.fr_to_mont(c, v % c.r), 4), dtype=np.uint64)
+    for i, v in enumerate((r_mod - 1, 1, 0, (1 << 253) + 12345, r_mod - 2)):
+        scalars[20 + i] = o.fr_to_mont(np.array(pymodel.to_limbs(v % r_mod, 4), dtype=np.uint64))[0]
     bases[100:140] = bases[100]                     # many copies of one point, random scalars
     with msm.MSMGpu(name) as ctx:
         _check_msm(o, name, ctx, bases, scalars)
@@ -175,7 +213,7 @@ def test_msm_edge_cases(oracles, torch_cuda, name):
         _check_msm(o, name, ctx, same, o.generate_scalars(43, n))   # all bases equal
 
 
-@pytest.mark.parametrize("name", CURVES)
+@pytest.mark.parametrize("name", ALL)
 def test_msm_window_sweep(oracles, torch_cuda, name):
     o = oracles[name]
     n = 3000
@@ -189,7 +227,7 @@ def test_msm_window_sweep(oracles, torch_cuda, name):
             assert ctx.last_timing()["window_bits"] == cbits
 
 
-@pytest.mark.parametrize("name", CURVES)
+@pytest.mark.parametrize("name", ALL)
 def test_msm_device_resident_inputs(oracles, torch_cuda, name):
     o = oracles[name]
     n = 1 << 13
@@ -376,7 +414,8 @@ def test_dump_and_replay_cli(oracles, torch_cuda, name, tmp_path, monkeypatch):
 # are chains P_(j,d) = 2^d H_j, so MSM(P, s) == MSM(H, fold(s)) with
 # fold(s)_j = sum_d s_(j,d) 2^d mod r — a 2^12-times smaller MSM the oracle does in
 # milliseconds.
-@pytest.mark.parametrize("name,logn", [("bn254", 16), ("bn254", 20), ("bls12_381", 18)])
+@pytest.mark.parametrize("name,logn", [("bn254", 16), ("bn254", 20), ("bls12_381", 18), ("bn254_g2", 16),
+                                       ("bls12_381_g2", 14)])
 def test_msm_full_size_chain_fold(oracles, torch_cuda, name, logn):
     o = oracles[name]
     n = 1 << logn

@@ -16,8 +16,9 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 def test_header_symbols_exported():
     hdr = open(os.path.join(ROOT, "include", "tachyon_msm_b200.h")).read()
     # per-curve declarations live in the TACHYON_B200_DECLARE_CURVE macro
-    macro_names = set(re.findall(r"(tachyon_##C##_\w+)\s*\(", hdr))
-    declared = {n.replace("##C##", c) for n in macro_names for c in _lib.CURVES}
+    macro_names = set(re.findall(r"(tachyon_##C##_[#\w]+)\s*\(", hdr))
+    declared = {n.replace("##C##", c).replace("##G##", g) for n in macro_names for c in _lib.CURVES
+                for g in (_lib.GROUPS if "##G##" in n else ("",))}
     declared |= set(re.findall(r"\b(tachyon_b200_\w+)\s*\(", hdr))
     assert declared == set(_lib.all_symbols())
     L = _lib.load()
@@ -39,6 +40,9 @@ def test_header_compiles_as_c(tmp_path):
                    "_Static_assert(sizeof(struct tachyon_bls12_381_g1_affine) == 96, \"\");\n"
                    "_Static_assert(sizeof(struct tachyon_bls12_381_g1_jacobian) == 144, \"\");\n"
                    "_Static_assert(sizeof(struct tachyon_bls12_381_g1_xyzz) == 192, \"\");\n"
+                   "_Static_assert(sizeof(struct tachyon_bn254_g2_affine) == 128, \"\");\n"
+                   "_Static_assert(sizeof(struct tachyon_bn254_g2_jacobian) == 192, \"\");\n"
+                   "_Static_assert(sizeof(struct tachyon_bls12_381_g2_xyzz) == 384, \"\");\n"
                    "int main(void) { return 0; }\n")
     import subprocess
     subprocess.check_call(["/usr/bin/gcc", "-std=c11", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"),
@@ -56,7 +60,7 @@ def test_window_rule_host():
     assert msm.window_bits(1 << 24, 254) >= msm.window_bits(1 << 16, 254)
 
 
-@pytest.mark.parametrize("name", ["bn254", "bls12_381"])
+@pytest.mark.parametrize("name", ["bn254", "bls12_381", "bn254_g2", "bls12_381_g2"])
 def test_host_point_helpers_vs_oracle(oracles, name):
     o = oracles[name]
     pts = o.generate_points(5, 6)
@@ -74,7 +78,7 @@ def test_host_point_helpers_vs_oracle(oracles, name):
     assert (o.xyzz_to_affine(msm.xyzz_add(name, xs[5], neg)) == 0).all()
 
 
-@pytest.mark.parametrize("name", ["bn254", "bls12_381"])
+@pytest.mark.parametrize("name", ["bn254", "bls12_381", "bn254_g2", "bls12_381_g2"])
 def test_batch_normalize_vs_oracle(oracles, name):
     # point_xyzz.h:109-163 BatchNormalize: one inversion for the whole batch, identity -> (0, 0)
     o = oracles[name]

@@ -92,6 +92,8 @@ def test_zkey_montgomery_layout(oracles):
     o, c = oracles["bn254"], pymodel.BN254
     assert int(fx["q"]) == c.p and int(fx["r"]) == c.r
     for name, hx in fx["montgomery_bytes_hex"].items():
+        if name.endswith("_g2"):
+            continue  # the G2 header points are checked in tests/test_oracle_g2.py
         limbs = np.frombuffer(bytes.fromhex(hx), dtype="<u8").reshape(2, 4)
         canon = o.fq_from_mont(limbs)
         got = [pymodel.from_limbs(canon[0]), pymodel.from_limbs(canon[1])]

@@ -13,7 +13,8 @@ from tachyon_b200 import msm
 curve = sys.argv[1] if len(sys.argv) > 1 else "bn254"
 lg = int(sys.argv[2]) if len(sys.argv) > 2 else 20
 count = int(sys.argv[3]) if len(sys.argv) > 3 else 16
-fq = 4 if curve == "bn254" else 6
+from tachyon_b200 import _lib
+fq = _lib.element_limbs(curve)
 n = 1 << lg
 bases = torch.empty((n, 2 * fq), dtype=torch.int64, device="cuda")
 msm.generate_bases_device(curve, 1, n, bases.data_ptr())

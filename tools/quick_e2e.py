@@ -12,7 +12,8 @@ from tachyon_b200 import msm
 curve = sys.argv[1] if len(sys.argv) > 1 else "bn254"
 lg = int(sys.argv[2]) if len(sys.argv) > 2 else 24
 ranges = [int(x) for x in sys.argv[3].split(",")] if len(sys.argv) > 3 else [0, 1, 2, 4, 8, 16]
-fq = 4 if curve == "bn254" else 6
+from tachyon_b200 import _lib
+fq = _lib.element_limbs(curve)
 n = 1 << lg
 bases = torch.empty((n, 2 * fq), dtype=torch.int64, device="cuda")
 scalars = torch.empty((n, 4), dtype=torch.int64, device="cuda")

@@ -12,7 +12,8 @@ from tachyon_b200 import msm
 curve = sys.argv[1] if len(sys.argv) > 1 else "bn254"
 logs = [int(x) for x in sys.argv[2].split(",")] if len(sys.argv) > 2 else [16, 18, 20, 22]
 opts = dict(kv.split("=") for kv in sys.argv[3:])
-fq = 4 if curve == "bn254" else 6
+from tachyon_b200 import _lib
+fq = _lib.element_limbs(curve)
 print("imad peak variant0 %.3e  variant1 %.3e products/s" % (msm.imad_peak(0, 0), msm.imad_peak(0, 1)))
 nmax = 1 << max(logs)
 bases = torch.empty((nmax, 2 * fq), dtype=torch.int64, device="cuda")
