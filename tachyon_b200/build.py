@@ -13,10 +13,14 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB_DIR = os.path.join(HERE, "lib")
 LIB = os.path.join(LIB_DIR, "libtachyon_msm_b200.so")
-SOURCES = ["msm_api.cu"]
+# one translation unit per (curve, group) + the common part: compiled in parallel
+SOURCES = ["msm_api.cu", "msm_api_bn254_g1.cu", "msm_api_bls12_381_g1.cu", "msm_api_bn254_g2.cu",
+           "msm_api_bls12_381_g2.cu"]
+OBJ_DIR = os.path.join(HERE, "build")
 REPLAY = os.path.join(LIB_DIR, "msm_gpu_replay")
 REPLAY_SRC = os.path.join(CSRC, "tools", "msm_gpu_replay.cc")
-HEADERS = ["fp.cuh", "xyzz.cuh", "msm_kernels.cuh", "msm_engine.cuh", "host_math.h", "parallel_memcpy.h",
+HEADERS = ["fp.cuh", "xyzz.cuh", "msm_kernels.cuh", "msm_engine.cuh", "msm_api_common.cuh", "host_math.h",
+           "parallel_memcpy.h",
            "field_constants.h", os.path.join("..", "..", "include", "tachyon_msm_b200.h")]
 
 NVCC_FLAGS = [
@@ -24,9 +28,9 @@ NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-lineinfo",
     "-Xcompiler", "-fPIC,-fvisibility=hidden,-march=x86-64-v3,-mtune=generic",
-    "-cudart", "static",
-    "-shared",
 ]
+LINK_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-cudart", "static", "-shared",
+              "-Xcompiler", "-fPIC"]
 
 
 def nvcc():
@@ -50,17 +54,32 @@ def build(force=False, verbose=False):
     if not force and up_to_date():
         return LIB
     os.makedirs(LIB_DIR, exist_ok=True)
-    cmd = [nvcc()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + \
-          ["-o", LIB] + [os.path.join(CSRC, s) for s in SOURCES]
+    os.makedirs(OBJ_DIR, exist_ok=True)
     env = dict(os.environ)
     # nvcc's host compiler must be the system g++ (the image's CXX lacks libstdc++ specs)
     env.pop("CXX", None)
     env.pop("CC", None)
+    procs = []
+    for src in SOURCES:
+        obj = os.path.join(OBJ_DIR, src.replace(".cu", ".o"))
+        cmd = [nvcc()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + \
+              ["-c", "-o", obj, os.path.join(CSRC, src)]
+        procs.append((src, obj, subprocess.Popen(cmd, cwd=CSRC, env=env, stdout=subprocess.PIPE,
+                                                 stderr=subprocess.STDOUT, text=True)))
+    failed = False
+    for src, obj, proc in procs:
+        out, _ = proc.communicate()
+        if verbose or proc.returncode != 0:
+            sys.stderr.write(out)
+        failed = failed or proc.returncode != 0
+    if failed:
+        raise RuntimeError("nvcc failed building libtachyon_msm_b200.so")
+    cmd = [nvcc()] + LINK_FLAGS + ["-o", LIB] + [obj for _, obj, _ in procs]
     res = subprocess.run(cmd, cwd=CSRC, env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
     if verbose or res.returncode != 0:
         sys.stderr.write(res.stdout)
     if res.returncode != 0:
-        raise RuntimeError("nvcc failed building libtachyon_msm_b200.so")
+        raise RuntimeError("nvcc failed linking libtachyon_msm_b200.so")
     # the replay CLI: plain C++ over the C ABI
     cmd = ["/usr/bin/g++", "-O2", "-std=c++17", "-march=x86-64-v3", "-o", REPLAY, REPLAY_SRC,
            "-L" + LIB_DIR, "-ltachyon_msm_b200", "-Wl,-rpath,$ORIGIN"]

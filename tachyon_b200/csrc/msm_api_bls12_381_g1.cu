@@ -1,0 +1,4 @@
+// Entry points tachyon_bls12_381_g1_* (include/tachyon_msm_b200.h) and the kernels they instantiate.
+#include "msm_api_common.cuh"
+
+TB200_INSTANTIATE_GROUP(bls12_381, g1, Bls381Curve)

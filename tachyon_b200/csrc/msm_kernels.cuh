@@ -189,7 +189,7 @@ __global__ void __launch_bounds__(256) digits_hist_kernel(const uint32_t* __rest
 // The scalar-major form wrote 4-byte words at random over the whole n*W array: 14.7 GB of
 // DRAM traffic and L2-missing atomics at n = 2^24 (profiles/r1_b_*).
 // cursor[key] starts at offset[key]; the value returned by the atomic is the slot.
-__global__ void __launch_bounds__(256) digits_scatter_kernel(const uint32_t* __restrict__ digits,
+static __global__ void __launch_bounds__(256) digits_scatter_kernel(const uint32_t* __restrict__ digits,
                                                              MsmPlan plan,
                                                              uint32_t* __restrict__ cursor,
                                                              uint32_t* __restrict__ sorted) {
@@ -251,7 +251,7 @@ TB_DEV uint64_t block_exclusive_scan(uint64_t v, uint64_t* total, uint64_t* smem
   return warp_prefix + x - v;
 }
 
-__global__ void __launch_bounds__(kScanThreads) scan_block_sums_kernel(
+static __global__ void __launch_bounds__(kScanThreads) scan_block_sums_kernel(
     const uint32_t* __restrict__ count, uint32_t n, uint32_t seg, uint32_t R,
     uint64_t* __restrict__ block_sums) {
   __shared__ uint64_t smem[kScanThreads / 32];
@@ -268,7 +268,7 @@ __global__ void __launch_bounds__(kScanThreads) scan_block_sums_kernel(
 }
 
 // single block; nblocks <= kScanItems
-__global__ void __launch_bounds__(kScanThreads) scan_top_kernel(uint64_t* __restrict__ block_sums,
+static __global__ void __launch_bounds__(kScanThreads) scan_top_kernel(uint64_t* __restrict__ block_sums,
                                                                 uint32_t nblocks,
                                                                 MsmTotals* __restrict__ totals) {
   __shared__ uint64_t smem[kScanThreads / 32];
@@ -304,7 +304,7 @@ constexpr uint32_t kTaskKeyMask = 0x00ffffffu;
 // Writes offset[] (TB+1 entries), cursor[] (= offset, consumed by the scatter)
 // and the tasks of every bucket.  Buckets split into more than one task are
 // appended to multi_keys.
-__global__ void __launch_bounds__(kScanThreads) scan_apply_build_tasks_kernel(
+static __global__ void __launch_bounds__(kScanThreads) scan_apply_build_tasks_kernel(
     const uint32_t* __restrict__ count, uint32_t n, uint32_t seg, uint32_t R,
     const uint64_t* __restrict__ block_prefix, uint32_t* __restrict__ offset,
     uint32_t* __restrict__ cursor, uint32_t* __restrict__ task_base, uint2* __restrict__ tasks,
@@ -359,7 +359,7 @@ constexpr int kMaxSegment = 1024;
 constexpr int kOrderThreads = 256;
 constexpr int kOrderPerThread = 8;
 
-__global__ void __launch_bounds__(kOrderThreads) order_hist_kernel(
+static __global__ void __launch_bounds__(kOrderThreads) order_hist_kernel(
     const uint2* __restrict__ tasks, const MsmTotals* __restrict__ totals,
     uint32_t* __restrict__ len_hist) {
   __shared__ uint32_t sh[kMaxSegment + 1];
@@ -379,7 +379,7 @@ __global__ void __launch_bounds__(kOrderThreads) order_hist_kernel(
 
 // in: len_hist[0..kMaxSegment] counts; out: len_hist[l] = first slot of length l when
 // lengths are laid out in DEscending order.
-__global__ void __launch_bounds__(1024) order_scan_kernel(uint32_t* __restrict__ len_hist) {
+static __global__ void __launch_bounds__(1024) order_scan_kernel(uint32_t* __restrict__ len_hist) {
   __shared__ uint32_t sh[kMaxSegment + 1];
   __shared__ uint32_t warp_sums[32];
   // position p = kMaxSegment - l, so ascending p = descending length
@@ -412,7 +412,7 @@ __global__ void __launch_bounds__(1024) order_scan_kernel(uint32_t* __restrict__
   if (p == 0) len_hist[0] = warp_sums[31];
 }
 
-__global__ void __launch_bounds__(kOrderThreads) order_scatter_kernel(
+static __global__ void __launch_bounds__(kOrderThreads) order_scatter_kernel(
     const uint2* __restrict__ tasks, const MsmTotals* __restrict__ totals,
     uint32_t* __restrict__ len_cursor, uint32_t* __restrict__ order) {
   __shared__ uint32_t cnt[kMaxSegment + 1];
