@@ -337,9 +337,95 @@ TB_DEV void fp_mul2(Fp<F>& r, const Fp<F>& a, const Fp<F>& b, const Fp<F>& a2, c
   fp_reduce_once<F>(r, t);
 }
 
+// Squaring: a^2 = sum_i a_i * (a_i 2^(32 i) + sum_(j > i) 2 a_j 2^(32 j)) 2^(32 i).  Row i
+// multiplies a_i with the vector m_i = [0, .., 0, a_i, b_(i+1), .., b_(N-1)], b = 2a (fits N limbs:
+// both moduli leave two spare bits; limb i+1 with its lowest bit cleared — that bit is the top
+// bit of a_i, which belongs to the part of a that is NOT doubled in row i), so it has N - i
+// products instead of N: N (N + 1) / 2 + N^2
+// + N = 108 instead of 136 (BN254).  The rows keep the interleaved structure of fp_mul; where
+// the multiplicand limb is zero the offset chain only moves its carry on (two adds on the
+// idle ALU pipe instead of one IMAD.WIDE on the busy one) and the aligned chain starts later.
+// Bounds: m_i < 2p keeps V < 3p + 2^33 p < 2^(32 (N + 1)); the total is a^2 + M p < R p + p^2,
+// so the result is < 2p exactly as for fp_mul.
+template <class F, int N, int kSkip>
+TB_DEV void mont_sqr_row(uint32_t (&X)[N], uint32_t (&Y)[N], const uint32_t (&m)[N], uint32_t bi) {
+  X[0] = add_cc(X[0], Y[1]);
+#pragma unroll
+  for (int j = 0; j < N; j += 2) {
+    uint32_t c_lo = (j + 2 < N) ? Y[j + 2] : 0u;
+    uint32_t c_hi = (j + 3 < N) ? Y[j + 3] : 0u;
+    if (j + 1 < kSkip) {
+      Y[j] = addc_cc(c_lo, 0u);
+      Y[j + 1] = addc_cc(c_hi, 0u);
+    } else {
+      Y[j] = madc_lo_cc(m[j + 1], bi, c_lo);
+      Y[j + 1] = madc_hi_cc(m[j + 1], bi, c_hi);
+    }
+  }
+  constexpr int j0 = (kSkip + 1) & ~1;  // first even multiplicand index that is not zero
+  if (j0 < N) {
+    X[j0] = mad_lo_cc(m[j0], bi, X[j0]);
+    X[j0 + 1] = madc_hi_cc(m[j0], bi, X[j0 + 1]);
+#pragma unroll
+    for (int j = j0 + 2; j < N; j += 2) {
+      X[j] = madc_lo_cc(m[j], bi, X[j]);
+      X[j + 1] = madc_hi_cc(m[j], bi, X[j + 1]);
+    }
+    Y[N - 1] = addc(Y[N - 1], 0u);
+  }
+  mont_reduce_row<F, N>(X, Y);
+}
+
+template <class F, int N, int kRow>
+struct SqrRows {
+  // rows kRow, kRow + 1 (roles of the accumulators alternate), then the rest
+  static TB_DEV void run(uint32_t (&E)[N], uint32_t (&O)[N], const uint32_t (&a)[N],
+                         const uint32_t (&b)[N]) {
+    uint32_t m[N];
+#pragma unroll
+    for (int j = 0; j < N; ++j)
+      m[j] = j < kRow ? 0u : (j == kRow ? a[j] : (j == kRow + 1 ? (b[j] & ~1u) : b[j]));
+    mont_sqr_row<F, N, kRow>(O, E, m, a[kRow]);
+    if (kRow + 1 < N) {
+      uint32_t m2[N];
+#pragma unroll
+      for (int j = 0; j < N; ++j)
+        m2[j] = j < kRow + 1 ? 0u : (j == kRow + 1 ? a[j] : (j == kRow + 2 ? (b[j] & ~1u) : b[j]));
+      mont_sqr_row<F, N, kRow + 1>(E, O, m2, a[kRow + 1]);
+    }
+    SqrRows<F, N, kRow + 2>::run(E, O, a, b);
+  }
+};
+template <class F, int N>
+struct SqrRows<F, N, N + 1> {
+  static TB_DEV void run(uint32_t (&)[N], uint32_t (&)[N], const uint32_t (&)[N],
+                         const uint32_t (&)[N]) {}
+};
+
 template <class F>
 TB_DEV void fp_sqr(Fp<F>& r, const Fp<F>& a) {
-  fp_mul<F>(r, a, a);
+  constexpr int N = Fp<F>::N;
+  static_assert(N % 2 == 0, "limb count must be even");
+  uint32_t b[N];  // 2a, no reduction: a < p < 2^(32N - 2)
+  b[0] = a.l[0] << 1;
+#pragma unroll
+  for (int j = 1; j < N; ++j) b[j] = __funnelshift_l(a.l[j - 1], a.l[j], 1);
+  uint32_t E[N], O[N];
+  // row 0: a_0 * [a_0, b_1, .., b_(N-1)]
+#pragma unroll
+  for (int j = 0; j < N; j += 2) {
+    mul_wide(E[j], E[j + 1], j == 0 ? a.l[0] : b[j], a.l[0]);
+    mul_wide(O[j], O[j + 1], j == 0 ? (b[1] & ~1u) : b[j + 1], a.l[0]);
+  }
+  mont_reduce_row<F, N>(E, O);
+  SqrRows<F, N, 1>::run(E, O, a.l, b);
+  // N rows in total, N even: the last row had X = O (O[0] == 0), Y = E
+  uint32_t t[N];
+  t[0] = add_cc(E[0], O[1]);
+#pragma unroll
+  for (int j = 1; j < N - 1; ++j) t[j] = addc_cc(E[j], O[j + 1]);
+  t[N - 1] = addc(E[N - 1], 0u);
+  fp_reduce_once<F>(r, t);
 }
 
 // Montgomery -> canonical: a * 1 * R^-1  (value of big_int.h:1049-1076
