@@ -483,7 +483,7 @@ def main():
                      "points_per_s": (1 << 20) / (ms20 * 1e-3),
                      "imad_frac": a20["products"] / (ms20 * 1e-3) / peak if peak else None}
             del nb, ns
-        if not args.no_cpu_baseline:
+        if not args.no_cpu_baseline and world == 1:   # reported on rank 0 at N = 1 only
             from oracle import cpu_oracle
             o = cpu_oracle.CurveOracle(curve)
             threads = os.cpu_count() or cpu_oracle.max_threads()  # torchrun pins OMP_NUM_THREADS=1

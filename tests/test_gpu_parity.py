@@ -434,3 +434,18 @@ def test_msm_full_size_chain_fold(oracles, torch_cuda, name, logn):
         a = ctx.msm_xyzz(bases.data_ptr(), scalars.data_ptr(), half)
         b = ctx.msm_xyzz(bases.data_ptr() + half * 2 * fq * 8, scalars.data_ptr() + half * 32, half)
         assert (o.xyzz_to_affine(msm.xyzz_add(name, a, b)) == want).all()
+
+
+# Maximum sizes: an MSM above the engine's 2^26-point piece limit (u32 index arithmetic) runs as
+# independent pieces whose sums are added on the host (the serial chunk loop of
+# icicle_msm_bn254_g1.cc:56-73, without its dropped remainder); checked through chain-fold.
+def test_msm_beyond_piece_limit(oracles, torch_cuda):
+    name, n = "bn254", (1 << 26) + 3 * 4096
+    o = oracles[name]
+    bases, scalars = _device_inputs(torch_cuda, name, o, 171, n, "uniform")
+    hs = _to_np(scalars)
+    heads = np.stack([o.generate_points(171, 1, first=j * 4096)[0] for j in range(n // 4096)])
+    want = o.msm_affine(heads, o.fold_chain_scalars(hs))
+    with msm.MSMGpu(name) as ctx:
+        got = o.jacobian_to_affine(ctx.affine_msm(bases.data_ptr(), scalars.data_ptr(), n))
+        assert (got == want).all()
