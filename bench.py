@@ -283,6 +283,69 @@ def run_groth16(args, rank, world, local_rank):
         dist.destroy_process_group()
 
 
+def run_table(args):
+    """`-k K [-k K ...] [--test_set random|non_uniform] [--check_results]`: the protocol and flags
+    of the reference's own benchmark (benchmark/msm/msm_config.cc:39-59, msm_runner.h:46-61,
+    msm_benchmark_gpu.cc:47-70): ONE test set of the largest size, prefixes of it for the
+    smaller sizes, ONE un-warmed wall-clock sample per size, host (pageable) pointers through
+    the C API, seconds per MSM in a table beside the CPU implementation."""
+    import torch
+    from oracle import cpu_oracle
+    from tachyon_b200 import msm
+    curve, fq = args.curve, FQ_LIMBS[args.curve]
+    ks = sorted(args.k)
+    nmax = 1 << ks[-1]
+    dist = {"random": "uniform", "uniform": "uniform", "non_uniform": "non_uniform"}[args.test_set]
+    torch.cuda.set_device(0)
+    b = torch.empty((nmax, 2 * fq), dtype=torch.int64, device="cuda")
+    sc = torch.empty((nmax, 4), dtype=torch.int64, device="cuda")
+    msm.generate_bases_device(curve, SEED + 2, nmax, b.data_ptr())
+    msm.generate_scalars_device(curve, SEED + 3, nmax, sc.data_ptr(), dist)
+    torch.cuda.synchronize()
+    hb, hs = b.cpu().numpy().view(np.uint64), sc.cpu().numpy().view(np.uint64)   # pageable, like std::vector
+    del b, sc
+    o = cpu_oracle.CurveOracle(curve)
+    threads = os.cpu_count() or cpu_oracle.max_threads()
+    ctx = msm.MSMGpu(curve, degree=ks[-1], device=0, banner=True)
+    # all GPU samples first, then the CPU column (msm_benchmark_gpu.cc:52-66 also runs one
+    # implementation over every size before the next; it also keeps the OpenMP team of the
+    # CPU run from competing with this library's copy threads on a small host)
+    gpu = {}
+    for k in ks:
+        n = 1 << k
+        t0 = time.perf_counter()
+        jac = ctx.affine_msm(hb[:n], hs[:n], n)
+        gpu[k] = (time.perf_counter() - t0, jac)
+    rows = []
+    for k in ks:
+        n = 1 << k
+        cpu_s, cpu_pt = None, None
+        if k <= args.cpu_sample_log:
+            t0 = time.perf_counter()
+            cpu_pt = o.msm_affine(hb[:n], hs[:n], threads=threads)
+            cpu_s = time.perf_counter() - t0
+        gpu_s, jac = gpu[k]
+        ok = None
+        if args.check_results:
+            got = o.jacobian_to_affine(jac)
+            if cpu_pt is None:   # too large for the CPU column: chain-fold value instead
+                pad = (-n) % 4096
+                fs = hs[:n] if not pad else np.concatenate([hs[:n], np.zeros((pad, 4), dtype=np.uint64)])
+                cpu_pt = o.msm_affine(hb[:n:4096], o.fold_chain_scalars(fs))
+            ok = bool((got == cpu_pt).all())
+            if not ok:
+                raise SystemExit(f"--check_results: GPU result differs from the CPU result at k={k}")
+        rows.append((k, cpu_s, gpu_s, ok))
+    print(f"| Exponent | Tachyon CPU restatement ({threads} threads) | B200 (this library, first call un-warmed) |")
+    print("| :------: | ------------ | ------------ |")
+    for k, c, g, ok in rows:
+        print(f"|    {k}    | {'-' if c is None else '%.6f' % c} | **{g:.6f}** |")
+    for k, c, g, ok in rows:
+        print(json.dumps({"k": k, "curve": curve, "test_set": args.test_set, "cpu_s": c, "gpu_s": g,
+                          "check_results": ok, "protocol": "one un-warmed sample, pageable host pointers"}), flush=True)
+    ctx.close()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -299,6 +362,11 @@ def main():
     ap.add_argument("--window-bits", type=int, default=0)
     ap.add_argument("--ranges", type=int, default=0, help="point ranges per MSM (0 = automatic)")
     ap.add_argument("--workload", default="msm", choices=["msm", "groth16"])
+    ap.add_argument("-k", type=int, action="append", default=None,
+                    help="table mode with the reference benchmark's flags: exponent(s) of the sizes")
+    ap.add_argument("--test_set", default="random", choices=["random", "uniform", "non_uniform"])
+    ap.add_argument("--check_results", action="store_true")
+    ap.add_argument("--vendor", action="append", default=None, help="accepted and ignored (no third-party MSMs here)")
     ap.add_argument("--log-m", type=int, default=20, help="groth16: log2 of the constraint count")
     ap.add_argument("--groth16-split", default="auto", choices=["auto", "msm", "range"])
     args = ap.parse_args()
@@ -308,6 +376,10 @@ def main():
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     if args.impl == "reference":
         run_reference(args, rank, world)
+        return
+    if args.k:
+        if rank == 0:
+            run_table(args)
         return
     if args.workload == "groth16":
         run_groth16(args, rank, world, local_rank)

@@ -449,3 +449,24 @@ def test_msm_beyond_piece_limit(oracles, torch_cuda):
     with msm.MSMGpu(name) as ctx:
         got = o.jacobian_to_affine(ctx.affine_msm(bases.data_ptr(), scalars.data_ptr(), n))
         assert (got == want).all()
+
+
+# Host inputs large enough for the pipelined paths: pageable numpy memory goes through the pinned
+# bounce buffers filled by host threads (>= 8 MB per copy), pinned memory straight to the DMA
+# engine; several geometric point ranges; both against the chain-fold value.
+@pytest.mark.parametrize("name,logn", [("bn254", 20), ("bls12_381", 19)])
+def test_msm_large_host_inputs_pageable_and_pinned(oracles, torch_cuda, name, logn):
+    import torch
+    o = oracles[name]
+    n = (1 << logn) + 4096 * 3 + 0
+    bases, scalars = _device_inputs(torch_cuda, name, o, 181, n, "uniform")
+    hb, hs = _to_np(bases), _to_np(scalars)                 # pageable
+    heads = np.stack([o.generate_points(181, 1, first=j * 4096)[0] for j in range(n // 4096)])
+    want = o.msm_affine(heads, o.fold_chain_scalars(hs))
+    pb, ps = bases.cpu().pin_memory(), scalars.cpu().pin_memory()
+    with msm.MSMGpu(name) as ctx:
+        assert (o.jacobian_to_affine(ctx.affine_msm(hb, hs)) == want).all()
+        assert ctx.last_timing()["ranges"] > 1
+        assert (o.jacobian_to_affine(ctx.affine_msm(pb.data_ptr(), ps.data_ptr(), n)) == want).all()
+        # device bases (resident SRS), pageable scalars
+        assert (o.jacobian_to_affine(ctx.affine_msm(bases.data_ptr(), hs, n)) == want).all()

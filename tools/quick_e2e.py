@@ -14,11 +14,12 @@ lg = int(sys.argv[2]) if len(sys.argv) > 2 else 24
 ranges = [int(x) for x in sys.argv[3].split(",")] if len(sys.argv) > 3 else [0, 1, 2, 4, 8, 16]
 from tachyon_b200 import _lib
 fq = _lib.element_limbs(curve)
+dist = sys.argv[4] if len(sys.argv) > 4 else "uniform"
 n = 1 << lg
 bases = torch.empty((n, 2 * fq), dtype=torch.int64, device="cuda")
 scalars = torch.empty((n, 4), dtype=torch.int64, device="cuda")
 msm.generate_bases_device(curve, 1, n, bases.data_ptr())
-msm.generate_scalars_device(curve, 2, n, scalars.data_ptr(), "uniform")
+msm.generate_scalars_device(curve, 2, n, scalars.data_ptr(), dist)
 hb = torch.empty((n, 2 * fq), dtype=torch.int64).pin_memory()
 hs = torch.empty((n, 4), dtype=torch.int64).pin_memory()
 hb.copy_(bases)
@@ -39,6 +40,6 @@ for r in ranges:
             best = min(best, (time.perf_counter() - t0) * 1e3)
         t = ctx.last_timing()
         same = bool((out == ref).all())
-        print("2^%d %s ranges=%d(%d) wall %.3f ms | total %.3f h2d %.3f sort %.3f acc %.3f reduce %.3f host %.3f | c=%d tasks=%d same_bits=%s"
-              % (lg, kind, r, t["ranges"], best, t["total_ms"], t["h2d_ms"], t["sort_ms"], t["accumulate_ms"],
+        print("2^%d %s ranges=%d(%d) wall %.3f ms | enq %.3f total %.3f h2d %.3f sort %.3f acc %.3f reduce %.3f host %.3f | c=%d tasks=%d same_bits=%s"
+              % (lg, kind, r, t["ranges"], best, t["enqueue_ms"], t["total_ms"], t["h2d_ms"], t["sort_ms"], t["accumulate_ms"],
                  t["reduce_ms"], t["host_ms"], t["window_bits"], t["tasks"], same), flush=True)
