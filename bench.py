@@ -143,7 +143,7 @@ def run_reference(args, rank, world):
     print(json.dumps({
         "impl": "reference", "metric": f"{args.curve} G1 MSM throughput", "value": value, "unit": "points/s",
         "n_gpus": args.gpus, "steps": steps, "warmup": 1, "ms_per_step": dt * 1e3, "higher_is_better": True,
-        "scaling": "strong", "vs_baseline": None, "dtype": "u32 limbs (Montgomery, u64 on CPU)",
+        "scaling": "strong", "vs_baseline": None, "dtype": "u64",
         "data": "synthetic",
         "config": {"workload": f"{args.curve} G1 MSM 2^{args.log_n} points, {args.dist} scalars", "sample": sample},
         "cpu_baseline": {"value": value, "unit": "points/s", "cores": threads, "kind": "port", "sample": sample},
@@ -263,7 +263,7 @@ def run_groth16(args, rank, world, local_rank):
         print(json.dumps({
             "metric": f"{curve} Groth16 G1 MSM set throughput", "value": total / (ms_step * 1e-3), "unit": "points/s",
             "n_gpus": world, "steps": args.steps, "warmup": warm, "ms_per_step": ms_step, "higher_is_better": True,
-            "scaling": "strong", "vs_baseline": None, "dtype": "u32 limbs (254/381-bit Montgomery)", "data": "synthetic",
+            "scaling": "strong", "vs_baseline": None, "dtype": "u32", "data": "synthetic",
             "config": {"workload": f"Groth16 G1 MSM set (A, B1, L, H) of a synthetic 2^{args.log_m}-constraint circuit, "
                                    f"{curve}; witness-like assignment (40% 0, 30% 1, 20% <2^32, 10% full), uniform h",
                        "sizes": dict(zip(names, sizes)), "split": args.groth16_split,
@@ -588,9 +588,10 @@ def main():
             "metric": f"{curve} G1 MSM throughput", "value": value, "unit": "points/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step,
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
-            "dtype": "u32 limbs (254/381-bit Montgomery)", "data": "synthetic",
+            "dtype": "u32", "data": "synthetic",
             "config": {"workload": f"{curve} G1 MSM 2^{args.log_n} points, {args.dist} scalars",
                        "partition": f"point range over {world} GPU(s), {n_local} points per GPU",
+                       "arithmetic": "254/381-bit Montgomery field elements as u32 limbs (IMAD.WIDE carry chains)",
                        "window_bits": timing["window_bits"], "windows": timing["windows"],
                        "l2": "inputs + workspace exceed the 126 MB L2 every step"},
             "wall_ms_per_step": wall_step,

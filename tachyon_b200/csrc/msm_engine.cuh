@@ -196,6 +196,17 @@ class MsmEngine {
     return total;
   }
 
+  // Allocates everything an n-point MSM with host inputs needs (workspace, staging ring,
+  // bounce buffers, copy threads) so that the first call does not pay for it — what the
+  // advisory `degree` of tachyon_<c>_g1_create_msm_gpu is good for (msm_gpu.h:35 ignores it).
+  void Prewarm(size_t n) {
+    TB_CUDA(cudaSetDevice(device_));
+    if (n == 0) return;
+    if (n > kMaxPiece) n = kMaxPiece;
+    Enqueue(nullptr, nullptr, n, 0, /*reserve_only=*/true);
+    EnsureBounce();
+  }
+
   // Keeps a private device copy of `n` bases (host or device source) for later MSMs — the
   // SRS of kzg.h:91-113, uploaded once instead of once per commitment.
   void RegisterBases(const void* bases, size_t n) {
@@ -294,6 +305,15 @@ class MsmEngine {
     return attr.type == cudaMemoryTypeUnregistered;
   }
 
+  void EnsureBounce() {
+    if (bounce_) return;
+    TB_CUDA(cudaMallocHost(&bounce_, kBounceSlots * kBounceBytes));
+    int hw = (int)std::thread::hardware_concurrency();
+    int want = hw >= 4 ? (hw * 3 / 4 > 16 ? 16 : hw * 3 / 4) : 1;
+    if (const char* e = getenv("TACHYON_B200_COPY_THREADS")) want = atoi(e);
+    copier_.reset(new ParallelMemcpy(want));
+  }
+
   // Host -> device on the copy stream.  Pinned sources go straight to the DMA engine;
   // pageable ones are copied by a few host threads into a ring of pinned bounce buffers
   // first (a pageable cudaMemcpyAsync runs at ~11 GB/s on this platform, PCIe at ~55).
@@ -302,13 +322,7 @@ class MsmEngine {
       TB_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, copy_stream_));
       return;
     }
-    if (!bounce_) {
-      TB_CUDA(cudaMallocHost(&bounce_, kBounceSlots * kBounceBytes));
-      int hw = (int)std::thread::hardware_concurrency();
-      int want = hw >= 4 ? (hw * 3 / 4 > 16 ? 16 : hw * 3 / 4) : 1;
-      if (const char* e = getenv("TACHYON_B200_COPY_THREADS")) want = atoi(e);
-      copier_.reset(new ParallelMemcpy(want));
-    }
+    EnsureBounce();
     for (size_t off = 0; off < bytes; off += kBounceBytes) {
       size_t len = bytes - off < kBounceBytes ? bytes - off : kBounceBytes;
       size_t slot = bounce_seq_++ % kBounceSlots;
@@ -443,7 +457,8 @@ class MsmEngine {
   // kernels and the final D2H on the compute stream); Finish() waits and runs the host
   // epilogue.  All device buffers except the staging ring are shared by consecutive MSMs,
   // which is safe because their kernels are ordered on the one compute stream.
-  Pending Enqueue(const void* bases, const void* scalars, size_t n, int slot) {
+  Pending Enqueue(const void* bases, const void* scalars, size_t n, int slot,
+                  bool reserve_only = false) {
     auto wall0 = std::chrono::steady_clock::now();
     const uint32_t c = WindowBitsFor(n);
     const bool bases_dev = IsDevicePointer(bases), scalars_dev = IsDevicePointer(scalars);
@@ -553,6 +568,7 @@ class MsmEngine {
                 {&tree_[1], tree_b[1]},
                 {&bases_stage_, bases_dev ? 0 : m * kStageSlots * kAffineBytes},
                 {&scalars_stage_, scalars_dev ? 0 : m * kStageSlots * kScalarBytes}});
+    if (reserve_only) return pd;
     const size_t bases_slot_bytes = bases_stage_.bytes / kStageSlots / 256 * 256;
     const size_t scalars_slot_bytes = scalars_stage_.bytes / kStageSlots / 256 * 256;
 
