@@ -91,6 +91,10 @@ extern "C" {
       tachyon_##C##_##G##_msm_gpu_ptr ptr, void* cuda_stream);                                  \
   /* name: "window_bits" (0 = automatic), "segment" (max entries per accumulation task),    \
      "devices" (point-range sharding over the first k devices; 1 = this context's device),  \
+     "sort_mode" (0 = one-level atomic counting sort, 1/-1 = two-level shared-memory sort    \
+     where eligible),                                                                        \
+     "prewarm" (reserve workspace, staging and copy threads for an MSM of `value` points now),\
+     "release_workspace" (free the grow-only workspace; registered bases are kept),           \
      "ranges" (point ranges one MSM is pipelined over; 0 = automatic), "pair_rounds"        \
      (experimental batched-affine rounds before the XYZZ accumulation; -1 = none, the       \
      default; -2 = chosen from the bucket occupancy; 0..4 = forced). */                       \

@@ -19,7 +19,7 @@ SOURCES = ["msm_api.cu", "msm_api_bn254_g1.cu", "msm_api_bls12_381_g1.cu", "msm_
 OBJ_DIR = os.path.join(HERE, "build")
 REPLAY = os.path.join(LIB_DIR, "msm_gpu_replay")
 REPLAY_SRC = os.path.join(CSRC, "tools", "msm_gpu_replay.cc")
-HEADERS = ["fp.cuh", "xyzz.cuh", "msm_kernels.cuh", "msm_engine.cuh", "msm_api_common.cuh", "host_math.h",
+HEADERS = ["fp.cuh", "xyzz.cuh", "msm_kernels.cuh", "msm_sort.cuh", "msm_engine.cuh", "msm_api_common.cuh", "host_math.h",
            "parallel_memcpy.h",
            "field_constants.h", os.path.join("..", "..", "include", "tachyon_msm_b200.h")]
 

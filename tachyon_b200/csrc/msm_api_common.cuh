@@ -514,6 +514,12 @@ using namespace tb200;
         for (auto& e : ptr->engines) e->options().segment = (uint32_t)value;                   \
       } else if (k == "aggregate") {                                                           \
         for (auto& e : ptr->engines) e->options().aggregate = (int)value;                      \
+      } else if (k == "sort_mode") {                                                           \
+        for (auto& e : ptr->engines) e->options().sort_mode = (int)value;                      \
+      } else if (k == "release_workspace") {                                                   \
+        for (auto& e : ptr->engines) e->ReleaseWorkspace();                                    \
+      } else if (k == "prewarm") { /* value = number of points to reserve for */                \
+        for (auto& e : ptr->engines) e->Prewarm((size_t)value / ptr->engines.size());          \
       } else if (k == "pair_rounds") {                                                         \
         for (auto& e : ptr->engines) e->options().pair_rounds = (int)value;                    \
       } else if (k == "ranges") {                                                              \

@@ -21,6 +21,7 @@
 #include "host_math.h"
 #include "parallel_memcpy.h"
 #include "msm_kernels.cuh"
+#include "msm_sort.cuh"
 
 namespace tb200 {
 
@@ -78,6 +79,8 @@ struct MsmOptions {
   uint32_t segment = 0;      // 0 = default
   int aggregate = -1;        // -1 = default
   uint32_t ranges = 0;       // point ranges per MSM; 0 = 1 for device inputs, pipelined for host
+  int sort_mode = -1;        // 0 = one-level atomic counting sort, 1 = two-level shared-memory
+                             // sort (msm_sort.cuh) where eligible, -1 = automatic
   int pair_rounds = -1;      // batched-affine pair rounds before the XYZZ accumulation:
                              // -1 = none (default), -2 = from bucket occupancy, >= 0 = forced
 };
@@ -195,6 +198,18 @@ class MsmEngine {
     }
     return total;
   }
+
+  // Frees the grow-only workspace (not the registered bases); the next call re-allocates.
+  void ReleaseWorkspace() {
+    TB_CUDA(cudaSetDevice(device_));
+    TB_CUDA(cudaStreamSynchronize(copy_stream_));
+    TB_CUDA(cudaStreamSynchronize(stream_));
+    for (const DeviceBuffer* b : AllBuffers())
+      if (b != &registered_) const_cast<DeviceBuffer*>(b)->Free();
+    for (auto& u : stage_used_) u = false;
+    budget_ = 0;
+  }
+  size_t workspace_bytes() const { return OwnedBytes(); }
 
   // Allocates everything an n-point MSM with host inputs needs (workspace, staging ring,
   // bounce buffers, copy threads) so that the first call does not pay for it — what the
@@ -390,6 +405,26 @@ class MsmEngine {
     return p;
   }
 
+  // The two-level sort needs at least two coarse bins per window and at most
+  // kMaxCoarsePerWindow of them; tiny ranges are not worth its extra passes.
+  bool UseTwoLevelSort(const MsmPlan& p) const {
+    bool eligible = p.c >= 12 && (p.B >> kFineBits) <= kMaxCoarsePerWindow && p.n >= (1u << 15);
+    if (options_.sort_mode == 0) return false;
+    if (options_.sort_mode == 1) return eligible;
+    // Automatic: measured on B200 with uniform scalars the two-level sort wins once a window
+    // has >= 2^18 buckets (c >= 19: 2^24 points 4.44 -> 3.78 ms, 2^23 2.30 -> 2.19) and loses a
+    // few percent below (2^21: 0.63 -> 0.68 ms).  On skewed scalars it wins everywhere (witness-
+    // like 2^24: 4.13 -> 2.27 ms), but the skew is not known before the first pass.
+    return eligible && p.c >= 19;
+  }
+  static SortPlan MakeSortPlan(const MsmPlan& p) {
+    SortPlan sp{};
+    sp.Cw = p.B >> kFineBits;
+    sp.regions = p.W * sp.Cw;
+    sp.max_tiles = (uint32_t)(((uint64_t)p.n * p.W) / kSortTile + sp.regions + 1);
+    return sp;
+  }
+
   // Upper bound of the padded entry count of a range (what totals->entries can reach).
   static uint64_t PaddedBound(const MsmPlan& p) {
     uint64_t entries = (uint64_t)p.n * p.W;
@@ -411,6 +446,7 @@ class MsmEngine {
     MsmPlan p = MakePlan(m, c);
     size_t b = (size_t)m * p.W * 4 + PaddedBound(p) * 4;  // digits + sorted
     if (p.R) b += PaddedBound(p) * (kAffineBytes + kAffineBytes / 4);  // pair outputs + prefixes
+    if (UseTwoLevelSort(p)) b += (size_t)m * p.W * 8;                  // coarse-sorted entries
     b += (size_t)p.max_tasks * (8 + 4 + 4 + kXyzzBytes);  // tasks, meta, order, task_out
     b += (size_t)(p.TB + 1) * 4 * 5;                      // count, offset, cursor, task_base, multi
     if (stage_bases) b += (size_t)m * kAffineBytes * kStageSlots;
@@ -552,6 +588,8 @@ class MsmEngine {
                 {&order_, (size_t)big.max_tasks * 4},
                 {&task_out_, (size_t)big.max_tasks * kXyzzBytes},
                 {&sorted_, (size_t)PaddedBound(big) * 4},
+                {&mid_, UseTwoLevelSort(big) ? (size_t)m * big.W * 8 : 0},
+                {&coarse_, UseTwoLevelSort(big) ? (size_t)(MakeSortPlan(big).regions + 1) * 4 * 4 + 64 : 0},
                 {&pair_prefix_, big.R ? (size_t)((PaddedBound(big) >> 1) + PairThreads(big, 0)) *
                                             (kAffineBytes / 2)
                                       : 0},
@@ -626,8 +664,38 @@ class MsmEngine {
       // ---- sort: histogram, scan, tasks, scatter ----------------------------------
       TB_CUDA(cudaMemsetAsync(count_.ptr, 0, (size_t)(plan.TB + 1) * 4, stream_));
       uint32_t sgrid = (plan.n + 255) / 256;
-      Launch(digits_hist_kernel<C>, sgrid, 256, d_scalars, plan, digits_.as<uint32_t>(),
-             count_.as<uint32_t>());
+      const bool two_level = UseTwoLevelSort(plan);
+      SortPlan sp = MakeSortPlan(plan);
+      // coarse_: [count | offset | cursor | tile_offset], each regions + 1 words, then totals
+      uint32_t* coarse_count = coarse_.as<uint32_t>();
+      uint32_t* coarse_offset = coarse_count + (sp.regions + 1);
+      uint32_t* coarse_cursor = coarse_offset + (sp.regions + 1);
+      uint32_t* tile_offset = coarse_cursor + (sp.regions + 1);
+      SortTotals* sort_totals = reinterpret_cast<SortTotals*>(tile_offset + (sp.regions + 1));
+      uint32_t tgrid = (plan.n + kSortTile - 1) / kSortTile;
+      if (two_level) {
+        TB_CUDA(cudaMemsetAsync(coarse_count, 0, (size_t)(sp.regions + 1) * 4, stream_));
+        size_t smem = (size_t)sp.regions * 4;
+        if (smem > sort_smem_set_) {
+          TB_CUDA(cudaFuncSetAttribute(digits_coarse_hist_kernel<C>,
+                                       cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+          sort_smem_set_ = smem;
+        }
+        digits_coarse_hist_kernel<C><<<tgrid, kSortThreads, smem, stream_>>>(
+            d_scalars, plan, sp, digits_.as<uint32_t>(), coarse_count);
+        TB_CUDA(cudaGetLastError());
+        ++launches_;
+        g_kernel_launches.fetch_add(1, std::memory_order_relaxed);
+        Launch(coarse_scan_kernel, 1, 1024, coarse_count, sp.regions, coarse_offset, coarse_cursor,
+               tile_offset, sort_totals);
+        LaunchGrid(coarse_scatter_kernel, dim3(tgrid, plan.W), kSortThreads, digits_.as<uint32_t>(),
+                   plan, sp, coarse_cursor, mid_.as<uint2>());
+        Launch(fine_hist_kernel, sp.max_tiles, kSortThreads, mid_.as<uint2>(), sp, tile_offset,
+               coarse_offset, sort_totals, count_.as<uint32_t>());
+      } else {
+        Launch(digits_hist_kernel<C>, sgrid, 256, d_scalars, plan, digits_.as<uint32_t>(),
+               count_.as<uint32_t>());
+      }
       Launch(scan_block_sums_kernel, scan_blocks, kScanThreads, count_.as<uint32_t>(), plan.TB,
              plan.seg, plan.R, block_sums_.as<uint64_t>());
       Launch(scan_top_kernel, 1, kScanThreads, block_sums_.as<uint64_t>(), scan_blocks, totals_);
@@ -635,8 +703,12 @@ class MsmEngine {
              plan.TB, plan.seg, plan.R, block_sums_.as<uint64_t>(), offset_.as<uint32_t>(),
              cursor_.as<uint32_t>(), task_base_.as<uint32_t>(), tasks_.as<uint2>(),
              task_meta_.as<uint32_t>(), multi_.as<uint32_t>(), sorted_.as<uint32_t>(), totals_);
-      LaunchGrid(digits_scatter_kernel, dim3(sgrid, plan.W), 256, digits_.as<uint32_t>(), plan,
-                 cursor_.as<uint32_t>(), sorted_.as<uint32_t>());
+      if (two_level)
+        Launch(fine_scatter_kernel, sp.max_tiles, kSortThreads, mid_.as<uint2>(), sp, tile_offset,
+               coarse_offset, sort_totals, cursor_.as<uint32_t>(), sorted_.as<uint32_t>());
+      else
+        LaunchGrid(digits_scatter_kernel, dim3(sgrid, plan.W), 256, digits_.as<uint32_t>(), plan,
+                   cursor_.as<uint32_t>(), sorted_.as<uint32_t>());
       // tasks by descending length
       TB_CUDA(cudaMemsetAsync(len_hist_.ptr, 0, (size_t)(kMaxSegment + 1) * 4, stream_));
       uint32_t ogrid = (plan.max_tasks + kOrderThreads * kOrderPerThread - 1) /
@@ -794,7 +866,8 @@ class MsmEngine {
     return {&registered_, &bases_stage_, &scalars_stage_, &state_, &count_, &offset_, &cursor_, &task_base_,
             &tasks_, &task_meta_, &multi_, &sorted_, &digits_, &task_out_, &block_sums_, &order_,
             &len_hist_, &lvl_a_[0], &lvl_a_[1], &lvl_c_[0], &lvl_c_[1], &tree_[0], &tree_[1],
-            &pair_prefix_, &pair_out_[0], &pair_out_[1], &pair_out_[2], &pair_out_[3]};
+            &pair_prefix_, &pair_out_[0], &pair_out_[1], &pair_out_[2], &pair_out_[3], &mid_,
+            &coarse_};
   }
 
   static uint32_t Log2(uint32_t x) {
@@ -839,7 +912,8 @@ class MsmEngine {
   size_t registered_n_ = 0;
   DeviceBuffer registered_, bases_stage_, scalars_stage_, state_, count_, offset_, cursor_, task_base_, tasks_,
       task_meta_, multi_, sorted_, digits_, task_out_, block_sums_, order_, len_hist_, lvl_a_[2],
-      lvl_c_[2], tree_[2], pair_prefix_, pair_out_[4];
+      lvl_c_[2], tree_[2], pair_prefix_, pair_out_[4], mid_, coarse_;
+  size_t sort_smem_set_ = 0;
 };
 
 }  // namespace tb200

@@ -266,6 +266,8 @@ def test_msm_point_ranges(oracles, torch_cuda, name):
         ctx.set_option("segment", 16)
         ctx.set_option("window_bits", 6)
         assert (o.jacobian_to_affine(ctx.affine_msm(bases, skew)) == want_skew).all()
+        ctx.set_option("release_workspace", 1)   # buffers are re-allocated on demand
+        ctx.set_option("prewarm", 1 << 14)
         ctx.set_option("ranges", 0)       # automatic again
         ctx.set_option("segment", 0)
         ctx.set_option("window_bits", 0)
@@ -301,6 +303,26 @@ def test_msm_pair_rounds(oracles, torch_cuda, name):
         ctx.set_option("ranges", 3)
         ctx.set_option("pair_rounds", 2)
         assert (o.jacobian_to_affine(ctx.affine_msm(bases, scalars)) == want).all()
+
+
+# Both sort implementations (one-level atomic counting sort, two-level shared-memory sort of
+# msm_sort.cuh) must feed the accumulation the same buckets: uniform, skewed and degenerate
+# scalars, ragged sizes, several ranges.
+@pytest.mark.parametrize("name", CURVES)
+def test_msm_sort_modes(oracles, torch_cuda, name):
+    o = oracles[name]
+    n = (1 << 16) + 777
+    bases = o.generate_points(121, n)
+    with msm.MSMGpu(name) as ctx:
+        for dist in ("uniform", "witness", "non_uniform"):
+            scalars = o.generate_scalars(122, n, dist)
+            want = o.msm_affine(bases, scalars)
+            for mode, cbits, ranges in ((0, 0, 0), (1, 0, 0), (1, 12, 0), (1, 17, 3), (1, 21, 1)):
+                ctx.set_option("sort_mode", mode)
+                ctx.set_option("window_bits", cbits)
+                ctx.set_option("ranges", ranges)
+                got = o.jacobian_to_affine(ctx.affine_msm(bases, scalars))
+                assert (got == want).all(), (dist, mode, cbits, ranges)
 
 
 # bases registered once (the SRS of kzg.h:91-113), then a batch of
