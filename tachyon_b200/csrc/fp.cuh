@@ -589,14 +589,14 @@ struct Fp2Field {
     fp_cneg<F>(r.c0, a.c0, n);
     fp_cneg<F>(r.c1, a.c1, n);
   }
-  static __device__ __noinline__ void mul(El& r, const El& a, const El& b) {
+  static TB_DEV void mul(El& r, const El& a, const El& b) {
     Fp<F> nb1, t0;
     fp_neg<F>(nb1, b.c1);
     fp_mul2<F>(t0, a.c0, b.c0, a.c1, nb1);    // c0 = a0 b0 - a1 b1
     fp_mul2<F>(r.c1, a.c0, b.c1, a.c1, b.c0);  // c1 = a0 b1 + a1 b0
     r.c0 = t0;
   }
-  static __device__ __noinline__ void sqr(El& r, const El& a) {
+  static TB_DEV void sqr(El& r, const El& a) {
     Fp<F> s, d, m;
     fp_add<F>(s, a.c0, a.c1);
     fp_sub<F>(d, a.c0, a.c1);
