@@ -187,10 +187,12 @@ class MsmEngine {
     timing_ = MsmTiming{};
     Point total = Point::Zero();
     if (n == 0) return total;  // pippenger_adapter.h:62-65
-    // Independent pieces only when the u32 index arithmetic requires it; unlike
-    // icicle_msm_bn254_g1.cc:56-62 the last piece keeps its remainder.
-    for (size_t off = 0; off < n; off += kMaxPiece) {
-      size_t len = n - off < kMaxPiece ? n - off : kMaxPiece;
+    // Independent pieces only when the u32 index arithmetic requires it (entries = points x
+    // windows must stay below 2^32, which a forced small window can hit before 2^26 points);
+    // unlike icicle_msm_bn254_g1.cc:56-62 the last piece keeps its remainder.
+    const size_t piece = PieceLimit(n);
+    for (size_t off = 0; off < n; off += piece) {
+      size_t len = n - off < piece ? n - off : piece;
       Pending p = Enqueue(static_cast<const char*>(bases) + off * kAffineBytes,
                           static_cast<const char*>(scalars) + off * kScalarBytes, len, 0);
       Point part = Finish(p);
@@ -252,7 +254,7 @@ class MsmEngine {
                         __LINE__};
     }
     auto bases_of = [&](size_t i) { return bases[i] ? bases[i] : registered_.ptr; };
-    if (biggest > kMaxPiece) {  // rare: fall back to one blocking call each
+    if (biggest > PieceLimit(biggest)) {  // rare: fall back to one blocking call each
       MsmTiming sum{};
       for (size_t i = 0; i < count; ++i) {
         out[i] = Run(bases_of(i), scalars[i], sizes[i]);
@@ -431,6 +433,14 @@ class MsmEngine {
     uint64_t nonempty = entries < p.TB ? entries : p.TB;
     uint64_t a = (uint64_t(1) << p.R) - 1;
     return ((entries + a * nonempty) + a) & ~a;
+  }
+
+  // Largest number of points one piece may hold: n * W (+ padding) must fit u32 offsets.
+  size_t PieceLimit(size_t n) const {
+    size_t lim = kMaxPiece;
+    uint32_t W = WindowsFor(Fr::kBits, WindowBitsFor(n < lim ? n : lim));
+    size_t by_entries = (size_t)0xE0000000u / W;
+    return by_entries < lim ? by_entries : lim;
   }
 
   uint32_t WindowBitsFor(size_t n) const {

@@ -458,6 +458,19 @@ def test_msm_full_size_chain_fold(oracles, torch_cuda, name, logn):
         assert (o.xyzz_to_affine(msm.xyzz_add(name, a, b)) == want).all()
 
 
+# A forced small window makes entries = points x windows the limiting quantity (u32 offsets):
+# the call must split itself into pieces rather than overflow.
+def test_msm_small_window_many_entries(oracles, torch_cuda):
+    name, n = "bn254", 1 << 16
+    o = oracles[name]
+    bases, scalars = o.generate_points(191, n), o.generate_scalars(192, n)
+    want = o.msm_affine(bases, scalars)
+    with msm.MSMGpu(name) as ctx:
+        ctx.set_option("window_bits", 4)          # W = 64 windows
+        assert (o.jacobian_to_affine(ctx.affine_msm(bases, scalars)) == want).all()
+        assert ctx.last_timing()["windows"] == 64
+
+
 # Maximum sizes: an MSM above the engine's 2^26-point piece limit (u32 index arithmetic) runs as
 # independent pieces whose sums are added on the host (the serial chunk loop of
 # icicle_msm_bn254_g1.cc:56-73, without its dropped remainder); checked through chain-fold.
