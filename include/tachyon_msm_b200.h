@@ -186,6 +186,40 @@ TACHYON_B200_DECLARE_GROUP(bls12_381, g1, tachyon_bls12_381_fq)
 TACHYON_B200_DECLARE_GROUP(bn254, g2, tachyon_bn254_fq2)
 TACHYON_B200_DECLARE_GROUP(bls12_381, g2, tachyon_bls12_381_fq2)
 
+/* Groth16 proof assembly over this library's MSMs (the MSM part of
+   tachyon/zk/r1cs/groth16/prove.h:33-165 CreateProofWithAssignment): five MSMs — L, H, A, B1 as
+   one batch on the G1 context, B2 concurrently on the G2 context — and the r / s blinding
+   arithmetic.  Query arrays may be host or device memory.  Sizes: a, b1, b2 queries have
+   full_size + 1 points (element 0 is added as is, prove.h:46), the l query witness_size, the h
+   query at least h_size - 1 (prove.h:100-112).  r == 0 selects the non-ZK branch (prove.h:135).
+   Circuit synthesis, the QAP witness map and zkey / wtns parsing stay with the caller.
+   0 or a negative error code. */
+#define TACHYON_B200_DECLARE_GROTH16(C)                                                       \
+  struct tachyon_##C##_groth16_proving_key_b200 {                                             \
+    struct tachyon_##C##_g1_affine alpha_g1, beta_g1, delta_g1;                               \
+    struct tachyon_##C##_g2_affine beta_g2, delta_g2;                                         \
+    const struct tachyon_##C##_g1_affine* a_g1_query; size_t a_g1_size;                       \
+    const struct tachyon_##C##_g1_affine* b_g1_query; size_t b_g1_size;                       \
+    const struct tachyon_##C##_g2_affine* b_g2_query; size_t b_g2_size;                       \
+    const struct tachyon_##C##_g1_affine* h_g1_query; size_t h_g1_size;                       \
+    const struct tachyon_##C##_g1_affine* l_g1_query; size_t l_g1_size;                       \
+  };                                                                                          \
+  struct tachyon_##C##_groth16_proof_b200 {                                                   \
+    struct tachyon_##C##_g1_affine a;                                                         \
+    struct tachyon_##C##_g2_affine b;                                                         \
+    struct tachyon_##C##_g1_affine c;                                                         \
+  };                                                                                          \
+  TACHYON_C_EXPORT int tachyon_##C##_groth16_prove_b200(                                      \
+      tachyon_##C##_g1_msm_gpu_ptr g1, tachyon_##C##_g2_msm_gpu_ptr g2,                       \
+      const struct tachyon_##C##_groth16_proving_key_b200* pk, const struct tachyon_##C##_fr* r, \
+      const struct tachyon_##C##_fr* s, const struct tachyon_##C##_fr* h_coefficients,        \
+      size_t h_size, const struct tachyon_##C##_fr* witness_assignments, size_t witness_size, \
+      const struct tachyon_##C##_fr* full_assignments, size_t full_size,                      \
+      struct tachyon_##C##_groth16_proof_b200* out);
+
+TACHYON_B200_DECLARE_GROTH16(bn254)
+TACHYON_B200_DECLARE_GROTH16(bls12_381)
+
 /* Number of CUDA devices visible, or a negative error. */
 TACHYON_C_EXPORT int tachyon_b200_device_count(void);
 /* Text of the last error recorded by an extension call on this thread. */

@@ -222,3 +222,22 @@ def gf7_scalar_mul(p_affine, k):
     out = np.zeros(2, dtype=np.uint64)
     L.oracle_gf7_scalar_mul(_p(p), ctypes.c_uint64(k), _p(out))
     return [int(v) for v in out]
+
+
+def groth16_prove(curve, pk, r, s, h, witness, full):
+    """tachyon/zk/r1cs/groth16/prove.h:54-165 CreateProofWithAssignment restated on the CPU MSMs.
+    pk: dict of numpy arrays (alpha_g1, beta_g1, delta_g1, beta_g2, delta_g2, a_g1_query,
+    b_g1_query, b_g2_query, h_g1_query, l_g1_query).  Returns (a, b, c) affine, Montgomery limbs."""
+    L = lib()
+    fq = getattr(L, f"oracle_{curve}_fq_limbs")()
+    pts = np.concatenate([_arr(pk[k]).reshape(-1) for k in ("alpha_g1", "beta_g1", "delta_g1", "beta_g2", "delta_g2")])
+    q = {k: _arr(pk[k]) for k in ("a_g1_query", "b_g1_query", "b_g2_query", "h_g1_query", "l_g1_query")}
+    out = np.zeros(8 * fq, dtype=np.uint64)
+    sz = ctypes.c_size_t
+    r, s, h, witness, full = (_arr(x) for x in (r, s, h, witness, full))
+    getattr(L, f"oracle_{curve}_groth16_prove")(
+        _p(pts), _p(q["a_g1_query"]), sz(len(q["a_g1_query"])), _p(q["b_g1_query"]), sz(len(q["b_g1_query"])),
+        _p(q["b_g2_query"]), sz(len(q["b_g2_query"])), _p(q["h_g1_query"]), sz(len(q["h_g1_query"])),
+        _p(q["l_g1_query"]), sz(len(q["l_g1_query"])), _p(r), _p(s), _p(h), sz(len(h)),
+        _p(witness), sz(len(witness)), _p(full), sz(len(full)), _p(out))
+    return out[:2 * fq], out[2 * fq:6 * fq], out[6 * fq:]

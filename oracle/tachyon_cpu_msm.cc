@@ -923,6 +923,93 @@ ORACLE_CURVE_API(bls12_381, Bls381Fq, Bls381Fr, g_bls381_gen)
 ORACLE_CURVE_API(bn254_g2, Bn254Fq2, Bn254Fr, g_bn254_g2_gen)
 ORACLE_CURVE_API(bls12_381_g2, Bls381Fq2, Bls381Fr, g_bls381_g2_gen)
 
+// ---------------------------------------------------------------------------
+// Groth16 proof from assignments: tachyon/zk/r1cs/groth16/prove.h:33-165
+// (CalculateCoeff :33-52, CreateProofWithAssignment :54-165), with the CPU MSMs above.
+// ---------------------------------------------------------------------------
+namespace {
+
+template <typename Fq, typename Fr>
+XYZZ<Fq> MsmForProof(const Affine<Fq>* bases, const Fr* scalars, size_t n) {
+  if (n == 0) return XYZZ<Fq>::Zero();
+  return MsmParallelTerm<Fq, Fr>(bases, scalars, n, omp_get_max_threads());
+}
+
+// prove.h:33-52
+template <typename Fq, typename Fr>
+XYZZ<Fq> CalculateCoeff(const XYZZ<Fq>& initial, const Affine<Fq>* query, size_t query_size,
+                        const Affine<Fq>& vk_param, const Fr* assignments) {
+  XYZZ<Fq> acc = MsmForProof<Fq, Fr>(query + 1, assignments, query_size - 1);
+  XYZZ<Fq> ret = initial.AddAffine(query[0]);
+  ret = ret.Add(acc);
+  ret = ret.AddAffine(vk_param);
+  return ret;
+}
+
+template <typename Fq, typename Fq2T, typename Fr>
+void Groth16Prove(const Affine<Fq>& alpha_g1, const Affine<Fq>& beta_g1, const Affine<Fq>& delta_g1,
+                  const Affine<Fq2T>& beta_g2, const Affine<Fq2T>& delta_g2,
+                  const Affine<Fq>* a_q, size_t a_n, const Affine<Fq>* b1_q, size_t b1_n,
+                  const Affine<Fq2T>* b2_q, size_t b2_n, const Affine<Fq>* h_q, size_t h_qn,
+                  const Affine<Fq>* l_q, size_t l_n, const Fr& r, const Fr& s, const Fr* h,
+                  size_t h_n, const Fr* witness, size_t witness_n, const Fr* full, size_t full_n,
+                  Affine<Fq>* out_a, Affine<Fq2T>* out_b, Affine<Fq>* out_c) {
+  (void)witness_n;
+  (void)full_n;
+  // :96-98
+  XYZZ<Fq> witness_acc = MsmForProof<Fq, Fr>(l_q, witness, l_n);
+  // :100-112
+  XYZZ<Fq> h_acc = h_n > h_qn ? MsmForProof<Fq, Fr>(h_q, h, h_n - 1) : MsmForProof<Fq, Fr>(h_q, h, h_n);
+  BigInt<Fr::N> rb = r.ToBigInt(), sb = s.ToBigInt();
+  // :116-121
+  XYZZ<Fq> r_delta = ScalarMul(XYZZ<Fq>::FromAffine(delta_g1), rb);
+  XYZZ<Fq> a = CalculateCoeff<Fq, Fr>(r_delta, a_q, a_n, alpha_g1, full);
+  // :123-131
+  XYZZ<Fq2T> s_delta2 = ScalarMul(XYZZ<Fq2T>::FromAffine(delta_g2), sb);
+  XYZZ<Fq2T> b2 = CalculateCoeff<Fq2T, Fr>(s_delta2, b2_q, b2_n, beta_g2, full);
+  // :133-149
+  XYZZ<Fq> c = ScalarMul(a, sb);
+  if (!r.IsZero()) {
+    XYZZ<Fq> s_delta = ScalarMul(XYZZ<Fq>::FromAffine(delta_g1), sb);
+    XYZZ<Fq> b1 = CalculateCoeff<Fq, Fr>(s_delta, b1_q, b1_n, beta_g1, full);
+    c = c.Add(ScalarMul(b1, rb));
+    c = c.Add(ScalarMul(r_delta, sb).Neg());
+  }
+  // :150-155
+  c = c.Add(witness_acc);
+  c = c.Add(h_acc);
+  *out_a = a.ToAffine();
+  *out_b = b2.ToAffine();
+  *out_c = c.ToAffine();
+}
+
+}  // namespace
+
+// points: alpha_g1, beta_g1, delta_g1 (G1 affine), beta_g2, delta_g2 (G2 affine), contiguous.
+#define ORACLE_GROTH16_API(PFX, FQ, FQ2, FR)                                                   \
+  extern "C" void oracle_##PFX##_groth16_prove(                                                \
+      const u64* points, const u64* a_q, size_t a_n, const u64* b1_q, size_t b1_n,             \
+      const u64* b2_q, size_t b2_n, const u64* h_q, size_t h_qn, const u64* l_q, size_t l_n,   \
+      const u64* r, const u64* s, const u64* h, size_t h_n, const u64* witness,                \
+      size_t witness_n, const u64* full, size_t full_n, u64* out) {                            \
+    const Affine<FQ>* g1 = (const Affine<FQ>*)points;                                          \
+    const Affine<FQ2>* g2 = (const Affine<FQ2>*)(g1 + 3);                                      \
+    Affine<FQ> oa, oc;                                                                         \
+    Affine<FQ2> ob;                                                                            \
+    Groth16Prove<FQ, FQ2, FR>(g1[0], g1[1], g1[2], g2[0], g2[1], (const Affine<FQ>*)a_q, a_n,  \
+                              (const Affine<FQ>*)b1_q, b1_n, (const Affine<FQ2>*)b2_q, b2_n,    \
+                              (const Affine<FQ>*)h_q, h_qn, (const Affine<FQ>*)l_q, l_n,       \
+                              *(const FR*)r, *(const FR*)s, (const FR*)h, h_n,                 \
+                              (const FR*)witness, witness_n, (const FR*)full, full_n, &oa, &ob, \
+                              &oc);                                                            \
+    memcpy(out, &oa, sizeof(oa));                                                              \
+    memcpy((char*)out + sizeof(oa), &ob, sizeof(ob));                                          \
+    memcpy((char*)out + sizeof(oa) + sizeof(ob), &oc, sizeof(oc));                             \
+  }
+
+ORACLE_GROTH16_API(bn254, Bn254Fq, Bn254Fq2, Bn254Fr)
+ORACLE_GROTH16_API(bls12_381, Bls381Fq, Bls381Fq2, Bls381Fr)
+
 // GF(7) toy curve y^2 = x^3 + 5 (short_weierstrass/test/sw_curve_config.h:31-45):
 // the same XYZZ/Jacobian templates run over a 1-limb Montgomery field so that
 // the reference's hard-coded KATs can be replayed.  Values cross the ABI as

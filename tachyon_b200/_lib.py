@@ -53,6 +53,7 @@ GROUP_SYMBOLS = [
     "tachyon_{c}_{g}_xyzz_batch_normalize_b200", "tachyon_{c}_{g}_msm_gpu_batch_b200",
 ]
 FIELD_SYMBOLS = ["tachyon_{c}_fq_op_b200", "tachyon_{c}_fr_op_b200", "tachyon_{c}_fq2_op_b200"]
+CURVE_SYMBOLS = ["tachyon_{c}_groth16_prove_b200"]
 GLOBAL_SYMBOLS = ["tachyon_b200_device_count", "tachyon_b200_last_error", "tachyon_b200_imad_peak",
                   "tachyon_b200_kernel_launch_count", "tachyon_b200_window_bits",
                   "tachyon_b200_window_count"]
@@ -60,7 +61,7 @@ GLOBAL_SYMBOLS = ["tachyon_b200_device_count", "tachyon_b200_last_error", "tachy
 
 def all_symbols():
     return ([s.format(c=c, g=g) for c in CURVES for g in GROUPS for s in GROUP_SYMBOLS] +
-            [s.format(c=c) for c in CURVES for s in FIELD_SYMBOLS] + GLOBAL_SYMBOLS)
+            [s.format(c=c) for c in CURVES for s in FIELD_SYMBOLS + CURVE_SYMBOLS] + GLOBAL_SYMBOLS)
 
 
 _lib = None
@@ -80,6 +81,7 @@ def load():
     for c in CURVES:
         for n in FIELD_SYMBOLS:
             getattr(lib, n.format(c=c)).argtypes = [i32, vp, vp, vp, sz]
+        getattr(lib, f"tachyon_{c}_groth16_prove_b200").argtypes = [vp, vp, vp, vp, vp, vp, sz, vp, sz, vp, sz, vp]
     for c, g in [(c, g) for c in CURVES for g in GROUPS]:
         f = lambda name: getattr(lib, name.format(c=c).replace("_g1_", "_%s_" % g))
         f("tachyon_{c}_g1_init").restype = None

@@ -15,7 +15,7 @@ LIB_DIR = os.path.join(HERE, "lib")
 LIB = os.path.join(LIB_DIR, "libtachyon_msm_b200.so")
 # one translation unit per (curve, group) + the common part: compiled in parallel
 SOURCES = ["msm_api.cu", "msm_api_bn254_g1.cu", "msm_api_bls12_381_g1.cu", "msm_api_bn254_g2.cu",
-           "msm_api_bls12_381_g2.cu"]
+           "msm_api_bls12_381_g2.cu", "groth16_api.cu"]
 OBJ_DIR = os.path.join(HERE, "build")
 REPLAY = os.path.join(LIB_DIR, "msm_gpu_replay")
 REPLAY_SRC = os.path.join(CSRC, "tools", "msm_gpu_replay.cc")

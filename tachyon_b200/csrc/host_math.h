@@ -242,6 +242,24 @@ void BatchNormalize(const HostPointXYZZ<E>* in, size_t n, HostPointAffine<E>* ou
   delete[] prefix;
 }
 
+// [k] p by double-and-add, k canonical little-endian u64 limbs (used for the r / s blinding
+// terms of a Groth16 proof, zk/r1cs/groth16/prove.h:113-148).
+template <class E>
+HostPointXYZZ<E> ScalarMul(const HostPointXYZZ<E>& p, const uint64_t* k, int limbs) {
+  HostPointXYZZ<E> acc = HostPointXYZZ<E>::Zero();
+  for (int i = limbs * 64 - 1; i >= 0; --i) {
+    acc = acc.Dbl();
+    if ((k[i >> 6] >> (i & 63)) & 1) acc = acc.Add(p);
+  }
+  return acc;
+}
+
+template <class E>
+HostPointXYZZ<E> FromAffine(const HostPointAffine<E>& a) {
+  if (a.x.IsZero() && a.y.IsZero()) return HostPointXYZZ<E>::Zero();
+  return HostPointXYZZ<E>{a.x, a.y, E::One(), E::One()};
+}
+
 // pippenger_base.h:59-77: Horner over window sums, c doublings per window.
 template <class E>
 HostPointXYZZ<E> CombineWindows(const HostPointXYZZ<E>* sums, uint32_t windows, uint32_t c) {

@@ -219,3 +219,38 @@ def window_bits(n, scalar_bits):
 
 def window_count(scalar_bits, c):
     return int(_lib.load().tachyon_b200_window_count(scalar_bits, c))
+
+
+def groth16_prove(g1_ctx, g2_ctx, pk, r, s, h, witness, full):
+    """Groth16 proof assembly (tachyon_<c>_groth16_prove_b200; zk/r1cs/groth16/prove.h:33-165).
+
+    pk: dict with affine points alpha_g1, beta_g1, delta_g1 (2 * fq limbs), beta_g2, delta_g2
+    (4 * fq limbs) and query arrays a_g1_query, b_g1_query, b_g2_query, h_g1_query, l_g1_query
+    (numpy arrays, or (device_pointer, count) tuples).  r, s: Montgomery Fr (4 limbs).
+    Returns (a, b, c) affine points as uint64 arrays."""
+    curve = g1_ctx.curve
+    fq = _lib.CURVES[curve]
+    parts = []
+    for k in ("alpha_g1", "beta_g1", "delta_g1", "beta_g2", "delta_g2"):
+        parts.append(np.ascontiguousarray(pk[k], dtype=np.uint64).reshape(-1))
+    keep = []
+    tail = []
+    for k in ("a_g1_query", "b_g1_query", "b_g2_query", "h_g1_query", "l_g1_query"):
+        q = pk[k]
+        if isinstance(q, tuple):
+            ptr, cnt = int(q[0]), int(q[1])
+        else:
+            q = np.ascontiguousarray(q, dtype=np.uint64)
+            keep.append(q)
+            ptr, cnt = q.ctypes.data, q.shape[0]
+        tail += [ptr, cnt]
+    blob = np.concatenate(parts + [np.array(tail, dtype=np.uint64)])
+    assert blob.size == 3 * 2 * fq + 2 * 4 * fq + 10
+    out = np.zeros(2 * fq + 4 * fq + 2 * fq, dtype=np.uint64)
+    r = np.ascontiguousarray(r, dtype=np.uint64)
+    s = np.ascontiguousarray(s, dtype=np.uint64)
+    rc = getattr(_lib.load(), f"tachyon_{curve}_groth16_prove_b200")(
+        ctypes.c_void_p(g1_ctx.ptr), ctypes.c_void_p(g2_ctx.ptr), _ptr(blob), _ptr(r), _ptr(s),
+        _ptr(h), len(h), _ptr(witness), len(witness), _ptr(full), len(full), _ptr(out))
+    _lib.check(rc, "groth16_prove")
+    return out[:2 * fq], out[2 * fq:6 * fq], out[6 * fq:]

@@ -394,6 +394,39 @@ def test_groth16_msm_set_batch(oracles, torch_cuda, name):
                 assert (got[j] == np.asarray(want[j]).reshape(-1)).all(), j
 
 
+# SURVEY 8f-3 (MSM part): the Groth16 proof from assignments — L, H, A, B1 batched on the G1
+# context, B2 concurrently on the G2 context, r / s blinding on the host — against the oracle's
+# restatement of zk/r1cs/groth16/prove.h:33-165 (itself pinned to the Python model).
+@pytest.mark.parametrize("curve", CURVES)
+def test_groth16_prove(oracles, torch_cuda, curve):
+    import torch
+    from oracle import cpu_oracle
+    from tests.groth16_util import make_case
+    with msm.MSMGpu(curve) as g1, msm.MSMGpu(curve + "_g2") as g2:
+        for blind, h_extra in ((True, 1), (False, 0)):
+            pk, r, s, h, witness, full = make_case(oracles, curve, n_full=3000, n_pub=17, h_size=2048 + h_extra,
+                                                   seed=70, h_query_size=2048, blind=blind)
+            want = cpu_oracle.groth16_prove(curve, pk, r, s, h, witness, full)
+            got = msm.groth16_prove(g1, g2, pk, r, s, h, witness, full)
+            for a, b in zip(got, want):
+                assert (a == b).all(), (blind, h_extra)
+        # device-resident proving key (a prover that keeps its zkey loaded)
+        dev = {k: torch.from_numpy(v.view(np.int64)).cuda() for k, v in pk.items() if k.endswith("_query")}
+        pk_dev = dict(pk)
+        for k, t in dev.items():
+            pk_dev[k] = (t.data_ptr(), t.shape[0])
+        got = msm.groth16_prove(g1, g2, pk_dev, r, s, h, witness, full)
+        for a, b in zip(got, want):
+            assert (a == b).all()
+        if msm.device_count() > 1:
+            g1.set_option("devices", min(msm.device_count(), 4))
+            got = msm.groth16_prove(g1, g2, pk, r, s, h, witness, full)
+            for a, b in zip(got, want):
+                assert (a == b).all()
+        with pytest.raises(RuntimeError):
+            msm.groth16_prove(g1, g2, pk, r, s, h, witness[:-1], full)   # l query / witness size mismatch
+
+
 # the dump written under TACHYON_MSM_GPU_INPUT_DIR (msm_gpu.h:99-119: u64 count,
 # canonical little-endian limbs) and the replay CLI (msm_gpu_replay.cc:40-88: --idx --degree
 # --input_dir, prints the time and the affine point as hex without leading zeros).
