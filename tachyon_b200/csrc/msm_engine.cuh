@@ -275,7 +275,11 @@ class MsmEngine {
         } else {
           // the other slot's MSM is still in flight: growing a buffer would wait for it,
           // which is correct (cudaFree synchronises) but serialises; sizes are usually equal
+          // from the second MSM on the copies overlap the PREVIOUS MSM's kernels, so one
+          // range is enough and the per-range bookkeeping is saved
+          in_batch_tail_ = live[slot ^ 1];
           pend[slot] = Enqueue(bases_of(i), scalars[i], sizes[i], slot);
+          in_batch_tail_ = false;
           pend[slot].index = i;
           live[slot] = true;
         }
@@ -518,7 +522,7 @@ class MsmEngine {
     size_t K = 1;
     if (options_.ranges > 0) {
       K = options_.ranges;
-    } else if (pd.any_host) {
+    } else if (pd.any_host && !in_batch_tail_) {
       K = n >> 18;  // ranges of >= 2^18 points on average, at most 8
       if (K > 8) K = 8;
       if (K < 1) K = 1;
@@ -908,6 +912,7 @@ class MsmEngine {
   cudaStream_t copy_stream_ = nullptr;
   std::vector<cudaEvent_t> events_;
   size_t stage_seq_ = 0;
+  bool in_batch_tail_ = false;
   char* bounce_ = nullptr;
   size_t bounce_seq_ = 0;
   bool bounce_used_[kBounceSlots] = {};
