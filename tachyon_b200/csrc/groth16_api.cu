@@ -94,6 +94,18 @@ struct Groth16 {
                          &b2_acc);
         if (g2_rc) g2_msg = g_last_error;  // thread-local in the worker
       });
+      // the blinding terms that do not depend on the MSMs are computed on a third host thread
+      // while the GPU works: r delta, s delta, s (r delta) in G1 and s delta2 in G2
+      P1 delta1 = FromAffine(pk.delta_g1), r_delta, s_delta, sr_delta;
+      P2 s_delta2;
+      std::thread pre_thread([&] {
+        r_delta = ScalarMul(delta1, rc.v, FrEl::N);
+        s_delta2 = ScalarMul(FromAffine(pk.delta_g2), sc.v, FrEl::N);
+        if (blind) {
+          s_delta = ScalarMul(delta1, sc.v, FrEl::N);
+          sr_delta = ScalarMul(r_delta, sc.v, FrEl::N);
+        }
+      });
       const void* bases[4] = {pk.l_g1_query, pk.h_g1_query,
                               static_cast<const char*>(pk.a_g1_query) + sizeof(A1),
                               static_cast<const char*>(pk.b_g1_query) + sizeof(A1)};
@@ -102,6 +114,7 @@ struct Groth16 {
       P1 acc[4];
       int g1_rc = T::G1Batch(g1, bases, scalars, sizes, blind ? 4 : 3, acc);
       g2_thread.join();
+      pre_thread.join();
       if (g1_rc) return g1_rc;  // g_last_error already set on this thread
       if (g2_rc) {
         g_last_error = g2_msg;
@@ -110,20 +123,16 @@ struct Groth16 {
       const P1 &witness_acc = acc[0], &h_acc = acc[1];
 
       // ---- assembly (prove.h:113-160) -------------------------------------------------------
-      P1 delta1 = FromAffine(pk.delta_g1);
-      P1 r_delta = ScalarMul(delta1, rc.v, FrEl::N);
       // [A]1 = r delta + a_query[0] + sum x_i a_i + alpha        (CalculateCoeff, :33-52)
       P1 a = r_delta.Add(FromAffine(Head<A1>(pk.a_g1_query))).Add(acc[2]).Add(FromAffine(pk.alpha_g1));
       // [B]2 = s delta2 + b2_query[0] + sum x_i b_i + beta2
-      P2 s_delta2 = ScalarMul(FromAffine(pk.delta_g2), sc.v, FrEl::N);
       P2 b2 = s_delta2.Add(FromAffine(Head<A2>(pk.b_g2_query))).Add(b2_acc).Add(FromAffine(pk.beta_g2));
       // [C]1 = s A (+ r B1 - s (r delta)) + witness_acc + h_acc
       P1 c = ScalarMul(a, sc.v, FrEl::N);
       if (blind) {
-        P1 s_delta = ScalarMul(delta1, sc.v, FrEl::N);
         P1 b1 = s_delta.Add(FromAffine(Head<A1>(pk.b_g1_query))).Add(acc[3]).Add(FromAffine(pk.beta_g1));
         c = c.Add(ScalarMul(b1, rc.v, FrEl::N));
-        P1 sub = ScalarMul(r_delta, sc.v, FrEl::N);
+        P1 sub = sr_delta;
         sub.y = E1::Zero().Sub(sub.y);
         c = c.Add(sub);
       }
