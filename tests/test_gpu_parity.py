@@ -538,3 +538,27 @@ def test_msm_large_host_inputs_pageable_and_pinned(oracles, torch_cuda, name, lo
         assert (o.jacobian_to_affine(ctx.affine_msm(pb.data_ptr(), ps.data_ptr(), n)) == want).all()
         # device bases (resident SRS), pageable scalars
         assert (o.jacobian_to_affine(ctx.affine_msm(bases.data_ptr(), hs, n)) == want).all()
+
+
+# Threading contract of the reference (msm_gpu.h:26-33): one context per host thread; contexts
+# are independent (own stream, workspace, copy stream) and may run concurrently.
+def test_concurrent_contexts_on_host_threads(oracles, torch_cuda):
+    import threading
+    jobs = [("bn254", 5000, 301), ("bls12_381", 3000, 302), ("bn254", 1 << 15, 303), ("bn254_g2", 2000, 304)]
+    inputs = [(oracles[c].generate_points(s, n), oracles[c].generate_scalars(s + 50, n)) for c, n, s in jobs]
+    want = [oracles[c].msm_affine(b, k) for (c, n, s), (b, k) in zip(jobs, inputs)]
+    got = [None] * len(jobs)
+
+    def work(i):
+        c = jobs[i][0]
+        with msm.MSMGpu(c) as ctx:
+            for _ in range(3):
+                got[i] = oracles[c].jacobian_to_affine(ctx.affine_msm(*inputs[i]))
+
+    threads = [threading.Thread(target=work, args=(i,)) for i in range(len(jobs))]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    for i in range(len(jobs)):
+        assert got[i] is not None and (got[i] == want[i]).all(), jobs[i]
