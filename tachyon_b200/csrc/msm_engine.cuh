@@ -391,7 +391,10 @@ class MsmEngine {
     p.aggregate = options_.aggregate < 0 ? 1u : (uint32_t)options_.aggregate;
     uint64_t entries = (uint64_t)n * p.W;
     uint64_t nonempty = entries < p.TB ? entries : p.TB;
-    p.max_tasks = (uint32_t)(nonempty + entries / p.seg);
+    // p.seg is the UPPER limit: choose_segment_kernel picks the actual task length on the
+    // device from the measured bucket occupancy, down to kMinSegment
+    uint32_t seg_floor = options_.segment ? p.seg : kMinSegment;
+    p.max_tasks = (uint32_t)(nonempty + entries / seg_floor);
     // Pair rounds (batched-affine pre-reduction) are OFF unless asked for: measured on B200
     // they lose to the XYZZ path at every size (BN254 2^24: accumulate 31.4 ms -> 37.7 ms at
     // R = 3).  "pair_rounds" = -2 picks R from the bucket occupancy:
@@ -462,6 +465,7 @@ class MsmEngine {
     if (p.R) b += PaddedBound(p) * (kAffineBytes + kAffineBytes / 4);  // pair outputs + prefixes
     if (UseTwoLevelSort(p)) b += (size_t)m * p.W * 8;                  // coarse-sorted entries
     b += (size_t)p.max_tasks * (8 + 4 + 4 + kXyzzBytes);  // tasks, meta, order, task_out
+    b += ((size_t)p.max_tasks / kFoldThreads + p.TB) * 8;  // fold jobs
     b += (size_t)(p.TB + 1) * 4 * 5;                      // count, offset, cursor, task_base, multi
     if (stage_bases) b += (size_t)m * kAffineBytes * kStageSlots;
     if (stage_scalars) b += (size_t)m * kScalarBytes * kStageSlots;
@@ -597,6 +601,8 @@ class MsmEngine {
                 {&cursor_, (size_t)(big.TB + 1) * 4},
                 {&task_base_, (size_t)big.TB * 4},
                 {&multi_, (size_t)big.TB * 4},
+                {&fold_jobs_, ((size_t)big.max_tasks / kFoldThreads + big.TB + 1) * sizeof(uint2)},
+                {&nonzero_slots_, (size_t)kNonzeroSlots * 4},
                 {&tasks_, (size_t)big.max_tasks * sizeof(uint2)},
                 {&task_meta_, (size_t)big.max_tasks * 4},
                 {&order_, (size_t)big.max_tasks * 4},
@@ -677,6 +683,7 @@ class MsmEngine {
 
       // ---- sort: histogram, scan, tasks, scatter ----------------------------------
       TB_CUDA(cudaMemsetAsync(count_.ptr, 0, (size_t)(plan.TB + 1) * 4, stream_));
+      TB_CUDA(cudaMemsetAsync(nonzero_slots_.ptr, 0, (size_t)kNonzeroSlots * 4, stream_));
       uint32_t sgrid = (plan.n + 255) / 256;
       const bool two_level = UseTwoLevelSort(plan);
       SortPlan sp = MakeSortPlan(plan);
@@ -701,22 +708,25 @@ class MsmEngine {
         ++launches_;
         g_kernel_launches.fetch_add(1, std::memory_order_relaxed);
         Launch(coarse_scan_kernel, 1, 1024, coarse_count, sp.regions, coarse_offset, coarse_cursor,
-               tile_offset, sort_totals);
+               tile_offset, sort_totals, nonzero_slots_.as<uint32_t>());
         LaunchGrid(coarse_scatter_kernel, dim3(tgrid, plan.W), kSortThreads, digits_.as<uint32_t>(),
                    plan, sp, coarse_cursor, mid_.as<uint2>());
         Launch(fine_hist_kernel, sp.max_tiles, kSortThreads, mid_.as<uint2>(), sp, tile_offset,
                coarse_offset, sort_totals, count_.as<uint32_t>());
       } else {
         Launch(digits_hist_kernel<C>, sgrid, 256, d_scalars, plan, digits_.as<uint32_t>(),
-               count_.as<uint32_t>());
+               count_.as<uint32_t>(), nonzero_slots_.as<uint32_t>());
       }
+      Launch(choose_segment_kernel, 1, 64, nonzero_slots_.as<uint32_t>(), plan.TB, plan.R, plan.seg,
+             options_.segment ? plan.seg : 0u, totals_);
       Launch(scan_block_sums_kernel, scan_blocks, kScanThreads, count_.as<uint32_t>(), plan.TB,
-             plan.seg, plan.R, block_sums_.as<uint64_t>());
+             totals_, plan.R, block_sums_.as<uint64_t>());
       Launch(scan_top_kernel, 1, kScanThreads, block_sums_.as<uint64_t>(), scan_blocks, totals_);
       Launch(scan_apply_build_tasks_kernel, scan_blocks, kScanThreads, count_.as<uint32_t>(),
-             plan.TB, plan.seg, plan.R, block_sums_.as<uint64_t>(), offset_.as<uint32_t>(),
+             plan.TB, plan.R, block_sums_.as<uint64_t>(), offset_.as<uint32_t>(),
              cursor_.as<uint32_t>(), task_base_.as<uint32_t>(), tasks_.as<uint2>(),
-             task_meta_.as<uint32_t>(), multi_.as<uint32_t>(), sorted_.as<uint32_t>(), totals_);
+             task_meta_.as<uint32_t>(), fold_jobs_.as<uint2>(), multi_.as<uint32_t>(),
+             sorted_.as<uint32_t>(), totals_);
       if (two_level)
         Launch(fine_scatter_kernel, sp.max_tiles, kSortThreads, mid_.as<uint2>(), sp, tile_offset,
                coarse_offset, sort_totals, cursor_.as<uint32_t>(), sorted_.as<uint32_t>());
@@ -754,9 +764,12 @@ class MsmEngine {
         Launch(accumulate_kernel<C, false>, agrid, kAccThreads, d_bases, sorted_.as<uint32_t>(),
                tasks_.as<uint2>(), task_meta_.as<uint32_t>(), order_.as<uint32_t>(), totals_,
                state_.as<uint32_t>(), task_out_.as<uint32_t>());
-      Launch(fold_partials_kernel<C>, sm_count_ * 4, kFoldThreads, multi_.as<uint32_t>(), totals_,
-             offset_.as<uint32_t>(), task_base_.as<uint32_t>(), plan.seg, plan.R,
-             task_out_.as<uint32_t>(), state_.as<uint32_t>());
+      Launch(fold_stage_a_kernel<C>, sm_count_ * 8, kFoldThreads, fold_jobs_.as<uint2>(), totals_,
+             offset_.as<uint32_t>(), task_base_.as<uint32_t>(), plan.R, task_out_.as<uint32_t>(),
+             state_.as<uint32_t>());
+      Launch(fold_stage_b_kernel<C>, sm_count_, kFoldThreads, multi_.as<uint32_t>(), totals_,
+             offset_.as<uint32_t>(), task_base_.as<uint32_t>(), plan.R, task_out_.as<uint32_t>(),
+             state_.as<uint32_t>());
       TB_CUDA(cudaMemcpyAsync(host_out + kHostWindowBytes + r * sizeof(MsmTotals), totals_,
                               sizeof(MsmTotals), cudaMemcpyDeviceToHost, stream_));
       TB_CUDA(cudaEventRecord(ev(r, 3), stream_));
@@ -881,7 +894,7 @@ class MsmEngine {
             &tasks_, &task_meta_, &multi_, &sorted_, &digits_, &task_out_, &block_sums_, &order_,
             &len_hist_, &lvl_a_[0], &lvl_a_[1], &lvl_c_[0], &lvl_c_[1], &tree_[0], &tree_[1],
             &pair_prefix_, &pair_out_[0], &pair_out_[1], &pair_out_[2], &pair_out_[3], &mid_,
-            &coarse_};
+            &coarse_, &fold_jobs_, &nonzero_slots_};
   }
 
   static uint32_t Log2(uint32_t x) {
@@ -927,7 +940,8 @@ class MsmEngine {
   size_t registered_n_ = 0;
   DeviceBuffer registered_, bases_stage_, scalars_stage_, state_, count_, offset_, cursor_, task_base_, tasks_,
       task_meta_, multi_, sorted_, digits_, task_out_, block_sums_, order_, len_hist_, lvl_a_[2],
-      lvl_c_[2], tree_[2], pair_prefix_, pair_out_[4], mid_, coarse_;
+      lvl_c_[2], tree_[2], pair_prefix_, pair_out_[4], mid_, coarse_,
+      fold_jobs_, nonzero_slots_;
   size_t sort_smem_set_ = 0;
 };
 

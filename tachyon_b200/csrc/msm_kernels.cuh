@@ -82,14 +82,54 @@ struct MsmPlan {
 
 constexpr uint32_t kNoEntry = 0xffffffffu;  // padding slot in `sorted`: the identity
 
-// totals written by the scan: [0] = entries (non-zero digits), [1] = tasks,
-// [2] = number of split buckets (filled by build_tasks)
+// Device-side totals of one point range.  entries / tasks / multi are written by the scan,
+// seg by choose_segment_kernel before it, fold_jobs / multi2 by the task builder.
 struct MsmTotals {
-  uint32_t entries;
-  uint32_t tasks;
-  uint32_t multi;
+  uint32_t entries;    // (padded) entries in `sorted`
+  uint32_t tasks;      // accumulation tasks
+  uint32_t multi;      // buckets split into several tasks
+  uint32_t seg;        // task length limit chosen from the measured bucket occupancy
+  uint32_t fold_jobs;  // chunks of kFoldThreads partial sums to fold (stage A)
+  uint32_t multi2;     // buckets with more than one chunk (stage B)
+  uint32_t nonzero;    // non-zero digits of the range
   uint32_t pad;
 };
+
+constexpr uint32_t kMinSegment = 16;
+constexpr int kNonzeroSlots = 64;  // partial counters of non-zero digits (spread the atomics)
+
+// Task length limit: the smallest power of two >= 4x the MEASURED mean bucket run, within
+// [kMinSegment, seg_max].  The host cannot know the occupancy: witness-like scalars (mostly
+// 0 / 1 / small) fill a fraction of the buckets a uniform draw would, and with the limit sized
+// for uniform scalars their few heavy buckets became a handful of 128-entry tasks that ran
+// alone for 0.9 ms (BN254 2^20: accumulate 1.32 ms for 0.35 ms of work).
+static __global__ void choose_segment_kernel(const uint32_t* __restrict__ nonzero_slots,
+                                             uint32_t total_buckets, uint32_t R, uint32_t seg_max,
+                                             uint32_t seg_forced, MsmTotals* __restrict__ totals) {
+  uint32_t v = threadIdx.x < kNonzeroSlots ? nonzero_slots[threadIdx.x] : 0u;
+#pragma unroll
+  for (int o = 16; o >= 1; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  __shared__ uint32_t part[2];
+  if ((threadIdx.x & 31) == 0) part[threadIdx.x >> 5] = v;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    uint32_t nonzero = part[0] + part[1];
+    uint32_t tb = total_buckets ? total_buckets : 1u;
+    uint32_t mean_run = ((nonzero + tb - 1) / tb) >> R;  // rounded up, as the host's n / B + 1
+    uint32_t seg = kMinSegment;
+    while (seg < seg_max && seg < 4u * mean_run + 4u) seg <<= 1;
+    // small MSMs end when their longest task ends (a 128-entry task runs ~0.9 ms): keep the
+    // limit near (entries / 32 K), but not below twice the mean run
+    uint32_t par = kMinSegment;
+    while (par < seg && par < (nonzero >> (15 + R))) par <<= 1;
+    while (par < seg && par < 2u * mean_run) par <<= 1;
+    seg = par;
+    totals->seg = seg_forced ? seg_forced : seg;
+    totals->nonzero = nonzero;
+    totals->fold_jobs = 0;
+    totals->multi2 = 0;
+  }
+}
 
 // ---------------------------------------------------------------------------
 // Scalar recoding.  Same digits as pippenger.h:27-51 FillDigits up to the
@@ -166,7 +206,8 @@ template <class C>
 __global__ void __launch_bounds__(256) digits_hist_kernel(const uint32_t* __restrict__ scalars,
                                                           MsmPlan plan,
                                                           uint32_t* __restrict__ digits,
-                                                          uint32_t* __restrict__ count) {
+                                                          uint32_t* __restrict__ count,
+                                                          uint32_t* __restrict__ nonzero_slots) {
   using Fr = typename C::Fr;
   uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   bool in = i < plan.n;
@@ -176,11 +217,24 @@ __global__ void __launch_bounds__(256) digits_hist_kernel(const uint32_t* __rest
   } else {
     fp_set_zero<Fr>(s);
   }
+  uint32_t nz = 0;
   for_each_digit<Fr>(s, plan, [&](uint32_t w, uint32_t mag, bool neg) {
     bool valid = in && mag != 0;
     if (in) digits[(size_t)w * plan.n + i] = mag | (neg ? 0x80000000u : 0u);
     bucket_inc(count, w * plan.B + mag - 1, valid, plan.aggregate != 0);
+    nz += valid;
   });
+  // non-zero digits of the CTA -> one of kNonzeroSlots counters (input of choose_segment)
+  __shared__ uint32_t warp_nz[8];
+  nz = __reduce_add_sync(0xffffffffu, nz);
+  if ((threadIdx.x & 31) == 0) warp_nz[threadIdx.x >> 5] = nz;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    uint32_t total = 0;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) total += warp_nz[k];
+    if (total) atomicAdd(nonzero_slots + (blockIdx.x % kNonzeroSlots), total);
+  }
 }
 
 // Pass 2, window-major (blockIdx.y = window): all CTAs of one window run before the next
@@ -252,9 +306,10 @@ TB_DEV uint64_t block_exclusive_scan(uint64_t v, uint64_t* total, uint64_t* smem
 }
 
 static __global__ void __launch_bounds__(kScanThreads) scan_block_sums_kernel(
-    const uint32_t* __restrict__ count, uint32_t n, uint32_t seg, uint32_t R,
-    uint64_t* __restrict__ block_sums) {
+    const uint32_t* __restrict__ count, uint32_t n, const MsmTotals* __restrict__ totals,
+    uint32_t R, uint64_t* __restrict__ block_sums) {
   __shared__ uint64_t smem[kScanThreads / 32];
+  const uint32_t seg = totals->seg;
   uint32_t base = blockIdx.x * kScanItems + threadIdx.x * kScanPerThread;
   uint64_t sum = 0;
 #pragma unroll
@@ -301,16 +356,21 @@ constexpr uint32_t kTaskFirst = 0x80000000u;
 constexpr uint32_t kTaskSingle = 0x40000000u;
 constexpr uint32_t kTaskKeyMask = 0x00ffffffu;
 
+constexpr int kFoldThreads = 128;  // partial sums folded by one CTA of stage A
+
 // Writes offset[] (TB+1 entries), cursor[] (= offset, consumed by the scatter)
-// and the tasks of every bucket.  Buckets split into more than one task are
-// appended to multi_keys.
+// and the tasks of every bucket.  A bucket split into t > 1 tasks gets ceil(t / kFoldThreads)
+// fold jobs {bucket, chunk} (stage A); with more than one chunk it is also listed in multi2
+// (stage B).
 static __global__ void __launch_bounds__(kScanThreads) scan_apply_build_tasks_kernel(
-    const uint32_t* __restrict__ count, uint32_t n, uint32_t seg, uint32_t R,
+    const uint32_t* __restrict__ count, uint32_t n, uint32_t R,
     const uint64_t* __restrict__ block_prefix, uint32_t* __restrict__ offset,
     uint32_t* __restrict__ cursor, uint32_t* __restrict__ task_base, uint2* __restrict__ tasks,
-    uint32_t* __restrict__ task_meta, uint32_t* __restrict__ multi_keys,
-    uint32_t* __restrict__ sorted, MsmTotals* __restrict__ totals) {
+    uint32_t* __restrict__ task_meta, uint2* __restrict__ fold_jobs,
+    uint32_t* __restrict__ multi2_keys, uint32_t* __restrict__ sorted,
+    MsmTotals* __restrict__ totals) {
   __shared__ uint64_t smem[kScanThreads / 32];
+  const uint32_t seg = totals->seg;
   uint32_t base = blockIdx.x * kScanItems + threadIdx.x * kScanPerThread;
   uint32_t cnt[kScanPerThread];
   uint64_t sum = 0;
@@ -340,7 +400,13 @@ static __global__ void __launch_bounds__(kScanThreads) scan_apply_build_tasks_ke
         task_meta[tb + s] = idx | (s == 0 ? kTaskFirst : 0u) | (t == 1 ? kTaskSingle : 0u);
       }
       for (uint32_t q = cnt[k]; q < cntp; ++q) sorted[off + q] = kNoEntry;
-      if (t > 1) multi_keys[atomicAdd(&totals->multi, 1u)] = idx;
+      if (t > 1) {
+        atomicAdd(&totals->multi, 1u);
+        uint32_t chunks = (t + kFoldThreads - 1) / kFoldThreads;
+        uint32_t jb = atomicAdd(&totals->fold_jobs, chunks);
+        for (uint32_t j = 0; j < chunks; ++j) fold_jobs[jb + j] = make_uint2(idx, j);
+        if (chunks > 1) multi2_keys[atomicAdd(&totals->multi2, 1u)] = idx;
+      }
       if (idx == n - 1) offset[n] = off + cntp;
     }
     prefix += scan_item(cnt[k], seg, R);
@@ -649,44 +715,83 @@ __global__ void __launch_bounds__(kPairThreads, AccMinBlocks<C>()) pair_round_ke
   }
 }
 
-// Buckets split over several tasks: one CTA per bucket sums the partials (the first of
-// which already carries the bucket's previous value) into `state`.  Grid-stride over the
-// split-bucket list.
-constexpr int kFoldThreads = 128;
+// Buckets split over several tasks: their partial sums (the first of which already carries
+// the bucket's previous value) are folded into `state` in two stages, so that a bucket holding
+// a large share of all entries (witness vectors: every scalar equal to 1 lands in one bucket)
+// is folded by many CTAs instead of one.
+//   stage A  one CTA per job {bucket, chunk}: tree-sum of <= kFoldThreads partials; the result
+//            goes to `state` when the bucket has a single chunk, else in place to the chunk's
+//            first slot
+//   stage B  one CTA per bucket with several chunks: sums the chunk results into `state`
+template <class K>
+TB_DEV void fold_tree(XYZZ<K>& acc, uint32_t live_count, uint32_t* sh) {
+  constexpr int kXyzzWords = 4 * K::kWords;
+  XYZZ<K> tmp;
+  int live = live_count < (uint32_t)kFoldThreads ? (int)live_count : kFoldThreads;
+  int top = 1;
+  while (top < live) top <<= 1;
+  for (int stride = top / 2; stride >= 1; stride >>= 1) {
+    if ((int)threadIdx.x >= stride && (int)threadIdx.x < 2 * stride)
+      xyzz_store<K>(sh + (threadIdx.x - stride) * kXyzzWords, acc);
+    __syncthreads();
+    if ((int)threadIdx.x < stride) {
+      xyzz_load<K>(tmp, sh + threadIdx.x * kXyzzWords);
+      xyzz_add<K>(acc, tmp);
+    }
+    __syncthreads();
+  }
+}
 
 template <class C>
-__global__ void __launch_bounds__(kFoldThreads) fold_partials_kernel(
-    const uint32_t* __restrict__ multi_keys, const MsmTotals* __restrict__ totals,
-    const uint32_t* __restrict__ offset, const uint32_t* __restrict__ task_base, uint32_t seg,
-    uint32_t R, const uint32_t* __restrict__ task_out, uint32_t* __restrict__ state) {
+__global__ void __launch_bounds__(kFoldThreads) fold_stage_a_kernel(
+    const uint2* __restrict__ fold_jobs, const MsmTotals* __restrict__ totals,
+    const uint32_t* __restrict__ offset, const uint32_t* __restrict__ task_base, uint32_t R,
+    uint32_t* __restrict__ task_out, uint32_t* __restrict__ state) {
   using K = typename C::Field;
   constexpr int kXyzzWords = 4 * K::kWords;
   __shared__ uint32_t sh[kFoldThreads / 2 * kXyzzWords];
-  for (uint32_t m = blockIdx.x; m < totals->multi; m += gridDim.x) {
-    uint32_t key = multi_keys[m];
+  const uint32_t seg = totals->seg;
+  for (uint32_t job = blockIdx.x; job < totals->fold_jobs; job += gridDim.x) {
+    uint2 jb = fold_jobs[job];
+    uint32_t key = jb.x;
     uint32_t cnt = (offset[key + 1] - offset[key]) >> R;  // padded run after the pair rounds
     uint32_t t = (cnt + seg - 1) / seg;
+    uint32_t first = jb.y * kFoldThreads;
+    uint32_t here = min((uint32_t)kFoldThreads, t - first);
+    uint32_t* slots = task_out + (size_t)(task_base[key] + first) * kXyzzWords;
+    XYZZ<K> acc;
+    xyzz_set_zero<K>(acc);
+    if (threadIdx.x < here) xyzz_load<K>(acc, slots + (size_t)threadIdx.x * kXyzzWords);
+    __syncthreads();  // every partial of the chunk is in registers before slot 0 is rewritten
+    fold_tree<K>(acc, here, sh);
+    if (threadIdx.x == 0)
+      xyzz_store<K>(t <= (uint32_t)kFoldThreads ? state + (size_t)key * kXyzzWords : slots, acc);
+    __syncthreads();
+  }
+}
+
+template <class C>
+__global__ void __launch_bounds__(kFoldThreads) fold_stage_b_kernel(
+    const uint32_t* __restrict__ multi2_keys, const MsmTotals* __restrict__ totals,
+    const uint32_t* __restrict__ offset, const uint32_t* __restrict__ task_base, uint32_t R,
+    const uint32_t* __restrict__ task_out, uint32_t* __restrict__ state) {
+  using K = typename C::Field;
+  constexpr int kXyzzWords = 4 * K::kWords;
+  __shared__ uint32_t sh[kFoldThreads / 2 * kXyzzWords];
+  const uint32_t seg = totals->seg;
+  for (uint32_t m = blockIdx.x; m < totals->multi2; m += gridDim.x) {
+    uint32_t key = multi2_keys[m];
+    uint32_t cnt = (offset[key + 1] - offset[key]) >> R;
+    uint32_t t = (cnt + seg - 1) / seg;
+    uint32_t chunks = (t + kFoldThreads - 1) / kFoldThreads;
     const uint32_t* slots = task_out + (size_t)task_base[key] * kXyzzWords;
     XYZZ<K> acc, tmp;
     xyzz_set_zero<K>(acc);
-    for (uint32_t s = threadIdx.x; s < t; s += kFoldThreads) {
-      xyzz_load<K>(tmp, slots + (size_t)s * kXyzzWords);
+    for (uint32_t j = threadIdx.x; j < chunks; j += kFoldThreads) {
+      xyzz_load<K>(tmp, slots + (size_t)j * kFoldThreads * kXyzzWords);
       xyzz_add<K>(acc, tmp);
     }
-    // tree over the threads that hold something: first power of two >= min(t, threads)
-    int live = t < (uint32_t)kFoldThreads ? (int)t : kFoldThreads;
-    int top = 1;
-    while (top < live) top <<= 1;
-    for (int stride = top / 2; stride >= 1; stride >>= 1) {
-      if ((int)threadIdx.x >= stride && (int)threadIdx.x < 2 * stride)
-        xyzz_store<K>(sh + (threadIdx.x - stride) * kXyzzWords, acc);
-      __syncthreads();
-      if ((int)threadIdx.x < stride) {
-        xyzz_load<K>(tmp, sh + threadIdx.x * kXyzzWords);
-        xyzz_add<K>(acc, tmp);
-      }
-      __syncthreads();
-    }
+    fold_tree<K>(acc, chunks, sh);
     if (threadIdx.x == 0) xyzz_store<K>(state + (size_t)key * kXyzzWords, acc);
     __syncthreads();
   }

@@ -138,7 +138,8 @@ __global__ void __launch_bounds__(kSortThreads) digits_coarse_hist_kernel(
 static __global__ void __launch_bounds__(1024) coarse_scan_kernel(
     const uint32_t* __restrict__ coarse_count, uint32_t regions,
     uint32_t* __restrict__ coarse_offset, uint32_t* __restrict__ coarse_cursor,
-    uint32_t* __restrict__ tile_offset, SortTotals* __restrict__ totals) {
+    uint32_t* __restrict__ tile_offset, SortTotals* __restrict__ totals,
+    uint32_t* __restrict__ nonzero_slots) {
   __shared__ uint32_t warp_e[32], warp_t[32];
   const uint32_t per = (regions + 1023) / 1024;
   const uint32_t lo = threadIdx.x * per, hi = min(regions, lo + per);
@@ -191,6 +192,7 @@ static __global__ void __launch_bounds__(1024) coarse_scan_kernel(
     coarse_offset[regions] = warp_e[31];
     tile_offset[regions] = warp_t[31];
     totals->tiles = warp_t[31];
+    nonzero_slots[0] = warp_e[31];  // the other slots were zeroed by the host
   }
 }
 
