@@ -91,6 +91,8 @@ extern "C" {
       tachyon_##C##_##G##_msm_gpu_ptr ptr, void* cuda_stream);                                  \
   /* name: "window_bits" (0 = automatic), "segment" (max entries per accumulation task),    \
      "devices" (point-range sharding over the first k devices; 1 = this context's device),  \
+     "sample_scalars" (1 = choose the window from the bit lengths of 1024 sampled scalars,   \
+     the default; 0 = from the size alone),                                                  \
      "sort_mode" (0 = one-level atomic counting sort, 1/-1 = two-level shared-memory sort    \
      where eligible),                                                                        \
      "prewarm" (reserve workspace, staging and copy threads for an MSM of `value` points now),\

@@ -514,6 +514,8 @@ using namespace tb200;
         for (auto& e : ptr->engines) e->options().segment = (uint32_t)value;                   \
       } else if (k == "aggregate") {                                                           \
         for (auto& e : ptr->engines) e->options().aggregate = (int)value;                      \
+      } else if (k == "sample_scalars") {                                                      \
+        for (auto& e : ptr->engines) e->options().sample_scalars = (int)value;                 \
       } else if (k == "sort_mode") {                                                           \
         for (auto& e : ptr->engines) e->options().sort_mode = (int)value;                      \
       } else if (k == "release_workspace") {                                                   \

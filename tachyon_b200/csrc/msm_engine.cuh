@@ -79,6 +79,7 @@ struct MsmOptions {
   uint32_t segment = 0;      // 0 = default
   int aggregate = -1;        // -1 = default
   uint32_t ranges = 0;       // point ranges per MSM; 0 = 1 for device inputs, pipelined for host
+  int sample_scalars = 1;    // choose the window from a sample of the scalars' bit lengths
   int sort_mode = -1;        // 0 = one-level atomic counting sort, 1 = two-level shared-memory
                              // sort (msm_sort.cuh) where eligible, -1 = automatic
   int pair_rounds = -1;      // batched-affine pair rounds before the XYZZ accumulation:
@@ -108,6 +109,35 @@ inline uint32_t ChooseWindowBits(size_t n, uint32_t scalar_bits) {
     double buckets = (double)W * (double)(1u << (c - 1));
     if (buckets > kMaxBuckets) break;
     double cost = kEntryCost * (double)n * W + kBucketCost * buckets;
+    if (cost < best) {
+      best = cost;
+      best_c = c;
+    }
+  }
+  return best_c;
+}
+
+// The same cost model with the scalars' actual lengths: `bit_hist[b]` = how many of `samples`
+// sampled scalars have bit length b (0 = the zero scalar).  A scalar of b bits contributes
+// about ceil(b / c) non-zero digits, so witness-like vectors (mostly 0 / 1 / small values)
+// have far fewer entries per point than the uniform draw the plain model assumes, and a
+// smaller window (fewer buckets to reduce) wins.
+inline uint32_t ChooseWindowBitsSampled(size_t n, uint32_t scalar_bits, const uint32_t* bit_hist,
+                                        uint32_t samples) {
+  constexpr double kEntryCost = 1.37, kBucketCost = 4.7;
+  constexpr uint32_t kMaxBuckets = 1u << 24;
+  double best = 1e300;
+  uint32_t best_c = kMinWindowBits;
+  for (uint32_t c = kMinWindowBits; c <= 22; ++c) {
+    uint32_t W = WindowsFor(scalar_bits, c);
+    double buckets = (double)W * (double)(1u << (c - 1));
+    if (buckets > kMaxBuckets) break;
+    double digits = 0;
+    for (uint32_t b = 1; b <= scalar_bits + 1; ++b)
+      if (bit_hist[b]) digits += (double)bit_hist[b] * (double)((b + c - 1) / c);
+    double entries = (double)n * digits / (double)samples;
+    // every (point, window) slot is still recoded, written and read once by the sort
+    double cost = kEntryCost * entries + kBucketCost * buckets + 0.05 * (double)n * W;
     if (cost < best) {
       best = cost;
       best_c = c;
@@ -154,6 +184,7 @@ class MsmEngine {
     TB_CUDA(cudaStreamCreateWithFlags(&own_stream_, cudaStreamNonBlocking));
     stream_ = own_stream_;
     TB_CUDA(cudaStreamCreateWithFlags(&copy_stream_, cudaStreamNonBlocking));
+    TB_CUDA(cudaStreamCreateWithFlags(&sample_stream_, cudaStreamNonBlocking));
     TB_CUDA(cudaMallocHost(&host_out_, 2 * kHostOutBytes));
     TB_CUDA(cudaMalloc(&totals_, sizeof(MsmTotals)));
     int sms = 0;
@@ -170,6 +201,7 @@ class MsmEngine {
     if (bounce_) cudaFreeHost(bounce_);
     for (auto& e : events_) cudaEventDestroy(e);
     cudaStreamDestroy(copy_stream_);
+    cudaStreamDestroy(sample_stream_);
     cudaStreamDestroy(own_stream_);
   }
   MsmEngine(const MsmEngine&) = delete;
@@ -442,6 +474,52 @@ class MsmEngine {
     return ((entries + a * nonempty) + a) & ~a;
   }
 
+  // Window size from a sample of the scalars (every n / 1024-th one): bit-length histogram ->
+  // ChooseWindowBitsSampled.  Host scalars are read in place; device scalars cost one small
+  // strided D2H copy (~30 us), so tiny MSMs keep the size-only rule.
+  uint32_t WindowBitsFromSample(const void* scalars, size_t n, bool scalars_dev) {
+    // Measured: the sampled choice pays from ~2^22 points (witness-like 2^24: 13.9 -> 10.0 ms);
+    // below, the few heavy buckets of such vectors dominate and the size-only window is as good.
+    if (options_.window_bits || n < (size_t(1) << 22) || !options_.sample_scalars)
+      return WindowBitsFor(n);
+    constexpr uint32_t kSamples = 1024;
+    using FrEl = HostFp<Fr>;
+    static_assert(sizeof(FrEl) == kScalarBytes, "scalar layout");
+    const size_t stride = n / kSamples;
+    FrEl sample[kSamples];
+    if (scalars_dev) {
+      // on the copy stream: the compute stream may still be busy with the previous MSM of a batch
+      TB_CUDA(cudaMemcpy2DAsync(sample, kScalarBytes, scalars, stride * kScalarBytes, kScalarBytes,
+                                kSamples, cudaMemcpyDeviceToHost, sample_stream_));
+      TB_CUDA(cudaStreamSynchronize(sample_stream_));
+    } else {
+      for (uint32_t k = 0; k < kSamples; ++k)
+        memcpy(&sample[k], static_cast<const char*>(scalars) + k * stride * kScalarBytes,
+               kScalarBytes);
+    }
+    uint32_t hist[Fr::kBits + 2] = {};
+    FrEl one = FrEl::Zero();
+    one.v[0] = 1;
+    for (uint32_t k = 0; k < kSamples; ++k) {
+      FrEl canon = sample[k].Mul(one);  // from Montgomery
+      uint32_t bits = 0;
+      for (int i = FrEl::N; i-- > 0;) {
+        if (canon.v[i]) {
+          bits = 64 * i + 64 - (uint32_t)__builtin_clzll(canon.v[i]);
+          break;
+        }
+      }
+      if (bits > Fr::kBits + 1) bits = Fr::kBits + 1;  // unreduced garbage: treat as full length
+      hist[bits]++;
+    }
+    uint32_t c = ChooseWindowBitsSampled(n, Fr::kBits, hist, kSamples);
+    uint32_t by_size = WindowBitsFor(n);
+    if (c > by_size) c = by_size;  // the sample may only argue for FEWER buckets
+    if (c < kMinWindowBits) c = kMinWindowBits;
+    while (c < 22 && (uint64_t)n * WindowsFor(Fr::kBits, c) > 0xE0000000ull) ++c;  // u32 offsets
+    return c;
+  }
+
   // Largest number of points one piece may hold: n * W (+ padding) must fit u32 offsets.
   size_t PieceLimit(size_t n) const {
     size_t lim = kMaxPiece;
@@ -514,8 +592,8 @@ class MsmEngine {
   Pending Enqueue(const void* bases, const void* scalars, size_t n, int slot,
                   bool reserve_only = false) {
     auto wall0 = std::chrono::steady_clock::now();
-    const uint32_t c = WindowBitsFor(n);
     const bool bases_dev = IsDevicePointer(bases), scalars_dev = IsDevicePointer(scalars);
+    const uint32_t c = reserve_only ? WindowBitsFor(n) : WindowBitsFromSample(scalars, n, scalars_dev);
     const bool bases_pageable = !bases_dev && IsPageable(bases);
     const bool scalars_pageable = !scalars_dev && IsPageable(scalars);
     Pending pd;
@@ -923,6 +1001,7 @@ class MsmEngine {
   cudaStream_t own_stream_ = nullptr;
   cudaStream_t stream_ = nullptr;
   cudaStream_t copy_stream_ = nullptr;
+  cudaStream_t sample_stream_ = nullptr;
   std::vector<cudaEvent_t> events_;
   size_t stage_seq_ = 0;
   bool in_batch_tail_ = false;
