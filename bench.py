@@ -47,8 +47,15 @@ def algorithmic_products(curve, n):
     per_mul = 2 * limbs * limbs + limbs
     if curve.endswith("_g2"):
         per_mul *= 3        # one Fq2 multiplication = 3 Fq multiplications (Karatsuba count)
+    # What the accumulation kernel ISSUES per mixed addition (xyzz.cuh xyzz_madd: 6 mul + 2 sqr
+    # + 1 fused two-product mul2; fp.cuh: mul 2L^2+L, sqr L(L+1)/2+L^2+L, mul2 3L^2+L wide
+    # products) — fewer than the canonical 10 multiplications, which is why `frac` can exceed 1.
+    issued_per_add = None
+    if not curve.endswith("_g2"):
+        L = limbs
+        issued_per_add = 6 * (2 * L * L + L) + 2 * (L * (L + 1) // 2 + L * L + L) + (3 * L * L + L)
     return dict(c=c, W=W, modmuls=modmuls, products=modmuls * per_mul,
-                accumulate_products=n * W * 10 * per_mul)
+                accumulate_products=n * W * 10 * per_mul, issued_per_add=issued_per_add)
 
 
 class ClockSampler:
@@ -730,6 +737,10 @@ def main():
                          "traffic": traffic.get("bytes"), "traffic_source": traffic.get("source"),
                          "peak_source": "measured live: tachyon_b200_imad_peak, best of IMAD.WIDE.X chains / IMAD.WIDE acc64 / IMAD+IMAD.HI",
                          "whole_msm_frac": alg["products"] / (ms_step * 1e-3) / (peak * world) if peak else None,
+                         # pipe occupancy: wide products the kernel actually issued (entries the
+                         # engine reports x issued products per mixed addition) / time / peak
+                         "issued_frac": (timing["entries"] * alg["issued_per_add"] / (acc_ms * 1e-3) / peak)
+                         if acc_ms and peak and alg["issued_per_add"] else None,
                          "algorithmic": {"c": alg["c"], "W": alg["W"], "products": alg["products"]}},
             "hbm": {"algorithmic_bytes": n_total * (2 * fq * 8 + 32),
                     "achieved_gbs": n_total * (2 * fq * 8 + 32) / (ms_step * 1e-3) / 1e9},

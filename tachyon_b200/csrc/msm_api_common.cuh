@@ -524,6 +524,12 @@ using namespace tb200;
         for (auto& e : ptr->engines) e->Prewarm((size_t)value / ptr->engines.size());          \
       } else if (k == "pair_rounds") {                                                         \
         for (auto& e : ptr->engines) e->options().pair_rounds = (int)value;                    \
+      } else if (k == "host_ranges") {                                                         \
+        for (auto& e : ptr->engines) e->options().host_ranges = (uint32_t)(value < 1 ? 1 : value); \
+      } else if (k == "reduce_mode") {                                                         \
+        for (auto& e : ptr->engines) e->options().reduce_mode = (int)value;                    \
+      } else if (k == "balance") {                                                             \
+        for (auto& e : ptr->engines) e->options().balance = (int)value;                        \
       } else if (k == "ranges") {                                                              \
         for (auto& e : ptr->engines) e->options().ranges = (uint32_t)value;                    \
       } else if (k == "devices") {                                                             \

@@ -84,6 +84,10 @@ struct MsmOptions {
                              // sort (msm_sort.cuh) where eligible, -1 = automatic
   int pair_rounds = -1;      // batched-affine pair rounds before the XYZZ accumulation:
                              // -1 = none (default), -2 = from bucket occupancy, >= 0 = forced
+  uint32_t host_ranges = 8;  // most ranges the automatic host-input pipeline cuts an MSM into
+  int reduce_mode = 1;       // 1 = two threads per block of buckets (reduce_blocks_kernel),
+                             // 0 = one thread per block (reduce_level_kernel)
+  int balance = 1;           // balanced windows (WideWindowsFor); 0 = equal widths, slack on top
 };
 
 // Window choice.  Cost in units of one mixed addition:
@@ -93,14 +97,41 @@ struct MsmOptions {
 // never carries out (see for_each_digit).
 inline uint32_t WindowsFor(uint32_t bits, uint32_t c) { return (bits + 1 + c - 1) / c; }
 
+// Balanced windows.  W * c usually exceeds bits + 1, and with equal widths the whole slack
+// lands in the top window: BN254 at c = 20 has 13 windows for 255 bits, the top one holds 15
+// bits, i.e. 2^14 of its 2^19 buckets take all n entries (1024 per bucket at 2^24 points, split
+// into tasks and folded again, in every point range).  Taking one bit from each of the top
+// `slack` windows instead gives every window a full set of 2^(cw-1) buckets and leaves fewer
+// non-empty buckets to reduce (8 * 2^19 + 5 * 2^18 instead of 13 * 2^19).  Returns how many
+// (low) windows keep c bits.
+inline uint32_t WideWindowsFor(uint32_t bits, uint32_t c, bool balance = true) {
+  uint32_t W = WindowsFor(bits, c);
+  if (!balance || c < 5) return W;
+  uint32_t slack = W * c - (bits + 1);
+  // slack >= W would make every window c - 1 bits wide: that is the plan of c - 1 with twice
+  // the bucket slots, so leave such a c unbalanced (the cost model then never prefers it)
+  return slack >= W ? W : W - slack;
+}
+// Buckets that can be non-empty.
+inline double PopulatedBuckets(uint32_t bits, uint32_t c, bool balance = true) {
+  uint32_t W = WindowsFor(bits, c), wide = WideWindowsFor(bits, c, balance);
+  return (double)wide * (double)(1u << (c - 1)) + (double)(W - wide) * (double)(1u << (c - 2));
+}
+
 // c >= 4 keeps W <= 64 (the size of the pinned result buffer).
 constexpr uint32_t kMinWindowBits = 4;
 constexpr uint32_t kMaxWindows = 64;
 
-inline uint32_t ChooseWindowBits(size_t n, uint32_t scalar_bits) {
+// Every point range after the first pays the O(buckets) bookkeeping again (counter reset, scan,
+// task list, one read-modify-write of each bucket value): ~0.65 ms per range for the 5.5 M
+// buckets of a 2^24-point BN254 MSM, i.e. 0.76 mixed additions per bucket and range.
+constexpr double kRangeBucketCost = 0.76;
+
+inline uint32_t ChooseWindowBits(size_t n, uint32_t scalar_bits, size_t ranges = 1) {
   // measured on B200 (BN254 2^24, c = 20): 0.155 ns per mixed addition, 0.057 ns of
   // sorting per entry, 0.73 ns of reduction per bucket
-  constexpr double kEntryCost = 1.37, kBucketCost = 4.7;
+  constexpr double kEntryCost = 1.37;
+  const double kBucketCost = 4.7 + kRangeBucketCost * (double)(ranges > 1 ? ranges - 1 : 0);
   constexpr uint32_t kMaxBuckets = 1u << 24;  // scan_top_kernel capacity
   double best = 1e300;
   uint32_t best_c = kMinWindowBits;
@@ -108,7 +139,7 @@ inline uint32_t ChooseWindowBits(size_t n, uint32_t scalar_bits) {
     uint32_t W = WindowsFor(scalar_bits, c);
     double buckets = (double)W * (double)(1u << (c - 1));
     if (buckets > kMaxBuckets) break;
-    double cost = kEntryCost * (double)n * W + kBucketCost * buckets;
+    double cost = kEntryCost * (double)n * W + kBucketCost * PopulatedBuckets(scalar_bits, c);
     if (cost < best) {
       best = cost;
       best_c = c;
@@ -123,8 +154,9 @@ inline uint32_t ChooseWindowBits(size_t n, uint32_t scalar_bits) {
 // have far fewer entries per point than the uniform draw the plain model assumes, and a
 // smaller window (fewer buckets to reduce) wins.
 inline uint32_t ChooseWindowBitsSampled(size_t n, uint32_t scalar_bits, const uint32_t* bit_hist,
-                                        uint32_t samples) {
-  constexpr double kEntryCost = 1.37, kBucketCost = 4.7;
+                                        uint32_t samples, size_t ranges = 1) {
+  constexpr double kEntryCost = 1.37;
+  const double kBucketCost = 4.7 + kRangeBucketCost * (double)(ranges > 1 ? ranges - 1 : 0);
   constexpr uint32_t kMaxBuckets = 1u << 24;
   double best = 1e300;
   uint32_t best_c = kMinWindowBits;
@@ -137,7 +169,8 @@ inline uint32_t ChooseWindowBitsSampled(size_t n, uint32_t scalar_bits, const ui
       if (bit_hist[b]) digits += (double)bit_hist[b] * (double)((b + c - 1) / c);
     double entries = (double)n * digits / (double)samples;
     // every (point, window) slot is still recoded, written and read once by the sort
-    double cost = kEntryCost * entries + kBucketCost * buckets + 0.05 * (double)n * W;
+    double cost = kEntryCost * entries + kBucketCost * PopulatedBuckets(scalar_bits, c) +
+                  0.05 * (double)n * W;
     if (cost < best) {
       best = cost;
       best_c = c;
@@ -414,6 +447,7 @@ class MsmEngine {
     p.W = WindowsFor(Fr::kBits, p.c);
     p.B = 1u << (p.c - 1);
     p.TB = p.W * p.B;
+    p.wide = WideWindowsFor(Fr::kBits, p.c, options_.balance != 0);
     // Tasks hold up to 4x the mean bucket size, so ordinary buckets are one task and only
     // genuinely oversized buckets (skewed scalars) are split and folded.
     uint32_t seg = 128;
@@ -477,11 +511,11 @@ class MsmEngine {
   // Window size from a sample of the scalars (every n / 1024-th one): bit-length histogram ->
   // ChooseWindowBitsSampled.  Host scalars are read in place; device scalars cost one small
   // strided D2H copy (~30 us), so tiny MSMs keep the size-only rule.
-  uint32_t WindowBitsFromSample(const void* scalars, size_t n, bool scalars_dev) {
+  uint32_t WindowBitsFromSample(const void* scalars, size_t n, bool scalars_dev, size_t ranges) {
     // Measured: the sampled choice pays from ~2^22 points (witness-like 2^24: 13.9 -> 10.0 ms);
     // below, the few heavy buckets of such vectors dominate and the size-only window is as good.
     if (options_.window_bits || n < (size_t(1) << 22) || !options_.sample_scalars)
-      return WindowBitsFor(n);
+      return WindowBitsFor(n, ranges);
     constexpr uint32_t kSamples = 1024;
     using FrEl = HostFp<Fr>;
     static_assert(sizeof(FrEl) == kScalarBytes, "scalar layout");
@@ -512,8 +546,8 @@ class MsmEngine {
       if (bits > Fr::kBits + 1) bits = Fr::kBits + 1;  // unreduced garbage: treat as full length
       hist[bits]++;
     }
-    uint32_t c = ChooseWindowBitsSampled(n, Fr::kBits, hist, kSamples);
-    uint32_t by_size = WindowBitsFor(n);
+    uint32_t c = ChooseWindowBitsSampled(n, Fr::kBits, hist, kSamples, ranges);
+    uint32_t by_size = WindowBitsFor(n, ranges);
     if (c > by_size) c = by_size;  // the sample may only argue for FEWER buckets
     if (c < kMinWindowBits) c = kMinWindowBits;
     while (c < 22 && (uint64_t)n * WindowsFor(Fr::kBits, c) > 0xE0000000ull) ++c;  // u32 offsets
@@ -528,8 +562,9 @@ class MsmEngine {
     return by_entries < lim ? by_entries : lim;
   }
 
-  uint32_t WindowBitsFor(size_t n) const {
-    uint32_t c = options_.window_bits ? options_.window_bits : ChooseWindowBits(n, Fr::kBits);
+  uint32_t WindowBitsFor(size_t n, size_t ranges = 1) const {
+    uint32_t c =
+        options_.window_bits ? options_.window_bits : ChooseWindowBits(n, Fr::kBits, ranges);
     if (c < kMinWindowBits) c = kMinWindowBits;
     if (c > 24) c = 24;
     return c;
@@ -593,7 +628,6 @@ class MsmEngine {
                   bool reserve_only = false) {
     auto wall0 = std::chrono::steady_clock::now();
     const bool bases_dev = IsDevicePointer(bases), scalars_dev = IsDevicePointer(scalars);
-    const uint32_t c = reserve_only ? WindowBitsFor(n) : WindowBitsFromSample(scalars, n, scalars_dev);
     const bool bases_pageable = !bases_dev && IsPageable(bases);
     const bool scalars_pageable = !scalars_dev && IsPageable(scalars);
     Pending pd;
@@ -606,11 +640,14 @@ class MsmEngine {
       K = options_.ranges;
     } else if (pd.any_host && !in_batch_tail_) {
       K = n >> 18;  // ranges of >= 2^18 points on average, at most 8
-      if (K > 8) K = 8;
+      if (K > options_.host_ranges) K = options_.host_ranges;
       if (K < 1) K = 1;
     }
     if (K > kMaxRanges) K = kMaxRanges;
     if (K > n) K = n;
+    // the window is chosen knowing the range count: every extra range repeats the per-bucket
+    // bookkeeping, so pipelined host inputs prefer a slightly smaller window
+    const uint32_t c = reserve_only ? WindowBitsFor(n, K) : WindowBitsFromSample(scalars, n, scalars_dev, K);
     MsmPlan whole = MakePlan(n, c);
     bool memory_bound = false;
     {
@@ -861,10 +898,17 @@ class MsmEngine {
 
     // ---- bucket reduction: one blocked running-sum level, then a merge tree ---------
     {
-      uint32_t threads = plan.W * nb;
-      Launch(reduce_level_kernel<C, true>, (threads + kReduceThreads - 1) / kReduceThreads,
-             kReduceThreads, state_.as<uint32_t>(), (const uint32_t*)nullptr, plan.B, nb, pd.L0,
-             0u, plan.W, lvl_a_[0].as<uint32_t>(), lvl_c_[0].as<uint32_t>());
+      uint32_t blocks = plan.W * nb;
+      if (options_.reduce_mode == 0) {
+        Launch(reduce_level_kernel<C, true>, (blocks + kReduceThreads - 1) / kReduceThreads,
+               kReduceThreads, state_.as<uint32_t>(), (const uint32_t*)nullptr, plan.B, nb, pd.L0,
+               0u, plan.W, lvl_a_[0].as<uint32_t>(), lvl_c_[0].as<uint32_t>());
+      } else {
+        constexpr uint32_t kSlots = ReduceSlots<C>();
+        Launch(reduce_blocks_kernel<C>, (blocks + kSlots - 1) / kSlots, 2 * kSlots,
+               state_.as<uint32_t>(), plan.B, nb, pd.L0, plan.W, plan.wide,
+               lvl_a_[0].as<uint32_t>(), lvl_c_[0].as<uint32_t>());
+      }
     }
     const uint32_t* tin = lvl_a_[0].as<uint32_t>();
     const uint32_t* tin_p = lvl_c_[0].as<uint32_t>();
@@ -915,8 +959,9 @@ class MsmEngine {
     Point result = Point::Zero();
     for (uint32_t w = plan.W; w-- > 0;) {
       const Point* v = hv + (size_t)w * vals;
-      for (uint32_t bit = plan.c; bit-- > 0;) {
-        if (w + 1 < plan.W || bit + 1 < plan.c) result = result.Dbl();
+      const uint32_t cw = plan.c - (w >= plan.wide ? 1u : 0u);  // balanced windows
+      for (uint32_t bit = cw; bit-- > 0;) {
+        if (w + 1 < plan.W || bit + 1 < cw) result = result.Dbl();
         if (bit >= l0 && bit - l0 < M) result = result.Add(v[2 + (bit - l0)]);
         if (bit == 0) result = result.Add(v[0]).Add(v[1]);
       }

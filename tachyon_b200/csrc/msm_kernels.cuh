@@ -78,6 +78,9 @@ struct MsmPlan {
   uint32_t aggregate;  // warp-aggregate the bucket atomics (pays off for repeated digits)
   uint32_t R;          // pair rounds of the batched-affine pre-reduction; bucket runs in
                        // `sorted` start at multiples of 2^R and are padded with kNoEntry
+  uint32_t wide;       // windows [0, wide) take c bits, windows [wide, W) take c - 1 (balanced
+                       // windows: the slack W * c - (bits + 1) is spread over the top windows
+                       // instead of leaving one nearly empty, heavily loaded top window)
 };
 
 constexpr uint32_t kNoEntry = 0xffffffffu;  // padding slot in `sorted`: the identity
@@ -154,13 +157,16 @@ TB_DEV uint32_t pop_window(uint32_t (&s)[N], uint32_t c) {
   return bits;
 }
 
-// Calls f(w, bucket_key, negative) for every non-zero digit.
+// Calls f(w, bucket_key, negative) for every non-zero digit.  Window w is cw = c or c - 1 bits
+// wide (plan.wide); its digits lie in [-2^(cw-1), 2^(cw-1)] and use the first 2^(cw-1) of the
+// window's B bucket slots.
 template <class Fr, class Fn>
 TB_DEV void for_each_digit(Fp<Fr>& s, const MsmPlan& plan, Fn f) {
   uint32_t carry = 0;
-  const uint32_t half = plan.B;  // 2^(c-1)
   for (uint32_t w = 0; w < plan.W; ++w) {
-    uint32_t d = pop_window(s.l, plan.c) + carry;
+    const uint32_t cw = plan.c - (w >= plan.wide ? 1u : 0u);
+    const uint32_t half = 1u << (cw - 1);
+    uint32_t d = pop_window(s.l, cw) + carry;
     bool neg = d > half;
     carry = neg ? 1u : 0u;
     uint32_t mag = neg ? (2u * half - d) : d;
@@ -310,11 +316,11 @@ static __global__ void __launch_bounds__(kScanThreads) scan_block_sums_kernel(
     uint32_t R, uint64_t* __restrict__ block_sums) {
   __shared__ uint64_t smem[kScanThreads / 32];
   const uint32_t seg = totals->seg;
-  uint32_t base = blockIdx.x * kScanItems + threadIdx.x * kScanPerThread;
+  uint32_t base = blockIdx.x * kScanItems + threadIdx.x;  // a sum: any order, so read coalesced
   uint64_t sum = 0;
 #pragma unroll
   for (int k = 0; k < kScanPerThread; ++k) {
-    uint32_t idx = base + k;
+    uint32_t idx = base + k * kScanThreads;
     if (idx < n) sum += scan_item(count[idx], seg, R);
   }
   uint64_t total;
@@ -369,33 +375,51 @@ static __global__ void __launch_bounds__(kScanThreads) scan_apply_build_tasks_ke
     uint32_t* __restrict__ task_meta, uint2* __restrict__ fold_jobs,
     uint32_t* __restrict__ multi2_keys, uint32_t* __restrict__ sorted,
     MsmTotals* __restrict__ totals) {
-  __shared__ uint64_t smem[kScanThreads / 32];
+  // A warp owns 32 * kScanPerThread consecutive buckets and walks them in rows of 32: lane l
+  // handles bucket row * 32 + l, so the loads of count[] and the stores of offset / cursor /
+  // task_base / tasks are coalesced (neighbouring lanes <-> neighbouring buckets <-> neighbouring
+  // task slots).  The exclusive prefix of a bucket = block prefix + earlier warps + earlier rows
+  // of this warp + a shuffle scan inside the row.
+  __shared__ uint64_t warp_total[kScanThreads / 32];
   const uint32_t seg = totals->seg;
-  uint32_t base = blockIdx.x * kScanItems + threadIdx.x * kScanPerThread;
+  const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const uint32_t wbase = blockIdx.x * kScanItems + warp * (32 * kScanPerThread) + lane;
   uint32_t cnt[kScanPerThread];
-  uint64_t sum = 0;
+  uint64_t pre[kScanPerThread];
+  uint64_t run = 0;
 #pragma unroll
   for (int k = 0; k < kScanPerThread; ++k) {
-    uint32_t idx = base + k;
+    uint32_t idx = wbase + k * 32;
     cnt[k] = (idx < n) ? count[idx] : 0;
-    sum += scan_item(cnt[k], seg, R);
+    uint64_t item = scan_item(cnt[k], seg, R);
+    uint64_t x = item;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      uint64_t y = __shfl_up_sync(0xffffffffu, x, o);
+      if (lane >= (uint32_t)o) x += y;
+    }
+    pre[k] = run + x - item;
+    run += __shfl_sync(0xffffffffu, x, 31);
   }
-  uint64_t total;
-  uint64_t prefix = block_exclusive_scan(sum, &total, smem) + block_prefix[blockIdx.x];
+  if (lane == 0) warp_total[warp] = run;
+  __syncthreads();
+  uint64_t before = block_prefix[blockIdx.x];
+  for (uint32_t v = 0; v < warp; ++v) before += warp_total[v];
 #pragma unroll
   for (int k = 0; k < kScanPerThread; ++k) {
-    uint32_t idx = base + k;
+    uint32_t idx = wbase + k * 32;
     if (idx < n) {
+      uint64_t prefix = before + pre[k];
       uint32_t off = (uint32_t)prefix;
       uint32_t tb = (uint32_t)(prefix >> 32);
       offset[idx] = off;
       cursor[idx] = off;
       task_base[idx] = tb;
       uint32_t cntp = padded_count(cnt[k], R);
-      uint32_t run = cntp >> R;  // points left after the pair rounds
-      uint32_t t = (run + seg - 1) / seg;
+      uint32_t run_len = cntp >> R;  // points left after the pair rounds
+      uint32_t t = (run_len + seg - 1) / seg;
       for (uint32_t s = 0; s < t; ++s) {
-        uint32_t len = min(seg, run - s * seg);
+        uint32_t len = min(seg, run_len - s * seg);
         tasks[tb + s] = make_uint2((off >> R) + s * seg, len);
         task_meta[tb + s] = idx | (s == 0 ? kTaskFirst : 0u) | (t == 1 ? kTaskSingle : 0u);
       }
@@ -409,7 +433,6 @@ static __global__ void __launch_bounds__(kScanThreads) scan_apply_build_tasks_ke
       }
       if (idx == n - 1) offset[n] = off + cntp;
     }
-    prefix += scan_item(cnt[k], seg, R);
   }
 }
 
@@ -841,6 +864,77 @@ __global__ void __launch_bounds__(kReduceThreads) reduce_level_kernel(
   xyzz_add<K>(csum, wt);
   xyzz_store<K>(out_a + (size_t)g * kXyzzWords, run);
   xyzz_store<K>(out_c + (size_t)g * kXyzzWords, csum);
+}
+
+// Level 0 of the bucket reduction with the two dependent additions of a running sum split over
+// TWO threads.  For a block of L bucket values (walked from the top) one thread keeps
+// run_k = run_(k+1) + B_k, the other wt += run_k; wt lags one step behind, so both additions of
+// a step proceed at the same time: the chain per block is L additions deep instead of 2 L - 1,
+// twice as many warps are in flight for the same work, and each thread holds two points instead
+// of three (the single-thread form spilled: 128 registers + 384 B of stack).  Roles are per
+// warp (no divergence); run values cross through a double-buffered shared-memory slot per
+// block, one __syncthreads per step.  Writes A = sum B_k to out_a and Wt = sum_k (k - lo) B_k
+// to out_c, like reduce_level_kernel<C, true> with shift = 0.
+//   wide / windows: blocks in the upper half of a narrow (c - 1 bit) window hold no entries by
+//   construction (balanced windows); a CTA that lies wholly inside one writes zeros and leaves.
+template <class C>
+constexpr int ReduceSlots() {
+  return 4 * C::Field::kWords > 64 ? 32 : 64;
+}
+
+template <class C>
+__global__ void __launch_bounds__(2 * ReduceSlots<C>()) reduce_blocks_kernel(
+    const uint32_t* __restrict__ state, uint32_t n_in, uint32_t n_out, uint32_t L,
+    uint32_t windows, uint32_t wide, uint32_t* __restrict__ out_a, uint32_t* __restrict__ out_c) {
+  using K = typename C::Field;
+  constexpr int kXyzzWords = 4 * K::kWords;
+  constexpr int kSlots = kXyzzWords > 64 ? 32 : 64;  // = ReduceSlots<C>()
+  constexpr int kStride = kXyzzWords + 4;  // 16-byte accesses of neighbouring slots hit distinct banks
+  __shared__ __align__(16) uint32_t sh[2 * kSlots * kStride];
+  const uint32_t slot = threadIdx.x % kSlots;
+  const bool summing = threadIdx.x >= (uint32_t)kSlots;  // role B: wt += run
+  const uint32_t total = n_out * windows;
+  const uint32_t g0 = blockIdx.x * kSlots;
+  const uint32_t g = g0 + slot;
+  {
+    // known-empty CTA (uniform decision: first and last block of the CTA)
+    uint32_t g1 = min(g0 + kSlots, total) - 1;
+    uint32_t w0 = g0 / n_out, w1 = g1 / n_out;
+    if (w0 == w1 && w0 >= wide && (g0 % n_out) * L >= n_in / 2) {
+      if (g < total) {
+        XYZZ<K> z;
+        xyzz_set_zero<K>(z);
+        xyzz_store<K>((summing ? out_c : out_a) + (size_t)g * kXyzzWords, z);
+      }
+      return;
+    }
+  }
+  const bool live = g < total;
+  const uint32_t w = live ? g / n_out : 0, t = live ? g % n_out : 0;
+  const uint32_t lo = t * L, hi = min(n_in, lo + L);
+  const uint32_t steps = live ? hi - lo : 0;
+  XYZZ<K> acc, in;
+  xyzz_set_zero<K>(acc);
+  uint32_t* mine = sh + slot * kStride;
+  // step i: role A adds bucket hi - 1 - i and publishes run in buffer i & 1; role B adds what
+  // was published in step i - 1 (all but the run that includes the block's lowest bucket)
+  for (uint32_t i = 0; i < L; ++i) {
+    if (!summing) {
+      if (i < steps) {
+        uint32_t idx = w * n_in + (hi - 1 - i);
+        xyzz_load<K>(in, state + (size_t)idx * kXyzzWords);
+        xyzz_add<K>(acc, in);
+        if (i + 1 < steps) xyzz_store<K>(mine + (i & 1) * (kSlots * kStride), acc);
+      }
+    } else {
+      if (i >= 1 && i < steps) {
+        xyzz_load<K>(in, mine + ((i - 1) & 1) * (kSlots * kStride));
+        xyzz_add<K>(acc, in);
+      }
+    }
+    __syncthreads();
+  }
+  if (live) xyzz_store<K>((summing ? out_c : out_a) + (size_t)g * kXyzzWords, acc);
 }
 
 // Tail of the bucket reduction.  After level 0 every window has m = 2^M blocks t with

@@ -218,13 +218,21 @@ def test_msm_window_sweep(oracles, torch_cuda, name):
     o = oracles[name]
     n = 3000
     bases, scalars = o.generate_points(51, n), o.generate_scalars(52, n)
+    # scalars that reach the top of the top window and carry through every window
+    r_mod, _ = _consts(name)
+    edge = (r_mod - 1, r_mod - 2, (1 << (r_mod.bit_length() - 1)) - 1, 1 << (r_mod.bit_length() - 1),
+            r_mod >> 1, (r_mod >> 1) + 1, int("55" * 31, 16), int("aa" * 31, 16))
+    for i, v in enumerate(edge):
+        scalars[i] = o.fr_to_mont(np.array(pymodel.to_limbs(v % r_mod, 4), dtype=np.uint64))[0]
     want = o.msm_affine(bases, scalars)
     with msm.MSMGpu(name) as ctx:
-        for cbits in (4, 5, 7, 8, 11, 13, 16):
-            ctx.set_option("window_bits", cbits)
-            got = o.jacobian_to_affine(ctx.affine_msm(bases, scalars))
-            assert (got == want).all(), cbits
-            assert ctx.last_timing()["window_bits"] == cbits
+        for balance in (1, 0):       # balanced windows (widths c / c - 1) and equal widths
+            ctx.set_option("balance", balance)
+            for cbits in (4, 5, 6, 7, 8, 11, 13, 16):
+                ctx.set_option("window_bits", cbits)
+                got = o.jacobian_to_affine(ctx.affine_msm(bases, scalars))
+                assert (got == want).all(), (balance, cbits)
+                assert ctx.last_timing()["window_bits"] == cbits
 
 
 @pytest.mark.parametrize("name", ALL)
@@ -323,6 +331,32 @@ def test_msm_sort_modes(oracles, torch_cuda, name):
                 ctx.set_option("ranges", ranges)
                 got = o.jacobian_to_affine(ctx.affine_msm(bases, scalars))
                 assert (got == want).all(), (dist, mode, cbits, ranges)
+
+
+# Bucket reduction: two threads per block of buckets (default) and the one-thread form, with
+# balanced and equal-width windows, for window sizes that give few / many blocks per window,
+# and the host-input pipeline cut into a different number of ranges.
+@pytest.mark.parametrize("name", ALL)
+def test_msm_reduce_modes(oracles, torch_cuda, name):
+    o = oracles[name]
+    n = 6000 if name in CURVES else 2500
+    bases, scalars = o.generate_points(131, n), o.generate_scalars(132, n)
+    want = o.msm_affine(bases, scalars)
+    with msm.MSMGpu(name) as ctx:
+        for mode in (1, 0):
+            ctx.set_option("reduce_mode", mode)
+            for balance, cbits in ((1, 0), (0, 0), (1, 5), (1, 9), (1, 14), (0, 14), (1, 18)):
+                ctx.set_option("balance", balance)
+                ctx.set_option("window_bits", cbits)
+                got = o.jacobian_to_affine(ctx.affine_msm(bases, scalars))
+                assert (got == want).all(), (mode, balance, cbits)
+        ctx.set_option("reduce_mode", 1)
+        ctx.set_option("balance", 1)
+        ctx.set_option("window_bits", 0)
+        for host_ranges in (1, 3, 16):
+            ctx.set_option("host_ranges", host_ranges)
+            got = o.jacobian_to_affine(ctx.affine_msm(bases, scalars))
+            assert (got == want).all(), host_ranges
 
 
 # bases registered once (the SRS of kzg.h:91-113), then a batch of

@@ -1,5 +1,5 @@
 """Development aid: end-to-end time of one MSM from pinned host buffers for several
-point-range counts.   python tools/quick_e2e.py bn254 24 1,2,4,8,16"""
+point-range counts.   python tools/quick_e2e.py bn254 24 1,2,4,8,16 uniform [option=value ...]"""
 import os
 import sys
 import time
@@ -28,6 +28,9 @@ torch.cuda.synchronize()
 pb = hb.numpy().copy()   # pageable copies
 ps = hs.numpy().copy()
 ctx = msm.MSMGpu(curve)
+for kv in sys.argv[5:]:          # engine options, e.g. host_ranges=6 window_bits=19
+    k, v = kv.split("=")
+    ctx.set_option(k, int(v))
 ref = ctx.msm_xyzz(bases.data_ptr(), scalars.data_ptr(), n)
 for r in ranges:
     ctx.set_option("ranges", r)
