@@ -451,7 +451,8 @@ class MsmEngine {
     // Tasks hold up to 4x the mean bucket size, so ordinary buckets are one task and only
     // genuinely oversized buckets (skewed scalars) are split and folded.
     uint32_t seg = 128;
-    while (seg < (uint32_t)kMaxSegment && seg < 4 * (n / p.B + 1)) seg <<= 1;
+    const uint32_t run_buckets = p.wide < p.W ? p.B / 2 : p.B;  // narrow windows: half the buckets
+    while (seg < (uint32_t)kMaxSegment && seg < 4 * (n / run_buckets + 1)) seg <<= 1;
     p.seg = options_.segment ? options_.segment : seg;
     if (p.seg > (uint32_t)kMaxSegment) p.seg = kMaxSegment;
     p.aggregate = options_.aggregate < 0 ? 1u : (uint32_t)options_.aggregate;
@@ -832,8 +833,11 @@ class MsmEngine {
         Launch(digits_hist_kernel<C>, sgrid, 256, d_scalars, plan, digits_.as<uint32_t>(),
                count_.as<uint32_t>(), nonzero_slots_.as<uint32_t>());
       }
-      Launch(choose_segment_kernel, 1, 64, nonzero_slots_.as<uint32_t>(), plan.TB, plan.R, plan.seg,
-             options_.segment ? plan.seg : 0u, totals_);
+      // mean run of the most loaded windows: the narrow (c - 1 bit) windows of a balanced plan
+      // spread the same n entries over half as many buckets
+      const uint32_t seg_buckets = plan.W * (plan.wide < plan.W ? plan.B / 2 : plan.B);
+      Launch(choose_segment_kernel, 1, 64, nonzero_slots_.as<uint32_t>(), seg_buckets, plan.R,
+             plan.seg, options_.segment ? plan.seg : 0u, totals_);
       Launch(scan_block_sums_kernel, scan_blocks, kScanThreads, count_.as<uint32_t>(), plan.TB,
              totals_, plan.R, block_sums_.as<uint64_t>());
       Launch(scan_top_kernel, 1, kScanThreads, block_sums_.as<uint64_t>(), scan_blocks, totals_);
