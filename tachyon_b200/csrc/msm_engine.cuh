@@ -491,7 +491,10 @@ class MsmEngine {
     // has >= 2^18 buckets (c >= 19: 2^24 points 4.44 -> 3.78 ms, 2^23 2.30 -> 2.19) and loses a
     // few percent below (2^21: 0.63 -> 0.68 ms).  On skewed scalars it wins everywhere (witness-
     // like 2^24: 4.13 -> 2.27 ms), but the skew is not known before the first pass.
-    return eligible && p.c >= 19;
+    // Skewed scalars (flagged by the sample): the two-level sort wins from ~2^20 points per range
+    // (witness-like 2^24: sort 4.09 -> 2.51 ms, 2^20: 0.455 -> 0.374); on the ~2^18-point ranges
+    // of a pipelined 2^20 MSM its extra passes cost more than the atomics they avoid.
+    return eligible && (p.c >= 19 || (skew_hint_ && p.n >= (1u << 20)));
   }
   static SortPlan MakeSortPlan(const MsmPlan& p) {
     SortPlan sp{};
@@ -515,7 +518,12 @@ class MsmEngine {
   uint32_t WindowBitsFromSample(const void* scalars, size_t n, bool scalars_dev, size_t ranges) {
     // Measured: the sampled choice pays from ~2^22 points (witness-like 2^24: 13.9 -> 10.0 ms);
     // below, the few heavy buckets of such vectors dominate and the size-only window is as good.
-    if (options_.window_bits || n < (size_t(1) << 22) || !options_.sample_scalars)
+    // The sample also tells whether the scalars are skewed (many tiny values: all of them meet in
+    // a handful of buckets, where the one-level sort's atomics serialise): then the two-level
+    // shared-memory sort is used at any eligible window size.  Host scalars are sampled in place
+    // from 2^16 points; device scalars (one strided D2H copy) from 2^22.
+    skew_hint_ = false;
+    if (!options_.sample_scalars || n < (size_t(1) << (scalars_dev ? 22 : 16)))
       return WindowBitsFor(n, ranges);
     constexpr uint32_t kSamples = 1024;
     using FrEl = HostFp<Fr>;
@@ -547,6 +555,10 @@ class MsmEngine {
       if (bits > Fr::kBits + 1) bits = Fr::kBits + 1;  // unreduced garbage: treat as full length
       hist[bits]++;
     }
+    uint32_t tiny = 0;
+    for (uint32_t b = 0; b <= 8; ++b) tiny += hist[b];
+    skew_hint_ = tiny * 20 > kSamples;  // more than 5 % of the scalars are below 2^8
+    if (options_.window_bits || n < (size_t(1) << 22)) return WindowBitsFor(n, ranges);
     uint32_t c = ChooseWindowBitsSampled(n, Fr::kBits, hist, kSamples, ranges);
     uint32_t by_size = WindowBitsFor(n, ranges);
     if (c > by_size) c = by_size;  // the sample may only argue for FEWER buckets
@@ -648,6 +660,7 @@ class MsmEngine {
     if (K > n) K = n;
     // the window is chosen knowing the range count: every extra range repeats the per-bucket
     // bookkeeping, so pipelined host inputs prefer a slightly smaller window
+    if (reserve_only) skew_hint_ = false;
     const uint32_t c = reserve_only ? WindowBitsFor(n, K) : WindowBitsFromSample(scalars, n, scalars_dev, K);
     MsmPlan whole = MakePlan(n, c);
     bool memory_bound = false;
@@ -1054,6 +1067,7 @@ class MsmEngine {
   std::vector<cudaEvent_t> events_;
   size_t stage_seq_ = 0;
   bool in_batch_tail_ = false;
+  bool skew_hint_ = false;  // the last sample of the scalars was skewed (WindowBitsFromSample)
   char* bounce_ = nullptr;
   size_t bounce_seq_ = 0;
   bool bounce_used_[kBounceSlots] = {};

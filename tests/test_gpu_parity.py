@@ -325,7 +325,9 @@ def test_msm_sort_modes(oracles, torch_cuda, name):
         for dist in ("uniform", "witness", "non_uniform"):
             scalars = o.generate_scalars(122, n, dist)
             want = o.msm_affine(bases, scalars)
-            for mode, cbits, ranges in ((0, 0, 0), (1, 0, 0), (1, 12, 0), (1, 17, 3), (1, 21, 1)):
+            # -1: automatic — the scalar sample flags the skewed sets for the two-level sort
+            for mode, cbits, ranges in ((0, 0, 0), (1, 0, 0), (1, 12, 0), (1, 17, 3), (1, 21, 1), (-1, 0, 0),
+                                        (-1, 15, 2)):
                 ctx.set_option("sort_mode", mode)
                 ctx.set_option("window_bits", cbits)
                 ctx.set_option("ranges", ranges)
@@ -572,6 +574,25 @@ def test_msm_large_host_inputs_pageable_and_pinned(oracles, torch_cuda, name, lo
         assert (o.jacobian_to_affine(ctx.affine_msm(pb.data_ptr(), ps.data_ptr(), n)) == want).all()
         # device bases (resident SRS), pageable scalars
         assert (o.jacobian_to_affine(ctx.affine_msm(bases.data_ptr(), hs, n)) == want).all()
+
+
+# Witness-like (skewed) scalars at a size where the scalar sample switches the sort to the
+# two-level shared-memory form: host scalars (sampled in place), one range and the automatic
+# pipeline, against the chain-fold value; the forced one-level sort must agree.
+def test_msm_skewed_large_host_scalars(oracles, torch_cuda):
+    name, n = "bn254", (1 << 21) + 4096
+    o = oracles[name]
+    bases, scalars = _device_inputs(torch_cuda, name, o, 191, n, "witness")
+    hs = _to_np(scalars)
+    heads = np.stack([o.generate_points(191, 1, first=j * 4096)[0] for j in range(n // 4096)])
+    want = o.msm_affine(heads, o.fold_chain_scalars(hs))
+    ps = scalars.cpu().pin_memory()
+    with msm.MSMGpu(name) as ctx:
+        for ranges, sort_mode in ((1, -1), (0, -1), (1, 0)):
+            ctx.set_option("ranges", ranges)
+            ctx.set_option("sort_mode", sort_mode)
+            got = o.jacobian_to_affine(ctx.affine_msm(bases.data_ptr(), ps.data_ptr(), n))
+            assert (got == want).all(), (ranges, sort_mode)
 
 
 # Threading contract of the reference (msm_gpu.h:26-33): one context per host thread; contexts
