@@ -618,9 +618,27 @@ class MsmEngine {
     bool grow = false;
     for (auto& w : wants) grow = grow || w.second > w.first->bytes;
     if (!grow) return;
+    static const bool trace = getenv("TACHYON_B200_TRACE") != nullptr;
+    auto t0 = std::chrono::steady_clock::now();
     TB_CUDA(cudaStreamSynchronize(copy_stream_));
     TB_CUDA(cudaStreamSynchronize(stream_));
-    for (auto& w : wants) w.first->Reserve(w.second);
+    int index = 0;
+    for (auto& w : wants) {
+      if (trace && w.second > w.first->bytes) {
+        auto t1 = std::chrono::steady_clock::now();
+        size_t had = w.first->bytes;
+        w.first->Reserve(w.second);
+        fprintf(stderr, "[tachyon_b200] workspace buffer %d grows %zu -> %zu bytes: %.2f ms\n", index,
+                had, w.first->bytes,
+                std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t1).count());
+      } else {
+        w.first->Reserve(w.second);
+      }
+      ++index;
+    }
+    if (trace)
+      fprintf(stderr, "[tachyon_b200] workspace growth took %.2f ms\n",
+              std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t0).count());
     for (auto& u : stage_used_) u = false;
     budget_ = 0;
   }
@@ -719,11 +737,23 @@ class MsmEngine {
     pd.L0 = ChooseLevelLength(big.B, big.W);
     const uint32_t nb = big.B / pd.L0;  // blocks per window, a power of two
     pd.M = Log2(nb);
-    size_t tree_b[2] = {0, 0};
-    for (uint32_t s = 0; s < pd.M; ++s) {
-      size_t need = (size_t)big.W * (nb >> (s + 1)) * (s + 3) * kXyzzBytes;
-      if (need > tree_b[s & 1]) tree_b[s & 1] = need;
-    }
+    size_t tree_b[2] = {0, 0}, lvl_b = 0;
+    auto reduction_bytes = [&](uint32_t cc) {  // level + tree buffers of window size cc
+      uint32_t Wc = WindowsFor(Fr::kBits, cc), Bc = 1u << (cc - 1);
+      uint32_t nbc = Bc / ChooseLevelLength(Bc, Wc), Mc = Log2(nbc);
+      size_t lv = (size_t)Wc * nbc * kXyzzBytes;
+      if (lv > lvl_b) lvl_b = lv;
+      for (uint32_t s = 0; s < Mc; ++s) {
+        size_t need = (size_t)Wc * (nbc >> (s + 1)) * (s + 3) * kXyzzBytes;
+        if (need > tree_b[s & 1]) tree_b[s & 1] = need;
+      }
+    };
+    reduction_bytes(c);
+    // Pre-reserving for 2^degree points: smaller MSMs run smaller windows with MORE windows, and
+    // these few-MB buffers scale with W — cover every window size a smaller call may choose, so
+    // that no later call has to grow the workspace (a growth drains both streams).
+    if (reserve_only)
+      for (uint32_t cc = kMinWindowBits; cc < c; ++cc) reduction_bytes(cc);
     ReserveAll({{&state_, (size_t)big.TB * kXyzzBytes},
                 {&count_, (size_t)(big.TB + 1) * 4},
                 {&offset_, (size_t)(big.TB + 1) * 4},
@@ -749,12 +779,19 @@ class MsmEngine {
                 {&digits_, (size_t)m * big.W * 4},
                 {&block_sums_, (size_t)scan_blocks * 8},
                 {&len_hist_, (size_t)(kMaxSegment + 1) * 4},
-                {&lvl_a_[0], (size_t)big.W * nb * kXyzzBytes},
-                {&lvl_c_[0], (size_t)big.W * nb * kXyzzBytes},
+                {&lvl_a_[0], lvl_b},
+                {&lvl_c_[0], lvl_b},
                 {&tree_[0], tree_b[0]},
                 {&tree_[1], tree_b[1]},
                 {&bases_stage_, bases_dev ? 0 : m * kStageSlots * kAffineBytes},
                 {&scalars_stage_, scalars_dev ? 0 : m * kStageSlots * kScalarBytes}});
+    static const bool trace = getenv("TACHYON_B200_TRACE") != nullptr;
+    auto since = [&] {
+      return std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - wall0).count();
+    };
+    if (trace)
+      fprintf(stderr, "[tachyon_b200] enqueue n=%zu c=%u W=%u K=%zu%s: planned + reserved at %.2f ms\n", n,
+              c, big.W, K, reserve_only ? " (reserve only)" : "", since());
     if (reserve_only) return pd;
     const size_t bases_slot_bytes = bases_stage_.bytes / kStageSlots / 256 * 256;
     const size_t scalars_slot_bytes = scalars_stage_.bytes / kStageSlots / 256 * 256;
@@ -951,6 +988,7 @@ class MsmEngine {
     }
     TB_CUDA(cudaEventRecord(ev_end, stream_));
     pd.launches = launches_;
+    if (trace) fprintf(stderr, "[tachyon_b200] enqueue n=%zu: everything queued at %.2f ms\n", n, since());
     timing_.enqueue_ms +=
         std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - wall0).count();
     return pd;

@@ -384,38 +384,40 @@ static __global__ void __launch_bounds__(kScanThreads) scan_apply_build_tasks_ke
   const uint32_t seg = totals->seg;
   const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const uint32_t wbase = blockIdx.x * kScanItems + warp * (32 * kScanPerThread) + lane;
-  uint32_t cnt[kScanPerThread];
-  uint64_t pre[kScanPerThread];
-  uint64_t run = 0;
+  // pass 1: this warp's total; pass 2 re-reads the counts (L2 hits) row by row with a running
+  // prefix, so nothing is kept in per-thread arrays (the one-pass form needed 254 registers)
+  uint64_t sum = 0;
 #pragma unroll
   for (int k = 0; k < kScanPerThread; ++k) {
     uint32_t idx = wbase + k * 32;
-    cnt[k] = (idx < n) ? count[idx] : 0;
-    uint64_t item = scan_item(cnt[k], seg, R);
+    if (idx < n) sum += scan_item(count[idx], seg, R);
+  }
+#pragma unroll
+  for (int o = 16; o >= 1; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+  if (lane == 0) warp_total[warp] = sum;
+  __syncthreads();
+  uint64_t run = block_prefix[blockIdx.x];
+  for (uint32_t v = 0; v < warp; ++v) run += warp_total[v];
+#pragma unroll 2
+  for (int k = 0; k < kScanPerThread; ++k) {
+    uint32_t idx = wbase + k * 32;
+    uint32_t cnt_k = (idx < n) ? count[idx] : 0;
+    uint64_t item = scan_item(cnt_k, seg, R);
     uint64_t x = item;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
       uint64_t y = __shfl_up_sync(0xffffffffu, x, o);
       if (lane >= (uint32_t)o) x += y;
     }
-    pre[k] = run + x - item;
+    uint64_t prefix = run + x - item;
     run += __shfl_sync(0xffffffffu, x, 31);
-  }
-  if (lane == 0) warp_total[warp] = run;
-  __syncthreads();
-  uint64_t before = block_prefix[blockIdx.x];
-  for (uint32_t v = 0; v < warp; ++v) before += warp_total[v];
-#pragma unroll
-  for (int k = 0; k < kScanPerThread; ++k) {
-    uint32_t idx = wbase + k * 32;
     if (idx < n) {
-      uint64_t prefix = before + pre[k];
       uint32_t off = (uint32_t)prefix;
       uint32_t tb = (uint32_t)(prefix >> 32);
       offset[idx] = off;
       cursor[idx] = off;
       task_base[idx] = tb;
-      uint32_t cntp = padded_count(cnt[k], R);
+      uint32_t cntp = padded_count(cnt_k, R);
       uint32_t run_len = cntp >> R;  // points left after the pair rounds
       uint32_t t = (run_len + seg - 1) / seg;
       for (uint32_t s = 0; s < t; ++s) {
@@ -423,7 +425,7 @@ static __global__ void __launch_bounds__(kScanThreads) scan_apply_build_tasks_ke
         tasks[tb + s] = make_uint2((off >> R) + s * seg, len);
         task_meta[tb + s] = idx | (s == 0 ? kTaskFirst : 0u) | (t == 1 ? kTaskSingle : 0u);
       }
-      for (uint32_t q = cnt[k]; q < cntp; ++q) sorted[off + q] = kNoEntry;
+      for (uint32_t q = cnt_k; q < cntp; ++q) sorted[off + q] = kNoEntry;
       if (t > 1) {
         atomicAdd(&totals->multi, 1u);
         uint32_t chunks = (t + kFoldThreads - 1) / kFoldThreads;
