@@ -196,6 +196,7 @@ def run_groth16(args, rank, world, local_rank):
     ctx = msm.MSMGpu(curve, degree=args.log_m, device=local_rank)
     ctx.set_stream(stream.cuda_stream)
     zero = np.zeros((4, fq), dtype=np.uint64)
+    set_gather = sharding.PartialGather((len(sizes), 4, fq), world) if world > 1 else None
 
     def step(sc):
         parts = np.stack([zero] * len(sizes))
@@ -206,8 +207,7 @@ def run_groth16(args, rank, world, local_rank):
                 parts[j] = o
         if world == 1:
             return parts
-        with torch.cuda.stream(stream):
-            g = sharding.gather_set_partials(parts, world, device="cuda")
+        g = set_gather(parts, stream)
         return sharding.combine_set(curve, g) if rank == 0 else parts
 
     def barrier():
@@ -547,15 +547,14 @@ def main():
     if args.ranges:
         ctx.set_option("ranges", args.ranges)
 
-    gather_buf = torch.empty((world, 4 * fq), dtype=torch.int64, device="cuda") if world > 1 else None
+    gather = sharding.PartialGather((4, fq), world) if world > 1 else None
 
     def step(b_ptr, s_ptr, count):
         """One whole MSM: local partial on this GPU, then (N > 1) gather + host add on rank 0."""
         part = ctx.msm_xyzz(b_ptr, s_ptr, count)
         if world == 1:
             return part
-        with torch.cuda.stream(stream):
-            parts = sharding.gather_partials(part, world, device="cuda", out=gather_buf)
+        parts = gather(part, stream)
         if rank != 0:
             return part
         return sharding.combine_partials(curve, list(parts))

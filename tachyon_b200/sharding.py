@@ -27,6 +27,40 @@ def gather_partials(partial, world, device=None, out=None):
     return out.cpu().numpy().view(np.uint64).reshape((world,) + partial.shape)
 
 
+class PartialGather:
+    """Reusable buffers for the per-step all-gather of XYZZ partials over NCCL: the partial goes
+    through a pinned host word to the device (asynchronous copy), one all_gather_into_tensor on
+    the caller's stream, one asynchronous copy back to pinned memory and ONE stream
+    synchronisation — instead of a pageable copy each way (two implicit synchronisations and an
+    allocation per step).  `shape` = shape of one rank's contribution, e.g. (4, fq_limbs) or
+    (k, 4, fq_limbs)."""
+
+    def __init__(self, shape, world, device="cuda"):
+        import torch
+        self.shape, self.world = tuple(shape), world
+        words = int(np.prod(self.shape))
+        self.pin_in = torch.empty(words, dtype=torch.int64).pin_memory()
+        self.pin_out = torch.empty(world * words, dtype=torch.int64).pin_memory()
+        self.dev_in = torch.empty(words, dtype=torch.int64, device=device)
+        self.dev_out = torch.empty(world * words, dtype=torch.int64, device=device)
+        self._in_np = self.pin_in.numpy().view(np.uint64)
+        self._out_np = self.pin_out.numpy().view(np.uint64).reshape((world,) + self.shape)
+
+    def __call__(self, partial, stream=None):
+        """(shape) uint64 -> (world,) + shape uint64 (a view of the pinned result buffer, valid
+        until the next call)."""
+        import torch
+        import torch.distributed as dist
+        self._in_np[:] = np.ascontiguousarray(partial).reshape(-1)
+        stream = stream if stream is not None else torch.cuda.current_stream()
+        with torch.cuda.stream(stream):
+            self.dev_in.copy_(self.pin_in, non_blocking=True)
+            dist.all_gather_into_tensor(self.dev_out, self.dev_in)
+            self.pin_out.copy_(self.dev_out, non_blocking=True)
+        stream.synchronize()
+        return self._out_np
+
+
 def combine_partials(curve, parts):
     """Host-side sum of the per-rank partials (pippenger_adapter.h:110-113)."""
     total = parts[0]
