@@ -535,11 +535,13 @@ static __global__ void __launch_bounds__(kOrderThreads) order_scatter_kernel(
 // task; the next point is fetched while the current one is being added.
 // ---------------------------------------------------------------------------
 constexpr int kAccThreads = 128;
-// resident CTAs per SM the register budget is held to: 4 x 128 threads x 128 registers
-// (BN254 G1), 3 x 128 x 168 (BLS12-381 G1), 2 x 128 x 255 (BN254 G2), 1 (BLS12-381 G2)
+// resident CTAs per SM the register budget is held to: 4 x 128 threads x 128 registers for
+// both G1 curves (BLS12-381 at 3 x 168 registers had no spills but fewer warps to hide the
+// multiply chains: accumulate 21.8 -> 21.4 ms at 2^22 with 152 B of spills), 2 x 128 x 255
+// (BN254 G2; 3 x 168 measured slower, 10.15 -> 10.69 ms at 2^20), 1 (BLS12-381 G2)
 template <class C>
 constexpr int AccMinBlocks() {
-  return C::Field::kWords <= 8 ? 4 : (C::Field::kWords <= 12 ? 3 : (C::Field::kWords <= 16 ? 2 : 1));
+  return C::Field::kWords <= 12 ? 4 : (C::Field::kWords <= 16 ? 2 : 1);
 }
 
 // kReduced: the task's points are a run of affine points left by the pair rounds (read in
