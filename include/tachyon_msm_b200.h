@@ -91,10 +91,13 @@ extern "C" {
       tachyon_##C##_##G##_msm_gpu_ptr ptr, void* cuda_stream);                                  \
   /* name: "window_bits" (0 = automatic), "segment" (max entries per accumulation task),    \
      "devices" (point-range sharding over the first k devices; 1 = this context's device),  \
-     "sample_scalars" (1 = choose the window from the bit lengths of 1024 sampled scalars,   \
-     the default; 0 = from the size alone),                                                  \
-     "sort_mode" (0 = one-level atomic counting sort, 1/-1 = two-level shared-memory sort    \
-     where eligible),                                                                        \
+     "sample_scalars" (1 = choose the window from the bit lengths of 1024 sampled scalars    \
+     and flag skewed vectors for the two-level sort, the default; 0 = from the size alone),  \
+     "sort_mode" (0 = one-level atomic counting sort, 1 = two-level shared-memory sort       \
+     where eligible, -1 = automatic),                                                        \
+     "balance" (1 = balanced window widths, the default; 0 = equal widths),                  \
+     "reduce_mode" (1 = two threads per block of buckets in the running-sum level, the       \
+     default; 0 = one), "host_ranges" (most ranges of the automatic host-input pipeline),    \
      "prewarm" (reserve workspace, staging and copy threads for an MSM of `value` points now),\
      "release_workspace" (free the grow-only workspace; registered bases are kept),           \
      "ranges" (point ranges one MSM is pipelined over; 0 = automatic), "pair_rounds"        \
