@@ -528,6 +528,8 @@ using namespace tb200;
         for (auto& e : ptr->engines) e->options().host_ranges = (uint32_t)(value < 1 ? 1 : value); \
       } else if (k == "reduce_mode") {                                                         \
         for (auto& e : ptr->engines) e->options().reduce_mode = (int)value;                    \
+      } else if (k == "level_fill") {                                                          \
+        for (auto& e : ptr->engines) e->options().level_fill = (uint32_t)value;                \
       } else if (k == "balance") {                                                             \
         for (auto& e : ptr->engines) e->options().balance = (int)value;                        \
       } else if (k == "ranges") {                                                              \

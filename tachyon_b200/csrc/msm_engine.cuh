@@ -87,6 +87,8 @@ struct MsmOptions {
   uint32_t host_ranges = 8;  // most ranges the automatic host-input pipeline cuts an MSM into
   int reduce_mode = 1;       // 1 = two threads per block of buckets (reduce_blocks_kernel),
                              // 0 = one thread per block (reduce_level_kernel)
+  uint32_t level_fill = 0;   // blocks per SM the running-sum level wants before it shortens its
+                             // blocks (0 = default: 384, 768 from 1.5 M bucket slots)
   int balance = 1;           // balanced windows (WideWindowsFor); 0 = equal widths, slack on top
 };
 
@@ -1081,13 +1083,18 @@ class MsmEngine {
     return r;
   }
 
-  // Blocks of the running-sum level: as long as possible while the grid still fills the
-  // chip (a thread costs 2 L full additions, the merge tree ~3 per block).
+  // Blocks of the running-sum level: as long as possible while the grid still fills the chip
+  // (a block costs 2 L full additions, the merge tree ~3 per block).  Measured sweep of the
+  // blocks wanted per SM (option "level_fill"): 384 is best up to ~1.5 M bucket slots; longer
+  // blocks (192, 96) lose although they drop merge-tree levels (2^21 points: 0.75 -> 0.82 ms);
+  // above, the equal-length CTAs run in few rounds and shorter blocks even out the last one
+  // (768: 2^24 points 3.34 -> 3.25 ms, BLS12-381 2^22 2.04 -> 1.86 ms).
   uint32_t ChooseLevelLength(uint32_t buckets_per_window, uint32_t windows) const {
     uint64_t items = (uint64_t)buckets_per_window * windows;
-    uint64_t want_threads = (uint64_t)sm_count_ * 384;
+    uint32_t fill = options_.level_fill ? options_.level_fill : (items >= 1500000 ? 768 : 384);
+    uint64_t want_blocks = (uint64_t)sm_count_ * fill;
     uint32_t L = 64;
-    while (L > 4 && items / L < want_threads) L >>= 1;
+    while (L > 4 && items / L < want_blocks) L >>= 1;
     if (L > buckets_per_window) L = buckets_per_window;
     return L;
   }
