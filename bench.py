@@ -491,6 +491,8 @@ def main():
     ap.add_argument("--groth16-split", default="auto", choices=["auto", "msm", "range"])
     args = ap.parse_args()
 
+    # stdout carries exactly one JSON line: NCCL's own banner / debug output goes to stderr
+    os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
