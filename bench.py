@@ -491,11 +491,17 @@ def main():
     ap.add_argument("--groth16-split", default="auto", choices=["auto", "msm", "range"])
     args = ap.parse_args()
 
-    # stdout carries exactly one JSON line: NCCL's own banner / debug output goes to stderr
-    os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        # stdout carries exactly one JSON line: NCCL prints its version banner with printf on
+        # fd 1 (NCCL_DEBUG=VERSION), so fd 1 is pointed at stderr for native code and Python's
+        # own stdout keeps a duplicate of the real one
+        sys.stdout.flush()
+        real = os.fdopen(os.dup(1), "w")
+        os.dup2(2, 1)
+        sys.stdout = real
     if args.impl == "reference":
         run_reference(args, rank, world)
         return
