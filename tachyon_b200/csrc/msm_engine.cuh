@@ -932,9 +932,12 @@ class MsmEngine {
                (const uint32_t*)nullptr, tasks_.as<uint2>(), task_meta_.as<uint32_t>(),
                order_.as<uint32_t>(), totals_, state_.as<uint32_t>(), task_out_.as<uint32_t>());
       else
-        Launch(accumulate_kernel<C, false>, agrid, kAccThreads, d_bases, sorted_.as<uint32_t>(),
-               tasks_.as<uint2>(), task_meta_.as<uint32_t>(), order_.as<uint32_t>(), totals_,
-               state_.as<uint32_t>(), task_out_.as<uint32_t>());
+        Launch((uint64_t)plan.n * plan.W < kAccSmallEntries
+                   ? accumulate_kernel<C, false, AccMinBlocksSmall<C>()>
+                   : accumulate_kernel<C, false>,
+               agrid, kAccThreads, d_bases, sorted_.as<uint32_t>(), tasks_.as<uint2>(),
+               task_meta_.as<uint32_t>(), order_.as<uint32_t>(), totals_, state_.as<uint32_t>(),
+               task_out_.as<uint32_t>());
       Launch(fold_stage_a_kernel<C>, sm_count_ * 8, kFoldThreads, fold_jobs_.as<uint2>(), totals_,
              offset_.as<uint32_t>(), task_base_.as<uint32_t>(), plan.R, task_out_.as<uint32_t>(),
              state_.as<uint32_t>());

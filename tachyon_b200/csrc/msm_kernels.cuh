@@ -544,10 +544,19 @@ constexpr int AccMinBlocks() {
   return C::Field::kWords <= 12 ? 4 : (C::Field::kWords <= 16 ? 2 : 1);
 }
 
+// Small ranges of the 12-limb curve are latency-bound rather than pipe-bound and run faster with
+// the spill-free 3 CTAs/SM build (BLS12-381 2^19 points: 3.71 ms against 3.96 at 4 CTAs/SM;
+// from 2^20 points the 4-CTA build wins): a second instantiation, picked by entry count.
+template <class C>
+constexpr int AccMinBlocksSmall() {
+  return C::Field::kWords == 12 ? 3 : AccMinBlocks<C>();
+}
+constexpr uint64_t kAccSmallEntries = 12u << 20;  // below: the AccMinBlocksSmall build
+
 // kReduced: the task's points are a run of affine points left by the pair rounds (read in
 // order, no index or sign); otherwise they are gathered from `bases` through `sorted`.
-template <class C, bool kReduced>
-__global__ void __launch_bounds__(kAccThreads, AccMinBlocks<C>()) accumulate_kernel(
+template <class C, bool kReduced, int kMinBlocks = AccMinBlocks<C>()>
+__global__ void __launch_bounds__(kAccThreads, kMinBlocks) accumulate_kernel(
     const uint32_t* __restrict__ bases, const uint32_t* __restrict__ sorted,
     const uint2* __restrict__ tasks, const uint32_t* __restrict__ task_meta,
     const uint32_t* __restrict__ order, const MsmTotals* __restrict__ totals,
