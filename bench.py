@@ -124,55 +124,72 @@ class ClockSampler:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["clock query unavailable: %s" % e], "samples": 0}
 
 
+def workload_config(curve, log_n, dist):
+    """`config` of the JSON line: identical for this repo's arm and for --impl reference (the
+    driver compares them); engine-specific detail goes under the top-level key "engine"."""
+    group = "G2" if curve.endswith("_g2") else "G1"
+    return {"workload": f"{curve} {group} MSM 2^{log_n} points, {dist} scalars",
+            "l2": "inputs + workspace exceed the 126 MB L2 every step"}
+
+
 def run_reference(args, rank, world):
-    """--impl reference: the CPU path (oracle restatement of Tachyon's OpenMP
-    Pippenger, VariableBaseMSM::Run) on all host threads; a step is an MSM over a
-    bounded prefix of the same workload."""
+    """--impl reference: the CPU path (oracle restatement of Tachyon's OpenMP Pippenger,
+    VariableBaseMSM::Run -> PippengerAdapter kParallelTerm) on all host threads, on the SAME
+    workload as this repo's arm: every timed step is one full 2^log_n-point MSM
+    (benchmark/msm/msm_benchmark_gpu.cc:56-66 runs CPU and GPU on the same sizes).  Warm-up steps
+    run on a 2^18-point prefix.  If K full MSMs would take more than --cpu-budget seconds the step
+    count is cut (and reported)."""
     if rank != 0:
         return
     from oracle import cpu_oracle
     cpu_oracle.build()
     o = cpu_oracle.CurveOracle(args.curve)
-    sample_log = min(args.log_n, args.cpu_sample_log)
-    n = 1 << sample_log
+    n = 1 << args.log_n
     threads = os.cpu_count() or cpu_oracle.max_threads()  # torchrun pins OMP_NUM_THREADS=1
     bases = o.generate_points(SEED + 2, n)
     scalars = o.generate_scalars(SEED + 3, n, args.dist)
-    for _ in range(max(1, min(args.warmup, 1))):
+    wn = min(n, 1 << 18)
+    for _ in range(max(1, args.warmup)):
+        o.msm(bases[:wn], scalars[:wn], threads=threads)
+    steps = max(1, args.steps)
+    times = []
+    t_begin = time.perf_counter()
+    for k in range(steps):
+        t0 = time.perf_counter()
         o.msm(bases, scalars, threads=threads)
-    steps = max(1, min(args.steps, 5))
-    t0 = time.perf_counter()
-    for _ in range(steps):
-        o.msm(bases, scalars, threads=threads)
-    dt = (time.perf_counter() - t0) / steps
+        times.append(time.perf_counter() - t0)
+        if k + 1 < steps and (time.perf_counter() - t_begin) + times[-1] > args.cpu_budget:
+            break
+    steps_done = len(times)
+    dt = sum(times) / steps_done
     value = n / dt
-    sample = f"2^{sample_log}-point prefix of the 2^{args.log_n} workload, {steps} timed MSMs"
+    sample = (f"full 2^{args.log_n}-point MSM per step, {steps_done} timed steps"
+              + ("" if steps_done == steps else f" (cut from {steps}: --cpu-budget {args.cpu_budget:.0f} s)")
+              + f"; {max(1, args.warmup)} warm-up MSMs on a 2^18-point prefix")
     print(json.dumps({
         "impl": "reference", "metric": f"{args.curve} G1 MSM throughput", "value": value, "unit": "points/s",
-        "n_gpus": args.gpus, "steps": steps, "warmup": 1, "ms_per_step": dt * 1e3, "higher_is_better": True,
-        "scaling": "strong", "vs_baseline": None, "dtype": "u64",
+        "n_gpus": args.gpus, "steps": steps_done, "warmup": max(1, args.warmup), "ms_per_step": dt * 1e3,
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "u64",
         "data": "synthetic",
-        "config": {"workload": f"{args.curve} G1 MSM 2^{args.log_n} points, {args.dist} scalars", "sample": sample},
-        "cpu_baseline": {"value": value, "unit": "points/s", "cores": threads, "kind": "port", "sample": sample},
+        "config": workload_config(args.curve, args.log_n, args.dist),
+        "cpu_baseline": {"value": value, "unit": "points/s", "cores": threads, "kind": "port", "sample": sample,
+                         "ms_per_msm": dt * 1e3, "ms_min": min(times) * 1e3, "ms_max": max(times) * 1e3},
         "e2e": {"value": value, "unit": "points/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }), flush=True)
 
 
-def run_groth16(args, rank, world, local_rank):
-    """--workload groth16 (BASELINE.json configs[4]): the G1 MSM set of one Groth16 proof of a
-    synthetic 2^log_m-constraint circuit — A, B1 (full assignment), L (witness part) and H
-    (quotient coefficients), zk/r1cs/groth16/prove.h:100-131 — dealt over the ranks
+def groth16_measure(args, d, steps, with_proof=False, curve="bn254"):
+    """The G1 MSM set of one Groth16 proof of a synthetic 2^log_m-constraint circuit
+    (BASELINE.json configs[4]) — A, B1 (full assignment), L (witness part) and H (quotient
+    coefficients), zk/r1cs/groth16/prove.h:100-131 — dealt over the ranks
     (tachyon_b200.sharding.deal_msms) and run through the batched C-ABI call.  The proving
     key (bases) is device-resident as in a prover that keeps its zkey loaded; scalars are
-    device-resident for `value` and pinned host memory for `e2e`."""
+    device-resident for `ms_per_step` and pinned host memory for `e2e_ms_per_step`."""
     import torch
-    import torch.distributed as dist
     from tachyon_b200 import msm, sharding
-    torch.cuda.set_device(local_rank)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-    curve, fq = args.curve, FQ_LIMBS[args.curve]
+    rank, world, local_rank = d.rank, d.world, d.local_rank
+    fq = FQ_LIMBS[curve]
     m = 1 << args.log_m
     n_pub = 64
     names = ["A", "B1", "L", "H"]
@@ -210,27 +227,19 @@ def run_groth16(args, rank, world, local_rank):
         g = set_gather(parts, stream)
         return sharding.combine_set(curve, g) if rank == 0 else parts
 
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    def timed(fn, steps):
+    def timed(fn, nsteps):
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        barrier()
+        d.barrier()
         t0 = time.perf_counter()
         e0.record(stream)
-        for _ in range(steps):
+        for _ in range(nsteps):
             out = fn()
         e1.record(stream)
-        barrier()
+        d.barrier()
         wall = (time.perf_counter() - t0) * 1e3
         ms = max(e0.elapsed_time(e1), wall)   # host epilogues of a batch overlap device work: wall bounds it
-        if world > 1:
-            t = torch.tensor([ms], device="cuda", dtype=torch.float64)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            ms = t.item()
-        return ms / steps, out
+        ms = d.max_float([ms])[0]
+        return ms / nsteps, out
 
     warm = max(args.warmup, 3)
     for _ in range(warm):
@@ -242,14 +251,14 @@ def run_groth16(args, rank, world, local_rank):
     sampler = ClockSampler(gpu_uuid, local_rank)
     sampler.start()
     l0 = msm.kernel_launch_count()
-    ms_step, result = timed(lambda: step(scalars), args.steps)
+    ms_step, result = timed(lambda: step(scalars), steps)
     launches = msm.kernel_launch_count() - l0
     clocks = sampler.stop()
     step(h_scalars)
-    e2e_ms, e2e_out = timed(lambda: step(h_scalars), max(2, min(args.steps, 5)))
+    e2e_ms, e2e_out = timed(lambda: step(h_scalars), max(2, min(steps, 5)))
     # ---- the whole proof (adds the G2 MSM B2 and the r / s arithmetic), one process -------------
     proof = None
-    if world == 1 and not curve.endswith("_g2"):
+    if with_proof and world == 1 and not curve.endswith("_g2"):
         g2fq = 2 * fq
         b2 = torch.empty((m + 1, 2 * g2fq), dtype=torch.int64, device="cuda")
         msm.generate_bases_device(curve + "_g2", SEED + 50, m + 1, b2.data_ptr())
@@ -274,7 +283,7 @@ def run_groth16(args, rank, world, local_rank):
         for _ in range(3):
             run_proof()
         t0 = time.perf_counter()
-        reps = max(3, min(args.steps, 10))
+        reps = max(3, min(steps, 10))
         for _ in range(reps):
             run_proof()
         proof = {"ms": (time.perf_counter() - t0) * 1e3 / reps,
@@ -283,36 +292,52 @@ def run_groth16(args, rank, world, local_rank):
         g2ctx.close()
         del b2, a_q, b1_q
 
-    parity = "skipped"
-    if not args.no_parity and rank == 0:
-        from oracle import cpu_oracle
-        o = cpu_oracle.CurveOracle(curve)
+    parity = "skipped (--no-parity)"
+    if not args.no_parity:
         ok = True
-        for j, n in enumerate(sizes):
-            hs = scalars[j].cpu().numpy().view(np.uint64)
-            pad = (-n) % 4096
-            if pad:
-                hs = np.concatenate([hs, np.zeros((pad, 4), dtype=np.uint64)])
-            heads = np.stack([o.generate_points(SEED + 40 + j, 1, first=c * 4096)[0] for c in range(len(hs) // 4096)])
-            want = o.msm_affine(heads, o.fold_chain_scalars(hs))
-            ok = ok and bool((o.xyzz_to_affine(result[j]) == want).all()) and bool((o.xyzz_to_affine(e2e_out[j]) == want).all())
+        if rank == 0:
+            from oracle import cpu_oracle
+            o = cpu_oracle.CurveOracle(curve)
+            for j, n in enumerate(sizes):
+                hs = scalars[j].cpu().numpy().view(np.uint64)
+                pad = (-n) % 4096
+                if pad:
+                    hs = np.concatenate([hs, np.zeros((pad, 4), dtype=np.uint64)])
+                heads = np.stack([o.generate_points(SEED + 40 + j, 1, first=c * 4096)[0] for c in range(len(hs) // 4096)])
+                want = o.msm_affine(heads, o.fold_chain_scalars(hs))
+                ok = ok and bool((o.xyzz_to_affine(result[j]) == want).all()) and bool((o.xyzz_to_affine(e2e_out[j]) == want).all())
         parity = "bit-exact vs CPU oracle (chain-fold), all four MSMs" if ok else "MISMATCH"
-    if world > 1:
-        dist.barrier()
+    d.barrier()
+    ctx.close()
+    total = sum(sizes)
+    return {"workload": f"Groth16 G1 MSM set (A, B1, L, H) of a synthetic 2^{args.log_m}-constraint circuit, "
+                        f"{curve}; witness-like assignment (40% 0, 30% 1, 20% <2^32, 10% full), uniform h; {world} GPU(s)",
+            "sizes": dict(zip(names, sizes)), "split": args.groth16_split,
+            "work_rank0": [[names[j], lo, hi] for j, lo, hi in work],
+            "ms_per_step": ms_step, "points_per_s": total / (ms_step * 1e-3), "e2e_ms_per_step": e2e_ms,
+            "total_points": total, "launches": int(launches), "clocks": clocks, "warmup": warm,
+            "parity": parity, "proof": proof}
+
+
+def run_groth16(args, rank, world, local_rank):
+    """--workload groth16: the set above as the headline of its own JSON line."""
+    from tachyon_b200 import msm
+    d = Dist(rank, world, local_rank)
+    curve = args.curve
+    g = groth16_measure(args, d, args.steps, with_proof=True, curve=curve)
     if rank == 0:
-        total = sum(sizes)
+        sizes = list(g["sizes"].values())
+        total, ms_step, e2e_ms = g["total_points"], g["ms_per_step"], g["e2e_ms_per_step"]
         alg = sum(algorithmic_products(curve, n)["products"] for n in sizes)
         peak = max(msm.imad_peak(local_rank, v, 3) for v in (0, 1, 2))
         print(json.dumps({
             "metric": f"{curve} Groth16 G1 MSM set throughput", "value": total / (ms_step * 1e-3), "unit": "points/s",
-            "n_gpus": world, "steps": args.steps, "warmup": warm, "ms_per_step": ms_step, "higher_is_better": True,
+            "n_gpus": world, "steps": args.steps, "warmup": g["warmup"], "ms_per_step": ms_step, "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": "u32", "data": "synthetic",
-            "config": {"workload": f"Groth16 G1 MSM set (A, B1, L, H) of a synthetic 2^{args.log_m}-constraint circuit, "
-                                   f"{curve}; witness-like assignment (40% 0, 30% 1, 20% <2^32, 10% full), uniform h",
-                       "sizes": dict(zip(names, sizes)), "split": args.groth16_split,
-                       "work_rank0": [[names[j], lo, hi] for j, lo, hi in work],
+            "config": {"workload": g["workload"], "sizes": g["sizes"], "split": g["split"],
+                       "work_rank0": g["work_rank0"],
                        "l2": "inputs + workspace exceed the 126 MB L2 every step"},
-            "clocks": clocks, "gpu_launches": int(launches),
+            "clocks": g["clocks"], "gpu_launches": g["launches"],
             "e2e": {"value": total / (e2e_ms * 1e-3), "unit": "points/s", "ms_per_step": e2e_ms,
                     "h2d_bytes_per_step": 32 * total, "d2h_bytes_per_step": 0,
                     "api": f"tachyon_{curve}_g1_msm_gpu_batch_b200: resident proving-key bases, pinned host scalars"},
@@ -320,10 +345,9 @@ def run_groth16(args, rank, world, local_rank):
                          "unit": "G products/s (32x32->64)", "frac": alg / (ms_step * 1e-3) / (peak * world),
                          "traffic": None, "note": "W_alg of SURVEY 8d summed over the four MSMs; witness scalars are "
                                                   "mostly 0/1 so far fewer additions are actually needed"},
-            "cpu_baseline": None, "parity": parity, "proof": proof}), flush=True)
-    ctx.close()
+            "cpu_baseline": None, "parity": g["parity"], "proof": g["proof"]}), flush=True)
     if world > 1:
-        dist.destroy_process_group()
+        d.dist.destroy_process_group()
 
 
 def run_commit_batch(args, local_rank):
@@ -475,6 +499,8 @@ def main():
     ap.add_argument("--log-n", type=int, default=24)
     ap.add_argument("--dist", default="uniform", choices=["uniform", "non_uniform", "witness"])
     ap.add_argument("--cpu-sample-log", type=int, default=20)
+    ap.add_argument("--cpu-budget", type=float, default=240.0,
+                    help="--impl reference: seconds of timed full-size CPU MSMs after which the step count is cut")
     ap.add_argument("--no-parity", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extra", action="store_true", help="skip the secondary 2^20 measurement")
@@ -522,78 +548,255 @@ def main():
         if world == 1 and args.gpus > 1:
             raise SystemExit("launch with torchrun --nproc-per-node %d for --gpus %d" % (args.gpus, args.gpus))
     args.warmup = max(args.warmup, 3)
+    run_msm(args, rank, world, local_rank)
 
-    import torch
-    import torch.distributed as dist
-    from tachyon_b200 import msm, sharding
 
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py needs a CUDA device (no CPU fallback)")
-    torch.cuda.set_device(local_rank)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+class Dist:
+    """Process-group plumbing of one bench run: NCCL for device tensors, a gloo group for
+    host-side barriers and object gathers (ranks parked on gloo leave their GPU idle)."""
 
-    curve, fq = args.curve, FQ_LIMBS[args.curve]
-    n_total = 1 << args.log_n
-    lo, hi = sharding.shard_range(n_total, rank, world)
-    n_local = hi - lo
-
-    def make_inputs(first, count, seed_shift=0):
-        b = torch.empty((count, 2 * fq), dtype=torch.int64, device="cuda")
-        s = torch.empty((count, 4), dtype=torch.int64, device="cuda")
-        msm.generate_bases_device(curve, SEED + 2 + seed_shift, count, b.data_ptr(), first=first)
-        msm.generate_scalars_device(curve, SEED + 3 + seed_shift, count, s.data_ptr(), args.dist, first=first)
-        torch.cuda.synchronize()
-        return b, s
-
-    bases, scalars = make_inputs(lo, n_local)
-    stream = torch.cuda.Stream()
-    ctx = msm.MSMGpu(curve, degree=args.log_n, device=local_rank)
-    ctx.set_stream(stream.cuda_stream)
-    if args.window_bits:
-        ctx.set_option("window_bits", args.window_bits)
-    if args.ranges:
-        ctx.set_option("ranges", args.ranges)
-
-    gather = sharding.PartialGather((4, fq), world) if world > 1 else None
-
-    def step(b_ptr, s_ptr, count):
-        """One whole MSM: local partial on this GPU, then (N > 1) gather + host add on rank 0."""
-        part = ctx.msm_xyzz(b_ptr, s_ptr, count)
-        if world == 1:
-            return part
-        parts = gather(part, stream)
-        if rank != 0:
-            return part
-        return sharding.combine_partials(curve, list(parts))
-
-    def barrier():
+    def __init__(self, rank, world, local_rank):
+        import torch
+        import torch.distributed as dist
+        self.rank, self.world, self.local_rank, self.torch, self.dist = rank, world, local_rank, torch, dist
+        torch.cuda.set_device(local_rank)
+        self.host = None
         if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
+            if not dist.is_initialized():
+                dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+            self.host = dist.new_group(backend="gloo")
 
-    def timed(fn, steps):
+    def barrier(self):
+        if self.world > 1:
+            self.dist.barrier()
+        self.torch.cuda.synchronize()
+
+    def host_barrier(self):
+        if self.world > 1:
+            self.dist.barrier(group=self.host)
+
+    def max_float(self, values):
+        if self.world == 1:
+            return list(values)
+        t = self.torch.tensor(list(values), device="cuda", dtype=self.torch.float64)
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+        return t.tolist()
+
+    def all_ok(self, ok):
+        if self.world == 1:
+            return ok
+        t = self.torch.tensor([1 if ok else 0], device="cuda")
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.MIN)
+        return bool(t.item())
+
+    def gather_objects(self, obj):
+        """list over ranks on rank 0, None elsewhere (gloo)."""
+        if self.world == 1:
+            return [obj]
+        out = [None] * self.world if self.rank == 0 else None
+        self.dist.gather_object(obj, out, dst=0, group=self.host)
+        return out
+
+    def broadcast_object(self, obj):
+        if self.world == 1:
+            return obj
+        box = [obj]
+        self.dist.broadcast_object_list(box, src=0, group=self.host)
+        return box[0]
+
+
+class MsmCase:
+    """One MSM workload on this rank: its point range resident in HBM (and in pinned host
+    memory for the end-to-end leg), a context that — at N > 1 — has joined the ranks, so that
+    every call returns the whole MSM: the only exchange, one ncclAllGather of the partial sums,
+    is issued by the library on the context's stream (tachyon_*_msm_gpu_join_ranks_b200)."""
+
+    def __init__(self, d, curve, log_n, dist_name, seed_shift=0, window_bits=0, ranges=0):
+        from tachyon_b200 import msm, sharding
+        torch = d.torch
+        self.d, self.msm, self.curve, self.log_n, self.dist_name = d, msm, curve, log_n, dist_name
+        self.fq = FQ_LIMBS[curve]
+        self.n_total = 1 << log_n
+        lo, hi = sharding.shard_range(self.n_total, d.rank, d.world)
+        self.lo, self.n_local = lo, hi - lo
+        self.bases = torch.empty((self.n_local, 2 * self.fq), dtype=torch.int64, device="cuda")
+        self.scalars = torch.empty((self.n_local, 4), dtype=torch.int64, device="cuda")
+        msm.generate_bases_device(curve, SEED + 2 + seed_shift, self.n_local, self.bases.data_ptr(), first=lo)
+        msm.generate_scalars_device(curve, SEED + 3 + seed_shift, self.n_local, self.scalars.data_ptr(), dist_name,
+                                    first=lo)
+        torch.cuda.synchronize()
+        self.stream = torch.cuda.Stream()
+        self.ctx = msm.MSMGpu(curve, degree=log_n, device=d.local_rank)
+        self.ctx.set_stream(self.stream.cuda_stream)
+        if window_bits:
+            self.ctx.set_option("window_bits", window_bits)
+        if ranges:
+            self.ctx.set_option("ranges", ranges)
+        if d.world > 1:
+            uid = d.broadcast_object(msm.nccl_unique_id() if d.rank == 0 else None)
+            self.ctx.join_ranks(uid, d.rank, d.world)
+        self.h_bases = self.h_scalars = None
+
+    def close(self):
+        self.ctx.close()
+        self.bases = self.scalars = self.h_bases = self.h_scalars = None
+
+    def resident(self):
+        return self.ctx.msm_xyzz(self.bases.data_ptr(), self.scalars.data_ptr(), self.n_local)
+
+    def pin_host(self):
+        torch = self.d.torch
+        if self.h_bases is None:
+            self.h_bases = torch.empty((self.n_local, 2 * self.fq), dtype=torch.int64).pin_memory()
+            self.h_scalars = torch.empty((self.n_local, 4), dtype=torch.int64).pin_memory()
+            self.h_bases.copy_(self.bases)
+            self.h_scalars.copy_(self.scalars)
+            torch.cuda.synchronize()
+
+    def e2e(self):
+        """The reference-shaped call (tachyon_<c>_g1_affine_msm_gpu) with pinned HOST buffers."""
+        return self.ctx.affine_msm(self.h_bases.data_ptr(), self.h_scalars.data_ptr(), self.n_local)
+
+    def timed(self, fn, steps, stage=None):
         """K steps bracketed by barrier + synchronize, CUDA events on the engine's stream; max over ranks."""
+        torch = self.d.torch
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        barrier()
+        self.d.barrier()
         t0 = time.perf_counter()
-        e0.record(stream)
+        e0.record(self.stream)
         for _ in range(steps):
             out = fn()
-        e1.record(stream)
-        barrier()
+            if stage is not None:
+                t = self.ctx.last_timing()
+                for k in stage:
+                    stage[k] += t[k]
+        e1.record(self.stream)
+        self.d.barrier()
         wall_ms = (time.perf_counter() - t0) * 1e3
-        ms = e0.elapsed_time(e1)
-        if world > 1:
-            t = torch.tensor([ms, wall_ms], device="cuda", dtype=torch.float64)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            ms, wall_ms = t.tolist()
+        ms, wall_ms = self.d.max_float([e0.elapsed_time(e1), wall_ms])
+        if stage is not None:
+            for k in stage:
+                stage[k] /= steps
         return ms / steps, wall_ms / steps, out
 
+    def parity(self, results_xyzz=(), results_jacobian=()):
+        """Chain-fold property against the CPU oracle (outside timing): the synthetic bases are
+        chains P(j, d) = 2^d H_j, so MSM(P, s) = MSM(H, fold(s)) with a 4096x smaller MSM the
+        oracle does in milliseconds.  Every rank checks its own partial; rank 0 checks the
+        combined point(s) against the sum of the CPU partials."""
+        from oracle import cpu_oracle
+        o = cpu_oracle.CurveOracle(self.curve)
+        hs = self.scalars.cpu().numpy().view(np.uint64)
+        pad = (-self.n_local) % 4096
+        if pad:
+            hs = np.concatenate([hs, np.zeros((pad, 4), dtype=np.uint64)])
+        heads = self.bases[::4096].cpu().numpy().view(np.uint64)
+        want_local = o.msm(heads, o.fold_chain_scalars(hs))
+        # this rank's own partial, through a context that has NOT joined the ranks
+        with self.msm.MSMGpu(self.curve, device=self.d.local_rank) as solo:
+            mine = solo.msm_xyzz(self.bases.data_ptr(), self.scalars.data_ptr(), self.n_local)
+        ok = bool((o.xyzz_to_affine(mine) == o.xyzz_to_affine(want_local)).all())
+        ok = self.d.all_ok(ok)
+        gathered = self.d.gather_objects(want_local)
+        if self.d.rank == 0:
+            tot = gathered[0]
+            for g in range(1, self.d.world):
+                tot = o.xyzz_add(tot, gathered[g])
+            want = o.xyzz_to_affine(tot)
+            for r in results_xyzz:
+                ok = ok and bool((o.xyzz_to_affine(np.asarray(r)) == want).all())
+            for r in results_jacobian:
+                ok = ok and bool((o.jacobian_to_affine(np.asarray(r)) == want).all())
+        return "bit-exact vs CPU oracle (chain-fold)" if ok else "MISMATCH"
+
+
+def measure_extra(d, curve, log_n, dist_name, steps, peak, seed_shift, e2e=False):
+    """A secondary configuration measured like the headline (device-resident, strong scaling
+    over the ranks) with its own parity check; returns the `extra_*` block of the JSON line."""
+    case = MsmCase(d, curve, log_n, dist_name, seed_shift=seed_shift)
+    for _ in range(3):
+        case.resident()
+    stage = {"sort_ms": 0.0, "accumulate_ms": 0.0, "reduce_ms": 0.0, "total_ms": 0.0}
+    ms, wall, result = case.timed(case.resident, steps, stage)
+    t = case.ctx.last_timing()
+    out = {"workload": f"{curve} MSM 2^{log_n} points, {dist_name} scalars, {d.world} GPU(s), device-resident",
+           "ms_per_msm": ms, "points_per_s": (1 << log_n) / (ms * 1e-3), "window_bits": t["window_bits"],
+           "windows": t["windows"], "low_windows": t["low_windows"], "stages_ms": stage}
+    alg = algorithmic_products(curve, 1 << log_n)
+    if peak:
+        out["imad_frac"] = alg["products"] / (ms * 1e-3) / (peak * d.world)
+    jac = []
+    if e2e:
+        case.pin_host()
+        case.e2e()
+        e_ms, e_wall, e_out = case.timed(case.e2e, max(2, min(steps, 5)))
+        out["e2e_ms_per_msm"] = max(e_ms, e_wall)
+        jac = [e_out]
+    out["parity"] = case.parity([result], jac)
+    case.close()
+    return out
+
+
+def measure_in_process_devices(d, curve, log_n, dist_name, steps):
+    """The product's own multi-GPU path, the one a drop-in caller of the reference's C API gets
+    (TACHYON_B200_MSM_DEVICES / set_option("devices", k), msm_api_common.cuh MsmGpuContext::Run):
+    ONE process, ONE call of tachyon_<c>_g1_affine_msm_gpu with host buffers, fanned out to k
+    engines on k GPUs from k host threads, partials added on the host.  Run by rank 0 after the
+    timed regions while the other ranks wait on a host-side (gloo) barrier."""
+    out = None
+    if d.rank == 0:
+        import torch
+        from oracle import cpu_oracle
+        from tachyon_b200 import msm
+        fq, n = FQ_LIMBS[curve], 1 << log_n
+        k = min(d.world, msm.device_count())
+        b = torch.empty((n, 2 * fq), dtype=torch.int64, device="cuda")
+        sc = torch.empty((n, 4), dtype=torch.int64, device="cuda")
+        msm.generate_bases_device(curve, SEED + 2, n, b.data_ptr())
+        msm.generate_scalars_device(curve, SEED + 3, n, sc.data_ptr(), dist_name)
+        torch.cuda.synchronize()
+        hb = torch.empty((n, 2 * fq), dtype=torch.int64).pin_memory()
+        hs = torch.empty((n, 4), dtype=torch.int64).pin_memory()
+        hb.copy_(b)
+        hs.copy_(sc)
+        heads = b[::4096].cpu().numpy().view(np.uint64)
+        del b, sc
+        torch.cuda.synchronize()
+        ctx = msm.MSMGpu(curve, degree=log_n, device=d.local_rank)
+        ctx.set_option("devices", k)
+        for _ in range(3):
+            jac = ctx.affine_msm(hb.data_ptr(), hs.data_ptr(), n)
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            jac = ctx.affine_msm(hb.data_ptr(), hs.data_ptr(), n)
+        ms = (time.perf_counter() - t0) * 1e3 / steps
+        t = ctx.last_timing()
+        o = cpu_oracle.CurveOracle(curve)
+        want = o.msm_affine(heads, o.fold_chain_scalars(hs.numpy().view(np.uint64)))
+        ok = bool((o.jacobian_to_affine(jac) == want).all())
+        ctx.close()
+        out = {"workload": f"{curve} MSM 2^{log_n} points through ONE tachyon_{curve}_g1_affine_msm_gpu call, "
+                           f"option devices = {k}, pinned host buffers (H2D inside the timed region)",
+               "devices": t["devices"], "ms_per_msm": ms, "points_per_s": n / (ms * 1e-3), "timing": "host wall clock",
+               "parity": "bit-exact vs CPU oracle (chain-fold)" if ok else "MISMATCH"}
+    d.host_barrier()
+    return out
+
+
+def run_msm(args, rank, world, local_rank):
+    import torch
+    from tachyon_b200 import msm
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (no CPU fallback)")
+    d = Dist(rank, world, local_rank)
+    curve, fq = args.curve, FQ_LIMBS[args.curve]
+    n_total = 1 << args.log_n
+    case = MsmCase(d, curve, args.log_n, args.dist, window_bits=args.window_bits, ranges=args.ranges)
+    ctx, n_local = case.ctx, case.n_local
+
     # ---- device-resident measurement ------------------------------------------------
-    resident = lambda: step(bases.data_ptr(), scalars.data_ptr(), n_local)
     for _ in range(args.warmup):
-        result = resident()
+        result = case.resident()
     try:
         gpu_uuid = str(torch.cuda.get_device_properties(local_rank).uuid)
     except Exception:  # noqa: BLE001
@@ -601,115 +804,72 @@ def main():
     sampler = ClockSampler(gpu_uuid, local_rank)
     sampler.start()
     launches0 = msm.kernel_launch_count()
-    stage = {"sort_ms": 0.0, "accumulate_ms": 0.0, "reduce_ms": 0.0, "host_ms": 0.0, "total_ms": 0.0}
-
-    def resident_with_stages():
-        r = resident()
-        t = ctx.last_timing()
-        for k in stage:
-            stage[k] += t[k]
-        return r
-
-    ms_step, wall_step, result = timed(resident_with_stages, args.steps)
+    stage = {"sort_ms": 0.0, "accumulate_ms": 0.0, "reduce_ms": 0.0, "host_ms": 0.0, "total_ms": 0.0,
+             "acc_kernel_ms": 0.0, "combine_ms": 0.0}
+    ms_step, wall_step, result = case.timed(case.resident, args.steps, stage)
     launches = (msm.kernel_launch_count() - launches0)
     clocks = sampler.stop()
     timing = ctx.last_timing()
-    for k in stage:
-        stage[k] /= args.steps
     value = n_total / (ms_step * 1e-3)
 
     # ---- end to end through the reference-shaped C-ABI call, pinned host buffers ----
-    h_bases = torch.empty((n_local, 2 * fq), dtype=torch.int64).pin_memory()
-    h_scalars = torch.empty((n_local, 4), dtype=torch.int64).pin_memory()
-    h_bases.copy_(bases)
-    h_scalars.copy_(scalars)
-    torch.cuda.synchronize()
-
-    def e2e_step():
-        if world == 1:
-            return ctx.affine_msm(h_bases.data_ptr(), h_scalars.data_ptr(), n_local)  # tachyon_*_g1_affine_msm_gpu
-        return step(h_bases.data_ptr(), h_scalars.data_ptr(), n_local)
-
+    case.pin_host()
     e2e_steps = max(2, min(args.steps, 5))
-    e2e_step()
-    e2e_ms, e2e_wall, e2e_out = timed(e2e_step, e2e_steps)
+    case.e2e()
+    e2e_ms, e2e_wall, e2e_out = case.timed(case.e2e, e2e_steps)
     e2e_timing = ctx.last_timing()
     h2d = n_local * (2 * fq * 8 + 32) * world
-    d2h = (2 * e2e_timing["windows"] * 4 * fq * 8 + 16) * world
+    d2h = (4 * fq * 8 * (world if world > 1 else 1) + 40 * e2e_timing["ranges"]) * world
     e2e_value = n_total / (max(e2e_ms, e2e_wall) * 1e-3)
 
-    # ---- parity: chain-fold property against the CPU oracle (outside timing) --------
-    parity = "skipped"
-    if not args.no_parity:
-        from oracle import cpu_oracle
-        o = cpu_oracle.CurveOracle(curve)
-        hs = h_scalars.numpy().view(np.uint64)
-        hb = h_bases.numpy().view(np.uint64)
-        folded = o.fold_chain_scalars(hs)
-        want_local = o.msm(hb[::4096], folded)        # this rank's partial sum, CPU
-        mine = ctx.msm_xyzz(bases.data_ptr(), scalars.data_ptr(), n_local)
-        ok = bool((o.xyzz_to_affine(mine) == o.xyzz_to_affine(want_local)).all())
-        if world > 1:
-            flag = torch.tensor([1 if ok else 0], device="cuda")
-            dist.all_reduce(flag, op=dist.ReduceOp.MIN)
-            ok = bool(flag.item())
-            if rank == 0:
-                # and the combined point equals the sum of the CPU partials
-                gathered = [None] * world
-                dist.gather_object(want_local, gathered, dst=0)
-                tot = gathered[0]
-                for g in range(1, world):
-                    tot = o.xyzz_add(tot, gathered[g])
-                ok = ok and bool((o.xyzz_to_affine(result) == o.xyzz_to_affine(tot)).all())
-            else:
-                dist.gather_object(want_local, None, dst=0)
-        else:
-            ok = ok and bool((o.xyzz_to_affine(result) == o.xyzz_to_affine(want_local)).all())
-            jac = np.asarray(e2e_out)
-            ok = ok and bool((o.jacobian_to_affine(jac) == o.xyzz_to_affine(want_local)).all())
-        parity = "bit-exact vs CPU oracle (chain-fold)" if ok else "MISMATCH"
+    parity = "skipped (--no-parity)" if args.no_parity else case.parity([result], [e2e_out])
 
     # ---- IMAD roofline ----------------------------------------------------------------
     alg = algorithmic_products(curve, n_total)
-    peak = max(msm.imad_peak(local_rank, v, 3) for v in (0, 1, 2)) if rank == 0 else 0.0
+    peaks = [msm.imad_peak(local_rank, v, 3) for v in (0, 1, 2)] if rank == 0 else [0.0]
+    peak = d.broadcast_object(max(peaks))
+    sm_count = torch.cuda.get_device_properties(local_rank).multi_processor_count
+    sm_mhz = clocks.get("sm_mhz") or clocks.get("sm_max_mhz") or 0.0
 
-    extra = None
+    extras = {}
     cpu_baseline = None
-    if rank == 0:
-        # secondary: 2^20 on this one GPU (BASELINE.json configs[1])
-        if not args.no_extra and world == 1 and args.log_n != 20:
-            nb, ns = make_inputs(0, 1 << 20, seed_shift=10)
-            f20 = lambda: ctx.msm_xyzz(nb.data_ptr(), ns.data_ptr(), 1 << 20)
-            for _ in range(3):
-                f20()
-            ms20, _, _ = timed(f20, max(args.steps, 10))
-            a20 = algorithmic_products(curve, 1 << 20)
-            extra = {"workload": f"{curve} G1 MSM 2^20 points, 1 GPU, device-resident", "ms_per_msm": ms20,
-                     "points_per_s": (1 << 20) / (ms20 * 1e-3),
-                     "imad_frac": a20["products"] / (ms20 * 1e-3) / peak if peak else None}
-            del nb, ns
-        if not args.no_cpu_baseline and world == 1:   # reported on rank 0 at N = 1 only
-            from oracle import cpu_oracle
-            o = cpu_oracle.CurveOracle(curve)
-            threads = os.cpu_count() or cpu_oracle.max_threads()  # torchrun pins OMP_NUM_THREADS=1
-            sl = min(args.log_n, args.cpu_sample_log)
-            cb = o.generate_points(SEED + 2, 1 << sl)
-            cs = o.generate_scalars(SEED + 3, 1 << sl, args.dist)
+    if not args.no_extra:
+        ex_steps = max(5, min(args.steps, 10))
+        if args.log_n != 20 and world == 1:
+            extras["extra_2p20"] = measure_extra(d, curve, 20, args.dist, max(args.steps, 10), peak, 10, e2e=True)
+        if world == 1:
+            extras["extra_2p16"] = measure_extra(d, curve, 16, args.dist, max(args.steps, 20), peak, 11)
+        if curve == "bn254" and args.log_n == 24:
+            # BASELINE.json configs[3]: BLS12-381 G1 2^22 on 1 / N GPUs (the 381-bit limb path)
+            extras["extra_bls12_381_2p22"] = measure_extra(d, "bls12_381", 22, args.dist, ex_steps, peak, 20,
+                                                           e2e=(world == 1))
+            # BASELINE.json configs[4]: the Groth16 G1 MSM set, dealt over the ranks
+            g = groth16_measure(args, d, ex_steps)
+            extras["extra_groth16"] = g
+        if world > 1:
+            extras["extra_in_process_devices"] = measure_in_process_devices(d, curve, args.log_n, args.dist,
+                                                                            max(3, min(args.steps, 5)))
+    if rank == 0 and not args.no_cpu_baseline and world == 1:   # reported on rank 0 at N = 1 only
+        from oracle import cpu_oracle
+        o = cpu_oracle.CurveOracle(curve)
+        threads = os.cpu_count() or cpu_oracle.max_threads()  # torchrun pins OMP_NUM_THREADS=1
+        sl = min(args.log_n, args.cpu_sample_log)
+        cb = o.generate_points(SEED + 2, 1 << sl)
+        cs = o.generate_scalars(SEED + 3, 1 << sl, args.dist)
+        o.msm(cb, cs, threads=threads)
+        reps = 3
+        t0 = time.perf_counter()
+        for _ in range(reps):
             o.msm(cb, cs, threads=threads)
-            reps = 3
-            t0 = time.perf_counter()
-            for _ in range(reps):
-                o.msm(cb, cs, threads=threads)
-            cdt = (time.perf_counter() - t0) / reps
-            cpu_baseline = {"value": (1 << sl) / cdt, "unit": "points/s", "cores": threads, "kind": "port",
-                            "ms_per_msm": cdt * 1e3,
-                            "sample": f"2^{sl}-point prefix of the workload, oracle OpenMP Pippenger "
-                                      f"(kParallelTerm), mean of {reps}"}
+        cdt = (time.perf_counter() - t0) / reps
+        cpu_baseline = {"value": (1 << sl) / cdt, "unit": "points/s", "cores": threads, "kind": "port",
+                        "ms_per_msm": cdt * 1e3,
+                        "sample": f"2^{sl}-point prefix of the workload, oracle OpenMP Pippenger "
+                                  f"(kParallelTerm), mean of {reps}; `bench.py --impl reference` times the full size"}
 
-    if world > 1:
-        dist.barrier()
+    d.barrier()
     if rank == 0:
-        acc_ms = stage["accumulate_ms"]
+        acc_ms, acc_entries = stage["acc_kernel_ms"], timing["acc_kernel_entries"]
         # DRAM bytes of the dominant kernel per launch, from the committed ncu --set full capture
         traffic = {}
         try:
@@ -717,48 +877,62 @@ def main():
                 traffic = json.load(f).get(f"{curve}:{args.log_n}:{world}", {})
         except OSError:
             pass
+        issued = alg["issued_per_add"]
+        canonical = 10 * (2 * (2 * BASE_LIMBS[curve]) ** 2 + 2 * BASE_LIMBS[curve]) * (3 if curve.endswith("_g2") else 1)
+        rate = lambda per_add: acc_entries * per_add / (acc_ms * 1e-3) if acc_ms and per_add else None
+        theoretical = sm_count * 32 * sm_mhz * 1e6
         line = {
             "metric": f"{curve} G1 MSM throughput", "value": value, "unit": "points/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step,
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "u32", "data": "synthetic",
-            "config": {"workload": f"{curve} G1 MSM 2^{args.log_n} points, {args.dist} scalars",
-                       "partition": f"point range over {world} GPU(s), {n_local} points per GPU",
+            "config": workload_config(curve, args.log_n, args.dist),
+            "engine": {"partition": f"point range over {world} GPU(s), {n_local} points per GPU; partial sums "
+                                    "exchanged by one ncclAllGather issued by the library on its stream" if world > 1
+                       else f"one GPU, {n_local} points",
                        "arithmetic": "254/381-bit Montgomery field elements as u32 limbs (IMAD.WIDE carry chains)",
                        "window_bits": timing["window_bits"], "windows": timing["windows"],
-                       "l2": "inputs + workspace exceed the 126 MB L2 every step"},
+                       "low_windows": timing["low_windows"]},
             "wall_ms_per_step": wall_step,
             "stages_ms": stage,
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": "points/s", "ms_per_step": max(e2e_ms, e2e_wall),
                     "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ranges": e2e_timing["ranges"], "h2d_ms": e2e_timing["h2d_ms"],
+                    "h2d_gbs_per_gpu": (h2d / world) / (e2e_timing["h2d_ms"] * 1e-3) / 1e9 if e2e_timing["h2d_ms"] else None,
                     "api": "tachyon_%s_%s_affine_msm_gpu, pinned host buffers; H2D of point range k+1 "
                            "overlaps sort/accumulate of range k" % (curve.replace("_g2", ""),
                                                                     "g2" if curve.endswith("_g2") else "g1")},
             "gpu_launches": int(launches),
+            # frac = wide products the dominant kernel ISSUED (mixed additions the engine reports x
+            # 32x32->64 products per addition in xyzz_madd) per second of that kernel's own launch
+            # time, over the measured pipe peak.  frac_alg uses the canonical 10 multiplications of
+            # 2 L^2 + L products per addition instead and can exceed 1.
             "roofline": {"bound": "int32-imad", "kernel": "accumulate_kernel",
-                         "achieved": alg["accumulate_products"] / world / (acc_ms * 1e-3) / 1e9 if acc_ms else None,
+                         "achieved": rate(issued) / 1e9 if rate(issued) else None,
                          "peak": peak / 1e9, "unit": "G products/s (32x32->64)",
-                         "frac": (alg["accumulate_products"] / world / (acc_ms * 1e-3) / peak) if acc_ms and peak else None,
+                         "frac": rate(issued) / peak if rate(issued) and peak else None,
+                         "frac_alg": rate(canonical) / peak if rate(canonical) and peak else None,
+                         "issued_products_per_madd": issued, "canonical_products_per_madd": canonical,
+                         "kernel_ms": acc_ms, "kernel_madds": acc_entries,
                          "traffic": traffic.get("bytes"), "traffic_source": traffic.get("source"),
-                         "peak_source": "measured live: tachyon_b200_imad_peak, best of IMAD.WIDE.X chains / IMAD.WIDE acc64 / IMAD+IMAD.HI",
+                         "peak_source": "measured live: tachyon_b200_imad_peak, best of IMAD.WIDE.X chains / "
+                                        "IMAD.WIDE acc64 / IMAD+IMAD.HI",
+                         "peak_variants": [p / 1e9 for p in peaks],
+                         "peak_theoretical": theoretical / 1e9,
+                         "peak_theoretical_source": f"{sm_count} SMs x 32 lanes/clk (half-rate wide IMAD) x {sm_mhz:.0f} MHz",
                          "whole_msm_frac": alg["products"] / (ms_step * 1e-3) / (peak * world) if peak else None,
-                         # pipe occupancy: wide products the kernel actually issued (entries the
-                         # engine reports x issued products per mixed addition) / time / peak
-                         "issued_frac": (timing["entries"] * alg["issued_per_add"] / (acc_ms * 1e-3) / peak)
-                         if acc_ms and peak and alg["issued_per_add"] else None,
                          "algorithmic": {"c": alg["c"], "W": alg["W"], "products": alg["products"]}},
             "hbm": {"algorithmic_bytes": n_total * (2 * fq * 8 + 32),
                     "achieved_gbs": n_total * (2 * fq * 8 + 32) / (ms_step * 1e-3) / 1e9},
             "cpu_baseline": cpu_baseline,
             "parity": parity,
-            "extra_2p20": extra,
         }
+        line.update(extras)
         print(json.dumps(line), flush=True)
-    ctx.close()
+    case.close()
     if world > 1:
-        dist.destroy_process_group()
+        d.dist.destroy_process_group()
 
 
 if __name__ == "__main__":

@@ -100,11 +100,23 @@ extern "C" {
      default; 0 = one), "host_ranges" (most ranges of the automatic host-input pipeline),    \
      "prewarm" (reserve workspace, staging and copy threads for an MSM of `value` points now),\
      "release_workspace" (free the grow-only workspace; registered bases are kept),           \
+     "low_windows" (windows accumulated last while the reduction and window combination of   \
+     the others run on a second stream; -1 = cost model, 0 = no split),                      \
      "ranges" (point ranges one MSM is pipelined over; 0 = automatic), "pair_rounds"        \
      (experimental batched-affine rounds before the XYZZ accumulation; -1 = none, the       \
      default; -2 = chosen from the bucket occupancy; 0..4 = forced). */                       \
   TACHYON_C_EXPORT int tachyon_##C##_##G##_msm_gpu_set_option_b200(                             \
       tachyon_##C##_##G##_msm_gpu_ptr ptr, const char* name, long value);                       \
+  /* Point-range sharding over `world` PROCESSES, one GPU each (the split of      \
+     pippenger_adapter.h:82-113 across GPUs).  Rank 0 obtains 128 bytes from                  \
+     tachyon_b200_nccl_unique_id() and distributes them by any means; after every rank has    \
+     joined, each MSM call on this context takes the rank's OWN point range and returns the   \
+     sum over all ranks on every rank: the ranks' XYZZ partials are exchanged with one        \
+     ncclAllGather issued on the context's stream behind the last kernel, and the `world`     \
+     points are added on the host.  Batch calls stay local.  world == 1 leaves.  NCCL is      \
+     dlopen()ed (libnccl.so.2, or $TACHYON_B200_NCCL_LIB).  0 or a negative error code. */     \
+  TACHYON_C_EXPORT int tachyon_##C##_##G##_msm_gpu_join_ranks_b200(                             \
+      tachyon_##C##_##G##_msm_gpu_ptr ptr, const void* nccl_unique_id, int rank, int world);   \
   /* MSM returning the un-normalised XYZZ sum by value into *out; returns 0 or a negative   \
      error code instead of aborting.  Pointers as for *_affine_msm_gpu. */                   \
   TACHYON_C_EXPORT int tachyon_##C##_##G##_msm_gpu_xyzz_b200(                                   \
@@ -165,9 +177,11 @@ struct tachyon_b200_msm_timing {
                            inputs); overlaps sort/accumulate of the earlier point ranges */
   float sort_ms;        /* recode + histogram + scan + task build + scatter */
   float accumulate_ms;  /* bucket accumulation (+ folding of split buckets) */
-  float reduce_ms;      /* bucket reduction levels + device->host of window sums */
+  float reduce_ms;      /* what remains after the last accumulation: bucket reduction, merge
+                           tree and window combination (of the low windows when split) + the
+                           device->host copy of the one result point */
   float total_ms;       /* first enqueue .. last device->host copy */
-  float host_ms;        /* host epilogue (window Horner, partial adds), wall clock */
+  float host_ms;        /* host epilogue (reading the result point; partial adds), wall clock */
   uint32_t window_bits;
   uint32_t windows;
   uint32_t tasks;       /* accumulation tasks (threads of the hot kernel) */
@@ -178,6 +192,12 @@ struct tachyon_b200_msm_timing {
   float enqueue_ms;     /* host wall clock spent queueing copies and kernels */
   float wait_ms;        /* host wall clock blocked waiting for the device */
   uint32_t pair_rounds; /* batched-affine pair rounds run before the XYZZ accumulation */
+  float acc_kernel_ms;  /* the accumulate launches that ran alone on the device (all but the low
+                           window group's, which overlaps the high group's reduction) ... */
+  uint32_t acc_kernel_entries; /* ... and the mixed additions they performed */
+  uint32_t low_windows; /* windows accumulated last, behind which the high windows' reduction
+                           and window combination are hidden (0 = windows not split) */
+  float combine_ms;     /* window_combine_kernel of the high group (or of all windows) */
 };
 
 TACHYON_B200_DECLARE_FIELDS(bn254, 4)
@@ -227,6 +247,8 @@ TACHYON_B200_DECLARE_GROTH16(bls12_381)
 
 /* Number of CUDA devices visible, or a negative error. */
 TACHYON_C_EXPORT int tachyon_b200_device_count(void);
+/* 128-byte ncclUniqueId for *_msm_gpu_join_ranks_b200 (call on one rank, hand to all). */
+TACHYON_C_EXPORT int tachyon_b200_nccl_unique_id(void* out128);
 /* Text of the last error recorded by an extension call on this thread. */
 TACHYON_C_EXPORT const char* tachyon_b200_last_error(void);
 /* Measured INT32 multiply-pipe peak of `device`: 32x32->64 multiply-adds per second

@@ -33,7 +33,9 @@ class MsmTiming(ctypes.Structure):
         ("window_bits", ctypes.c_uint32), ("windows", ctypes.c_uint32), ("tasks", ctypes.c_uint32),
         ("entries", ctypes.c_uint32), ("kernel_launches", ctypes.c_uint32), ("devices", ctypes.c_uint32),
         ("ranges", ctypes.c_uint32), ("enqueue_ms", ctypes.c_float), ("wait_ms", ctypes.c_float),
-        ("pair_rounds", ctypes.c_uint32),
+        ("pair_rounds", ctypes.c_uint32), ("acc_kernel_ms", ctypes.c_float),
+        ("acc_kernel_entries", ctypes.c_uint32), ("low_windows", ctypes.c_uint32),
+        ("combine_ms", ctypes.c_float),
     ]
 
     def as_dict(self):
@@ -51,12 +53,13 @@ GROUP_SYMBOLS = [
     "tachyon_{c}_{g}_xyzz_add_b200", "tachyon_{c}_{g}_xyzz_to_jacobian_b200",
     "tachyon_{c}_{g}_msm_gpu_register_bases_b200", "tachyon_{c}_{g}_msm_gpu_commit_batch_b200",
     "tachyon_{c}_{g}_xyzz_batch_normalize_b200", "tachyon_{c}_{g}_msm_gpu_batch_b200",
+    "tachyon_{c}_{g}_msm_gpu_join_ranks_b200",
 ]
 FIELD_SYMBOLS = ["tachyon_{c}_fq_op_b200", "tachyon_{c}_fr_op_b200", "tachyon_{c}_fq2_op_b200"]
 CURVE_SYMBOLS = ["tachyon_{c}_groth16_prove_b200"]
 GLOBAL_SYMBOLS = ["tachyon_b200_device_count", "tachyon_b200_last_error", "tachyon_b200_imad_peak",
                   "tachyon_b200_kernel_launch_count", "tachyon_b200_window_bits",
-                  "tachyon_b200_window_count"]
+                  "tachyon_b200_window_count", "tachyon_b200_nccl_unique_id"]
 
 
 def all_symbols():
@@ -111,6 +114,7 @@ def load():
         f("tachyon_{c}_g1_xyzz_batch_normalize_b200").argtypes = [vp, sz, vp]
         f("tachyon_{c}_g1_xyzz_to_jacobian_b200").restype = None
         f("tachyon_{c}_g1_xyzz_to_jacobian_b200").argtypes = [vp, vp]
+        f("tachyon_{c}_g1_msm_gpu_join_ranks_b200").argtypes = [vp, vp, i32, i32]
     lib.tachyon_b200_window_bits.restype = ctypes.c_uint32
     lib.tachyon_b200_window_bits.argtypes = [sz, ctypes.c_uint32]
     lib.tachyon_b200_window_count.restype = ctypes.c_uint32
@@ -119,6 +123,7 @@ def load():
     lib.tachyon_b200_imad_peak.restype = ctypes.c_double
     lib.tachyon_b200_imad_peak.argtypes = [i32, i32, i32]
     lib.tachyon_b200_kernel_launch_count.restype = u64
+    lib.tachyon_b200_nccl_unique_id.argtypes = [vp]
     _lib = lib
     return lib
 

@@ -539,6 +539,11 @@ struct FpField {
   static TB_DEV void load(El& r, const void* p) { fp_load<F>(r, p); }
   static TB_DEV void load_rw(El& r, const void* p) { fp_load_rw<F>(r, p); }
   static TB_DEV void store(void* p, const El& a) { fp_store<F>(p, a); }
+  // r = a of lane `src` (index inside a group of `width` lanes; `mask` names the group's lanes)
+  static TB_DEV void shfl(El& r, const El& a, uint32_t mask, int src, int width) {
+#pragma unroll
+    for (int i = 0; i < kWords; ++i) r.l[i] = __shfl_sync(mask, a.l[i], src, width);
+  }
 };
 
 // Fq2 = Fq[u] / (u^2 + 1): both curves use the non-residue -1
@@ -648,6 +653,13 @@ struct Fp2Field {
   static TB_DEV void store(void* p, const El& a) {
     fp_store<F>(p, a.c0);
     fp_store<F>(static_cast<char*>(p) + 4 * Fp<F>::N, a.c1);
+  }
+  static TB_DEV void shfl(El& r, const El& a, uint32_t mask, int src, int width) {
+#pragma unroll
+    for (int i = 0; i < Fp<F>::N; ++i) {
+      r.c0.l[i] = __shfl_sync(mask, a.c0.l[i], src, width);
+      r.c1.l[i] = __shfl_sync(mask, a.c1.l[i], src, width);
+    }
   }
 };
 

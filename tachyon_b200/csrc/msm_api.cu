@@ -34,6 +34,24 @@ uint32_t tachyon_b200_window_count(uint32_t scalar_bits, uint32_t window_bits) {
 
 const char* tachyon_b200_last_error(void) { return g_last_error.c_str(); }
 
+int tachyon_b200_nccl_unique_id(void* out128) {
+  if (!out128) return -1;
+  std::string why;
+  const NcclApi* nccl = NcclApi::Get(&why);
+  if (!nccl) {
+    g_last_error = why;
+    return -1;
+  }
+  NcclUniqueId id;
+  int rc = nccl->GetUniqueId(&id);
+  if (rc != 0) {
+    g_last_error = nccl->GetErrorString(rc);
+    return -1;
+  }
+  memcpy(out128, &id, sizeof(id));
+  return 0;
+}
+
 uint64_t tachyon_b200_kernel_launch_count(void) { return g_kernel_launches.load(); }
 
 double tachyon_b200_imad_peak(int device, int variant, int repeats) {

@@ -24,8 +24,12 @@ extern thread_local std::string g_last_error;
 
 static int Fail(const CudaError& e) {
   char buf[512];
-  snprintf(buf, sizeof(buf), "%s:%d: %s -> %s (%d)", e.file, e.line, e.what,
-           cudaGetErrorString(e.code), (int)e.code);
+  if (e.device >= 0)
+    snprintf(buf, sizeof(buf), "%s:%d: device %d: %s -> %s (%d)", e.file, e.line, e.device, e.what,
+             cudaGetErrorString(e.code), (int)e.code);
+  else
+    snprintf(buf, sizeof(buf), "%s:%d: %s -> %s (%d)", e.file, e.line, e.what,
+             cudaGetErrorString(e.code), (int)e.code);
   g_last_error = buf;
   return -(int)(e.code ? e.code : 1);
 }
@@ -61,9 +65,19 @@ struct MsmGpuContext {
     while ((int)engines.size() > k) engines.pop_back();
     while ((int)engines.size() < k) {
       int dev = (primary_device + (int)engines.size()) % avail;
-      engines.emplace_back(new Engine(dev));
+      try {
+        engines.emplace_back(new Engine(dev));
+      } catch (CudaError& e) {
+        e.device = dev;
+        throw;
+      }
       engines.back()->options() = engines[0]->options();
+      // bases registered before the device count was raised follow the new engines (the order
+      // of register_bases and set_option("devices") does not matter to the caller)
+      if (engines[0]->registered_size())
+        engines.back()->RegisterBases(engines[0]->registered_bases(), engines[0]->registered_size());
     }
+    TB_CUDA(cudaSetDevice(primary_device));
   }
 
   // The same bases on every engine's device (kzg.h:91-113: the SRS is uploaded once).
@@ -112,6 +126,7 @@ struct MsmGpuContext {
           for (size_t k = 0; k < idx.size(); ++k) out[idx[k]] = res[k];
         } catch (const CudaError& e) {
           errs[g] = e;
+          errs[g].device = engines[g]->device();
         }
       });
     }
@@ -132,6 +147,8 @@ struct MsmGpuContext {
       timing.entries += t.entries;
       timing.kernel_launches += t.kernel_launches;
       timing.ranges = std::max(timing.ranges, t.ranges);
+      timing.acc_kernel_ms = std::max(timing.acc_kernel_ms, t.acc_kernel_ms);
+      timing.acc_kernel_entries += t.acc_kernel_entries;
     }
     timing.total_ms =
         std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - wall0).count();
@@ -175,6 +192,7 @@ struct MsmGpuContext {
               static_cast<const char*>(scalars) + lo * Engine::kScalarBytes, hi - lo);
         } catch (const CudaError& e) {
           errs[g] = e;
+          errs[g].device = engines[g]->device();
         }
       });
     }
@@ -198,6 +216,10 @@ struct MsmGpuContext {
       timing.entries += t.entries;
       timing.kernel_launches += t.kernel_launches;
       timing.ranges = std::max(timing.ranges, t.ranges);
+      timing.acc_kernel_ms = std::max(timing.acc_kernel_ms, t.acc_kernel_ms);
+      timing.acc_kernel_entries += t.acc_kernel_entries;
+      timing.low_windows = t.low_windows;
+      timing.combine_ms = std::max(timing.combine_ms, t.combine_ms);
     }
     timing.devices = (uint32_t)G;
     TB_CUDA(cudaSetDevice(primary_device));
@@ -294,7 +316,7 @@ static Ctx* CreateContext(int device, bool banner, int degree = 0) {
     // msm_gpu.h:36-42
     std::cout << "\033[32mCreateMSMGpuApi()\033[0m" << std::endl;
   }
-  auto* ctx = new Ctx(device);
+  std::unique_ptr<Ctx> ctx(new Ctx(device));
   if (const char* d = getenv("TACHYON_MSM_GPU_INPUT_DIR")) ctx->input_dir = d;
   if (const char* l = getenv("TACHYON_LOG_MSM")) ctx->log_msm = std::string(l) == "1";
   if (const char* w = getenv("TACHYON_B200_MSM_WINDOW_BITS"))
@@ -307,11 +329,23 @@ static Ctx* CreateContext(int device, bool banner, int degree = 0) {
   if (const char* pw = getenv("TACHYON_B200_MSM_PREWARM_DEGREE")) prewarm = atoi(pw);
   else if (prewarm > 24) prewarm = 24;
   if (prewarm > 0 && prewarm <= 26) {
+    // Best effort: the reference ignores `degree` and allocates lazily (msm_gpu.h:35), so a busy
+    // or smaller GPU must not make create() fail where the reference would not.  On
+    // out-of-memory the partial reservation is released and the first MSM allocates what it
+    // needs (or runs in more point ranges).
     size_t per = (size_t(1) << prewarm) / ctx->engines.size();
-    for (auto& e : ctx->engines) e->Prewarm(per ? per : 1);
+    for (auto& e : ctx->engines) {
+      try {
+        e->Prewarm(per ? per : 1);
+      } catch (const CudaError& err) {
+        if (err.code != cudaErrorMemoryAllocation) throw;
+        cudaGetLastError();
+        e->ReleaseWorkspace();
+      }
+    }
     TB_CUDA(cudaSetDevice(device));
   }
-  return ctx;
+  return ctx.release();
 }
 
 // ---- element-wise hooks ------------------------------------------------------
@@ -503,6 +537,22 @@ using namespace tb200;
     ptr->engines[0]->SetStream(static_cast<cudaStream_t>(cuda_stream));                        \
     return 0;                                                                                  \
   }                                                                                            \
+  int tachyon_##CN##_##G##_msm_gpu_join_ranks_b200(tachyon_##CN##_##G##_msm_gpu_ptr ptr,          \
+                                                   const void* nccl_unique_id, int rank,       \
+                                                   int world) {                                \
+    if (!ptr || !nccl_unique_id || world < 1 || rank < 0 || rank >= world) return -1;          \
+    if (ptr->engines.size() != 1) {                                                            \
+      g_last_error = "join_ranks: a context sharded over in-process devices cannot join ranks"; \
+      return -1;                                                                               \
+    }                                                                                          \
+    try {                                                                                      \
+      if (world == 1) ptr->engines[0]->LeaveRanks();                                           \
+      else ptr->engines[0]->JoinRanks(nccl_unique_id, rank, world);                            \
+      return 0;                                                                                \
+    } catch (const CudaError& e) {                                                             \
+      return Fail(e);                                                                          \
+    }                                                                                          \
+  }                                                                                            \
   int tachyon_##CN##_##G##_msm_gpu_set_option_b200(tachyon_##CN##_##G##_msm_gpu_ptr ptr,             \
                                                 const char* name, long value) {                \
     if (!ptr || !name) return -1;                                                              \
@@ -532,6 +582,8 @@ using namespace tb200;
         for (auto& e : ptr->engines) e->options().level_fill = (uint32_t)value;                \
       } else if (k == "balance") {                                                             \
         for (auto& e : ptr->engines) e->options().balance = (int)value;                        \
+      } else if (k == "low_windows") {                                                         \
+        for (auto& e : ptr->engines) e->options().low_windows = (int)value;                    \
       } else if (k == "ranges") {                                                              \
         for (auto& e : ptr->engines) e->options().ranges = (uint32_t)value;                    \
       } else if (k == "devices") {                                                             \
@@ -623,6 +675,10 @@ using namespace tb200;
     out->enqueue_ms = t.enqueue_ms;                                                            \
     out->wait_ms = t.wait_ms;                                                                  \
     out->pair_rounds = t.pair_rounds;                                                          \
+    out->acc_kernel_ms = t.acc_kernel_ms;                                                      \
+    out->acc_kernel_entries = t.acc_kernel_entries;                                            \
+    out->low_windows = t.low_windows;                                                          \
+    out->combine_ms = t.combine_ms;                                                            \
     return 0;                                                                                  \
   }                                                                                            \
   int tachyon_##CN##_##G##_generate_bases_b200(uint64_t seed, size_t first, size_t n,             \

@@ -19,6 +19,7 @@
 #include <vector>
 
 #include "host_math.h"
+#include "nccl_dl.h"
 #include "parallel_memcpy.h"
 #include "msm_kernels.cuh"
 #include "msm_sort.cuh"
@@ -32,6 +33,7 @@ struct CudaError {
   const char* what;
   const char* file;
   int line;
+  int device = -1;  // filled in by multi-device callers: which GPU's worker failed
 };
 
 #define TB_CUDA(expr)                                                         \
@@ -72,6 +74,12 @@ struct MsmTiming {
   uint32_t ranges = 0;
   float enqueue_ms = 0, wait_ms = 0;  // host wall clock: queueing the work / blocked on the device
   uint32_t pair_rounds = 0;
+  // the accumulate launches that run alone on the device (every range's launch except the low
+  // window group's, which overlaps the high group's reduction): what the kernel roofline uses
+  float acc_kernel_ms = 0;
+  uint32_t acc_kernel_entries = 0;
+  uint32_t low_windows = 0;  // windows in the low group (0 = the windows were not split)
+  float combine_ms = 0;      // window_combine_kernel of the high group (hidden when split)
 };
 
 struct MsmOptions {
@@ -90,6 +98,9 @@ struct MsmOptions {
   uint32_t level_fill = 0;   // blocks per SM the running-sum level wants before it shortens its
                              // blocks (0 = default: 384, 768 from 1.5 M bucket slots)
   int balance = 1;           // balanced windows (WideWindowsFor); 0 = equal widths, slack on top
+  int low_windows = -1;      // windows of the low group (accumulated last, while the high group's
+                             // reduction and window combination run on the tail stream):
+                             // -1 = from the cost model, 0 = no split
 };
 
 // Window choice.  Cost in units of one mixed addition:
@@ -220,6 +231,14 @@ class MsmEngine {
     stream_ = own_stream_;
     TB_CUDA(cudaStreamCreateWithFlags(&copy_stream_, cudaStreamNonBlocking));
     TB_CUDA(cudaStreamCreateWithFlags(&sample_stream_, cudaStreamNonBlocking));
+    {
+      // the tail stream (reduction + window combination of the high windows) outranks the
+      // compute stream: its small latency-bound kernels must get SM slots as soon as CTAs of
+      // the concurrent low-window accumulation retire
+      int lo_prio = 0, hi_prio = 0;
+      TB_CUDA(cudaDeviceGetStreamPriorityRange(&lo_prio, &hi_prio));
+      TB_CUDA(cudaStreamCreateWithPriority(&tail_stream_, cudaStreamNonBlocking, hi_prio));
+    }
     TB_CUDA(cudaMallocHost(&host_out_, 2 * kHostOutBytes));
     TB_CUDA(cudaMalloc(&totals_, sizeof(MsmTotals)));
     int sms = 0;
@@ -227,8 +246,10 @@ class MsmEngine {
     sm_count_ = sms;
   }
   ~MsmEngine() {
+    LeaveRanks();
     cudaSetDevice(device_);
     cudaStreamSynchronize(stream_);
+    cudaStreamSynchronize(tail_stream_);
     cudaStreamSynchronize(copy_stream_);
     for (const DeviceBuffer* b : AllBuffers()) const_cast<DeviceBuffer*>(b)->Free();
     if (totals_) cudaFree(totals_);
@@ -237,6 +258,7 @@ class MsmEngine {
     for (auto& e : events_) cudaEventDestroy(e);
     cudaStreamDestroy(copy_stream_);
     cudaStreamDestroy(sample_stream_);
+    cudaStreamDestroy(tail_stream_);
     cudaStreamDestroy(own_stream_);
   }
   MsmEngine(const MsmEngine&) = delete;
@@ -253,11 +275,15 @@ class MsmEngine {
     TB_CUDA(cudaSetDevice(device_));
     timing_ = MsmTiming{};
     Point total = Point::Zero();
-    if (n == 0) return total;  // pippenger_adapter.h:62-65
+    if (n == 0) return world_ > 1 ? GatherHostPoint(total) : total;  // pippenger_adapter.h:62-65
     // Independent pieces only when the u32 index arithmetic requires it (entries = points x
     // windows must stay below 2^32, which a forced small window can hit before 2^26 points);
     // unlike icicle_msm_bn254_g1.cc:56-62 the last piece keeps its remainder.
     const size_t piece = PieceLimit(n);
+    if (n <= piece) {  // the usual case: with several ranks the gather rides the MSM's stream
+      Pending p = Enqueue(bases, scalars, n, 0, false, /*gather=*/world_ > 1);
+      return Finish(p);
+    }
     for (size_t off = 0; off < n; off += piece) {
       size_t len = n - off < piece ? n - off : piece;
       Pending p = Enqueue(static_cast<const char*>(bases) + off * kAffineBytes,
@@ -265,14 +291,54 @@ class MsmEngine {
       Point part = Finish(p);
       total = (off == 0) ? part : total.Add(part);
     }
-    return total;
+    return world_ > 1 ? GatherHostPoint(total) : total;
   }
+
+  // Point-range sharding over `world` processes, one GPU each: after this call every
+  // Run() returns the SUM of all ranks' partial sums.  The exchange is one ncclAllGather of the
+  // ranks' XYZZ partials, issued on this engine's stream right behind the window-combination
+  // kernel; the `world` points are added on the host ("only 8 points are combined").  `id` is
+  // the 128-byte ncclUniqueId that rank 0 obtained from tachyon_b200_nccl_unique_id().
+  void JoinRanks(const void* id, int rank, int world) {
+    TB_CUDA(cudaSetDevice(device_));
+    std::string why;
+    const NcclApi* nccl = NcclApi::Get(&why);
+    if (!nccl) {
+      static std::string keep;
+      keep = why;
+      throw CudaError{cudaErrorNotSupported, keep.c_str(), __FILE__, __LINE__};
+    }
+    LeaveRanks();
+    NcclUniqueId uid;
+    memcpy(&uid, id, sizeof(uid));
+    int rc = nccl->CommInitRank(&comm_, world, uid, rank);
+    if (rc != 0) throw CudaError{cudaErrorUnknown, nccl->GetErrorString(rc), __FILE__, __LINE__};
+    rank_ = rank;
+    world_ = world;
+    TB_CUDA(cudaMalloc(&gather_dev_, (size_t)world * kXyzzBytes));
+    TB_CUDA(cudaMallocHost(&gather_host_, 2 * (size_t)world * kXyzzBytes));
+  }
+  void LeaveRanks() {
+    if (!comm_) return;
+    cudaSetDevice(device_);
+    cudaStreamSynchronize(stream_);
+    if (const NcclApi* nccl = NcclApi::Get(nullptr)) nccl->CommDestroy(comm_);
+    comm_ = nullptr;
+    world_ = 1;
+    rank_ = 0;
+    if (gather_dev_) cudaFree(gather_dev_);
+    if (gather_host_) cudaFreeHost(gather_host_);
+    gather_dev_ = nullptr;
+    gather_host_ = nullptr;
+  }
+  int world() const { return world_; }
 
   // Frees the grow-only workspace (not the registered bases); the next call re-allocates.
   void ReleaseWorkspace() {
     TB_CUDA(cudaSetDevice(device_));
     TB_CUDA(cudaStreamSynchronize(copy_stream_));
     TB_CUDA(cudaStreamSynchronize(stream_));
+    TB_CUDA(cudaStreamSynchronize(tail_stream_));
     for (const DeviceBuffer* b : AllBuffers())
       if (b != &registered_) const_cast<DeviceBuffer*>(b)->Free();
     for (auto& u : stage_used_) u = false;
@@ -366,6 +432,8 @@ class MsmEngine {
   struct Pending {
     MsmPlan plan{};
     uint32_t L0 = 0, M = 0;
+    uint32_t low = 0;  // windows of the low group
+    bool gathered = false;  // the result is the all-gathered set of rank partials
     size_t K = 0;
     bool any_host = false;
     int slot = 0;       // host result buffer / event set
@@ -428,6 +496,14 @@ class MsmEngine {
   template <class K, class... Args>
   void Launch(K kernel, uint32_t grid, uint32_t block, Args... args) {
     kernel<<<grid, block, 0, stream_>>>(args...);
+    TB_CUDA(cudaGetLastError());
+    ++launches_;
+    g_kernel_launches.fetch_add(1, std::memory_order_relaxed);
+  }
+
+  template <class K, class... Args>
+  void LaunchOn(cudaStream_t st, K kernel, uint32_t grid, uint32_t block, Args... args) {
+    kernel<<<grid, block, 0, st>>>(args...);
     TB_CUDA(cudaGetLastError());
     ++launches_;
     g_kernel_launches.fetch_add(1, std::memory_order_relaxed);
@@ -608,9 +684,12 @@ class MsmEngine {
     }
     return events_[i];
   }
-  // event sets: per Pending slot, 0 begin, 1 end of accumulation, 2 end, 3 copy begin, then
-  // per range r: 4 + 4r copied, +1 sort start, +2 sort end, +3 accumulated
-  static constexpr size_t kEventsPerSlot = 4 + 4 * kMaxRanges;
+  // event sets: per Pending slot, 0 begin, 1 end of accumulation, 2 end, 3 copy begin, 4 high
+  // window group accumulated, 5 high group combined (tail stream), 6 / 7 around the high group's
+  // window_combine_kernel, then per range r: 8 + 5r copied, +1 sort start, +2 sort end,
+  // +3 accumulated, +4 after the range's first accumulate launch
+  static constexpr size_t kSlotEvents = 8, kRangeEvents = 5;
+  static constexpr size_t kEventsPerSlot = kSlotEvents + kRangeEvents * kMaxRanges;
   cudaEvent_t SlotEvent(int slot, size_t i) { return Event((size_t)slot * kEventsPerSlot + i); }
   cudaEvent_t StageFreeEvent(size_t stage) { return Event(2 * kEventsPerSlot + stage); }
 
@@ -624,6 +703,7 @@ class MsmEngine {
     auto t0 = std::chrono::steady_clock::now();
     TB_CUDA(cudaStreamSynchronize(copy_stream_));
     TB_CUDA(cudaStreamSynchronize(stream_));
+    TB_CUDA(cudaStreamSynchronize(tail_stream_));
     int index = 0;
     for (auto& w : wants) {
       if (trace && w.second > w.first->bytes) {
@@ -658,7 +738,7 @@ class MsmEngine {
   // epilogue.  All device buffers except the staging ring are shared by consecutive MSMs,
   // which is safe because their kernels are ordered on the one compute stream.
   Pending Enqueue(const void* bases, const void* scalars, size_t n, int slot,
-                  bool reserve_only = false) {
+                  bool reserve_only = false, bool gather = false) {
     auto wall0 = std::chrono::steady_clock::now();
     const bool bases_dev = IsDevicePointer(bases), scalars_dev = IsDevicePointer(scalars);
     const bool bases_pageable = !bases_dev && IsPageable(bases);
@@ -731,24 +811,27 @@ class MsmEngine {
     pd.plan = big;
     pd.K = K;
     launches_ = 0;
+    pd.low = reserve_only ? 0u : ChooseLowWindows(big, bound[K] - bound[K - 1]);
 
     // ---- workspace ----------------------------------------------------------------
+    // staging ring: kStageSlots slots of one 256-byte-aligned range each, plus one alignment unit
+    // per slot, so that the stride derived from the (grow-only) buffer below always holds a range
+    const size_t bases_slot_want = (m * kAffineBytes + 255) / 256 * 256 + 256;
+    const size_t scalars_slot_want = (m * kScalarBytes + 255) / 256 * 256 + 256;
     uint32_t scan_blocks = (big.TB + kScanItems - 1) / kScanItems;
     if (scan_blocks > (uint32_t)kScanItems)
       throw CudaError{cudaErrorInvalidValue, "too many buckets", __FILE__, __LINE__};
     pd.L0 = ChooseLevelLength(big.B, big.W);
     const uint32_t nb = big.B / pd.L0;  // blocks per window, a power of two
     pd.M = Log2(nb);
-    size_t tree_b[2] = {0, 0}, lvl_b = 0;
-    auto reduction_bytes = [&](uint32_t cc) {  // level + tree buffers of window size cc
+    // reduction tree buffers: per window a slice of 2 nb points (the leaves (A_t, P_t)); the
+    // scratch and stage-output buffers use the same slicing (reduce_tree_kernel)
+    size_t tree_b = 0;
+    auto reduction_bytes = [&](uint32_t cc) {
       uint32_t Wc = WindowsFor(Fr::kBits, cc), Bc = 1u << (cc - 1);
-      uint32_t nbc = Bc / ChooseLevelLength(Bc, Wc), Mc = Log2(nbc);
-      size_t lv = (size_t)Wc * nbc * kXyzzBytes;
-      if (lv > lvl_b) lvl_b = lv;
-      for (uint32_t s = 0; s < Mc; ++s) {
-        size_t need = (size_t)Wc * (nbc >> (s + 1)) * (s + 3) * kXyzzBytes;
-        if (need > tree_b[s & 1]) tree_b[s & 1] = need;
-      }
+      uint32_t nbc = Bc / ChooseLevelLength(Bc, Wc);
+      size_t lv = (size_t)Wc * nbc * 2 * kXyzzBytes;
+      if (lv > tree_b) tree_b = lv;
     };
     reduction_bytes(c);
     // Pre-reserving for 2^degree points: smaller MSMs run smaller windows with MORE windows, and
@@ -780,13 +863,25 @@ class MsmEngine {
                 {&pair_out_[3], big.R > 3 ? (size_t)(PaddedBound(big) >> 4) * kAffineBytes : 0},
                 {&digits_, (size_t)m * big.W * 4},
                 {&block_sums_, (size_t)scan_blocks * 8},
-                {&len_hist_, (size_t)(kMaxSegment + 1) * 4},
-                {&lvl_a_[0], lvl_b},
-                {&lvl_c_[0], lvl_b},
-                {&tree_[0], tree_b[0]},
-                {&tree_[1], tree_b[1]},
-                {&bases_stage_, bases_dev ? 0 : m * kStageSlots * kAffineBytes},
-                {&scalars_stage_, scalars_dev ? 0 : m * kStageSlots * kScalarBytes}});
+                {&len_hist_, (size_t)kOrderBins * 4},
+                {&leaves_, tree_b},
+                {&tree_[0], tree_b},
+                {&tree_[1], tree_b},
+                {&stage_out_[0], tree_b},
+                {&stage_out_[1], tree_b},
+                {&combine_, (size_t)(2 * kTermSlots + 2) * kXyzzBytes},
+                {&bases_stage_, bases_dev ? 0 : bases_slot_want * kStageSlots},
+                {&scalars_stage_, scalars_dev ? 0 : scalars_slot_want * kStageSlots}});
+    // The slot stride is a property of the BUFFER, not of the call: MSMs of different sizes are in
+    // flight together (RunBatch) and the per-slot events only protect a fixed slot geometry; it
+    // changes only when the buffer is re-allocated, which drains both streams first.  The
+    // reservation above guarantees stride >= this call's range.
+    const size_t bases_slot_bytes = bases_stage_.bytes / kStageSlots / 256 * 256;
+    const size_t scalars_slot_bytes = scalars_stage_.bytes / kStageSlots / 256 * 256;
+    if ((!bases_dev && bases_slot_bytes < m * kAffineBytes) ||
+        (!scalars_dev && scalars_slot_bytes < m * kScalarBytes))
+      throw CudaError{cudaErrorInvalidValue, "staging slot smaller than a point range", __FILE__,
+                      __LINE__};
     static const bool trace = getenv("TACHYON_B200_TRACE") != nullptr;
     auto since = [&] {
       return std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - wall0).count();
@@ -795,12 +890,10 @@ class MsmEngine {
       fprintf(stderr, "[tachyon_b200] enqueue n=%zu c=%u W=%u K=%zu%s: planned + reserved at %.2f ms\n", n,
               c, big.W, K, reserve_only ? " (reserve only)" : "", since());
     if (reserve_only) return pd;
-    const size_t bases_slot_bytes = bases_stage_.bytes / kStageSlots / 256 * 256;
-    const size_t scalars_slot_bytes = scalars_stage_.bytes / kStageSlots / 256 * 256;
 
     cudaEvent_t ev_begin = SlotEvent(slot, 0), ev_acc_end = SlotEvent(slot, 1),
                 ev_end = SlotEvent(slot, 2), ev_copy_begin = SlotEvent(slot, 3);
-    auto ev = [&](size_t r, int which) { return SlotEvent(slot, 4 + 4 * r + which); };
+    auto ev = [&](size_t r, int which) { return SlotEvent(slot, kSlotEvents + kRangeEvents * r + which); };
 
     TB_CUDA(cudaEventRecord(ev_begin, stream_));
     TB_CUDA(cudaMemsetAsync(state_.ptr, 0, (size_t)big.TB * kXyzzBytes, stream_));
@@ -811,8 +904,8 @@ class MsmEngine {
       const size_t lo = bound[r], len = bound[r + 1] - bound[r];
       if (len == 0) {  // degenerate split: keep the event bookkeeping of Finish() simple
         TB_CUDA(cudaEventRecord(ev(r, 0), copy_stream_));
-        for (int w = 1; w <= 3; ++w) TB_CUDA(cudaEventRecord(ev(r, w), stream_));
-        memset(host_out + kHostWindowBytes + r * sizeof(MsmTotals), 0, sizeof(MsmTotals));
+        for (int w = 1; w <= 4; ++w) TB_CUDA(cudaEventRecord(ev(r, w), stream_));
+        memset(host_out + kHostPartialBytes + r * sizeof(MsmTotals), 0, sizeof(MsmTotals));
         continue;
       }
       MsmPlan plan = MakePlan(len, c);
@@ -904,47 +997,83 @@ class MsmEngine {
       else
         LaunchGrid(digits_scatter_kernel, dim3(sgrid, plan.W), 256, digits_.as<uint32_t>(), plan,
                    cursor_.as<uint32_t>(), sorted_.as<uint32_t>());
-      // tasks by descending length
-      TB_CUDA(cudaMemsetAsync(len_hist_.ptr, 0, (size_t)(kMaxSegment + 1) * 4, stream_));
+      // tasks by window group (last range only: high windows first), then descending length
+      const bool split = pd.low > 0 && r + 1 == K;
+      const uint32_t split_key = split ? pd.low * plan.B : 0u;
+      TB_CUDA(cudaMemsetAsync(len_hist_.ptr, 0, (size_t)kOrderBins * 4, stream_));
       uint32_t ogrid = (plan.max_tasks + kOrderThreads * kOrderPerThread - 1) /
                        (kOrderThreads * kOrderPerThread);
-      Launch(order_hist_kernel, ogrid, kOrderThreads, tasks_.as<uint2>(), totals_,
-             len_hist_.as<uint32_t>());
-      Launch(order_scan_kernel, 1, 1024, len_hist_.as<uint32_t>());
-      Launch(order_scatter_kernel, ogrid, kOrderThreads, tasks_.as<uint2>(), totals_,
-             len_hist_.as<uint32_t>(), order_.as<uint32_t>());
+      Launch(order_hist_kernel, ogrid, kOrderThreads, tasks_.as<uint2>(), task_meta_.as<uint32_t>(),
+             totals_, split_key, len_hist_.as<uint32_t>());
+      Launch(order_scan_kernel, 1, 1024, len_hist_.as<uint32_t>(), offset_.as<uint32_t>(), split_key,
+             totals_);
+      Launch(order_scatter_kernel, ogrid, kOrderThreads, tasks_.as<uint2>(),
+             task_meta_.as<uint32_t>(), totals_, split_key, len_hist_.as<uint32_t>(),
+             order_.as<uint32_t>());
       TB_CUDA(cudaEventRecord(ev(r, 2), stream_));
 
       // ---- batched-affine pair rounds, then XYZZ accumulation into the bucket values ----
-      for (uint32_t r = 0; r < plan.R; ++r) {
-        uint32_t grid = PairThreads(plan, r) / kPairThreads;
-        if (r == 0)
+      for (uint32_t pr = 0; pr < plan.R; ++pr) {
+        uint32_t grid = PairThreads(plan, pr) / kPairThreads;
+        if (pr == 0)
           Launch(pair_round_kernel<C, true>, grid, kPairThreads, d_bases, sorted_.as<uint32_t>(),
-                 totals_, r, pair_prefix_.as<uint32_t>(), pair_out_[0].as<uint32_t>());
+                 totals_, pr, pair_prefix_.as<uint32_t>(), pair_out_[0].as<uint32_t>());
         else
           Launch(pair_round_kernel<C, false>, grid, kPairThreads, (const uint32_t*)nullptr,
-                 pair_out_[r - 1].as<uint32_t>(), totals_, r, pair_prefix_.as<uint32_t>(),
-                 pair_out_[r].as<uint32_t>());
+                 pair_out_[pr - 1].as<uint32_t>(), totals_, pr, pair_prefix_.as<uint32_t>(),
+                 pair_out_[pr].as<uint32_t>());
       }
-      uint32_t agrid = (plan.max_tasks + kAccThreads - 1) / kAccThreads;
-      if (plan.R)
-        Launch(accumulate_kernel<C, true>, agrid, kAccThreads, pair_out_[plan.R - 1].as<uint32_t>(),
-               (const uint32_t*)nullptr, tasks_.as<uint2>(), task_meta_.as<uint32_t>(),
-               order_.as<uint32_t>(), totals_, state_.as<uint32_t>(), task_out_.as<uint32_t>());
-      else
-        Launch((uint64_t)plan.n * plan.W < kAccSmallEntries
-                   ? accumulate_kernel<C, false, AccMinBlocksSmall<C>()>
-                   : accumulate_kernel<C, false>,
-               agrid, kAccThreads, d_bases, sorted_.as<uint32_t>(), tasks_.as<uint2>(),
-               task_meta_.as<uint32_t>(), order_.as<uint32_t>(), totals_, state_.as<uint32_t>(),
-               task_out_.as<uint32_t>());
-      Launch(fold_stage_a_kernel<C>, sm_count_ * 8, kFoldThreads, fold_jobs_.as<uint2>(), totals_,
-             offset_.as<uint32_t>(), task_base_.as<uint32_t>(), plan.R, task_out_.as<uint32_t>(),
-             state_.as<uint32_t>());
-      Launch(fold_stage_b_kernel<C>, sm_count_, kFoldThreads, multi_.as<uint32_t>(), totals_,
-             offset_.as<uint32_t>(), task_base_.as<uint32_t>(), plan.R, task_out_.as<uint32_t>(),
-             state_.as<uint32_t>());
-      TB_CUDA(cudaMemcpyAsync(host_out + kHostWindowBytes + r * sizeof(MsmTotals), totals_,
+      auto accumulate = [&](uint32_t part, uint32_t max_tasks) {
+        uint32_t agrid = (max_tasks + kAccThreads - 1) / kAccThreads;
+        if (agrid == 0) agrid = 1;
+        if (plan.R)
+          Launch(accumulate_kernel<C, true>, agrid, kAccThreads, pair_out_[plan.R - 1].as<uint32_t>(),
+                 (const uint32_t*)nullptr, tasks_.as<uint2>(), task_meta_.as<uint32_t>(),
+                 order_.as<uint32_t>(), totals_, part, state_.as<uint32_t>(), task_out_.as<uint32_t>());
+        else
+          Launch((uint64_t)plan.n * plan.W < kAccSmallEntries
+                     ? accumulate_kernel<C, false, AccMinBlocksSmall<C>()>
+                     : accumulate_kernel<C, false>,
+                 agrid, kAccThreads, d_bases, sorted_.as<uint32_t>(), tasks_.as<uint2>(),
+                 task_meta_.as<uint32_t>(), order_.as<uint32_t>(), totals_, part,
+                 state_.as<uint32_t>(), task_out_.as<uint32_t>());
+      };
+      auto fold = [&](uint32_t part) {
+        Launch(fold_stage_a_kernel<C>, sm_count_ * 8, kFoldThreads, fold_jobs_.as<uint2>(), totals_,
+               offset_.as<uint32_t>(), task_base_.as<uint32_t>(), plan.R, part, split_key,
+               task_out_.as<uint32_t>(), state_.as<uint32_t>());
+        Launch(fold_stage_b_kernel<C>, sm_count_, kFoldThreads, multi_.as<uint32_t>(), totals_,
+               offset_.as<uint32_t>(), task_base_.as<uint32_t>(), plan.R, part, split_key,
+               task_out_.as<uint32_t>(), state_.as<uint32_t>());
+      };
+      if (!split) {
+        accumulate(kPartAll, plan.max_tasks);
+        TB_CUDA(cudaEventRecord(ev(r, 4), stream_));
+        fold(kPartAll);
+      } else {
+        // high windows first; their reduction and window combination then run on the tail
+        // stream while this stream accumulates the low windows
+        accumulate(kPartHigh, plan.max_tasks);
+        TB_CUDA(cudaEventRecord(ev(r, 4), stream_));
+        fold(kPartHigh);
+        TB_CUDA(cudaEventRecord(SlotEvent(slot, 4), stream_));
+        TB_CUDA(cudaStreamWaitEvent(tail_stream_, SlotEvent(slot, 4), 0));
+        uint32_t* terms_hi = combine_.as<uint32_t>();
+        EnqueueReduction(tail_stream_, big, pd.low, big.W - pd.low, pd.L0, terms_hi);
+        TB_CUDA(cudaEventRecord(SlotEvent(slot, 6), tail_stream_));
+        LaunchOn(tail_stream_, window_combine_kernel<C>, 1, kCombineThreads, terms_hi,
+                 TotalBits(big), WindowBitOffset(big, pd.low), (const uint32_t*)nullptr, HiSum());
+        TB_CUDA(cudaEventRecord(SlotEvent(slot, 7), tail_stream_));
+        TB_CUDA(cudaEventRecord(SlotEvent(slot, 5), tail_stream_));
+        // low group: at most low * B buckets, each non-empty one a task, plus the split ones
+        uint64_t lo_entries = (uint64_t)plan.n * pd.low;
+        uint64_t lo_buckets = (uint64_t)pd.low * plan.B;
+        uint32_t seg_floor = options_.segment ? plan.seg : kMinSegment;
+        accumulate(kPartLow, (uint32_t)((lo_entries < lo_buckets ? lo_entries : lo_buckets) +
+                                        lo_entries / seg_floor));
+        fold(kPartLow);
+      }
+      TB_CUDA(cudaMemcpyAsync(host_out + kHostPartialBytes + r * sizeof(MsmTotals), totals_,
                               sizeof(MsmTotals), cudaMemcpyDeviceToHost, stream_));
       TB_CUDA(cudaEventRecord(ev(r, 3), stream_));
       if (pd.any_host) {
@@ -953,43 +1082,29 @@ class MsmEngine {
       }
     }
     TB_CUDA(cudaEventRecord(ev_acc_end, stream_));
-    const MsmPlan& plan = big;
 
-    // ---- bucket reduction: one blocked running-sum level, then a merge tree ---------
-    {
-      uint32_t blocks = plan.W * nb;
-      if (options_.reduce_mode == 0) {
-        Launch(reduce_level_kernel<C, true>, (blocks + kReduceThreads - 1) / kReduceThreads,
-               kReduceThreads, state_.as<uint32_t>(), (const uint32_t*)nullptr, plan.B, nb, pd.L0,
-               0u, plan.W, lvl_a_[0].as<uint32_t>(), lvl_c_[0].as<uint32_t>());
-      } else {
-        constexpr uint32_t kSlots = ReduceSlots<C>();
-        Launch(reduce_blocks_kernel<C>, (blocks + kSlots - 1) / kSlots, 2 * kSlots,
-               state_.as<uint32_t>(), plan.B, nb, pd.L0, plan.W, plan.wide,
-               lvl_a_[0].as<uint32_t>(), lvl_c_[0].as<uint32_t>());
-      }
-    }
-    const uint32_t* tin = lvl_a_[0].as<uint32_t>();
-    const uint32_t* tin_p = lvl_c_[0].as<uint32_t>();
-    for (uint32_t s = 0; s < pd.M; ++s) {
-      uint32_t m_out = nb >> (s + 1);
-      DeviceBuffer& dst = tree_[s & 1];
-      uint32_t threads = plan.W * m_out * (s + 3);
-      Launch(reduce_merge_kernel<C>, (threads + kReduceThreads - 1) / kReduceThreads,
-             kReduceThreads, tin, tin_p, s, m_out, plan.W, dst.as<uint32_t>());
-      tin = dst.as<uint32_t>();
-      tin_p = nullptr;
-    }
-    // per window: (A, P, D_0 .. D_(M-1)); finished on the host
-    uint32_t vals = pd.M + 2;
-    size_t win_bytes = (size_t)plan.W * vals * kXyzzBytes;
-    if (pd.M == 0) {
-      TB_CUDA(cudaMemcpy2DAsync(host_out, 2 * kXyzzBytes, lvl_a_[0].ptr, kXyzzBytes, kXyzzBytes,
-                                plan.W, cudaMemcpyDeviceToHost, stream_));
-      TB_CUDA(cudaMemcpy2DAsync(host_out + kXyzzBytes, 2 * kXyzzBytes, lvl_c_[0].ptr, kXyzzBytes,
-                                kXyzzBytes, plan.W, cudaMemcpyDeviceToHost, stream_));
+    // ---- bucket reduction (running-sum level + fused merge tree) and window combination ----
+    // With a window split the high group is already on its way on the tail stream; this stream
+    // finishes the low windows and adds the high group's sum.  The result is ONE XYZZ point.
+    if (pd.low > 0) {
+      uint32_t* terms_lo = combine_.as<uint32_t>() + (size_t)kTermSlots * kXyzzWords;
+      EnqueueReduction(stream_, big, 0, pd.low, pd.L0, terms_lo);
+      TB_CUDA(cudaStreamWaitEvent(stream_, SlotEvent(slot, 5), 0));
+      Launch(window_combine_kernel<C>, 1, kCombineThreads, terms_lo, WindowBitOffset(big, pd.low), 0u,
+             (const uint32_t*)HiSum(), Partial());
     } else {
-      TB_CUDA(cudaMemcpyAsync(host_out, tin, win_bytes, cudaMemcpyDeviceToHost, stream_));
+      uint32_t* terms = combine_.as<uint32_t>();
+      EnqueueReduction(stream_, big, 0, big.W, pd.L0, terms);
+      TB_CUDA(cudaEventRecord(SlotEvent(slot, 6), stream_));
+      Launch(window_combine_kernel<C>, 1, kCombineThreads, terms, TotalBits(big), 0u,
+             (const uint32_t*)nullptr, Partial());
+      TB_CUDA(cudaEventRecord(SlotEvent(slot, 7), stream_));
+    }
+    pd.gathered = gather;
+    if (gather) {
+      EnqueueGather(Partial());
+    } else {
+      TB_CUDA(cudaMemcpyAsync(host_out, Partial(), kXyzzBytes, cudaMemcpyDeviceToHost, stream_));
     }
     TB_CUDA(cudaEventRecord(ev_end, stream_));
     pd.launches = launches_;
@@ -999,46 +1114,49 @@ class MsmEngine {
     return pd;
   }
 
+  static bool bound_nonempty(const MsmTotals& t) { return t.tasks != 0; }
+
   Point Finish(const Pending& pd) {
     const MsmPlan& plan = pd.plan;
     const int slot = pd.slot;
-    auto ev = [&](size_t r, int which) { return SlotEvent(slot, 4 + 4 * r + which); };
+    auto ev = [&](size_t r, int which) { return SlotEvent(slot, kSlotEvents + kRangeEvents * r + which); };
     auto wait0 = std::chrono::steady_clock::now();
     TB_CUDA(cudaEventSynchronize(SlotEvent(slot, 2)));
     timing_.wait_ms +=
         std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - wait0).count();
     const char* host_out = host_out_ + (size_t)slot * kHostOutBytes;
 
-    // ---- host epilogue ------------------------------------------------------------
-    // total = sum_w 2^(c w) [A_w + P_w + L0 sum_j 2^j D_(w,j)]: one Horner over bit
-    // positions from the top (the c doublings per window of pippenger_base.h:59-77),
-    // adding every term at its own bit, so the bucket-tree weights cost no extra doubling.
+    // ---- host epilogue: none.  The device left ONE point — bucket reduction, merge tree and
+    // window combination (pippenger_base.h:59-77) all ran as kernels. ------------------------
     auto host0 = std::chrono::steady_clock::now();
-    const Point* hv = reinterpret_cast<const Point*>(host_out);
-    const uint32_t l0 = Log2(pd.L0), M = pd.M, vals = M + 2;
-    Point result = Point::Zero();
-    for (uint32_t w = plan.W; w-- > 0;) {
-      const Point* v = hv + (size_t)w * vals;
-      const uint32_t cw = plan.c - (w >= plan.wide ? 1u : 0u);  // balanced windows
-      for (uint32_t bit = cw; bit-- > 0;) {
-        if (w + 1 < plan.W || bit + 1 < cw) result = result.Dbl();
-        if (bit >= l0 && bit - l0 < M) result = result.Add(v[2 + (bit - l0)]);
-        if (bit == 0) result = result.Add(v[0]).Add(v[1]);
-      }
+    Point result;
+    if (pd.gathered) {
+      result = SumGathered();
+    } else {
+      memcpy(&result, host_out, sizeof(result));
     }
     auto host1 = std::chrono::steady_clock::now();
 
     float ms;
     for (size_t r = 0; r < pd.K; ++r) {
       MsmTotals tot;
-      memcpy(&tot, host_out + kHostWindowBytes + r * sizeof(MsmTotals), sizeof(tot));
+      memcpy(&tot, host_out + kHostPartialBytes + r * sizeof(MsmTotals), sizeof(tot));
       timing_.tasks += tot.tasks;
       timing_.entries += tot.entries;
       TB_CUDA(cudaEventElapsedTime(&ms, ev(r, 1), ev(r, 2)));
       timing_.sort_ms += ms;
       TB_CUDA(cudaEventElapsedTime(&ms, ev(r, 2), ev(r, 3)));
       timing_.accumulate_ms += ms;
+      if (bound_nonempty(tot)) {
+        // the range's first accumulate launch ran alone on the device
+        TB_CUDA(cudaEventElapsedTime(&ms, ev(r, 2), ev(r, 4)));
+        timing_.acc_kernel_ms += ms;
+        timing_.acc_kernel_entries += tot.entries - (r + 1 == pd.K ? tot.entries_lo : 0u);
+      }
     }
+    TB_CUDA(cudaEventElapsedTime(&ms, SlotEvent(slot, 6), SlotEvent(slot, 7)));
+    timing_.combine_ms += ms;
+    timing_.low_windows = pd.low;
     if (pd.any_host) {
       // time the copy engine was busy or waiting for a free slot; overlaps the bucket work
       TB_CUDA(cudaEventElapsedTime(&ms, SlotEvent(slot, 3), ev(pd.K - 1, 0)));
@@ -1055,6 +1173,119 @@ class MsmEngine {
     timing_.pair_rounds = plan.R;
     timing_.kernel_launches += pd.launches;
     return result;
+  }
+
+  // All-gather of the ranks' partials (device pointer `partial`, one XYZZ point) on the
+  // compute stream, then one copy of the `world` points to pinned host memory.
+  void EnqueueGather(const void* partial) {
+    const NcclApi* nccl = NcclApi::Get(nullptr);
+    int rc = nccl->AllGather(partial, gather_dev_, kXyzzBytes, NcclApi::kUint8, comm_, stream_);
+    if (rc != 0) throw CudaError{cudaErrorUnknown, nccl->GetErrorString(rc), __FILE__, __LINE__};
+    TB_CUDA(cudaMemcpyAsync(gather_host_, gather_dev_, (size_t)world_ * kXyzzBytes,
+                            cudaMemcpyDeviceToHost, stream_));
+  }
+  Point SumGathered() const {  // pippenger_adapter.h:110-113
+    Point total;
+    for (int g = 0; g < world_; ++g) {
+      Point part;
+      memcpy(&part, gather_host_ + (size_t)g * kXyzzBytes, sizeof(part));
+      total = g == 0 ? part : total.Add(part);
+    }
+    return total;
+  }
+  // The rare paths (empty input, several pieces): the local sum is already on the host.
+  Point GatherHostPoint(const Point& local) {
+    char* up = gather_host_ + (size_t)world_ * kXyzzBytes;
+    memcpy(up, &local, sizeof(local));
+    TB_CUDA(cudaMemcpyAsync(Scratch(), up, kXyzzBytes, cudaMemcpyHostToDevice, stream_));
+    EnqueueGather(Scratch());
+    TB_CUDA(cudaStreamSynchronize(stream_));
+    return SumGathered();
+  }
+  uint32_t* Scratch() {
+    if (!combine_.ptr) combine_.Reserve((size_t)(2 * kTermSlots + 2) * kXyzzBytes);
+    return Partial();
+  }
+
+  // Bit position of window w's lowest bit / of the end of the top window (balanced windows).
+  static uint32_t WindowBitOffset(const MsmPlan& p, uint32_t w) {
+    return w * p.c - (w > p.wide ? w - p.wide : 0u);
+  }
+  static uint32_t TotalBits(const MsmPlan& p) { return WindowBitOffset(p, p.W); }
+  uint32_t* HiSum() { return combine_.as<uint32_t>() + (size_t)2 * kTermSlots * kXyzzWords; }
+  uint32_t* Partial() { return HiSum() + kXyzzWords; }
+
+  // Bucket reduction of windows [w0, w0 + wn) on stream `st`: one blocked running-sum level,
+  // then the merge tree in stages of <= kTreeStageLevels levels per launch; the last stage
+  // scatters every window's (A, P, D_j) to the bit positions of `terms`.
+  void EnqueueReduction(cudaStream_t st, const MsmPlan& plan, uint32_t w0, uint32_t wn, uint32_t L0,
+                        uint32_t* terms) {
+    const uint32_t nb = plan.B / L0, M = Log2(nb), l0 = Log2(L0);
+    const size_t slice_words = (size_t)nb * 2 * kXyzzWords;
+    uint32_t* leaves = leaves_.as<uint32_t>() + (size_t)w0 * slice_words;
+    const uint32_t* bucket0 = state_.as<uint32_t>() + (size_t)w0 * plan.B * kXyzzWords;
+    const uint32_t wide_local = plan.wide > w0 ? plan.wide - w0 : 0u;
+    const uint32_t blocks = wn * nb;
+    if (options_.reduce_mode == 0) {
+      LaunchOn(st, reduce_level_kernel<C, true>, (blocks + kReduceThreads - 1) / kReduceThreads,
+               kReduceThreads, bucket0, (const uint32_t*)nullptr, plan.B, nb, L0, 0u, wn, leaves,
+               leaves + kXyzzWords);
+    } else {
+      constexpr uint32_t kSlots = ReduceSlots<C>();
+      LaunchOn(st, reduce_blocks_kernel<C>, (blocks + kSlots - 1) / kSlots, 2 * kSlots, bucket0,
+               plan.B, nb, L0, wn, wide_local, leaves, leaves + kXyzzWords);
+    }
+    const uint32_t* in = leaves;
+    uint32_t vin = 2, nodes = nb, remaining = M, stage = 0;
+    do {
+      const uint32_t levels = remaining > kTreeStageLevels ? kTreeStageLevels : remaining;
+      const bool last = levels == remaining;
+      const uint32_t ctas = nodes >> levels;
+      uint32_t* out = stage_out_[stage & 1].as<uint32_t>() + (size_t)w0 * slice_words;
+      TreeFinal fin{last ? 1u : 0u, w0, plan.c, plan.wide, l0, terms};
+      LaunchOn(st, reduce_tree_kernel<C>, wn * ctas, (uint32_t)kTreeThreads, in, vin, levels, ctas,
+               slice_words, tree_[0].as<uint32_t>() + (size_t)w0 * slice_words,
+               tree_[1].as<uint32_t>() + (size_t)w0 * slice_words, out, fin);
+      in = out;
+      vin += levels;
+      nodes >>= levels;
+      remaining -= levels;
+      ++stage;
+    } while (remaining > 0);
+  }
+
+  // How many low windows to accumulate last.  The window combination of the high group is a
+  // chain of ~(bits above the split) point doublings, latency-bound on one lane; it is free as
+  // long as the low group's accumulation (n mixed additions per window at the pipe rate) lasts
+  // longer.  What remains exposed after the low group is its own reduction plus the doublings
+  // below the split.  Picks the split with the smallest exposed time; 0 = no split.
+  uint32_t ChooseLowWindows(const MsmPlan& p, size_t n_last) const {
+    if (options_.low_windows >= 0)
+      return (uint32_t)options_.low_windows < p.W ? (uint32_t)options_.low_windows : p.W - 1;
+    if (p.R) return 0;  // pair rounds: experimental path, single group
+    // measured on B200: microseconds per doubling of the combine chain (four-lane form,
+    // tools/probe/chain_probe.cu), nanoseconds per mixed addition of the accumulation kernel at
+    // full occupancy
+    constexpr int kW = C::Field::kWords;
+    const double dbl_us = kW <= 8 ? 1.64 : (kW <= 12 ? 3.28 : (kW <= 16 ? 4.41 : 9.6));
+    const double madd_ns = kW <= 8 ? 0.138 : (kW <= 12 ? 0.34 : (kW <= 16 ? 0.61 : 1.3));
+    const double kHighFixedUs = 100.0;  // running-sum level + tree of the high group (latency)
+    const double kSplitFixedUs = 40.0;  // second accumulate launch, second reduction, their tails
+    const uint32_t total_bits = TotalBits(p);
+    double best = kHighFixedUs + dbl_us * total_bits;  // no split: the whole chain is exposed
+    uint32_t best_low = 0;
+    for (uint32_t low = 1; low < p.W; ++low) {
+      const uint32_t below = WindowBitOffset(p, low);
+      const double hidden_by = (double)low * (double)n_last * madd_ns * 1e-3;
+      const double chain_hi = kHighFixedUs + dbl_us * (total_bits - below);
+      double exposed = (chain_hi > hidden_by ? chain_hi - hidden_by : 0.0) + dbl_us * below +
+                       kSplitFixedUs;
+      if (exposed < best) {
+        best = exposed;
+        best_low = low;
+      }
+    }
+    return best_low;
   }
 
   // Threads of pair round r: kPairBatch pairs each, but never fewer than a full grid.
@@ -1075,7 +1306,7 @@ class MsmEngine {
   std::vector<const DeviceBuffer*> AllBuffers() const {
     return {&registered_, &bases_stage_, &scalars_stage_, &state_, &count_, &offset_, &cursor_, &task_base_,
             &tasks_, &task_meta_, &multi_, &sorted_, &digits_, &task_out_, &block_sums_, &order_,
-            &len_hist_, &lvl_a_[0], &lvl_a_[1], &lvl_c_[0], &lvl_c_[1], &tree_[0], &tree_[1],
+            &len_hist_, &leaves_, &stage_out_[0], &stage_out_[1], &combine_, &tree_[0], &tree_[1],
             &pair_prefix_, &pair_out_[0], &pair_out_[1], &pair_out_[2], &pair_out_[3], &mid_,
             &coarse_, &fold_jobs_, &nonzero_slots_};
   }
@@ -1102,9 +1333,11 @@ class MsmEngine {
     return L;
   }
 
-  // per window (A, P, D_0..D_(M-1)), M <= 22, then one MsmTotals per range
-  static constexpr size_t kHostWindowBytes = kMaxWindows * 24 * kXyzzBytes;
-  static constexpr size_t kHostOutBytes = kHostWindowBytes + kMaxRanges * sizeof(MsmTotals);
+  // pinned result buffer per Pending slot: the MSM's point, then one MsmTotals per range
+  static constexpr size_t kHostPartialBytes = (kXyzzBytes + 255) / 256 * 256;
+  static constexpr size_t kHostOutBytes = kHostPartialBytes + kMaxRanges * sizeof(MsmTotals);
+  // bit positions of the window-combination term arrays: W * c < 256 + c
+  static constexpr uint32_t kTermSlots = 320;
 
   int device_;
   int sm_count_ = 148;
@@ -1112,6 +1345,7 @@ class MsmEngine {
   cudaStream_t stream_ = nullptr;
   cudaStream_t copy_stream_ = nullptr;
   cudaStream_t sample_stream_ = nullptr;
+  cudaStream_t tail_stream_ = nullptr;
   std::vector<cudaEvent_t> events_;
   size_t stage_seq_ = 0;
   bool in_batch_tail_ = false;
@@ -1129,10 +1363,15 @@ class MsmEngine {
   char* host_out_ = nullptr;
   size_t registered_n_ = 0;
   DeviceBuffer registered_, bases_stage_, scalars_stage_, state_, count_, offset_, cursor_, task_base_, tasks_,
-      task_meta_, multi_, sorted_, digits_, task_out_, block_sums_, order_, len_hist_, lvl_a_[2],
-      lvl_c_[2], tree_[2], pair_prefix_, pair_out_[4], mid_, coarse_,
+      task_meta_, multi_, sorted_, digits_, task_out_, block_sums_, order_, len_hist_, leaves_,
+      stage_out_[2], combine_, tree_[2], pair_prefix_, pair_out_[4], mid_, coarse_,
       fold_jobs_, nonzero_slots_;
   size_t sort_smem_set_ = 0;
+  // multi-process point-range sharding (JoinRanks)
+  NcclApi::Comm comm_ = nullptr;
+  int rank_ = 0, world_ = 1;
+  char* gather_dev_ = nullptr;
+  char* gather_host_ = nullptr;
 };
 
 }  // namespace tb200

@@ -95,8 +95,17 @@ struct MsmTotals {
   uint32_t fold_jobs;  // chunks of kFoldThreads partial sums to fold (stage A)
   uint32_t multi2;     // buckets with more than one chunk (stage B)
   uint32_t nonzero;    // non-zero digits of the range
+  uint32_t tasks_hi;   // tasks of the HIGH window group (bucket keys >= split_key); they come
+                       // first in `order`, the low group's follow
+  uint32_t entries_lo; // entries of the low window group (= offset[split_key])
   uint32_t pad;
 };
+
+// Which tasks a launch of the accumulation / fold kernels covers.  The windows of the last point
+// range are processed as two groups: the high windows first, so that their bucket reduction and
+// the long doubling chain of the window combination (window_combine_kernel) run on a second
+// stream WHILE the low windows are still being accumulated.
+enum : uint32_t { kPartAll = 0, kPartHigh = 1, kPartLow = 2 };
 
 constexpr uint32_t kMinSegment = 16;
 constexpr int kNonzeroSlots = 64;  // partial counters of non-zero digits (spread the atomics)
@@ -449,35 +458,47 @@ static __global__ void __launch_bounds__(kScanThreads) scan_apply_build_tasks_ke
 constexpr int kMaxSegment = 1024;
 constexpr int kOrderThreads = 256;
 constexpr int kOrderPerThread = 8;
+// sort key of a task: window group (0 = high, 1 = low) major, then DEscending length
+constexpr int kOrderBins = 2 * (kMaxSegment + 1);
+TB_DEV uint32_t order_bin(uint32_t len, uint32_t meta, uint32_t split_key) {
+  uint32_t low = (meta & kTaskKeyMask) < split_key ? 1u : 0u;
+  return low * (kMaxSegment + 1) + (kMaxSegment - len);
+}
 
 static __global__ void __launch_bounds__(kOrderThreads) order_hist_kernel(
-    const uint2* __restrict__ tasks, const MsmTotals* __restrict__ totals,
-    uint32_t* __restrict__ len_hist) {
-  __shared__ uint32_t sh[kMaxSegment + 1];
-  for (int i = threadIdx.x; i <= kMaxSegment; i += kOrderThreads) sh[i] = 0;
+    const uint2* __restrict__ tasks, const uint32_t* __restrict__ task_meta,
+    const MsmTotals* __restrict__ totals, uint32_t split_key, uint32_t* __restrict__ len_hist) {
+  __shared__ uint32_t sh[kOrderBins];
+  for (int i = threadIdx.x; i < kOrderBins; i += kOrderThreads) sh[i] = 0;
   __syncthreads();
   uint32_t T = totals->tasks;
   uint32_t base = blockIdx.x * (kOrderThreads * kOrderPerThread);
 #pragma unroll
   for (int k = 0; k < kOrderPerThread; ++k) {
     uint32_t g = base + k * kOrderThreads + threadIdx.x;
-    if (g < T) atomicAdd(&sh[tasks[g].y], 1u);
+    if (g < T) atomicAdd(&sh[order_bin(tasks[g].y, task_meta[g], split_key)], 1u);
   }
   __syncthreads();
-  for (int i = threadIdx.x; i <= kMaxSegment; i += kOrderThreads)
+  for (int i = threadIdx.x; i < kOrderBins; i += kOrderThreads)
     if (sh[i]) atomicAdd(&len_hist[i], sh[i]);
 }
 
-// in: len_hist[0..kMaxSegment] counts; out: len_hist[l] = first slot of length l when
-// lengths are laid out in DEscending order.
-static __global__ void __launch_bounds__(1024) order_scan_kernel(uint32_t* __restrict__ len_hist) {
-  __shared__ uint32_t sh[kMaxSegment + 1];
+// in: len_hist[bin] counts; out: len_hist[bin] = first slot of the bin (exclusive scan in bin
+// order); totals->tasks_hi = first slot of the low group; totals->entries_lo from the offsets.
+static __global__ void __launch_bounds__(1024) order_scan_kernel(
+    uint32_t* __restrict__ len_hist, const uint32_t* __restrict__ offset, uint32_t split_key,
+    MsmTotals* __restrict__ totals) {
   __shared__ uint32_t warp_sums[32];
-  // position p = kMaxSegment - l, so ascending p = descending length
-  uint32_t p = threadIdx.x;
-  uint32_t v = len_hist[kMaxSegment - p];
-  uint32_t lane = p & 31, warp = p >> 5;
-  uint32_t x = v;
+  constexpr int kPer = (kOrderBins + 1023) / 1024;  // bins per thread, consecutive
+  const uint32_t first = threadIdx.x * kPer;
+  uint32_t v[kPer], sum = 0;
+#pragma unroll
+  for (int k = 0; k < kPer; ++k) {
+    v[k] = first + k < (uint32_t)kOrderBins ? len_hist[first + k] : 0u;
+    sum += v[k];
+  }
+  uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  uint32_t x = sum;
 #pragma unroll
   for (int o = 1; o < 32; o <<= 1) {
     uint32_t y = __shfl_up_sync(0xffffffffu, x, o);
@@ -486,47 +507,52 @@ static __global__ void __launch_bounds__(1024) order_scan_kernel(uint32_t* __res
   if (lane == 31) warp_sums[warp] = x;
   __syncthreads();
   if (warp == 0) {
-    uint32_t s = warp_sums[lane];
+    uint32_t t = warp_sums[lane];
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
-      uint32_t y = __shfl_up_sync(0xffffffffu, s, o);
-      if (lane >= (uint32_t)o) s += y;
+      uint32_t y = __shfl_up_sync(0xffffffffu, t, o);
+      if (lane >= (uint32_t)o) t += y;
     }
-    warp_sums[lane] = s;
+    warp_sums[lane] = t;
   }
   __syncthreads();
-  uint32_t excl = (warp ? warp_sums[warp - 1] : 0) + x - v;
-  sh[kMaxSegment - p] = excl;
-  __syncthreads();
-  len_hist[kMaxSegment - p] = sh[kMaxSegment - p];
-  // length 0 never occurs (tasks are non-empty); its slot is left as the total
-  if (p == 0) len_hist[0] = warp_sums[31];
+  uint32_t run = (warp ? warp_sums[warp - 1] : 0) + x - sum;
+#pragma unroll
+  for (int k = 0; k < kPer; ++k) {
+    if (first + k < (uint32_t)kOrderBins) {
+      len_hist[first + k] = run;
+      if (first + k == (uint32_t)(kMaxSegment + 1)) totals->tasks_hi = run;
+    }
+    run += v[k];
+  }
+  if (threadIdx.x == 0) totals->entries_lo = split_key ? offset[split_key] : 0u;
 }
 
 static __global__ void __launch_bounds__(kOrderThreads) order_scatter_kernel(
-    const uint2* __restrict__ tasks, const MsmTotals* __restrict__ totals,
-    uint32_t* __restrict__ len_cursor, uint32_t* __restrict__ order) {
-  __shared__ uint32_t cnt[kMaxSegment + 1];
-  __shared__ uint32_t start[kMaxSegment + 1];
-  for (int i = threadIdx.x; i <= kMaxSegment; i += kOrderThreads) cnt[i] = 0;
+    const uint2* __restrict__ tasks, const uint32_t* __restrict__ task_meta,
+    const MsmTotals* __restrict__ totals, uint32_t split_key, uint32_t* __restrict__ len_cursor,
+    uint32_t* __restrict__ order) {
+  __shared__ uint32_t cnt[kOrderBins];
+  __shared__ uint32_t start[kOrderBins];
+  for (int i = threadIdx.x; i < kOrderBins; i += kOrderThreads) cnt[i] = 0;
   __syncthreads();
   uint32_t T = totals->tasks;
   uint32_t base = blockIdx.x * (kOrderThreads * kOrderPerThread);
-  uint32_t len[kOrderPerThread], rank[kOrderPerThread];
+  uint32_t bin[kOrderPerThread], rank[kOrderPerThread];
 #pragma unroll
   for (int k = 0; k < kOrderPerThread; ++k) {
     uint32_t g = base + k * kOrderThreads + threadIdx.x;
-    len[k] = (g < T) ? tasks[g].y : 0;
-    rank[k] = len[k] ? atomicAdd(&cnt[len[k]], 1u) : 0;
+    bin[k] = (g < T) ? order_bin(tasks[g].y, task_meta[g], split_key) : 0xffffffffu;
+    rank[k] = (g < T) ? atomicAdd(&cnt[bin[k]], 1u) : 0;
   }
   __syncthreads();
-  for (int i = threadIdx.x + 1; i <= kMaxSegment; i += kOrderThreads)
+  for (int i = threadIdx.x; i < kOrderBins; i += kOrderThreads)
     if (cnt[i]) start[i] = atomicAdd(&len_cursor[i], cnt[i]);
   __syncthreads();
 #pragma unroll
   for (int k = 0; k < kOrderPerThread; ++k) {
     uint32_t g = base + k * kOrderThreads + threadIdx.x;
-    if (len[k]) order[start[len[k]] + rank[k]] = g;
+    if (bin[k] != 0xffffffffu) order[start[bin[k]] + rank[k]] = g;
   }
 }
 
@@ -559,13 +585,14 @@ template <class C, bool kReduced, int kMinBlocks = AccMinBlocks<C>()>
 __global__ void __launch_bounds__(kAccThreads, kMinBlocks) accumulate_kernel(
     const uint32_t* __restrict__ bases, const uint32_t* __restrict__ sorted,
     const uint2* __restrict__ tasks, const uint32_t* __restrict__ task_meta,
-    const uint32_t* __restrict__ order, const MsmTotals* __restrict__ totals,
+    const uint32_t* __restrict__ order, const MsmTotals* __restrict__ totals, uint32_t part,
     uint32_t* __restrict__ state, uint32_t* __restrict__ task_out) {
   using K = typename C::Field;
   constexpr int kAffineWords = 2 * K::kWords;
   constexpr int kXyzzWords = 4 * K::kWords;
-  uint32_t slot = blockIdx.x * blockDim.x + threadIdx.x;
-  if (slot >= totals->tasks) return;
+  // slots [0, tasks_hi) are the high window group, [tasks_hi, tasks) the low one
+  uint32_t slot = blockIdx.x * blockDim.x + threadIdx.x + (part == kPartLow ? totals->tasks_hi : 0u);
+  if (slot >= (part == kPartHigh ? totals->tasks_hi : totals->tasks)) return;
   uint32_t g = order[slot];  // tasks in descending length: warps stay convergent
   uint2 task = tasks[g];
   uint32_t meta = task_meta[g];
@@ -782,7 +809,8 @@ template <class C>
 __global__ void __launch_bounds__(kFoldThreads) fold_stage_a_kernel(
     const uint2* __restrict__ fold_jobs, const MsmTotals* __restrict__ totals,
     const uint32_t* __restrict__ offset, const uint32_t* __restrict__ task_base, uint32_t R,
-    uint32_t* __restrict__ task_out, uint32_t* __restrict__ state) {
+    uint32_t part, uint32_t split_key, uint32_t* __restrict__ task_out,
+    uint32_t* __restrict__ state) {
   using K = typename C::Field;
   constexpr int kXyzzWords = 4 * K::kWords;
   __shared__ uint32_t sh[kFoldThreads / 2 * kXyzzWords];
@@ -790,6 +818,7 @@ __global__ void __launch_bounds__(kFoldThreads) fold_stage_a_kernel(
   for (uint32_t job = blockIdx.x; job < totals->fold_jobs; job += gridDim.x) {
     uint2 jb = fold_jobs[job];
     uint32_t key = jb.x;
+    if (part != kPartAll && (key < split_key) != (part == kPartLow)) continue;  // other group
     uint32_t cnt = (offset[key + 1] - offset[key]) >> R;  // padded run after the pair rounds
     uint32_t t = (cnt + seg - 1) / seg;
     uint32_t first = jb.y * kFoldThreads;
@@ -810,13 +839,15 @@ template <class C>
 __global__ void __launch_bounds__(kFoldThreads) fold_stage_b_kernel(
     const uint32_t* __restrict__ multi2_keys, const MsmTotals* __restrict__ totals,
     const uint32_t* __restrict__ offset, const uint32_t* __restrict__ task_base, uint32_t R,
-    const uint32_t* __restrict__ task_out, uint32_t* __restrict__ state) {
+    uint32_t part, uint32_t split_key, const uint32_t* __restrict__ task_out,
+    uint32_t* __restrict__ state) {
   using K = typename C::Field;
   constexpr int kXyzzWords = 4 * K::kWords;
   __shared__ uint32_t sh[kFoldThreads / 2 * kXyzzWords];
   const uint32_t seg = totals->seg;
   for (uint32_t m = blockIdx.x; m < totals->multi2; m += gridDim.x) {
     uint32_t key = multi2_keys[m];
+    if (part != kPartAll && (key < split_key) != (part == kPartLow)) continue;  // other group
     uint32_t cnt = (offset[key + 1] - offset[key]) >> R;
     uint32_t t = (cnt + seg - 1) / seg;
     uint32_t chunks = (t + kFoldThreads - 1) / kFoldThreads;
@@ -875,8 +906,9 @@ __global__ void __launch_bounds__(kReduceThreads) reduce_level_kernel(
   }
   for (uint32_t s = 0; s < shift; ++s) xyzz_dbl<K>(wt);
   xyzz_add<K>(csum, wt);
-  xyzz_store<K>(out_a + (size_t)g * kXyzzWords, run);
-  xyzz_store<K>(out_c + (size_t)g * kXyzzWords, csum);
+  // leaf node g of the reduction tree: (A, P) side by side (out_c = out_a + one point)
+  xyzz_store<K>(out_a + (size_t)g * 2 * kXyzzWords, run);
+  xyzz_store<K>(out_c + (size_t)g * 2 * kXyzzWords, csum);
 }
 
 // Level 0 of the bucket reduction with the two dependent additions of a running sum split over
@@ -887,7 +919,10 @@ __global__ void __launch_bounds__(kReduceThreads) reduce_level_kernel(
 // of three (the single-thread form spilled: 128 registers + 384 B of stack).  Roles are per
 // warp (no divergence); run values cross through a double-buffered shared-memory slot per
 // block, one __syncthreads per step.  Writes A = sum B_k to out_a and Wt = sum_k (k - lo) B_k
-// to out_c, like reduce_level_kernel<C, true> with shift = 0.
+// to out_c, like reduce_level_kernel<C, true> with shift = 0: block g is leaf node g of the
+// reduction tree, its two values (A, P) stored side by side (out_c = out_a + one point).  The
+// caller passes pointers offset to the first window of the group it reduces and `wide` relative
+// to that window.
 //   wide / windows: blocks in the upper half of a narrow (c - 1 bit) window hold no entries by
 //   construction (balanced windows); a CTA that lies wholly inside one writes zeros and leaves.
 template <class C>
@@ -917,7 +952,7 @@ __global__ void __launch_bounds__(2 * ReduceSlots<C>()) reduce_blocks_kernel(
       if (g < total) {
         XYZZ<K> z;
         xyzz_set_zero<K>(z);
-        xyzz_store<K>((summing ? out_c : out_a) + (size_t)g * kXyzzWords, z);
+        xyzz_store<K>((summing ? out_c : out_a) + (size_t)g * 2 * kXyzzWords, z);
       }
       return;
     }
@@ -947,47 +982,163 @@ __global__ void __launch_bounds__(2 * ReduceSlots<C>()) reduce_blocks_kernel(
     }
     __syncthreads();
   }
-  if (live) xyzz_store<K>((summing ? out_c : out_a) + (size_t)g * kXyzzWords, acc);
+  if (live) xyzz_store<K>((summing ? out_c : out_a) + (size_t)g * 2 * kXyzzWords, acc);
 }
 
-// Tail of the bucket reduction.  After level 0 every window has m = 2^M blocks t with
-// (A_t, Wt_t) and  S_w = sum_t A_t + sum_t Wt_t + L * sum_t t A_t.  Writing t in binary,
+// Tail of the bucket reduction.  After level 0 every window has nb = 2^M blocks t with
+// (A_t, P_t) and  S_w = sum_t A_t + sum_t P_t + L * sum_t t A_t.  Writing t in binary,
 // sum_t t A_t = sum_j 2^j D_j with D_j = sum of A_t over the t whose bit j is set, so only
-// PLAIN sums remain and the powers of two are applied once, on the host, inside the window
-// Horner that doubles anyway.  A binary tree carries per node the vector
-// (A, P, D_0 .. D_(s-1)) of its 2^s blocks; a merge is  A = A_l + A_r, P = P_l + P_r,
-// D_i = D_i,l + D_i,r, D_s = A_r — all independent, one thread each — so every level is
-// ONE addition deep (the blocked running sums it replaces were ~27 sequential point
-// operations per level).  Level s input: nodes with s + 2 values; level 0 reads A and P
-// from the two arrays reduce_level_kernel wrote.
+// PLAIN sums remain and the powers of two are applied once, by window_combine_kernel, which
+// doubles anyway.  A binary tree carries per node the vector (A, P, D_0 .. D_(s-1)) of its 2^s
+// blocks; a merge is  A = A_l + A_r, P = P_l + P_r, D_i = D_i,l + D_i,r, D_s = A_r — all
+// independent, one thread each — so every level is ONE addition deep.
+//
+// reduce_tree_kernel runs `levels` levels of that tree in ONE launch: a CTA owns 2^levels
+// consecutive input nodes of one window (vin values each) and ping-pongs between two private
+// scratch regions in global memory (L1/L2 resident; a __syncthreads per level), so a 12-14
+// level tree is two launches instead of 12-14 latency-bound ones.  The stage that ends with one
+// node per window (`fin.enabled`) scatters that node's values to the window's bit positions of
+// the term array Y consumed by window_combine_kernel:
+//   Y[off_w]          = A + P
+//   Y[off_w + l0 + j] = D_j          (weight L = 2^l0 of the blocked running sums)
+//   other positions of the window    = identity
+struct TreeFinal {
+  uint32_t enabled;
+  uint32_t w_begin;  // global index of the launch's first window
+  uint32_t c, wide;  // window widths: c bits for w < wide, c - 1 above (balanced windows)
+  uint32_t l0;       // log2 of the level-0 block length
+  uint32_t* terms;   // Y, one XYZZ per bit position
+};
+constexpr int kTreeThreads = 256;
+constexpr uint32_t kTreeStageLevels = 7;  // levels per launch: 128 input nodes per CTA
+
+TB_DEV uint32_t window_bit_offset(uint32_t w, uint32_t c, uint32_t wide) {
+  return w * c - (w > wide ? w - wide : 0u);
+}
+
 template <class C>
-__global__ void __launch_bounds__(kReduceThreads) reduce_merge_kernel(
-    const uint32_t* __restrict__ in, const uint32_t* __restrict__ in_p0, uint32_t s,
-    uint32_t m_out, uint32_t windows, uint32_t* __restrict__ out) {
+__global__ void __launch_bounds__(kTreeThreads) reduce_tree_kernel(
+    const uint32_t* in, uint32_t vin, uint32_t levels, uint32_t ctas_per_window,
+    size_t slice_words, uint32_t* ping, uint32_t* pong, uint32_t* out, TreeFinal fin) {
   using K = typename C::Field;
   constexpr int kXyzzWords = 4 * K::kWords;
-  uint32_t vin = s + 2, vout = s + 3;
-  uint32_t g = blockIdx.x * blockDim.x + threadIdx.x;
-  if (g >= windows * m_out * vout) return;
-  uint32_t v = g % vout;
-  uint32_t node = (g / vout) % m_out;
-  uint32_t w = g / (vout * m_out);
-  uint32_t m_in = 2 * m_out;
-  size_t left = (size_t)w * m_in + 2 * node, right = left + 1;
-  auto src = [&](size_t nd, uint32_t val) -> const uint32_t* {
-    if (s == 0) return (val == 0 ? in : in_p0) + nd * kXyzzWords;
-    return in + (nd * vin + val) * kXyzzWords;
-  };
-  XYZZ<K> a;
-  if (v == s + 2) {
-    xyzz_load<K>(a, src(right, 0));  // D_s = A_r
-  } else {
-    XYZZ<K> b;
-    xyzz_load<K>(a, src(left, v));
-    xyzz_load<K>(b, src(right, v));
-    xyzz_add<K>(a, b);
+  // every buffer is cut into per-window slices of slice_words; inside its window's slice a CTA
+  // owns the nodes [chunk * 2^levels, (chunk + 1) * 2^levels) of vin values each
+  const uint32_t n0 = 1u << levels;
+  const uint32_t lw = blockIdx.x / ctas_per_window, chunk = blockIdx.x % ctas_per_window;
+  const size_t region = (size_t)lw * slice_words + (size_t)chunk * n0 * vin * kXyzzWords;
+  const uint32_t* src = in + region;
+  uint32_t* bufs[2] = {ping + region, pong + region};
+  const uint32_t vfinal = vin + levels;
+  const uint32_t group = threadIdx.x >> 2, lane = threadIdx.x & 3, mask = 0xfu << (threadIdx.x & 28);
+  for (uint32_t l = 1; l <= levels; ++l) {
+    const uint32_t m = n0 >> l, vout = vin + l, vprev = vout - 1;
+    // the last level of a stage that is not the final one writes the compact output array
+    uint32_t* dst = (l == levels && !fin.enabled)
+                        ? out + (size_t)lw * slice_words + (size_t)chunk * vfinal * kXyzzWords
+                        : bufs[l & 1];
+    // one work item (node, value) per group of four lanes (Coop4: an addition is 4
+    // multiplication levels deep instead of 14 multiplications)
+    for (uint32_t it = group; it < m * vout; it += kTreeThreads / 4) {
+      const uint32_t node = it / vout, v = it % vout;
+      const uint32_t* left = src + (size_t)(2 * node) * vprev * kXyzzWords;
+      const uint32_t* right = left + (size_t)vprev * kXyzzWords;
+      XYZZ<K> a;
+      if (v == vout - 1) {
+        xyzz_load<K>(a, right);  // D_new = A_r
+      } else {
+        XYZZ<K> b;
+        xyzz_load<K>(a, left + (size_t)v * kXyzzWords);
+        xyzz_load<K>(b, right + (size_t)v * kXyzzWords);
+        Coop4<K>::add(a, b, lane, mask);
+      }
+      if (lane == 0) xyzz_store<K>(dst + (size_t)it * kXyzzWords, a);
+    }
+    __syncthreads();
+    src = dst;
   }
-  xyzz_store<K>(out + (size_t)g * kXyzzWords, a);
+  if (!fin.enabled) return;
+  // one node per window left (ctas_per_window == 1): values (A, P, D_0 .. D_(M-1)) at src
+  const uint32_t w = fin.w_begin + lw;
+  const uint32_t cw = fin.c - (w >= fin.wide ? 1u : 0u);
+  const uint32_t base = window_bit_offset(w, fin.c, fin.wide);
+  const uint32_t M = vfinal - 2;
+  for (uint32_t bit = group; bit < cw; bit += kTreeThreads / 4) {
+    XYZZ<K> a;
+    xyzz_set_zero<K>(a);
+    if (bit == 0) {
+      XYZZ<K> b;
+      xyzz_load<K>(a, src);
+      xyzz_load<K>(b, src + kXyzzWords);
+      Coop4<K>::add(a, b, lane, mask);
+    }
+    if (bit >= fin.l0 && bit - fin.l0 < M) {
+      XYZZ<K> d;
+      xyzz_load<K>(d, src + (size_t)(2 + bit - fin.l0) * kXyzzWords);
+      Coop4<K>::add(a, d, lane, mask);  // (l0 >= 1, so bit 0 never carries a D term; kept general)
+    }
+    if (lane == 0) xyzz_store<K>(fin.terms + (size_t)(base + bit) * kXyzzWords, a);
+  }
+}
+
+// Window combination (pippenger_base.h:59-77 AccumulateWindowSums, the Horner over the window
+// sums) on the device: the MSM value is  sum_b 2^b Y_b  over the bit-positioned terms Y the
+// reduction tree left.  A pairing tree computes it in place: round r adds 2^(2^r) * Y[right] to
+// Y[left] for right = left + 2^r, so the doublings of different subtrees proceed in parallel and
+// the term at bit b is doubled exactly b times in total — the c doublings per window of the
+// reference's Horner, (W - 1) c in all on the longest path, plus log2 additions instead of one
+// per term.  One CTA.  Positions [0, clear_below) are reset to the identity first (the low
+// window group writes its own term array).  The result, plus *add_in when given (the high
+// group's sum), goes to out.
+//
+// The doubling chain is latency-bound and is the one serial part of an MSM: 3.8 us per 254-bit
+// doubling on one lane, 1.6 us with the four-lane form used here (tools/probe/chain_probe.cu;
+// 381-bit: 8.0 -> 3.3 us, Fq2: 12.6 -> 4.4 and 46 -> 9.6 us), i.e. ~0.45 ms for the ~255
+// doublings of a BN254 MSM.  The engine hides it behind the accumulation of the low windows.
+constexpr int kCombineThreads = 128;
+
+template <class C>
+__global__ void __launch_bounds__(kCombineThreads) window_combine_kernel(
+    uint32_t* terms, uint32_t count, uint32_t clear_below, const uint32_t* add_in,
+    uint32_t* out) {
+  using K = typename C::Field;
+  constexpr int kXyzzWords = 4 * K::kWords;
+  constexpr uint32_t kGroups = kCombineThreads / 4;
+  // groups of four lanes share one (left, right) pair: Coop4 doublings and additions
+  const uint32_t group = threadIdx.x >> 2, lane = threadIdx.x & 3, mask = 0xfu << (threadIdx.x & 28);
+  for (uint32_t b = threadIdx.x; b < clear_below; b += kCombineThreads) {
+    XYZZ<K> z;
+    xyzz_set_zero<K>(z);
+    xyzz_store<K>(terms + (size_t)b * kXyzzWords, z);
+  }
+  __syncthreads();
+  for (uint32_t stride = 1; stride < count; stride <<= 1) {
+    for (uint32_t left = group * 2 * stride; left + stride < count; left += kGroups * 2 * stride) {
+      XYZZ<K> t, a;
+      xyzz_load<K>(t, terms + (size_t)(left + stride) * kXyzzWords);
+      if (!xyzz_is_zero<K>(t)) {  // uniform inside the group
+        for (uint32_t d = 0; d < stride; ++d) Coop4<K>::dbl_nz(t, lane, mask);
+        xyzz_load<K>(a, terms + (size_t)left * kXyzzWords);
+        Coop4<K>::add(a, t, lane, mask);
+        if (lane == 0) xyzz_store<K>(terms + (size_t)left * kXyzzWords, a);
+      }
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x < 4) {
+    XYZZ<K> a;
+    if (count) {
+      xyzz_load<K>(a, terms);
+    } else {
+      xyzz_set_zero<K>(a);
+    }
+    if (add_in) {
+      XYZZ<K> b;
+      xyzz_load<K>(b, add_in);
+      Coop4<K>::add(a, b, lane, mask);
+    }
+    if (lane == 0) xyzz_store<K>(out, a);
+  }
 }
 
 // ---------------------------------------------------------------------------

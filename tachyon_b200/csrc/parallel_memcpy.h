@@ -5,6 +5,7 @@
 // speed instead of the ~11 GB/s of a pageable cudaMemcpyAsync.
 #pragma once
 #include <condition_variable>
+#include <cstdint>
 #include <cstring>
 #include <mutex>
 #include <thread>

@@ -184,4 +184,114 @@ TB_DEV void xyzz_add(XYZZ<K>& acc, const XYZZ<K>& b) {
   }
 }
 
+// ---------------------------------------------------------------------------
+// Four-lane cooperative point operations for the LATENCY-bound parts of an MSM (merge tree of
+// the bucket reduction, window combination): one lane per independent field multiplication of
+// a formula level, results exchanged with warp shuffles.  A lane running a point doubling alone
+// executes its 9 multiplications back to back (~4 us for 254-bit limbs: every IMAD.WIDE waits
+// for the carry of the previous one); four lanes do the same doubling in 3 multiplication
+// levels, an addition in 4 instead of 14 — the same number of multiply instructions per point
+// operation, spread over lanes that would otherwise idle.
+//
+// All four lanes of a group hold the same operands and end with the same result.  `lane` is
+// the lane's index inside its group (0..3), `mask` the group's four lanes; branches are
+// uniform inside a group, so groups of one warp may diverge from each other.
+// ---------------------------------------------------------------------------
+template <class K>
+struct Coop4 {
+  using El = typename K::El;
+
+  static TB_DEV void pick(El& r, uint32_t lane, const El& a0, const El& a1, const El& a2,
+                          const El& a3) {
+    El lo, hi;
+    K::select(lo, (lane & 1) == 0, a0, a1);
+    K::select(hi, (lane & 1) == 0, a2, a3);
+    K::select(r, lane < 2, lo, hi);
+  }
+
+  // p = 2 p, p != identity  (dbl-2008-s-1, a = 0: the levels of xyzz_dbl_nz)
+  static TB_DEV void dbl_nz(XYZZ<K>& p, uint32_t lane, uint32_t mask) {
+    El u, a, b, r, v, xx, m, t, w, s, mm;
+    K::dbl(u, p.y);
+    // level 1: V = U^2 | XX = X^2
+    K::select(a, (lane & 1) == 0, u, p.x);
+    K::sqr(r, a);
+    K::shfl(v, r, mask, 0, 4);
+    K::shfl(xx, r, mask, 1, 4);
+    K::dbl(t, xx);
+    K::add(m, xx, t);  // M = 3 X^2
+    // level 2: W = U V | S = X V | ZZ3 = V ZZ | MM = M M
+    pick(a, lane, u, p.x, v, m);
+    pick(b, lane, v, v, p.zz, m);
+    K::mul(r, a, b);
+    K::shfl(w, r, mask, 0, 4);
+    K::shfl(s, r, mask, 1, 4);
+    K::shfl(p.zz, r, mask, 2, 4);
+    K::shfl(mm, r, mask, 3, 4);
+    K::dbl(t, s);
+    K::sub(mm, mm, t);  // X3 = M^2 - 2 S
+    K::sub(t, s, mm);   // S - X3
+    // level 3: ZZZ3 = W ZZZ | WY = W Y | MT = M (S - X3)
+    pick(a, lane, w, w, m, m);
+    pick(b, lane, p.zzz, p.y, t, t);
+    K::mul(r, a, b);
+    K::shfl(p.zzz, r, mask, 0, 4);
+    K::shfl(a, r, mask, 1, 4);
+    K::shfl(b, r, mask, 2, 4);
+    p.x = mm;
+    K::sub(p.y, b, a);  // Y3 = M (S - X3) - W Y1
+  }
+
+  // acc += b with the reference's case analysis (point_xyzz_impl.h:14-97, add-2008-s)
+  static TB_DEV void add(XYZZ<K>& acc, const XYZZ<K>& b, uint32_t lane, uint32_t mask) {
+    const bool az = xyzz_is_zero<K>(acc), bz = xyzz_is_zero<K>(b);
+    if (az || bz) {  // uniform inside the group
+      if (az) acc = b;
+      return;
+    }
+    El x, y, r, u1, s1, u2, s2, p, rr, pp, zz12, zzz12, ppp, q, t;
+    // level 1: U1 = X1 ZZ2 | S1 = Y1 ZZZ2 | U2 = X2 ZZ1 | S2 = Y2 ZZZ1
+    pick(x, lane, acc.x, acc.y, b.x, b.y);
+    pick(y, lane, b.zz, b.zzz, acc.zz, acc.zzz);
+    K::mul(r, x, y);
+    K::shfl(u1, r, mask, 0, 4);
+    K::shfl(s1, r, mask, 1, 4);
+    K::shfl(u2, r, mask, 2, 4);
+    K::shfl(s2, r, mask, 3, 4);
+    K::sub(p, u2, u1);
+    K::sub(rr, s2, s1);
+    if (K::is_zero(p) && K::is_zero(rr)) {  // equal points: double
+      dbl_nz(acc, lane, mask);
+      return;
+    }
+    // level 2: PP = P^2 | RR = R^2 | ZZ12 = ZZ1 ZZ2 | ZZZ12 = ZZZ1 ZZZ2
+    pick(x, lane, p, rr, acc.zz, acc.zzz);
+    pick(y, lane, p, rr, b.zz, b.zzz);
+    K::mul(r, x, y);
+    K::shfl(pp, r, mask, 0, 4);
+    K::shfl(t, r, mask, 1, 4);  // R^2
+    K::shfl(zz12, r, mask, 2, 4);
+    K::shfl(zzz12, r, mask, 3, 4);
+    // level 3: PPP = P PP | Q = U1 PP | ZZ3 = ZZ12 PP
+    pick(x, lane, p, u1, zz12, zz12);
+    K::mul(r, x, pp);
+    K::shfl(ppp, r, mask, 0, 4);
+    K::shfl(q, r, mask, 1, 4);
+    K::shfl(acc.zz, r, mask, 2, 4);
+    K::sub(t, t, ppp);  // X3 = R^2 - PPP - 2 Q
+    K::dbl(x, q);
+    K::sub(t, t, x);
+    K::sub(q, q, t);    // Q - X3
+    // level 4: ZZZ3 = ZZZ12 PPP | S1 PPP | R (Q - X3)
+    pick(x, lane, zzz12, s1, rr, rr);
+    pick(y, lane, ppp, ppp, q, q);
+    K::mul(r, x, y);
+    K::shfl(acc.zzz, r, mask, 0, 4);
+    K::shfl(x, r, mask, 1, 4);
+    K::shfl(y, r, mask, 2, 4);
+    acc.x = t;
+    K::sub(acc.y, y, x);  // Y3 = R (Q - X3) - S1 PPP
+  }
+};
+
 }  // namespace tb200

@@ -62,6 +62,14 @@ class MSMGpu:
     def set_stream(self, cuda_stream):
         _lib.check(self._f("g1_msm_gpu_set_stream_b200")(self.ptr, ctypes.c_void_p(cuda_stream)), "set_stream")
 
+    def join_ranks(self, unique_id, rank, world):
+        """Point-range sharding over `world` processes (one GPU each): afterwards every MSM call
+        returns the sum over all ranks (one ncclAllGather of the partials on the context's
+        stream).  unique_id: the 128 bytes of nccl_unique_id(), the same on every rank."""
+        buf = (ctypes.c_char * 128).from_buffer_copy(bytes(unique_id))
+        _lib.check(self._f("g1_msm_gpu_join_ranks_b200")(self.ptr, ctypes.cast(buf, ctypes.c_void_p), rank, world),
+                   "join_ranks")
+
     def _jacobian(self, fn, bases, scalars, size):
         """Calls the reference-shaped entry point; returns (3, fq_limbs) and frees the result."""
         p = self._f(fn)(self.ptr, _ptr(bases), _ptr(scalars), size)
@@ -175,6 +183,13 @@ def imad_peak(device=0, variant=0, repeats=5):
     if v < 0:
         raise RuntimeError("imad_peak failed: " + _lib.last_error())
     return v
+
+
+def nccl_unique_id():
+    """128-byte ncclUniqueId (call on rank 0, broadcast to the others)."""
+    buf = (ctypes.c_char * 128)()
+    _lib.check(_lib.load().tachyon_b200_nccl_unique_id(ctypes.cast(buf, ctypes.c_void_p)), "nccl_unique_id")
+    return bytes(buf)
 
 
 def kernel_launch_count():

@@ -361,6 +361,59 @@ def test_msm_reduce_modes(oracles, torch_cuda, name):
             assert (got == want).all(), host_ranges
 
 
+# Window groups: the windows of the last point range are accumulated as two groups (high first)
+# so that the high group's bucket reduction, merge tree and window combination — the device-side
+# Horner of pippenger_base.h:59-77 — run on a second stream behind the low group's accumulation.
+# Every split, window size, range count and scalar distribution must give the same point; skewed
+# scalars exercise the per-group filter of the bucket-fold kernels.
+@pytest.mark.parametrize("name", ALL)
+def test_msm_window_groups(oracles, torch_cuda, name):
+    o = oracles[name]
+    n = 5000 if name in CURVES else 2000
+    bases = o.generate_points(141, n)
+    cases = {"uniform": o.generate_scalars(142, n), "witness": o.generate_scalars(143, n, "witness"),
+             "non_uniform": o.generate_scalars(144, n, "non_uniform")}
+    want = {k: o.msm_affine(bases, v) for k, v in cases.items()}
+    with msm.MSMGpu(name) as ctx:
+        for cbits in (0, 5, 9, 13):
+            ctx.set_option("window_bits", cbits)
+            for low in (-1, 0, 1, 2, 5, 200):          # 200: clamped to W - 1
+                ctx.set_option("low_windows", low)
+                for ranges in (1, 3):
+                    ctx.set_option("ranges", ranges)
+                    for dist, sc in cases.items():
+                        if dist != "uniform" and (ranges == 3 or cbits == 13):
+                            continue
+                        got = o.jacobian_to_affine(ctx.affine_msm(bases, sc))
+                        assert (got == want[dist]).all(), (cbits, low, ranges, dist)
+                        t = ctx.last_timing()
+                        if low in (0, 1, 2, 5):
+                            assert t["low_windows"] == low
+        ctx.set_option("low_windows", 2)
+        ctx.set_option("window_bits", 6)
+        ctx.set_option("ranges", 1)
+        ctx.set_option("segment", 16)                  # every bucket split: fold jobs in both groups
+        got = o.jacobian_to_affine(ctx.affine_msm(bases, cases["witness"]))
+        assert (got == want["witness"]).all()
+
+
+# The H2D staging ring is grow-only; its slot stride must follow THIS call's range size, not the
+# size the buffer happens to have (a stride a few bytes short of a range let the copy stream
+# overwrite the tail of a range the kernels had not consumed yet).  Calls of different sizes and
+# range counts on one context, sizes chosen around the 1/3 marks of the reserved buffer.
+@pytest.mark.parametrize("name", CURVES)
+def test_msm_staging_ring_reuse(oracles, torch_cuda, name):
+    o = oracles[name]
+    nmax = 33000
+    bases, scalars = o.generate_points(151, nmax), o.generate_scalars(152, nmax)
+    with msm.MSMGpu(name) as ctx:
+        for n, ranges in ((9000, 1), (32763, 3), (32764, 3), (10921, 1), (10922, 1), (32765, 3),
+                          (32767, 3), (21845, 2), (33000, 3), (10923, 4)):
+            ctx.set_option("ranges", ranges)
+            got = o.jacobian_to_affine(ctx.affine_msm(bases[:n], scalars[:n]))
+            assert (got == o.msm_affine(bases[:n], scalars[:n])).all(), (n, ranges)
+
+
 # bases registered once (the SRS of kzg.h:91-113), then a batch of
 # commitments with fresh scalars (kzg.h:217-313), results batch-normalised (point_xyzz.h:109-163).
 @pytest.mark.parametrize("name", CURVES)

@@ -34,6 +34,6 @@ for lg in logs:
         ctx.msm_xyzz(bases.data_ptr(), scalars.data_ptr(), n)
         wall = (time.time() - t0) * 1e3
         t = ctx.last_timing()
-    print("2^%d wall %.3f ms | total %.3f sort %.3f acc %.3f reduce %.3f host %.3f enq %.3f wait %.3f | c=%d W=%d R=%d tasks=%d entries=%d launches=%d"
+    print("2^%d wall %.3f ms | total %.3f sort %.3f acc %.3f reduce %.3f host %.3f enq %.3f wait %.3f | c=%d W=%d R=%d tasks=%d entries=%d launches=%d low=%d acck=%.3f comb=%.3f"
           % (lg, wall, t["total_ms"], t["sort_ms"], t["accumulate_ms"], t["reduce_ms"], t["host_ms"], t["enqueue_ms"], t["wait_ms"],
-             t["window_bits"], t["windows"], t["pair_rounds"], t["tasks"], t["entries"], t["kernel_launches"]))
+             t["window_bits"], t["windows"], t["pair_rounds"], t["tasks"], t["entries"], t["kernel_launches"], t["low_windows"], t["acc_kernel_ms"], t["combine_ms"]))
