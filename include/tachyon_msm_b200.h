@@ -217,7 +217,6 @@ TACHYON_B200_DECLARE_GROUP(bls12_381, g2, tachyon_bls12_381_fq2)
    arithmetic.  Query arrays may be host or device memory.  Sizes: a, b1, b2 queries have
    full_size + 1 points (element 0 is added as is, prove.h:46), the l query witness_size, the h
    query at least h_size - 1 (prove.h:100-112).  r == 0 selects the non-ZK branch (prove.h:135).
-   Circuit synthesis, the QAP witness map and zkey / wtns parsing stay with the caller.
    0 or a negative error code. */
 #define TACHYON_B200_DECLARE_GROTH16(C)                                                       \
   struct tachyon_##C##_groth16_proving_key_b200 {                                             \
@@ -240,7 +239,25 @@ TACHYON_B200_DECLARE_GROUP(bls12_381, g2, tachyon_bls12_381_fq2)
       const struct tachyon_##C##_fr* s, const struct tachyon_##C##_fr* h_coefficients,        \
       size_t h_size, const struct tachyon_##C##_fr* witness_assignments, size_t witness_size, \
       const struct tachyon_##C##_fr* full_assignments, size_t full_size,                      \
-      struct tachyon_##C##_groth16_proof_b200* out);
+      struct tachyon_##C##_groth16_proof_b200* out);                                          \
+  /* The whole prover entry of vendors/circom/prover_main.cc:81-186 (CreateProof): parse a      \
+     snarkjs .zkey (circomlib/zkey/zkey.h:88-317, v1; the query sections are used zero-copy   \
+     out of the memory-mapped file as MSM bases, zkey.h:176-183) and a .wtns witness          \
+     (circomlib/wtns/wtns.h:66-154, v2), run the QAP witness map on the host                  \
+     (circomlib/circuit/quadratic_arithmetic_program.h:25-118), the five MSMs on the two      \
+     contexts, and write — when the paths are not NULL — snarkjs's proof.json and public.json \
+     (circomlib/json/groth16_proof.h, points.h, prime_field.h).  r, s: the blinding scalars   \
+     in Montgomery form; NULL = 0, the --no_zk mode (prove.h:177-187).  0 or negative. */      \
+  TACHYON_C_EXPORT int tachyon_##C##_groth16_prove_from_files_b200(                           \
+      tachyon_##C##_g1_msm_gpu_ptr g1, tachyon_##C##_g2_msm_gpu_ptr g2, const char* zkey_path,  \
+      const char* wtns_path, const struct tachyon_##C##_fr* r, const struct tachyon_##C##_fr* s, \
+      struct tachyon_##C##_groth16_proof_b200* out, const char* proof_json_path,              \
+      const char* public_json_path);                                                          \
+  /* Host-only half of the above (no GPU): the files' domain size and public-input count, and \
+     — when h_out is not NULL — the h scalars of the witness map in Montgomery form. */       \
+  TACHYON_C_EXPORT int tachyon_##C##_groth16_witness_map_from_files_b200(                     \
+      const char* zkey_path, const char* wtns_path, struct tachyon_##C##_fr* h_out,           \
+      size_t capacity, size_t* domain_size, size_t* num_public);
 
 TACHYON_B200_DECLARE_GROTH16(bn254)
 TACHYON_B200_DECLARE_GROTH16(bls12_381)

@@ -56,7 +56,8 @@ GROUP_SYMBOLS = [
     "tachyon_{c}_{g}_msm_gpu_join_ranks_b200",
 ]
 FIELD_SYMBOLS = ["tachyon_{c}_fq_op_b200", "tachyon_{c}_fr_op_b200", "tachyon_{c}_fq2_op_b200"]
-CURVE_SYMBOLS = ["tachyon_{c}_groth16_prove_b200"]
+CURVE_SYMBOLS = ["tachyon_{c}_groth16_prove_b200", "tachyon_{c}_groth16_prove_from_files_b200",
+                 "tachyon_{c}_groth16_witness_map_from_files_b200"]
 GLOBAL_SYMBOLS = ["tachyon_b200_device_count", "tachyon_b200_last_error", "tachyon_b200_imad_peak",
                   "tachyon_b200_kernel_launch_count", "tachyon_b200_window_bits",
                   "tachyon_b200_window_count", "tachyon_b200_nccl_unique_id"]
@@ -85,6 +86,10 @@ def load():
         for n in FIELD_SYMBOLS:
             getattr(lib, n.format(c=c)).argtypes = [i32, vp, vp, vp, sz]
         getattr(lib, f"tachyon_{c}_groth16_prove_b200").argtypes = [vp, vp, vp, vp, vp, vp, sz, vp, sz, vp, sz, vp]
+        getattr(lib, f"tachyon_{c}_groth16_prove_from_files_b200").argtypes = [
+            vp, vp, ctypes.c_char_p, ctypes.c_char_p, vp, vp, vp, ctypes.c_char_p, ctypes.c_char_p]
+        getattr(lib, f"tachyon_{c}_groth16_witness_map_from_files_b200").argtypes = [
+            ctypes.c_char_p, ctypes.c_char_p, vp, sz, ctypes.POINTER(sz), ctypes.POINTER(sz)]
     for c, g in [(c, g) for c in CURVES for g in GROUPS]:
         f = lambda name: getattr(lib, name.format(c=c).replace("_g1_", "_%s_" % g))
         f("tachyon_{c}_g1_init").restype = None

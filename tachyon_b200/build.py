@@ -20,13 +20,16 @@ OBJ_DIR = os.path.join(HERE, "build")
 REPLAY = os.path.join(LIB_DIR, "msm_gpu_replay")
 REPLAY_SRC = os.path.join(CSRC, "tools", "msm_gpu_replay.cc")
 HEADERS = ["fp.cuh", "xyzz.cuh", "msm_kernels.cuh", "msm_sort.cuh", "msm_engine.cuh", "msm_api_common.cuh", "host_math.h",
-           "parallel_memcpy.h",
+           "parallel_memcpy.h", "nccl_dl.h",
            "field_constants.h", os.path.join("..", "..", "include", "tachyon_msm_b200.h")]
 
 NVCC_FLAGS = [
     "-O3", "-std=c++17",
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-lineinfo",
+    # kernels of one translation unit are optimised by parallel ptxas jobs (the 24-limb G2
+    # instantiations dominate the build otherwise)
+    "--split-compile", "0",
     "-Xcompiler", "-fPIC,-fvisibility=hidden,-march=x86-64-v3,-mtune=generic",
 ]
 LINK_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-cudart", "static", "-shared",

@@ -17,6 +17,7 @@
 #include <thread>
 
 #include "../../include/tachyon_msm_b200.h"
+#include "groth16_files.h"
 #include "host_math.h"
 
 namespace tb200 {
@@ -153,14 +154,85 @@ struct Groth16 {
   }
 };
 
+// Proof from a .zkey and a .wtns file (vendors/circom/prover_main.cc:81-186 CreateProof): parse
+// both, run the QAP witness map on the host, hand the five MSMs to the contexts (query sections
+// zero-copy out of the mapped file), write the snarkjs JSON files when asked to.
+template <class T>
+static int ProveFromFiles(typename T::G1Ctx g1, typename T::G2Ctx g2, const char* zkey_path,
+                          const char* wtns_path, const void* r_mont, const void* s_mont,
+                          typename Groth16<T>::Proof* out, const char* proof_json,
+                          const char* public_json) {
+  using G = Groth16<T>;
+  using FrEl = typename G::FrEl;
+  try {
+    MappedFile zfile(zkey_path), wfile(wtns_path);
+    Zkey<typename T::Fq, typename T::Fr> zk(zfile);
+    std::vector<FrEl> full = ReadWitness<typename T::Fr>(wfile);
+    if (full.size() != zk.num_vars) throw FileError{"wtns: witness count differs from the zkey's variable count"};
+    std::vector<FrEl> h = WitnessMap(zk, full, T::kFrGenerator);
+    typename G::Key pk;
+    memcpy(&pk.alpha_g1, zk.alpha_g1, sizeof(pk.alpha_g1));
+    memcpy(&pk.beta_g1, zk.beta_g1, sizeof(pk.beta_g1));
+    memcpy(&pk.delta_g1, zk.delta_g1, sizeof(pk.delta_g1));
+    memcpy(&pk.beta_g2, zk.beta_g2, sizeof(pk.beta_g2));
+    memcpy(&pk.delta_g2, zk.delta_g2, sizeof(pk.delta_g2));
+    pk.a_g1_query = zk.a_g1;
+    pk.a_g1_size = zk.num_vars;
+    pk.b_g1_query = zk.b_g1;
+    pk.b_g1_size = zk.num_vars;
+    pk.b_g2_query = zk.b_g2;
+    pk.b_g2_size = zk.num_vars;
+    pk.h_g1_query = zk.h_g1;
+    pk.h_g1_size = zk.domain_size;
+    pk.l_g1_query = zk.c_g1;
+    pk.l_g1_size = zk.num_vars - zk.num_public - 1;
+    FrEl zero = FrEl::Zero();
+    const size_t n_inst = (size_t)zk.num_public + 1;  // instance variables incl. the constant 1
+    // prover_main.cc:150-165: instance = full[1, n_inst), witness = full[n_inst, ..), full[1, ..)
+    int rc = G::Prove(g1, g2, pk, r_mont ? r_mont : &zero, s_mont ? s_mont : &zero, h.data(), h.size(),
+                      full.data() + n_inst, full.size() - n_inst, full.data() + 1, full.size() - 1, out);
+    if (rc) return rc;
+    if (proof_json) WriteTextFile(proof_json, ProofJson<typename T::Fq>(out->a, out->b, out->c, T::kSnarkjsName));
+    if (public_json) WriteTextFile(public_json, PublicJson<typename T::Fr>(full.data() + 1, n_inst - 1));
+    return 0;
+  } catch (const FileError& e) {
+    g_last_error = e.what;
+    return -1;
+  }
+}
+
+// Host-only half of the above, for parity tests without a GPU: the h scalars (Montgomery form).
+template <class T>
+static int WitnessMapFromFiles(const char* zkey_path, const char* wtns_path, void* h_out,
+                               size_t capacity, size_t* domain_size, size_t* num_public) {
+  try {
+    MappedFile zfile(zkey_path), wfile(wtns_path);
+    Zkey<typename T::Fq, typename T::Fr> zk(zfile);
+    auto full = ReadWitness<typename T::Fr>(wfile);
+    if (full.size() != zk.num_vars) throw FileError{"wtns: witness count differs from the zkey's variable count"};
+    if (domain_size) *domain_size = zk.domain_size;
+    if (num_public) *num_public = zk.num_public;
+    if (!h_out) return 0;
+    if (capacity < zk.domain_size) throw FileError{"h buffer too small"};
+    auto h = WitnessMap(zk, full, T::kFrGenerator);
+    memcpy(h_out, h.data(), h.size() * sizeof(h[0]));
+    return 0;
+  } catch (const FileError& e) {
+    g_last_error = e.what;
+    return -1;
+  }
+}
+
 }  // namespace tb200
 
 using namespace tb200;
 
-#define TB200_DEFINE_GROTH16(CN, FQ, FR)                                                        \
+#define TB200_DEFINE_GROTH16(CN, FQ, FR, FR_GENERATOR, SNARKJS_NAME)                            \
   struct Groth16Traits_##CN {                                                                    \
     using Fq = FQ;                                                                               \
     using Fr = FR;                                                                               \
+    static constexpr uint32_t kFrGenerator = FR_GENERATOR; /* multiplicative generator of Fr */  \
+    static constexpr const char* kSnarkjsName = SNARKJS_NAME; /* groth16_proof.h:32-39 */        \
     using G1Ctx = tachyon_##CN##_g1_msm_gpu_ptr;                                                 \
     using G2Ctx = tachyon_##CN##_g2_msm_gpu_ptr;                                                 \
     static int G1Batch(G1Ctx c, const void* const* bases, const void* const* scalars,            \
@@ -191,7 +263,25 @@ using namespace tb200;
     return G::Prove(g1, g2, *reinterpret_cast<const G::Key*>(pk), r, s, h_coefficients, h_size,  \
                     witness_assignments, witness_size, full_assignments, full_size,              \
                     reinterpret_cast<G::Proof*>(out));                                           \
+  }                                                                                              \
+  extern "C" int tachyon_##CN##_groth16_prove_from_files_b200(                                   \
+      tachyon_##CN##_g1_msm_gpu_ptr g1, tachyon_##CN##_g2_msm_gpu_ptr g2, const char* zkey_path, \
+      const char* wtns_path, const tachyon_##CN##_fr* r, const tachyon_##CN##_fr* s,             \
+      tachyon_##CN##_groth16_proof_b200* out, const char* proof_json_path,                       \
+      const char* public_json_path) {                                                            \
+    if (!g1 || !g2 || !zkey_path || !wtns_path || !out) return -1;                               \
+    using G = Groth16<Groth16Traits_##CN>;                                                       \
+    return ProveFromFiles<Groth16Traits_##CN>(g1, g2, zkey_path, wtns_path, r, s,                \
+                                              reinterpret_cast<G::Proof*>(out), proof_json_path, \
+                                              public_json_path);                                 \
+  }                                                                                              \
+  extern "C" int tachyon_##CN##_groth16_witness_map_from_files_b200(                             \
+      const char* zkey_path, const char* wtns_path, tachyon_##CN##_fr* h_out, size_t capacity,   \
+      size_t* domain_size, size_t* num_public) {                                                 \
+    if (!zkey_path || !wtns_path) return -1;                                                     \
+    return WitnessMapFromFiles<Groth16Traits_##CN>(zkey_path, wtns_path, h_out, capacity,        \
+                                                   domain_size, num_public);                     \
   }
 
-TB200_DEFINE_GROTH16(bn254, Bn254FqParams, Bn254FrParams)
-TB200_DEFINE_GROTH16(bls12_381, Bls381FqParams, Bls381FrParams)
+TB200_DEFINE_GROTH16(bn254, Bn254FqParams, Bn254FrParams, 5, "bn128")
+TB200_DEFINE_GROTH16(bls12_381, Bls381FqParams, Bls381FrParams, 7, "bls12381")

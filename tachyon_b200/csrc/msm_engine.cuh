@@ -428,11 +428,18 @@ class MsmEngine {
   }
 
  private:
+  // reduction-tree buffers of a window group: leaves (A_t, P_t), two scratch regions, two
+  // stage outputs, all cut into per-window slices of 2 * (blocks per window) points
+  struct TreeBuffers {
+    DeviceBuffer leaves, ping, pong, out[2];
+  };
+
   // One enqueued MSM: everything the host epilogue needs once the device is done.
   struct Pending {
     MsmPlan plan{};
     uint32_t L0 = 0, M = 0;
-    uint32_t low = 0;  // windows of the low group
+    uint32_t low = 0;     // windows of the low group
+    uint32_t L0_low = 0;  // its running-sum block length
     bool gathered = false;  // the result is the all-gathered set of rank partials
     size_t K = 0;
     bool any_host = false;
@@ -686,9 +693,10 @@ class MsmEngine {
   }
   // event sets: per Pending slot, 0 begin, 1 end of accumulation, 2 end, 3 copy begin, 4 high
   // window group accumulated, 5 high group combined (tail stream), 6 / 7 around the high group's
-  // window_combine_kernel, then per range r: 8 + 5r copied, +1 sort start, +2 sort end,
-  // +3 accumulated, +4 after the range's first accumulate launch
-  static constexpr size_t kSlotEvents = 8, kRangeEvents = 5;
+  // window_combine_kernel, 8 low group's tree done, 9 high group's sum available to the compute
+  // stream, 10 tail stream: high group's running-sum level done, then per range r: 12 + 5r copied,
+  // +1 sort start, +2 sort end, +3 accumulated, +4 after the range's first accumulate launch
+  static constexpr size_t kSlotEvents = 12, kRangeEvents = 5;
   static constexpr size_t kEventsPerSlot = kSlotEvents + kRangeEvents * kMaxRanges;
   cudaEvent_t SlotEvent(int slot, size_t i) { return Event((size_t)slot * kEventsPerSlot + i); }
   cudaEvent_t StageFreeEvent(size_t stage) { return Event(2 * kEventsPerSlot + stage); }
@@ -839,6 +847,10 @@ class MsmEngine {
     // that no later call has to grow the workspace (a growth drains both streams).
     if (reserve_only)
       for (uint32_t cc = kMinWindowBits; cc < c; ++cc) reduction_bytes(cc);
+    // the low window group has its own, shorter running-sum blocks (its reduction is what
+    // remains exposed at the end of the MSM: latency, not throughput, counts) and its own buffers
+    pd.L0_low = LowLevelLength(big, pd.low);
+    const size_t tree_lo_b = (size_t)pd.low * (big.B / pd.L0_low) * 2 * kXyzzBytes;
     ReserveAll({{&state_, (size_t)big.TB * kXyzzBytes},
                 {&count_, (size_t)(big.TB + 1) * 4},
                 {&offset_, (size_t)(big.TB + 1) * 4},
@@ -864,11 +876,16 @@ class MsmEngine {
                 {&digits_, (size_t)m * big.W * 4},
                 {&block_sums_, (size_t)scan_blocks * 8},
                 {&len_hist_, (size_t)kOrderBins * 4},
-                {&leaves_, tree_b},
-                {&tree_[0], tree_b},
-                {&tree_[1], tree_b},
-                {&stage_out_[0], tree_b},
-                {&stage_out_[1], tree_b},
+                {&tree_hi_.leaves, tree_b},
+                {&tree_hi_.ping, tree_b},
+                {&tree_hi_.pong, tree_b},
+                {&tree_hi_.out[0], tree_b},
+                {&tree_hi_.out[1], tree_b},
+                {&tree_lo_.leaves, tree_lo_b},
+                {&tree_lo_.ping, tree_lo_b},
+                {&tree_lo_.pong, tree_lo_b},
+                {&tree_lo_.out[0], tree_lo_b},
+                {&tree_lo_.out[1], tree_lo_b},
                 {&combine_, (size_t)(2 * kTermSlots + 2) * kXyzzBytes},
                 {&bases_stage_, bases_dev ? 0 : bases_slot_want * kStageSlots},
                 {&scalars_stage_, scalars_dev ? 0 : scalars_slot_want * kStageSlots}});
@@ -1057,9 +1074,13 @@ class MsmEngine {
         TB_CUDA(cudaEventRecord(ev(r, 4), stream_));
         fold(kPartHigh);
         TB_CUDA(cudaEventRecord(SlotEvent(slot, 4), stream_));
-        TB_CUDA(cudaStreamWaitEvent(tail_stream_, SlotEvent(slot, 4), 0));
+        // the running-sum level of the high windows is throughput-bound like the accumulation:
+        // it stays on this stream, ahead of the low windows (on a second stream it shares the
+        // SMs with them and ends as late as they do: 2^21 points 1.02 ms instead of 0.48); only
+        // the latency-bound merge tree and doubling chain move to the tail stream
         uint32_t* terms_hi = combine_.as<uint32_t>();
-        EnqueueReduction(tail_stream_, big, pd.low, big.W - pd.low, pd.L0, terms_hi);
+        EnqueueReduction(tail_stream_, big, pd.low, big.W - pd.low, pd.L0, tree_hi_, terms_hi, stream_,
+                         SlotEvent(slot, 10));
         TB_CUDA(cudaEventRecord(SlotEvent(slot, 6), tail_stream_));
         LaunchOn(tail_stream_, window_combine_kernel<C>, 1, kCombineThreads, terms_hi,
                  TotalBits(big), WindowBitOffset(big, pd.low), (const uint32_t*)nullptr, HiSum());
@@ -1088,13 +1109,15 @@ class MsmEngine {
     // finishes the low windows and adds the high group's sum.  The result is ONE XYZZ point.
     if (pd.low > 0) {
       uint32_t* terms_lo = combine_.as<uint32_t>() + (size_t)kTermSlots * kXyzzWords;
-      EnqueueReduction(stream_, big, 0, pd.low, pd.L0, terms_lo);
+      EnqueueReduction(stream_, big, 0, pd.low, pd.L0_low, tree_lo_, terms_lo);
+      TB_CUDA(cudaEventRecord(SlotEvent(slot, 8), stream_));
       TB_CUDA(cudaStreamWaitEvent(stream_, SlotEvent(slot, 5), 0));
+      TB_CUDA(cudaEventRecord(SlotEvent(slot, 9), stream_));
       Launch(window_combine_kernel<C>, 1, kCombineThreads, terms_lo, WindowBitOffset(big, pd.low), 0u,
              (const uint32_t*)HiSum(), Partial());
     } else {
       uint32_t* terms = combine_.as<uint32_t>();
-      EnqueueReduction(stream_, big, 0, big.W, pd.L0, terms);
+      EnqueueReduction(stream_, big, 0, big.W, pd.L0, tree_hi_, terms);
       TB_CUDA(cudaEventRecord(SlotEvent(slot, 6), stream_));
       Launch(window_combine_kernel<C>, 1, kCombineThreads, terms, TotalBits(big), 0u,
              (const uint32_t*)nullptr, Partial());
@@ -1157,6 +1180,24 @@ class MsmEngine {
     TB_CUDA(cudaEventElapsedTime(&ms, SlotEvent(slot, 6), SlotEvent(slot, 7)));
     timing_.combine_ms += ms;
     timing_.low_windows = pd.low;
+    if (pd.low > 0) {
+      static const bool trace = getenv("TACHYON_B200_TRACE") != nullptr;
+      if (trace) {
+        float hi_level, hi_total, lo_tree, lo_wait, lo_rest;
+        TB_CUDA(cudaEventElapsedTime(&hi_level, SlotEvent(slot, 4), SlotEvent(slot, 10)));
+        TB_CUDA(cudaEventElapsedTime(&hi_total, SlotEvent(slot, 4), SlotEvent(slot, 5)));
+        TB_CUDA(cudaEventElapsedTime(&lo_tree, SlotEvent(slot, 1), SlotEvent(slot, 8)));
+        TB_CUDA(cudaEventElapsedTime(&lo_wait, SlotEvent(slot, 8), SlotEvent(slot, 9)));
+        TB_CUDA(cudaEventElapsedTime(&lo_rest, SlotEvent(slot, 9), SlotEvent(slot, 2)));
+        float acc_lo;
+        TB_CUDA(cudaEventElapsedTime(&acc_lo, SlotEvent(slot, 4), SlotEvent(slot, 1)));
+        fprintf(stderr,
+                "[tachyon_b200] window groups: low=%u | after the high group's accumulation: high level "
+                "%.3f, high level+tree+combine %.3f, low accumulate %.3f | after the low group's: level+tree "
+                "%.3f, wait for high %.3f, combine+copy %.3f ms\n",
+                pd.low, hi_level, hi_total, acc_lo, lo_tree, lo_wait, lo_rest);
+      }
+    }
     if (pd.any_host) {
       // time the copy engine was busy or waiting for a free slot; overlaps the bucket work
       TB_CUDA(cudaEventElapsedTime(&ms, SlotEvent(slot, 3), ev(pd.K - 1, 0)));
@@ -1218,40 +1259,67 @@ class MsmEngine {
   // Bucket reduction of windows [w0, w0 + wn) on stream `st`: one blocked running-sum level,
   // then the merge tree in stages of <= kTreeStageLevels levels per launch; the last stage
   // scatters every window's (A, P, D_j) to the bit positions of `terms`.
+  // `level_stream` runs the (throughput-bound) running-sum level, `st` the (latency-bound) tree;
+  // when they differ, `after_level` orders the two.
   void EnqueueReduction(cudaStream_t st, const MsmPlan& plan, uint32_t w0, uint32_t wn, uint32_t L0,
-                        uint32_t* terms) {
+                        TreeBuffers& set, uint32_t* terms, cudaStream_t level_stream = nullptr,
+                        cudaEvent_t after_level = nullptr) {
+    if (!level_stream) level_stream = st;
     const uint32_t nb = plan.B / L0, M = Log2(nb), l0 = Log2(L0);
     const size_t slice_words = (size_t)nb * 2 * kXyzzWords;
-    uint32_t* leaves = leaves_.as<uint32_t>() + (size_t)w0 * slice_words;
+    uint32_t* leaves = set.leaves.template as<uint32_t>() + (size_t)w0 * slice_words;
     const uint32_t* bucket0 = state_.as<uint32_t>() + (size_t)w0 * plan.B * kXyzzWords;
     const uint32_t wide_local = plan.wide > w0 ? plan.wide - w0 : 0u;
     const uint32_t blocks = wn * nb;
     if (options_.reduce_mode == 0) {
-      LaunchOn(st, reduce_level_kernel<C, true>, (blocks + kReduceThreads - 1) / kReduceThreads,
+      LaunchOn(level_stream, reduce_level_kernel<C, true>, (blocks + kReduceThreads - 1) / kReduceThreads,
                kReduceThreads, bucket0, (const uint32_t*)nullptr, plan.B, nb, L0, 0u, wn, leaves,
                leaves + kXyzzWords);
     } else {
       constexpr uint32_t kSlots = ReduceSlots<C>();
-      LaunchOn(st, reduce_blocks_kernel<C>, (blocks + kSlots - 1) / kSlots, 2 * kSlots, bucket0,
+      LaunchOn(level_stream, reduce_blocks_kernel<C>, (blocks + kSlots - 1) / kSlots, 2 * kSlots, bucket0,
                plan.B, nb, L0, wn, wide_local, leaves, leaves + kXyzzWords);
     }
+    if (after_level) {
+      TB_CUDA(cudaEventRecord(after_level, level_stream));
+      if (level_stream != st) TB_CUDA(cudaStreamWaitEvent(st, after_level, 0));
+    }
+    // Stages of the merge tree.  The LAST stage is one CTA per window, so it is kept to
+    // kTreeLastLevels levels (its first level has 2^(levels-1) x (values per node) additions for
+    // 64 lane groups); the levels below it are cut into equal stages of <= kTreeStageLevels.
+    const uint32_t last_levels = M < kTreeLastLevels ? M : kTreeLastLevels;
+    const uint32_t lower = M - last_levels;
+    const uint32_t lower_stages = (lower + kTreeStageLevels - 1) / kTreeStageLevels;
     const uint32_t* in = leaves;
     uint32_t vin = 2, nodes = nb, remaining = M, stage = 0;
     do {
-      const uint32_t levels = remaining > kTreeStageLevels ? kTreeStageLevels : remaining;
+      uint32_t levels = last_levels;
+      if (stage < lower_stages) {  // spread `lower` levels over the lower stages, larger ones first
+        const uint32_t left = remaining - last_levels, stages_left = lower_stages - stage;
+        levels = (left + stages_left - 1) / stages_left;
+      }
       const bool last = levels == remaining;
       const uint32_t ctas = nodes >> levels;
-      uint32_t* out = stage_out_[stage & 1].as<uint32_t>() + (size_t)w0 * slice_words;
+      uint32_t* out = set.out[stage & 1].template as<uint32_t>() + (size_t)w0 * slice_words;
       TreeFinal fin{last ? 1u : 0u, w0, plan.c, plan.wide, l0, terms};
       LaunchOn(st, reduce_tree_kernel<C>, wn * ctas, (uint32_t)kTreeThreads, in, vin, levels, ctas,
-               slice_words, tree_[0].as<uint32_t>() + (size_t)w0 * slice_words,
-               tree_[1].as<uint32_t>() + (size_t)w0 * slice_words, out, fin);
+               slice_words, set.ping.template as<uint32_t>() + (size_t)w0 * slice_words,
+               set.pong.template as<uint32_t>() + (size_t)w0 * slice_words, out, fin);
       in = out;
       vin += levels;
       nodes >>= levels;
       remaining -= levels;
       ++stage;
     } while (remaining > 0);
+  }
+
+  // Running-sum block length of the low group: a block costs L0 sequential additions (~7 us
+  // each when latency-bound), every halving adds a tree level (~3 us) and doubles the tree's
+  // work; 4 up to 2^18 bucket slots, 8 above.
+  static uint32_t LowLevelLength(const MsmPlan& p, uint32_t low) {
+    uint32_t L = (uint64_t)low * p.B <= (1u << 18) ? 4u : 8u;
+    while (L > 2 && L > p.B) L >>= 1;
+    return L;
   }
 
   // How many low windows to accumulate last.  The window combination of the high group is a
@@ -1263,23 +1331,33 @@ class MsmEngine {
     if (options_.low_windows >= 0)
       return (uint32_t)options_.low_windows < p.W ? (uint32_t)options_.low_windows : p.W - 1;
     if (p.R) return 0;  // pair rounds: experimental path, single group
+    // Below ~2^24 entries the accumulation is latency-bound (it ends when its longest task ends,
+    // whatever the number of windows), so a second accumulate launch adds its own critical path
+    // instead of hiding anything: measured, 2^18 points 2.33 -> 2.62 ms, 2^16 1.08 -> 1.44 ms.
+    if ((uint64_t)n_last * p.W < (uint64_t(1) << 24)) return 0;
     // measured on B200: microseconds per doubling of the combine chain (four-lane form,
     // tools/probe/chain_probe.cu), nanoseconds per mixed addition of the accumulation kernel at
     // full occupancy
     constexpr int kW = C::Field::kWords;
     const double dbl_us = kW <= 8 ? 1.64 : (kW <= 12 ? 3.28 : (kW <= 16 ? 4.41 : 9.6));
     const double madd_ns = kW <= 8 ? 0.138 : (kW <= 12 ? 0.34 : (kW <= 16 ? 0.61 : 1.3));
-    const double kHighFixedUs = 100.0;  // running-sum level + tree of the high group (latency)
-    const double kSplitFixedUs = 40.0;  // second accumulate launch, second reduction, their tails
+    // timeline after the high group's accumulation and running-sum level (t = 0), tail stream:
+    // merge tree (latency), doubling chain; compute stream: accumulation of the low windows, then
+    // their level + tree, then their chain, which needs the high group's sum.  Minimise what is
+    // NOT accumulation work.
+    const double kTreeUs = 130.0;     // merge tree of a window group (latency-bound)
+    const double kLowFixedUs = 110.0; // low group: running-sum level + tree
+    const double kSplitUs = 30.0;     // second accumulate launch and its partial last wave
     const uint32_t total_bits = TotalBits(p);
-    double best = kHighFixedUs + dbl_us * total_bits;  // no split: the whole chain is exposed
+    auto chain = [&](uint32_t bits) { return bits ? dbl_us * (bits + 8) + 20.0 : 0.0; };
+    double best = kTreeUs + chain(total_bits);  // no split: everything after the level is exposed
     uint32_t best_low = 0;
     for (uint32_t low = 1; low < p.W; ++low) {
       const uint32_t below = WindowBitOffset(p, low);
-      const double hidden_by = (double)low * (double)n_last * madd_ns * 1e-3;
-      const double chain_hi = kHighFixedUs + dbl_us * (total_bits - below);
-      double exposed = (chain_hi > hidden_by ? chain_hi - hidden_by : 0.0) + dbl_us * below +
-                       kSplitFixedUs;
+      const double acc_low = (double)low * (double)n_last * madd_ns * 1e-3;
+      const double hi_ready = kTreeUs + chain(total_bits - below);
+      const double lo_ready = acc_low + kLowFixedUs;
+      const double exposed = (hi_ready > lo_ready ? hi_ready : lo_ready) + chain(below) - acc_low + kSplitUs;
       if (exposed < best) {
         best = exposed;
         best_low = low;
@@ -1306,7 +1384,9 @@ class MsmEngine {
   std::vector<const DeviceBuffer*> AllBuffers() const {
     return {&registered_, &bases_stage_, &scalars_stage_, &state_, &count_, &offset_, &cursor_, &task_base_,
             &tasks_, &task_meta_, &multi_, &sorted_, &digits_, &task_out_, &block_sums_, &order_,
-            &len_hist_, &leaves_, &stage_out_[0], &stage_out_[1], &combine_, &tree_[0], &tree_[1],
+            &len_hist_, &tree_hi_.leaves, &tree_hi_.ping, &tree_hi_.pong, &tree_hi_.out[0],
+            &tree_hi_.out[1], &tree_lo_.leaves, &tree_lo_.ping, &tree_lo_.pong, &tree_lo_.out[0],
+            &tree_lo_.out[1], &combine_,
             &pair_prefix_, &pair_out_[0], &pair_out_[1], &pair_out_[2], &pair_out_[3], &mid_,
             &coarse_, &fold_jobs_, &nonzero_slots_};
   }
@@ -1363,9 +1443,10 @@ class MsmEngine {
   char* host_out_ = nullptr;
   size_t registered_n_ = 0;
   DeviceBuffer registered_, bases_stage_, scalars_stage_, state_, count_, offset_, cursor_, task_base_, tasks_,
-      task_meta_, multi_, sorted_, digits_, task_out_, block_sums_, order_, len_hist_, leaves_,
-      stage_out_[2], combine_, tree_[2], pair_prefix_, pair_out_[4], mid_, coarse_,
+      task_meta_, multi_, sorted_, digits_, task_out_, block_sums_, order_, len_hist_, combine_,
+      pair_prefix_, pair_out_[4], mid_, coarse_,
       fold_jobs_, nonzero_slots_;
+  TreeBuffers tree_hi_, tree_lo_;
   size_t sort_smem_set_ = 0;
   // multi-process point-range sharding (JoinRanks)
   NcclApi::Comm comm_ = nullptr;

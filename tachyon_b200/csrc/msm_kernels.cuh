@@ -1010,7 +1010,8 @@ struct TreeFinal {
   uint32_t* terms;   // Y, one XYZZ per bit position
 };
 constexpr int kTreeThreads = 256;
-constexpr uint32_t kTreeStageLevels = 7;  // levels per launch: 128 input nodes per CTA
+constexpr uint32_t kTreeStageLevels = 7;  // most levels per launch: 128 input nodes per CTA
+constexpr uint32_t kTreeLastLevels = 5;   // levels of the final, one-CTA-per-window stage
 
 TB_DEV uint32_t window_bit_offset(uint32_t w, uint32_t c, uint32_t wide) {
   return w * c - (w > wide ? w - wide : 0u);
@@ -1083,11 +1084,11 @@ __global__ void __launch_bounds__(kTreeThreads) reduce_tree_kernel(
 
 // Window combination (pippenger_base.h:59-77 AccumulateWindowSums, the Horner over the window
 // sums) on the device: the MSM value is  sum_b 2^b Y_b  over the bit-positioned terms Y the
-// reduction tree left.  A pairing tree computes it in place: round r adds 2^(2^r) * Y[right] to
-// Y[left] for right = left + 2^r, so the doublings of different subtrees proceed in parallel and
-// the term at bit b is doubled exactly b times in total — the c doublings per window of the
-// reference's Horner, (W - 1) c in all on the longest path, plus log2 additions instead of one
-// per term.  One CTA.  Positions [0, clear_below) are reset to the identity first (the low
+// reduction tree left.  A pairing tree computes it in place: a segment's sum is its left half
+// plus 2^(length of the left half) times its right half, so the doublings of different
+// subtrees proceed in parallel and the term at bit b is doubled exactly b times in total — the
+// c doublings per window of the reference's Horner, (W - 1) c in all on the longest path, plus
+// log2 additions instead of one per term.  One CTA.  Positions [0, clear_below) are reset to the identity first (the low
 // window group writes its own term array).  The result, plus *add_in when given (the high
 // group's sum), goes to out.
 //
@@ -1112,15 +1113,25 @@ __global__ void __launch_bounds__(kCombineThreads) window_combine_kernel(
     xyzz_store<K>(terms + (size_t)b * kXyzzWords, z);
   }
   __syncthreads();
-  for (uint32_t stride = 1; stride < count; stride <<= 1) {
-    for (uint32_t left = group * 2 * stride; left + stride < count; left += kGroups * 2 * stride) {
+  // Balanced pairing: at depth d the positions are cut into 2^d segments with boundaries
+  // b(d, i) = ceil(i * count / 2^d); segment (d, i) = its left child + 2^(shift) * its right
+  // child, shift = length of the left child.  Bottom-up, in place (a segment's sum lives at its
+  // first position), so the longest chain is ~count + log2(count) doublings for any count.
+  uint32_t depth = 0;
+  while ((1u << depth) < count) ++depth;
+  for (uint32_t d = depth; d-- > 0;) {
+    for (uint32_t i = group; i < (1u << d); i += kGroups) {
+      const uint32_t lo = (uint32_t)(((uint64_t)i * count + (1u << d) - 1) >> d);
+      const uint32_t mid = (uint32_t)(((uint64_t)(2 * i + 1) * count + (2u << d) - 1) >> (d + 1));
+      const uint32_t hi = (uint32_t)(((uint64_t)(i + 1) * count + (1u << d) - 1) >> d);
+      if (mid <= lo || mid >= hi) continue;  // a child is empty: nothing to merge
       XYZZ<K> t, a;
-      xyzz_load<K>(t, terms + (size_t)(left + stride) * kXyzzWords);
+      xyzz_load<K>(t, terms + (size_t)mid * kXyzzWords);
       if (!xyzz_is_zero<K>(t)) {  // uniform inside the group
-        for (uint32_t d = 0; d < stride; ++d) Coop4<K>::dbl_nz(t, lane, mask);
-        xyzz_load<K>(a, terms + (size_t)left * kXyzzWords);
+        for (uint32_t k = lo; k < mid; ++k) Coop4<K>::dbl_nz(t, lane, mask);
+        xyzz_load<K>(a, terms + (size_t)lo * kXyzzWords);
         Coop4<K>::add(a, t, lane, mask);
-        if (lane == 0) xyzz_store<K>(terms + (size_t)left * kXyzzWords, a);
+        if (lane == 0) xyzz_store<K>(terms + (size_t)lo * kXyzzWords, a);
       }
     }
     __syncthreads();

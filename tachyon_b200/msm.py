@@ -269,3 +269,32 @@ def groth16_prove(g1_ctx, g2_ctx, pk, r, s, h, witness, full):
         _ptr(h), len(h), _ptr(witness), len(witness), _ptr(full), len(full), _ptr(out))
     _lib.check(rc, "groth16_prove")
     return out[:2 * fq], out[2 * fq:6 * fq], out[6 * fq:]
+
+
+def groth16_witness_map_from_files(curve, zkey_path, wtns_path):
+    """Host-only: (h scalars (domain_size, 4) uint64 Montgomery, domain_size, num_public) of a
+    .zkey + .wtns pair (tachyon_<c>_groth16_witness_map_from_files_b200)."""
+    fn = getattr(_lib.load(), f"tachyon_{curve}_groth16_witness_map_from_files_b200")
+    dom, pub = ctypes.c_size_t(0), ctypes.c_size_t(0)
+    _lib.check(fn(zkey_path.encode(), wtns_path.encode(), None, 0, ctypes.byref(dom), ctypes.byref(pub)),
+               "witness_map_from_files")
+    h = np.zeros((dom.value, 4), dtype=np.uint64)
+    _lib.check(fn(zkey_path.encode(), wtns_path.encode(), _ptr(h), dom.value, ctypes.byref(dom), ctypes.byref(pub)),
+               "witness_map_from_files")
+    return h, dom.value, pub.value
+
+
+def groth16_prove_from_files(g1_ctx, g2_ctx, zkey_path, wtns_path, r=None, s=None, proof_json=None,
+                             public_json=None):
+    """Proof (a, b, c) from a snarkjs .zkey and a .wtns (tachyon_<c>_groth16_prove_from_files_b200;
+    vendors/circom/prover_main.cc:81-186).  r, s: Montgomery Fr (4 limbs) or None (= --no_zk)."""
+    curve = g1_ctx.curve
+    fq = _lib.CURVES[curve]
+    out = np.zeros(2 * fq + 4 * fq + 2 * fq, dtype=np.uint64)
+    rp = _ptr(np.ascontiguousarray(r, dtype=np.uint64)) if r is not None else None
+    sp = _ptr(np.ascontiguousarray(s, dtype=np.uint64)) if s is not None else None
+    rc = getattr(_lib.load(), f"tachyon_{curve}_groth16_prove_from_files_b200")(
+        ctypes.c_void_p(g1_ctx.ptr), ctypes.c_void_p(g2_ctx.ptr), zkey_path.encode(), wtns_path.encode(), rp, sp,
+        _ptr(out), proof_json.encode() if proof_json else None, public_json.encode() if public_json else None)
+    _lib.check(rc, "groth16_prove_from_files")
+    return out[:2 * fq], out[2 * fq:6 * fq], out[6 * fq:]

@@ -10,7 +10,9 @@ that the reference's own unit test expects for them
 R = 2^256, the limb order and from-Montgomery of the oracle.
 """
 import json
+import os
 import re
+import shutil
 import struct
 
 REF = "/root/reference/vendors/circom"
@@ -29,7 +31,17 @@ def sections(buf):
     return out
 
 
+def copy_file_fixtures():
+    """The two reference-held binary fixtures the file-level Groth16 tests run on (test-only
+    copies: vendors/circom/examples/multiplier_3.zkey, circomlib/wtns/multiplier_3.wtns — the
+    files zkey_unittest.cc:56-58 and wtns_unittest.cc:24-26 parse)."""
+    here = os.path.dirname(os.path.abspath(__file__))
+    shutil.copyfile(f"{REF}/examples/multiplier_3.zkey", os.path.join(here, "multiplier_3.zkey"))
+    shutil.copyfile(f"{REF}/circomlib/wtns/multiplier_3.wtns", os.path.join(here, "multiplier_3.wtns"))
+
+
 def main():
+    copy_file_fixtures()
     buf = open(f"{REF}/examples/multiplier_3.zkey", "rb").read()
     hdr = sections(buf)[2]
     off = 0

@@ -516,6 +516,48 @@ def test_groth16_prove(oracles, torch_cuda, curve):
             msm.groth16_prove(g1, g2, pk, r, s, h, witness[:-1], full)   # l query / witness size mismatch
 
 
+# SURVEY 8f-3, file level (vendors/circom/prover_main.cc:81-186): proof straight from a snarkjs
+# .zkey and a .wtns — the reference-held fixtures multiplier_3.zkey / multiplier_3.wtns — through
+# tachyon_bn254_groth16_prove_from_files_b200, against the oracle's groth16_prove fed by the
+# independent Python model of the formats and of the witness map (oracle/circom_model.py); the
+# snarkjs JSON it writes must carry the same points as decimal strings.
+@pytest.mark.parametrize("blind", [True, False])
+def test_groth16_prove_from_files(oracles, torch_cuda, tmp_path, blind):
+    import json
+    import os
+    from oracle import circom_model, cpu_oracle
+    golden = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+    zkey, wtns = os.path.join(golden, "multiplier_3.zkey"), os.path.join(golden, "multiplier_3.wtns")
+    o = oracles["bn254"]
+    z = circom_model.parse_zkey(zkey)
+    _, w = circom_model.parse_wtns(wtns)
+    as_fr = lambda ints: o.fr_to_mont(np.array([pymodel.to_limbs(v, 4) for v in ints], dtype=np.uint64))
+    pts = lambda raw, limbs: np.frombuffer(raw, dtype=np.uint64).reshape(-1, limbs).copy()
+    pk = {"alpha_g1": pts(z["alpha_g1"], 8)[0], "beta_g1": pts(z["beta_g1"], 8)[0], "delta_g1": pts(z["delta_g1"], 8)[0],
+          "beta_g2": pts(z["beta_g2"], 16)[0], "delta_g2": pts(z["delta_g2"], 16)[0],
+          "a_g1_query": pts(z["a_g1"], 8), "b_g1_query": pts(z["b_g1"], 8), "b_g2_query": pts(z["b_g2"], 16),
+          "h_g1_query": pts(z["h_g1"], 8), "l_g1_query": pts(z["c_g1"], 8)}
+    n_inst = z["num_public"] + 1
+    full, witness = as_fr(w[1:]), as_fr(w[n_inst:])
+    h = as_fr(circom_model.witness_map("bn254", z, w))
+    rs = o.generate_scalars(171, 2, "uniform")
+    r, s_ = (rs[0], rs[1]) if blind else (np.zeros(4, dtype=np.uint64), np.zeros(4, dtype=np.uint64))
+    want = cpu_oracle.groth16_prove("bn254", pk, r, s_, h, witness, full)
+    pj, uj = str(tmp_path / "proof.json"), str(tmp_path / "public.json")
+    with msm.MSMGpu("bn254") as g1, msm.MSMGpu("bn254_g2") as g2:
+        got = msm.groth16_prove_from_files(g1, g2, zkey, wtns, r if blind else None, s_ if blind else None, pj, uj)
+    for a, b in zip(got, want):
+        assert (np.asarray(a).reshape(-1) == np.asarray(b).reshape(-1)).all()
+    c = pymodel.CURVES["bn254"]
+    dec = lambda limbs: str(pymodel.from_limbs(limbs) * pow(c.fq_R, -1, c.p) % c.p)
+    a, b, cc = (np.asarray(x).reshape(-1, 4) for x in want)
+    proof = json.load(open(pj))
+    assert proof["pi_a"] == [dec(a[0]), dec(a[1]), "1"] and proof["pi_c"] == [dec(cc[0]), dec(cc[1]), "1"]
+    assert proof["pi_b"] == [[dec(b[0]), dec(b[1])], [dec(b[2]), dec(b[3])], ["1", "0"]]
+    assert proof["protocol"] == "groth16" and proof["curve"] == "bn128"
+    assert json.load(open(uj)) == [str(v) for v in w[1:n_inst]] == ["60"]
+
+
 # the dump written under TACHYON_MSM_GPU_INPUT_DIR (msm_gpu.h:99-119: u64 count,
 # canonical little-endian limbs) and the replay CLI (msm_gpu_replay.cc:40-88: --idx --degree
 # --input_dir, prints the time and the affine point as hex without leading zeros).
