@@ -100,8 +100,11 @@ extern "C" {
      default; 0 = one), "host_ranges" (most ranges of the automatic host-input pipeline),    \
      "prewarm" (reserve workspace, staging and copy threads for an MSM of `value` points now),\
      "release_workspace" (free the grow-only workspace; registered bases are kept),           \
-     "low_windows" (windows accumulated last while the reduction and window combination of   \
-     the others run on a second stream; -1 = cost model, 0 = no split),                      \
+     "device_ladder" (where the final ladder over the W window sums runs — ~255 strictly     \
+     sequential point doublings: 0 = on the host, the default, 65 us; 1 = as a kernel,        \
+     430 us for BN254, hidden behind the accumulation of the low windows where possible),    \
+     "low_windows" (device ladder: windows accumulated last while the merge tree and doubling \
+     chain of the others run on a second stream; -1 = cost model, 0 = no split),              \
      "ranges" (point ranges one MSM is pipelined over; 0 = automatic), "pair_rounds"        \
      (experimental batched-affine rounds before the XYZZ accumulation; -1 = none, the       \
      default; -2 = chosen from the bucket occupancy; 0..4 = forced). */                       \

@@ -582,6 +582,10 @@ using namespace tb200;
         for (auto& e : ptr->engines) e->options().level_fill = (uint32_t)value;                \
       } else if (k == "balance") {                                                             \
         for (auto& e : ptr->engines) e->options().balance = (int)value;                        \
+      } else if (k == "stage_points") {                                                        \
+        for (auto& e : ptr->engines) e->options().stage_points = (int)value;                   \
+      } else if (k == "device_ladder") {                                                       \
+        for (auto& e : ptr->engines) e->options().device_ladder = (int)value;                  \
       } else if (k == "low_windows") {                                                         \
         for (auto& e : ptr->engines) e->options().low_windows = (int)value;                    \
       } else if (k == "ranges") {                                                              \

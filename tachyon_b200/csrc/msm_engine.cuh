@@ -98,7 +98,14 @@ struct MsmOptions {
   uint32_t level_fill = 0;   // blocks per SM the running-sum level wants before it shortens its
                              // blocks (0 = default: 384, 768 from 1.5 M bucket slots)
   int balance = 1;           // balanced windows (WideWindowsFor); 0 = equal widths, slack on top
-  int low_windows = -1;      // windows of the low group (accumulated last, while the high group's
+  int stage_points = 0;      // 1 = accumulate_staged_kernel: the next point of a task travels
+                             // through shared memory (cp.async) instead of registers
+  int device_ladder = 0;     // where the final ladder sum_w 2^(offset of w) S_w runs: 0 = on the
+                             // host (default: ~255 strictly sequential point doublings take
+                             // 65 us on one host core, 430 us on the GPU's fastest form,
+                             // tools/probe/chain_probe.cu), 1 = on the device, hidden behind the
+                             // accumulation of the low windows where the cost model finds room
+  int low_windows = -1;      // device ladder: windows of the low group (accumulated last, while the high group's
                              // reduction and window combination run on the tail stream):
                              // -1 = from the cost model, 0 = no split
 };
@@ -282,7 +289,8 @@ class MsmEngine {
     const size_t piece = PieceLimit(n);
     if (n <= piece) {  // the usual case: with several ranks the gather rides the MSM's stream
       Pending p = Enqueue(bases, scalars, n, 0, false, /*gather=*/world_ > 1);
-      return Finish(p);
+      Point part = Finish(p);
+      return (world_ > 1 && !p.gathered) ? GatherHostPoint(part) : part;
     }
     for (size_t off = 0; off < n; off += piece) {
       size_t len = n - off < piece ? n - off : piece;
@@ -441,6 +449,7 @@ class MsmEngine {
     uint32_t low = 0;     // windows of the low group
     uint32_t L0_low = 0;  // its running-sum block length
     bool gathered = false;  // the result is the all-gathered set of rank partials
+    bool device_ladder = false;  // the device left one point (else: one sum per window)
     size_t K = 0;
     bool any_host = false;
     int slot = 0;       // host result buffer / event set
@@ -819,7 +828,9 @@ class MsmEngine {
     pd.plan = big;
     pd.K = K;
     launches_ = 0;
-    pd.low = reserve_only ? 0u : ChooseLowWindows(big, bound[K] - bound[K - 1]);
+    pd.device_ladder = options_.device_ladder != 0;
+    gather = gather && pd.device_ladder;  // host ladder: the partial is gathered after Finish()
+    pd.low = (reserve_only || !pd.device_ladder) ? 0u : ChooseLowWindows(big, bound[K] - bound[K - 1]);
 
     // ---- workspace ----------------------------------------------------------------
     // staging ring: kStageSlots slots of one 256-byte-aligned range each, plus one alignment unit
@@ -886,7 +897,7 @@ class MsmEngine {
                 {&tree_lo_.pong, tree_lo_b},
                 {&tree_lo_.out[0], tree_lo_b},
                 {&tree_lo_.out[1], tree_lo_b},
-                {&combine_, (size_t)(2 * kTermSlots + 2) * kXyzzBytes},
+                {&combine_, (size_t)(2 * kTermSlots + 2 + kMaxWindows) * kXyzzBytes},
                 {&bases_stage_, bases_dev ? 0 : bases_slot_want * kStageSlots},
                 {&scalars_stage_, scalars_dev ? 0 : scalars_slot_want * kStageSlots}});
     // The slot stride is a property of the BUFFER, not of the call: MSMs of different sizes are in
@@ -1047,6 +1058,10 @@ class MsmEngine {
           Launch(accumulate_kernel<C, true>, agrid, kAccThreads, pair_out_[plan.R - 1].as<uint32_t>(),
                  (const uint32_t*)nullptr, tasks_.as<uint2>(), task_meta_.as<uint32_t>(),
                  order_.as<uint32_t>(), totals_, part, state_.as<uint32_t>(), task_out_.as<uint32_t>());
+        else if (options_.stage_points)
+          Launch(accumulate_staged_kernel<C>, agrid, kAccThreads, d_bases, sorted_.as<uint32_t>(),
+                 tasks_.as<uint2>(), task_meta_.as<uint32_t>(), order_.as<uint32_t>(), totals_, part,
+                 state_.as<uint32_t>(), task_out_.as<uint32_t>());
         else
           Launch((uint64_t)plan.n * plan.W < kAccSmallEntries
                      ? accumulate_kernel<C, false, AccMinBlocksSmall<C>()>
@@ -1083,7 +1098,8 @@ class MsmEngine {
                          SlotEvent(slot, 10));
         TB_CUDA(cudaEventRecord(SlotEvent(slot, 6), tail_stream_));
         LaunchOn(tail_stream_, window_combine_kernel<C>, 1, kCombineThreads, terms_hi,
-                 TotalBits(big), WindowBitOffset(big, pd.low), (const uint32_t*)nullptr, HiSum());
+                 TotalBits(big), WindowBitOffset(big, pd.low), (const uint32_t*)nullptr, HiSum(),
+                 PerWindow{0, 0, 0});
         TB_CUDA(cudaEventRecord(SlotEvent(slot, 7), tail_stream_));
         TB_CUDA(cudaEventRecord(SlotEvent(slot, 5), tail_stream_));
         // low group: at most low * B buckets, each non-empty one a task, plus the split ones
@@ -1114,20 +1130,27 @@ class MsmEngine {
       TB_CUDA(cudaStreamWaitEvent(stream_, SlotEvent(slot, 5), 0));
       TB_CUDA(cudaEventRecord(SlotEvent(slot, 9), stream_));
       Launch(window_combine_kernel<C>, 1, kCombineThreads, terms_lo, WindowBitOffset(big, pd.low), 0u,
-             (const uint32_t*)HiSum(), Partial());
+             (const uint32_t*)HiSum(), Partial(), PerWindow{0, 0, 0});
     } else {
       uint32_t* terms = combine_.as<uint32_t>();
       EnqueueReduction(stream_, big, 0, big.W, pd.L0, tree_hi_, terms);
       TB_CUDA(cudaEventRecord(SlotEvent(slot, 6), stream_));
-      Launch(window_combine_kernel<C>, 1, kCombineThreads, terms, TotalBits(big), 0u,
-             (const uint32_t*)nullptr, Partial());
+      if (pd.device_ladder)
+        Launch(window_combine_kernel<C>, 1, kCombineThreads, terms, TotalBits(big), 0u,
+               (const uint32_t*)nullptr, Partial(), PerWindow{0, 0, 0});
+      else  // the parallel part only: one CTA per window, S_w to WindowSums()
+        Launch(window_combine_kernel<C>, big.W, kCombineThreads, terms, 0u, 0u, (const uint32_t*)nullptr,
+               WindowSums(), PerWindow{big.c, big.wide, 0});
       TB_CUDA(cudaEventRecord(SlotEvent(slot, 7), stream_));
     }
     pd.gathered = gather;
     if (gather) {
       EnqueueGather(Partial());
-    } else {
+    } else if (pd.device_ladder) {
       TB_CUDA(cudaMemcpyAsync(host_out, Partial(), kXyzzBytes, cudaMemcpyDeviceToHost, stream_));
+    } else {
+      TB_CUDA(cudaMemcpyAsync(host_out, WindowSums(), (size_t)big.W * kXyzzBytes, cudaMemcpyDeviceToHost,
+                              stream_));
     }
     TB_CUDA(cudaEventRecord(ev_end, stream_));
     pd.launches = launches_;
@@ -1155,8 +1178,18 @@ class MsmEngine {
     Point result;
     if (pd.gathered) {
       result = SumGathered();
-    } else {
+    } else if (pd.device_ladder) {
       memcpy(&result, host_out, sizeof(result));
+    } else {
+      // The ladder of pippenger_base.h:59-77 over the W window sums the device produced: from the
+      // top window down, c_w doublings then one addition.  Strictly sequential work on one point.
+      const Point* sums = reinterpret_cast<const Point*>(host_out);
+      result = Point::Zero();
+      for (uint32_t w = plan.W; w-- > 0;) {
+        const uint32_t cw = plan.c - (w >= plan.wide ? 1u : 0u);
+        for (uint32_t k = 0; k < cw && w + 1 < plan.W; ++k) result = result.Dbl();
+        result = result.Add(sums[w]);
+      }
     }
     auto host1 = std::chrono::steady_clock::now();
 
@@ -1244,7 +1277,7 @@ class MsmEngine {
     return SumGathered();
   }
   uint32_t* Scratch() {
-    if (!combine_.ptr) combine_.Reserve((size_t)(2 * kTermSlots + 2) * kXyzzBytes);
+    if (!combine_.ptr) combine_.Reserve((size_t)(2 * kTermSlots + 2 + kMaxWindows) * kXyzzBytes);
     return Partial();
   }
 
@@ -1255,6 +1288,7 @@ class MsmEngine {
   static uint32_t TotalBits(const MsmPlan& p) { return WindowBitOffset(p, p.W); }
   uint32_t* HiSum() { return combine_.as<uint32_t>() + (size_t)2 * kTermSlots * kXyzzWords; }
   uint32_t* Partial() { return HiSum() + kXyzzWords; }
+  uint32_t* WindowSums() { return Partial() + kXyzzWords; }  // kMaxWindows points
 
   // Bucket reduction of windows [w0, w0 + wn) on stream `st`: one blocked running-sum level,
   // then the merge tree in stages of <= kTreeStageLevels levels per launch; the last stage
@@ -1414,7 +1448,7 @@ class MsmEngine {
   }
 
   // pinned result buffer per Pending slot: the MSM's point, then one MsmTotals per range
-  static constexpr size_t kHostPartialBytes = (kXyzzBytes + 255) / 256 * 256;
+  static constexpr size_t kHostPartialBytes = (kMaxWindows * kXyzzBytes + 255) / 256 * 256;
   static constexpr size_t kHostOutBytes = kHostPartialBytes + kMaxRanges * sizeof(MsmTotals);
   // bit positions of the window-combination term arrays: W * c < 256 + c
   static constexpr uint32_t kTermSlots = 320;

@@ -628,6 +628,79 @@ __global__ void __launch_bounds__(kAccThreads, kMinBlocks) accumulate_kernel(
   xyzz_store<K>((meta & kTaskSingle) ? bucket : task_out + (size_t)g * kXyzzWords, acc);
 }
 
+// The same accumulation with the NEXT point staged through shared memory instead of registers:
+// cp.async (LDGSTS) copies the gathered point straight from L2 into the thread's private slot
+// while the current mixed addition runs, so nothing of the point in flight is live in registers
+// across the addition (the register form holds 16 / 24 / 32 / 48 words there — with the 128
+// register budget of 4 CTAs/SM that is what spills on the 12-limb curve).  Two slots per thread
+// (the slot being read and the slot being filled), laid out [slot][16-byte chunk][thread] so
+// that the 128-bit shared-memory accesses of a warp are conflict-free.
+TB_DEV void cp_async16(uint32_t smem_addr, const void* gmem) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_addr), "l"(gmem) : "memory");
+}
+TB_DEV void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+TB_DEV void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+
+template <class C, int kMinBlocks = AccMinBlocks<C>()>
+__global__ void __launch_bounds__(kAccThreads, kMinBlocks) accumulate_staged_kernel(
+    const uint32_t* __restrict__ bases, const uint32_t* __restrict__ sorted,
+    const uint2* __restrict__ tasks, const uint32_t* __restrict__ task_meta,
+    const uint32_t* __restrict__ order, const MsmTotals* __restrict__ totals, uint32_t part,
+    uint32_t* __restrict__ state, uint32_t* __restrict__ task_out) {
+  using K = typename C::Field;
+  constexpr int kAffineWords = 2 * K::kWords;
+  constexpr int kXyzzWords = 4 * K::kWords;
+  constexpr int kChunks = kAffineWords / 4;  // 16-byte chunks of one affine point
+  __shared__ uint4 stage[2][kChunks][kAccThreads];
+  uint32_t slot = blockIdx.x * blockDim.x + threadIdx.x + (part == kPartLow ? totals->tasks_hi : 0u);
+  if (slot >= (part == kPartHigh ? totals->tasks_hi : totals->tasks)) return;
+  uint32_t g = order[slot];
+  uint2 task = tasks[g];
+  uint32_t meta = task_meta[g];
+  uint32_t* bucket = state + (size_t)(meta & kTaskKeyMask) * kXyzzWords;
+  const uint32_t* ent = sorted + task.x;
+  const uint32_t my = (uint32_t)__cvta_generic_to_shared(&stage[0][0][threadIdx.x]);
+  constexpr uint32_t kChunkStride = kAccThreads * 16, kSlotStride = kChunks * kChunkStride;
+  auto fetch = [&](uint32_t entry, uint32_t buf) {
+    const uint4* src = reinterpret_cast<const uint4*>(bases + (size_t)(entry & 0x7fffffffu) * kAffineWords);
+#pragma unroll
+    for (int q = 0; q < kChunks; ++q) cp_async16(my + buf * kSlotStride + q * kChunkStride, src + q);
+    cp_async_commit();
+  };
+  uint32_t e = ent[0];
+  fetch(e, 0);
+  uint32_t e_next = task.y > 1 ? ent[1] : 0u;
+  XYZZ<K> acc;
+  if (meta & kTaskFirst) {
+    xyzz_load<K>(acc, bucket);
+  } else {
+    xyzz_set_zero<K>(acc);
+  }
+  for (uint32_t j = 0; j < task.y; ++j) {
+    cp_async_wait_all();  // point j has landed in slot j & 1
+    Affine<K> cur;
+    {
+      uint32_t* w = reinterpret_cast<uint32_t*>(&cur);
+#pragma unroll
+      for (int q = 0; q < kChunks; ++q) {
+        uint4 v = stage[j & 1][q][threadIdx.x];
+        w[4 * q] = v.x;
+        w[4 * q + 1] = v.y;
+        w[4 * q + 2] = v.z;
+        w[4 * q + 3] = v.w;
+      }
+    }
+    const bool neg = e >> 31;
+    if (j + 1 < task.y) {
+      e = e_next;
+      fetch(e, (j + 1) & 1);
+      if (j + 2 < task.y) e_next = ent[j + 2];
+    }
+    xyzz_madd<K>(acc, cur, neg);
+  }
+  xyzz_store<K>((meta & kTaskSingle) ? bucket : task_out + (size_t)g * kXyzzWords, acc);
+}
+
 // ---------------------------------------------------------------------------
 // Batched-affine pre-reduction ("pair rounds").  A mixed XYZZ addition costs 10 field
 // multiplications; an affine + affine addition costs 3 (lambda, lambda^2, y3) plus one
@@ -1098,13 +1171,30 @@ __global__ void __launch_bounds__(kTreeThreads) reduce_tree_kernel(
 // doublings of a BN254 MSM.  The engine hides it behind the accumulation of the low windows.
 constexpr int kCombineThreads = 128;
 
+// per_window.c != 0: one CTA per window — CTA b combines only the bit positions of window
+// per_window.w_begin + b and writes that window's sum S_w = sum_k (k + 1) B_k to out[b]
+// (`count`, `clear_below`, `add_in` unused).  This is the parallel part of the window
+// combination; what is left — sum_w 2^(offset of w) S_w, ~255 strictly sequential doublings of
+// one point — is the ladder the engine runs on the host by default (msm_engine.cuh, Finish).
+struct PerWindow {
+  uint32_t c, wide, w_begin;
+};
+
 template <class C>
 __global__ void __launch_bounds__(kCombineThreads) window_combine_kernel(
     uint32_t* terms, uint32_t count, uint32_t clear_below, const uint32_t* add_in,
-    uint32_t* out) {
+    uint32_t* out, PerWindow per_window) {
   using K = typename C::Field;
   constexpr int kXyzzWords = 4 * K::kWords;
   constexpr uint32_t kGroups = kCombineThreads / 4;
+  if (per_window.c) {
+    const uint32_t w = per_window.w_begin + blockIdx.x;
+    terms += (size_t)window_bit_offset(w, per_window.c, per_window.wide) * kXyzzWords;
+    count = per_window.c - (w >= per_window.wide ? 1u : 0u);
+    clear_below = 0;
+    add_in = nullptr;
+    out += (size_t)blockIdx.x * kXyzzWords;
+  }
   // groups of four lanes share one (left, right) pair: Coop4 doublings and additions
   const uint32_t group = threadIdx.x >> 2, lane = threadIdx.x & 3, mask = 0xfu << (threadIdx.x & 28);
   for (uint32_t b = threadIdx.x; b < clear_below; b += kCombineThreads) {

@@ -361,9 +361,12 @@ def test_msm_reduce_modes(oracles, torch_cuda, name):
             assert (got == want).all(), host_ranges
 
 
-# Window groups: the windows of the last point range are accumulated as two groups (high first)
-# so that the high group's bucket reduction, merge tree and window combination — the device-side
-# Horner of pippenger_base.h:59-77 — run on a second stream behind the low group's accumulation.
+# Window combination (pippenger_base.h:59-77).  Default: the device reduces every window to its sum
+# S_w (running-sum level, fused merge tree, per-window combine kernel) and the host runs the final,
+# strictly sequential ladder over the W sums.  Option "device_ladder": the ladder runs as a kernel
+# too, and the windows of the last point range are accumulated as two groups (high first) so that
+# the high group's merge tree and doubling chain run on a second stream behind the low group's
+# accumulation.
 # Every split, window size, range count and scalar distribution must give the same point; skewed
 # scalars exercise the per-group filter of the bucket-fold kernels.
 @pytest.mark.parametrize("name", ALL)
@@ -375,6 +378,14 @@ def test_msm_window_groups(oracles, torch_cuda, name):
              "non_uniform": o.generate_scalars(144, n, "non_uniform")}
     want = {k: o.msm_affine(bases, v) for k, v in cases.items()}
     with msm.MSMGpu(name) as ctx:
+        # default: the device leaves one sum per window, the host runs the final ladder
+        for cbits in (0, 5, 9, 13):
+            ctx.set_option("window_bits", cbits)
+            for dist, sc in cases.items():
+                got = o.jacobian_to_affine(ctx.affine_msm(bases, sc))
+                assert (got == want[dist]).all(), ("host ladder", cbits, dist)
+                assert ctx.last_timing()["low_windows"] == 0
+        ctx.set_option("device_ladder", 1)             # the ladder as a kernel too: ONE point leaves
         for cbits in (0, 5, 9, 13):
             ctx.set_option("window_bits", cbits)
             for low in (-1, 0, 1, 2, 5, 200):          # 200: clamped to W - 1
