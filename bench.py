@@ -374,7 +374,12 @@ def run_commit_batch(args, local_rank):
     stream = torch.cuda.Stream()
     ctx = msm.MSMGpu(curve, degree=args.log_n, device=local_rank)
     ctx.set_stream(stream.cuda_stream)
+    if args.precompute:
+        ctx.set_option("precompute", 1)
+    t_reg = time.perf_counter()
     ctx.register_bases(bases.data_ptr(), n)
+    torch.cuda.synchronize()
+    t_reg = (time.perf_counter() - t_reg) * 1e3
 
     def timed(ptrs, steps):
         for _ in range(3):
@@ -415,6 +420,8 @@ def run_commit_batch(args, local_rank):
         "scaling": "strong", "vs_baseline": None, "dtype": "u32", "data": "synthetic",
         "config": {"workload": f"{count} commitments of 2^{args.log_n} points over registered (device-resident) "
                                f"{curve} bases, {args.dist} scalars, batch-normalised", "ms_per_commitment": ms_dev / count,
+                   "precompute": bool(args.precompute), "register_ms": t_reg,
+                   "window_bits": ctx.last_timing()["window_bits"], "windows": ctx.last_timing()["windows"],
                    "l2": "inputs + workspace exceed the 126 MB L2 every step"},
         "clocks": clocks, "gpu_launches": int(launches),
         "e2e": {"value": n * count / (ms_host * 1e-3), "unit": "points/s", "ms_per_step": ms_host,
@@ -508,6 +515,8 @@ def main():
     ap.add_argument("--ranges", type=int, default=0, help="point ranges per MSM (0 = automatic)")
     ap.add_argument("--workload", default="msm", choices=["msm", "groth16", "commit_batch"])
     ap.add_argument("--batch", type=int, default=16, help="commit_batch: number of MSMs per step")
+    ap.add_argument("--precompute", action="store_true",
+                    help="commit_batch: register the bases with the table of window multiples")
     ap.add_argument("-k", type=int, action="append", default=None,
                     help="table mode with the reference benchmark's flags: exponent(s) of the sizes")
     ap.add_argument("--test_set", default="random", choices=["random", "uniform", "non_uniform"])

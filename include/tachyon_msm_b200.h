@@ -100,6 +100,12 @@ extern "C" {
      default; 0 = one), "host_ranges" (most ranges of the automatic host-input pipeline),    \
      "prewarm" (reserve workspace, staging and copy threads for an MSM of `value` points now),\
      "release_workspace" (free the grow-only workspace; registered bases are kept),           \
+     "precompute" (1 = the next register_bases call also builds the table of window           \
+     multiples 2^(bit offset of window w) * P — the full precompute_factor of                 \
+     icicle_msm.h:21 — so that MSMs over the registered bases use one bucket set for all      \
+     windows: W times the base memory, a W times smaller bucket reduction, no ladder),        \
+     "stage_points" (1 = the accumulation stages the next point through shared memory with    \
+     cp.async instead of registers),                                                          \
      "device_ladder" (where the final ladder over the W window sums runs — ~255 strictly     \
      sequential point doublings: 0 = on the host, the default, 65 us; 1 = as a kernel,        \
      430 us for BN254, hidden behind the accumulation of the low windows where possible),    \

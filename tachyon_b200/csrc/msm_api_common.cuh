@@ -582,6 +582,8 @@ using namespace tb200;
         for (auto& e : ptr->engines) e->options().level_fill = (uint32_t)value;                \
       } else if (k == "balance") {                                                             \
         for (auto& e : ptr->engines) e->options().balance = (int)value;                        \
+      } else if (k == "precompute") {                                                          \
+        for (auto& e : ptr->engines) e->options().precompute = (int)value;                     \
       } else if (k == "stage_points") {                                                        \
         for (auto& e : ptr->engines) e->options().stage_points = (int)value;                   \
       } else if (k == "device_ladder") {                                                       \

@@ -98,6 +98,10 @@ struct MsmOptions {
   uint32_t level_fill = 0;   // blocks per SM the running-sum level wants before it shortens its
                              // blocks (0 = default: 384, 768 from 1.5 M bucket slots)
   int balance = 1;           // balanced windows (WideWindowsFor); 0 = equal widths, slack on top
+  int precompute = 0;        // RegisterBases also builds the table of window multiples
+                             // 2^(bit offset of window w) * P (precompute_factor of
+                             // icicle_msm.h:21, here always the full factor): MSMs over the
+                             // registered bases then use ONE set of buckets for all windows
   int stage_points = 0;      // 1 = accumulate_staged_kernel: the next point of a task travels
                              // through shared memory (cp.async) instead of registers
   int device_ladder = 0;     // where the final ladder sum_w 2^(offset of w) S_w runs: 0 = on the
@@ -160,6 +164,24 @@ inline uint32_t ChooseWindowBits(size_t n, uint32_t scalar_bits, size_t ranges =
     double buckets = (double)W * (double)(1u << (c - 1));
     if (buckets > kMaxBuckets) break;
     double cost = kEntryCost * (double)n * W + kBucketCost * PopulatedBuckets(scalar_bits, c);
+    if (cost < best) {
+      best = cost;
+      best_c = c;
+    }
+  }
+  return best_c;
+}
+
+// Window choice when all windows share one bucket set (precomputed table of window multiples):
+// the reduction covers 2^(c-1) buckets once instead of once per window, so larger windows pay.
+inline uint32_t ChooseWindowBitsShared(size_t n, uint32_t scalar_bits) {
+  constexpr double kEntryCost = 1.37, kBucketCost = 4.7;
+  double best = 1e300;
+  uint32_t best_c = kMinWindowBits;
+  for (uint32_t c = kMinWindowBits; c <= 24; ++c) {
+    uint32_t W = WindowsFor(scalar_bits, c);
+    if ((uint64_t)n * W >= (uint64_t(1) << 31)) continue;  // table index + sign bit in one word
+    double cost = kEntryCost * (double)n * W + kBucketCost * (double)(1u << (c - 1));
     if (cost < best) {
       best = cost;
       best_c = c;
@@ -367,14 +389,39 @@ class MsmEngine {
 
   // Keeps a private device copy of `n` bases (host or device source) for later MSMs — the
   // SRS of kzg.h:91-113, uploaded once instead of once per commitment.
+  // With option "precompute" the copy is followed by the table of window multiples
+  // T[w][i] = 2^(bit offset of window w) * P_i for the window size the cost model picks for n
+  // points sharing one bucket set; slice 0 of the table is the bases themselves.
   void RegisterBases(const void* bases, size_t n) {
     TB_CUDA(cudaSetDevice(device_));
     TB_CUDA(cudaStreamSynchronize(stream_));
     TB_CUDA(cudaStreamSynchronize(copy_stream_));
-    registered_.Reserve(n * kAffineBytes);
+    table_c_ = 0;
+    uint32_t W = 1;
+    if (options_.precompute && n) {
+      table_c_ = options_.window_bits ? options_.window_bits : ChooseWindowBitsShared(n, Fr::kBits);
+      if (table_c_ < kMinWindowBits) table_c_ = kMinWindowBits;
+      W = WindowsFor(Fr::kBits, table_c_);
+      if ((uint64_t)n * W >= (uint64_t(1) << 31))
+        throw CudaError{cudaErrorInvalidValue, "precomputed table too large for 31-bit indices", __FILE__,
+                        __LINE__};
+    }
+    registered_.Reserve(n * W * kAffineBytes);
     if (n) TB_CUDA(cudaMemcpy(registered_.ptr, bases, n * kAffineBytes, cudaMemcpyDefault));
     registered_n_ = n;
+    if (table_c_) {
+      const uint32_t wide = WideWindowsFor(Fr::kBits, table_c_, options_.balance != 0);
+      table_wide_ = wide;
+      // in place: the kernel reads slice 0 (the bases) and writes every slice
+      precompute_table_kernel<C><<<(uint32_t)((n + 127) / 128), 128, 0, stream_>>>(
+          registered_.as<uint32_t>(), (uint32_t)n, (uint32_t)n, W, table_c_, wide,
+          registered_.as<uint32_t>());
+      TB_CUDA(cudaGetLastError());
+      g_kernel_launches.fetch_add(1, std::memory_order_relaxed);
+      TB_CUDA(cudaStreamSynchronize(stream_));
+    }
   }
+  uint32_t table_window_bits() const { return table_c_; }
   const void* registered_bases() const { return registered_.ptr; }
   size_t registered_size() const { return registered_n_; }
 
@@ -395,7 +442,7 @@ class MsmEngine {
                         __LINE__};
     }
     auto bases_of = [&](size_t i) { return bases[i] ? bases[i] : registered_.ptr; };
-    if (biggest > PieceLimit(biggest)) {  // rare: fall back to one blocking call each
+    if (biggest > PieceLimit(biggest) && !table_c_) {  // rare: fall back to one blocking call each
       MsmTiming sum{};
       for (size_t i = 0; i < count; ++i) {
         out[i] = Run(bases_of(i), scalars[i], sizes[i]);
@@ -419,7 +466,8 @@ class MsmEngine {
           // from the second MSM on the copies overlap the PREVIOUS MSM's kernels, so one
           // range is enough and the per-range bookkeeping is saved
           in_batch_tail_ = live[slot ^ 1];
-          pend[slot] = Enqueue(bases_of(i), scalars[i], sizes[i], slot);
+          pend[slot] = Enqueue(bases_of(i), scalars[i], sizes[i], slot, false, false,
+                               /*table=*/!bases[i] && table_c_ != 0);
           in_batch_tail_ = false;
           pend[slot].index = i;
           live[slot] = true;
@@ -445,6 +493,7 @@ class MsmEngine {
   // One enqueued MSM: everything the host epilogue needs once the device is done.
   struct Pending {
     MsmPlan plan{};
+    MsmPlan red{};  // the plan as the reduction / window combination see it (ReductionPlan)
     uint32_t L0 = 0, M = 0;
     uint32_t low = 0;     // windows of the low group
     uint32_t L0_low = 0;  // its running-sum block length
@@ -534,19 +583,22 @@ class MsmEngine {
   }
 
   // Plan of one point range of `n` points inside an MSM whose window size is `c`.
-  MsmPlan MakePlan(size_t n, uint32_t c) const {
+  MsmPlan MakePlan(size_t n, uint32_t c, bool table = false) const {
     MsmPlan p{};
     p.n = (uint32_t)n;
     p.c = c;
     p.W = WindowsFor(Fr::kBits, p.c);
     p.B = 1u << (p.c - 1);
-    p.TB = p.W * p.B;
-    p.wide = WideWindowsFor(Fr::kBits, p.c, options_.balance != 0);
+    p.shared = table ? 1u : 0u;
+    p.stride = table ? (uint32_t)registered_n_ : 0u;
+    p.TB = table ? p.B : p.W * p.B;
+    p.wide = table ? table_wide_ : WideWindowsFor(Fr::kBits, p.c, options_.balance != 0);
     // Tasks hold up to 4x the mean bucket size, so ordinary buckets are one task and only
     // genuinely oversized buckets (skewed scalars) are split and folded.
     uint32_t seg = 128;
     const uint32_t run_buckets = p.wide < p.W ? p.B / 2 : p.B;  // narrow windows: half the buckets
-    while (seg < (uint32_t)kMaxSegment && seg < 4 * (n / run_buckets + 1)) seg <<= 1;
+    const size_t per_set = table ? n * p.W : n;                // entries per bucket set
+    while (seg < (uint32_t)kMaxSegment && seg < 4 * (per_set / run_buckets + 1)) seg <<= 1;
     p.seg = options_.segment ? options_.segment : seg;
     if (p.seg > (uint32_t)kMaxSegment) p.seg = kMaxSegment;
     p.aggregate = options_.aggregate < 0 ? 1u : (uint32_t)options_.aggregate;
@@ -578,6 +630,7 @@ class MsmEngine {
   // The two-level sort needs at least two coarse bins per window and at most
   // kMaxCoarsePerWindow of them; tiny ranges are not worth its extra passes.
   bool UseTwoLevelSort(const MsmPlan& p) const {
+    if (p.shared) return false;  // shared buckets: the one-level sort (its keys carry no window)
     bool eligible = p.c >= 12 && (p.B >> kFineBits) <= kMaxCoarsePerWindow && p.n >= (1u << 15);
     if (options_.sort_mode == 0) return false;
     if (options_.sort_mode == 1) return eligible;
@@ -679,8 +732,9 @@ class MsmEngine {
 
   // Device bytes one point range of m points needs besides the bucket values (the role of
   // the footprint model in icicle_msm_utils.cc:10-68, for this pipeline's buffers).
-  size_t RangeFootprint(size_t m, uint32_t c, bool stage_bases, bool stage_scalars) const {
-    MsmPlan p = MakePlan(m, c);
+  size_t RangeFootprint(size_t m, uint32_t c, bool stage_bases, bool stage_scalars,
+                        bool table = false) const {
+    MsmPlan p = MakePlan(m, c, table);
     size_t b = (size_t)m * p.W * 4 + PaddedBound(p) * 4;  // digits + sorted
     if (p.R) b += PaddedBound(p) * (kAffineBytes + kAffineBytes / 4);  // pair outputs + prefixes
     if (UseTwoLevelSort(p)) b += (size_t)m * p.W * 8;                  // coarse-sorted entries
@@ -755,7 +809,7 @@ class MsmEngine {
   // epilogue.  All device buffers except the staging ring are shared by consecutive MSMs,
   // which is safe because their kernels are ordered on the one compute stream.
   Pending Enqueue(const void* bases, const void* scalars, size_t n, int slot,
-                  bool reserve_only = false, bool gather = false) {
+                  bool reserve_only = false, bool gather = false, bool table = false) {
     auto wall0 = std::chrono::steady_clock::now();
     const bool bases_dev = IsDevicePointer(bases), scalars_dev = IsDevicePointer(scalars);
     const bool bases_pageable = !bases_dev && IsPageable(bases);
@@ -778,8 +832,10 @@ class MsmEngine {
     // the window is chosen knowing the range count: every extra range repeats the per-bucket
     // bookkeeping, so pipelined host inputs prefer a slightly smaller window
     if (reserve_only) skew_hint_ = false;
-    const uint32_t c = reserve_only ? WindowBitsFor(n, K) : WindowBitsFromSample(scalars, n, scalars_dev, K);
-    MsmPlan whole = MakePlan(n, c);
+    if (table) skew_hint_ = false;
+    const uint32_t c = table ? table_c_
+                             : (reserve_only ? WindowBitsFor(n, K) : WindowBitsFromSample(scalars, n, scalars_dev, K));
+    MsmPlan whole = MakePlan(n, c, table);
     bool memory_bound = false;
     {
       // Memory model (icicle_msm_utils.cc:10-68 analogue): more ranges when one range's
@@ -787,7 +843,7 @@ class MsmEngine {
       // only when this call needs more than the engine already owns.
       const size_t state_b = (size_t)whole.TB * kXyzzBytes;
       auto need = [&](size_t k) {
-        return state_b + RangeFootprint((n + k - 1) / k, c, !bases_dev, !scalars_dev);
+        return state_b + RangeFootprint((n + k - 1) / k, c, !bases_dev, !scalars_dev, table);
       };
       if (need(K) > OwnedBytes()) {
         if (budget_ == 0) {  // refreshed whenever the workspace grows (ReserveAll)
@@ -824,13 +880,15 @@ class MsmEngine {
     }
     size_t m = 0;  // the largest range: what the per-range workspace is sized for
     for (size_t r = 0; r < K; ++r) m = bound[r + 1] - bound[r] > m ? bound[r + 1] - bound[r] : m;
-    MsmPlan big = MakePlan(m, c);
+    MsmPlan big = MakePlan(m, c, table);
+    const MsmPlan red = ReductionPlan(big);
     pd.plan = big;
+    pd.red = red;
     pd.K = K;
     launches_ = 0;
     pd.device_ladder = options_.device_ladder != 0;
     gather = gather && pd.device_ladder;  // host ladder: the partial is gathered after Finish()
-    pd.low = (reserve_only || !pd.device_ladder) ? 0u : ChooseLowWindows(big, bound[K] - bound[K - 1]);
+    pd.low = (reserve_only || !pd.device_ladder || table) ? 0u : ChooseLowWindows(big, bound[K] - bound[K - 1]);
 
     // ---- workspace ----------------------------------------------------------------
     // staging ring: kStageSlots slots of one 256-byte-aligned range each, plus one alignment unit
@@ -840,14 +898,14 @@ class MsmEngine {
     uint32_t scan_blocks = (big.TB + kScanItems - 1) / kScanItems;
     if (scan_blocks > (uint32_t)kScanItems)
       throw CudaError{cudaErrorInvalidValue, "too many buckets", __FILE__, __LINE__};
-    pd.L0 = ChooseLevelLength(big.B, big.W);
+    pd.L0 = ChooseLevelLength(big.B, red.W);
     const uint32_t nb = big.B / pd.L0;  // blocks per window, a power of two
     pd.M = Log2(nb);
     // reduction tree buffers: per window a slice of 2 nb points (the leaves (A_t, P_t)); the
     // scratch and stage-output buffers use the same slicing (reduce_tree_kernel)
     size_t tree_b = 0;
     auto reduction_bytes = [&](uint32_t cc) {
-      uint32_t Wc = WindowsFor(Fr::kBits, cc), Bc = 1u << (cc - 1);
+      uint32_t Wc = table ? 1u : WindowsFor(Fr::kBits, cc), Bc = 1u << (cc - 1);
       uint32_t nbc = Bc / ChooseLevelLength(Bc, Wc);
       size_t lv = (size_t)Wc * nbc * 2 * kXyzzBytes;
       if (lv > tree_b) tree_b = lv;
@@ -860,7 +918,7 @@ class MsmEngine {
       for (uint32_t cc = kMinWindowBits; cc < c; ++cc) reduction_bytes(cc);
     // the low window group has its own, shorter running-sum blocks (its reduction is what
     // remains exposed at the end of the MSM: latency, not throughput, counts) and its own buffers
-    pd.L0_low = LowLevelLength(big, pd.low);
+    pd.L0_low = LowLevelLength(red, pd.low);
     const size_t tree_lo_b = (size_t)pd.low * (big.B / pd.L0_low) * 2 * kXyzzBytes;
     ReserveAll({{&state_, (size_t)big.TB * kXyzzBytes},
                 {&count_, (size_t)(big.TB + 1) * 4},
@@ -936,7 +994,7 @@ class MsmEngine {
         memset(host_out + kHostPartialBytes + r * sizeof(MsmTotals), 0, sizeof(MsmTotals));
         continue;
       }
-      MsmPlan plan = MakePlan(len, c);
+      MsmPlan plan = MakePlan(len, c, table);
       // ---- inputs of this range ---------------------------------------------------
       const uint32_t* d_bases;
       const uint32_t* d_scalars;
@@ -1008,7 +1066,7 @@ class MsmEngine {
       }
       // mean run of the most loaded windows: the narrow (c - 1 bit) windows of a balanced plan
       // spread the same n entries over half as many buckets
-      const uint32_t seg_buckets = plan.W * (plan.wide < plan.W ? plan.B / 2 : plan.B);
+      const uint32_t seg_buckets = plan.shared ? plan.B : plan.W * (plan.wide < plan.W ? plan.B / 2 : plan.B);
       Launch(choose_segment_kernel, 1, 64, nonzero_slots_.as<uint32_t>(), seg_buckets, plan.R,
              plan.seg, options_.segment ? plan.seg : 0u, totals_);
       Launch(scan_block_sums_kernel, scan_blocks, kScanThreads, count_.as<uint32_t>(), plan.TB,
@@ -1094,11 +1152,11 @@ class MsmEngine {
         // SMs with them and ends as late as they do: 2^21 points 1.02 ms instead of 0.48); only
         // the latency-bound merge tree and doubling chain move to the tail stream
         uint32_t* terms_hi = combine_.as<uint32_t>();
-        EnqueueReduction(tail_stream_, big, pd.low, big.W - pd.low, pd.L0, tree_hi_, terms_hi, stream_,
+        EnqueueReduction(tail_stream_, red, pd.low, red.W - pd.low, pd.L0, tree_hi_, terms_hi, stream_,
                          SlotEvent(slot, 10));
         TB_CUDA(cudaEventRecord(SlotEvent(slot, 6), tail_stream_));
         LaunchOn(tail_stream_, window_combine_kernel<C>, 1, kCombineThreads, terms_hi,
-                 TotalBits(big), WindowBitOffset(big, pd.low), (const uint32_t*)nullptr, HiSum(),
+                 TotalBits(red), WindowBitOffset(red, pd.low), (const uint32_t*)nullptr, HiSum(),
                  PerWindow{0, 0, 0});
         TB_CUDA(cudaEventRecord(SlotEvent(slot, 7), tail_stream_));
         TB_CUDA(cudaEventRecord(SlotEvent(slot, 5), tail_stream_));
@@ -1125,22 +1183,22 @@ class MsmEngine {
     // finishes the low windows and adds the high group's sum.  The result is ONE XYZZ point.
     if (pd.low > 0) {
       uint32_t* terms_lo = combine_.as<uint32_t>() + (size_t)kTermSlots * kXyzzWords;
-      EnqueueReduction(stream_, big, 0, pd.low, pd.L0_low, tree_lo_, terms_lo);
+      EnqueueReduction(stream_, red, 0, pd.low, pd.L0_low, tree_lo_, terms_lo);
       TB_CUDA(cudaEventRecord(SlotEvent(slot, 8), stream_));
       TB_CUDA(cudaStreamWaitEvent(stream_, SlotEvent(slot, 5), 0));
       TB_CUDA(cudaEventRecord(SlotEvent(slot, 9), stream_));
-      Launch(window_combine_kernel<C>, 1, kCombineThreads, terms_lo, WindowBitOffset(big, pd.low), 0u,
+      Launch(window_combine_kernel<C>, 1, kCombineThreads, terms_lo, WindowBitOffset(red, pd.low), 0u,
              (const uint32_t*)HiSum(), Partial(), PerWindow{0, 0, 0});
     } else {
       uint32_t* terms = combine_.as<uint32_t>();
-      EnqueueReduction(stream_, big, 0, big.W, pd.L0, tree_hi_, terms);
+      EnqueueReduction(stream_, red, 0, red.W, pd.L0, tree_hi_, terms);
       TB_CUDA(cudaEventRecord(SlotEvent(slot, 6), stream_));
       if (pd.device_ladder)
-        Launch(window_combine_kernel<C>, 1, kCombineThreads, terms, TotalBits(big), 0u,
+        Launch(window_combine_kernel<C>, 1, kCombineThreads, terms, TotalBits(red), 0u,
                (const uint32_t*)nullptr, Partial(), PerWindow{0, 0, 0});
       else  // the parallel part only: one CTA per window, S_w to WindowSums()
-        Launch(window_combine_kernel<C>, big.W, kCombineThreads, terms, 0u, 0u, (const uint32_t*)nullptr,
-               WindowSums(), PerWindow{big.c, big.wide, 0});
+        Launch(window_combine_kernel<C>, red.W, kCombineThreads, terms, 0u, 0u, (const uint32_t*)nullptr,
+               WindowSums(), PerWindow{red.c, red.wide, 0});
       TB_CUDA(cudaEventRecord(SlotEvent(slot, 7), stream_));
     }
     pd.gathered = gather;
@@ -1149,7 +1207,7 @@ class MsmEngine {
     } else if (pd.device_ladder) {
       TB_CUDA(cudaMemcpyAsync(host_out, Partial(), kXyzzBytes, cudaMemcpyDeviceToHost, stream_));
     } else {
-      TB_CUDA(cudaMemcpyAsync(host_out, WindowSums(), (size_t)big.W * kXyzzBytes, cudaMemcpyDeviceToHost,
+      TB_CUDA(cudaMemcpyAsync(host_out, WindowSums(), (size_t)red.W * kXyzzBytes, cudaMemcpyDeviceToHost,
                               stream_));
     }
     TB_CUDA(cudaEventRecord(ev_end, stream_));
@@ -1185,9 +1243,10 @@ class MsmEngine {
       // top window down, c_w doublings then one addition.  Strictly sequential work on one point.
       const Point* sums = reinterpret_cast<const Point*>(host_out);
       result = Point::Zero();
-      for (uint32_t w = plan.W; w-- > 0;) {
-        const uint32_t cw = plan.c - (w >= plan.wide ? 1u : 0u);
-        for (uint32_t k = 0; k < cw && w + 1 < plan.W; ++k) result = result.Dbl();
+      const MsmPlan& red = pd.red;  // one bucket set with the precomputed table: no ladder at all
+      for (uint32_t w = red.W; w-- > 0;) {
+        const uint32_t cw = red.c - (w >= red.wide ? 1u : 0u);
+        for (uint32_t k = 0; k < cw && w + 1 < red.W; ++k) result = result.Dbl();
         result = result.Add(sums[w]);
       }
     }
@@ -1279,6 +1338,16 @@ class MsmEngine {
   uint32_t* Scratch() {
     if (!combine_.ptr) combine_.Reserve((size_t)(2 * kTermSlots + 2 + kMaxWindows) * kXyzzBytes);
     return Partial();
+  }
+
+  // What the bucket reduction and the window combination see: W bucket sets, or — with the
+  // precomputed table — one set whose sum already is the MSM (no window weights left).
+  static MsmPlan ReductionPlan(MsmPlan p) {
+    if (p.shared) {
+      p.W = 1;
+      p.wide = 1;
+    }
+    return p;
   }
 
   // Bit position of window w's lowest bit / of the end of the top window (balanced windows).
@@ -1476,6 +1545,7 @@ class MsmEngine {
   MsmTotals* totals_ = nullptr;
   char* host_out_ = nullptr;
   size_t registered_n_ = 0;
+  uint32_t table_c_ = 0, table_wide_ = 0;  // window size of the precomputed table (0: none)
   DeviceBuffer registered_, bases_stage_, scalars_stage_, state_, count_, offset_, cursor_, task_base_, tasks_,
       task_meta_, multi_, sorted_, digits_, task_out_, block_sums_, order_, len_hist_, combine_,
       pair_prefix_, pair_out_[4], mid_, coarse_,

@@ -78,6 +78,11 @@ struct MsmPlan {
   uint32_t aggregate;  // warp-aggregate the bucket atomics (pays off for repeated digits)
   uint32_t R;          // pair rounds of the batched-affine pre-reduction; bucket runs in
                        // `sorted` start at multiples of 2^R and are padded with kNoEntry
+  uint32_t shared;     // 1: all windows share ONE set of B buckets — the bases are a table of
+                       // precomputed multiples T[w][i] = 2^(bit offset of window w) * P_i
+                       // (`stride` points per window), so the digit of window w selects
+                       // T[w][i] and no window weights remain (TB = B)
+  uint32_t stride;     // points per window slice of the precomputed table
   uint32_t wide;       // windows [0, wide) take c bits, windows [wide, W) take c - 1 (balanced
                        // windows: the slack W * c - (bits + 1) is spread over the top windows
                        // instead of leaving one nearly empty, heavily loaded top window)
@@ -236,7 +241,7 @@ __global__ void __launch_bounds__(256) digits_hist_kernel(const uint32_t* __rest
   for_each_digit<Fr>(s, plan, [&](uint32_t w, uint32_t mag, bool neg) {
     bool valid = in && mag != 0;
     if (in) digits[(size_t)w * plan.n + i] = mag | (neg ? 0x80000000u : 0u);
-    bucket_inc(count, w * plan.B + mag - 1, valid, plan.aggregate != 0);
+    bucket_inc(count, (plan.shared ? 0u : w * plan.B) + mag - 1, valid, plan.aggregate != 0);
     nz += valid;
   });
   // non-zero digits of the CTA -> one of kNonzeroSlots counters (input of choose_segment)
@@ -268,8 +273,9 @@ static __global__ void __launch_bounds__(256) digits_scatter_kernel(const uint32
   uint32_t d = in ? digits[(size_t)w * plan.n + i] : 0u;
   uint32_t mag = d & 0x7fffffffu;
   bool valid = mag != 0;
-  uint32_t pos = bucket_inc(cursor, w * plan.B + mag - 1, valid, plan.aggregate != 0);
-  if (valid) sorted[pos] = i | (d & 0x80000000u);
+  uint32_t pos = bucket_inc(cursor, (plan.shared ? 0u : w * plan.B) + mag - 1, valid, plan.aggregate != 0);
+  // shared buckets: the entry names the window's slice of the precomputed table
+  if (valid) sorted[pos] = (plan.shared ? w * plan.stride + i : i) | (d & 0x80000000u);
 }
 
 // ---------------------------------------------------------------------------
@@ -1316,6 +1322,43 @@ __global__ void point_op_kernel(int op, const uint32_t* a, const uint32_t* b, ui
     xyzz_dbl<K>(p);
   }
   xyzz_store<K>(out + (size_t)i * 4 * N, p);
+}
+
+// Table of precomputed multiples for REGISTERED bases (the role of precompute_factor in
+// algorithms/icicle/icicle_msm.h:21): T[w][i] = 2^(bit offset of window w) * P_i, affine.  One
+// thread per point walks up the windows (c_w doublings each) and normalises every multiple
+// (one field inversion each; this runs once per registration).  T[0] = the bases themselves.
+template <class C>
+__global__ void __launch_bounds__(128) precompute_table_kernel(const uint32_t* __restrict__ bases,
+                                                               uint32_t n, uint32_t stride, uint32_t W,
+                                                               uint32_t c, uint32_t wide,
+                                                               uint32_t* __restrict__ table) {
+  using K = typename C::Field;
+  constexpr int kAffineWords = 2 * K::kWords;
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  Affine<K> a;
+  affine_load<K>(a, bases + (size_t)i * kAffineWords);
+  affine_store<K>(table + (size_t)i * kAffineWords, a);
+  XYZZ<K> p;
+  xyzz_set_zero<K>(p);
+  xyzz_madd<K>(p, a, false);
+  for (uint32_t w = 1; w < W; ++w) {
+    const uint32_t cw = c - (w - 1 >= wide ? 1u : 0u);  // width of the window below
+    for (uint32_t k = 0; k < cw; ++k) xyzz_dbl<K>(p);
+    if (xyzz_is_zero<K>(p)) {
+      K::set_zero(a.x);
+      K::set_zero(a.y);
+    } else {
+      typename K::El zi3, zi2;
+      K::inv(zi3, p.zzz);
+      K::mul(zi2, zi3, p.zz);
+      K::sqr(zi2, zi2);
+      K::mul(a.x, p.x, zi2);
+      K::mul(a.y, p.y, zi3);
+    }
+    affine_store<K>(table + ((size_t)w * stride + i) * kAffineWords, a);
+  }
 }
 
 // ---------------------------------------------------------------------------

@@ -462,6 +462,51 @@ def test_registered_bases_commit_batch(oracles, torch_cuda, name):
                 assert (got[i] == np.asarray(want[i]).reshape(-1)).all(), i
 
 
+# Registered bases with the table of window multiples (option "precompute"; the role of
+# precompute_factor in algorithms/icicle/icicle_msm.h:21): all windows share one bucket set, the
+# digit of window w selects 2^(bit offset of w) * P from the table.  Same commitments, bit for
+# bit, for several window sizes (incl. balanced narrow top windows), ragged sizes, skewed
+# scalars, point ranges, identity bases, G2, and the general batch call mixing table and
+# explicit bases.
+@pytest.mark.parametrize("name", ALL)
+def test_registered_bases_precomputed_table(oracles, torch_cuda, name):
+    o = oracles[name]
+    n = 3000 if name in CURVES else 900
+    bases = o.generate_points(191, n)
+    bases[5] = 0                                      # an identity base stays the identity in every slice
+    sizes = [n, 1, 0, n - 400, 17, n]
+    scal = [o.generate_scalars(192 + i, s, ("witness", "uniform", "non_uniform")[i % 3]) for i, s in enumerate(sizes)]
+    r_mod, _ = _consts(name)
+    scal[0][0] = o.fr_to_mont(np.array(pymodel.to_limbs(r_mod - 1, 4), dtype=np.uint64))[0]
+    want = [np.asarray(o.msm_affine(bases[:s], scal[i])).reshape(-1) if s else np.zeros(bases.shape[1], dtype=np.uint64)
+            for i, s in enumerate(sizes)]
+    other = o.generate_points(193, 500)
+    other_sc = o.generate_scalars(194, 500)
+    other_want = np.asarray(o.msm_affine(other, other_sc)).reshape(-1)
+    with msm.MSMGpu(name) as ctx:
+        ctx.set_option("precompute", 1)
+        for cbits in (0, 5, 8, 13):
+            ctx.set_option("window_bits", cbits)
+            ctx.register_bases(bases)
+            for ranges in (0, 3):
+                ctx.set_option("ranges", ranges)
+                got = msm.batch_normalize(name, ctx.commit_batch(scal, sizes))
+                for i in range(len(sizes)):
+                    assert (got[i] == want[i]).all(), (cbits, ranges, i)
+            ctx.set_option("ranges", 0)
+        ctx.set_option("window_bits", 0)
+        # the general batch: registered table for one MSM, explicit bases for the other
+        got = msm.batch_normalize(name, ctx.msm_batch([None, other], [scal[5], other_sc], [n, 500]))
+        assert (got[0] == want[5]).all() and (got[1] == other_want).all()
+        # a plain MSM call on the same context is unaffected by the table
+        assert (np.asarray(o.jacobian_to_affine(ctx.affine_msm(other, other_sc))).reshape(-1) == other_want).all()
+        ctx.set_option("precompute", 0)               # back to a plain registration
+        ctx.register_bases(bases)
+        got = msm.batch_normalize(name, ctx.commit_batch(scal, sizes))
+        for i in range(len(sizes)):
+            assert (got[i] == want[i]).all(), i
+
+
 # BASELINE.json configs[4] in miniature: the four G1 MSMs of a Groth16 proof (A, B1 over the
 # full assignment, L over its witness part, H over uniform coefficients; prove.h:100-131),
 # each with its own bases, through the general batch call.
