@@ -401,6 +401,8 @@ def run_commit_batch(args, local_rank):
     ms_dev, aff_dev = timed([t.data_ptr() for t in dev], args.steps)
     launches = msm.kernel_launch_count() - l0
     clocks = sampler.stop()
+    t = ctx.last_timing()     # sums over the commitments of the last batch
+    stages = {k: t[k] / count for k in ("sort_ms", "accumulate_ms", "reduce_ms", "host_ms")}
     ms_host, aff_host = timed([t.data_ptr() for t in host], max(2, min(args.steps, 5)))
     parity = "skipped"
     if not args.no_parity:
@@ -420,7 +422,7 @@ def run_commit_batch(args, local_rank):
         "scaling": "strong", "vs_baseline": None, "dtype": "u32", "data": "synthetic",
         "config": {"workload": f"{count} commitments of 2^{args.log_n} points over registered (device-resident) "
                                f"{curve} bases, {args.dist} scalars, batch-normalised", "ms_per_commitment": ms_dev / count,
-                   "precompute": bool(args.precompute), "register_ms": t_reg,
+                   "precompute": bool(args.precompute), "register_ms": t_reg, "stages_ms_per_commitment": stages,
                    "window_bits": ctx.last_timing()["window_bits"], "windows": ctx.last_timing()["windows"],
                    "l2": "inputs + workspace exceed the 126 MB L2 every step"},
         "clocks": clocks, "gpu_launches": int(launches),

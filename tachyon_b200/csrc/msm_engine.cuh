@@ -151,11 +151,38 @@ constexpr uint32_t kMaxWindows = 64;
 // buckets of a 2^24-point BN254 MSM, i.e. 0.76 mixed additions per bucket and range.
 constexpr double kRangeBucketCost = 0.76;
 
-inline uint32_t ChooseWindowBits(size_t n, uint32_t scalar_bits, size_t ranges = 1) {
+// Mixed additions the accumulation kernel is charged for, uniform scalars.  Throughput-bound it
+// is n * W; but the kernel ends when its LONGEST task ends, and one task is one bucket: with few,
+// long buckets (small n, or the narrow top windows of a balanced plan, whose buckets hold twice
+// the entries) the resident threads all wait for ~mean + 4 sigma sequential additions.  Measured
+// (B200, BN254): 2^18 points 1.98 ms at c = 14 (110 K buckets of 45 / 90 entries) against 1.25 ms
+// at c = 15; 2^17 1.19 -> 0.89 ms.
+inline double AccumulateWork(size_t n, uint32_t scalar_bits, uint32_t c, bool balance = true,
+                             uint32_t resident_threads = 148 * 512) {
+  const uint32_t W = WindowsFor(scalar_bits, c), wide = WideWindowsFor(scalar_bits, c, balance);
+  const double per_bucket = (double)n / (double)(1u << (c - (wide < W ? 2 : 1)));  // narrow windows
+  const double longest = per_bucket + 4.0 * std::sqrt(per_bucket);
+  const double tasks = PopulatedBuckets(scalar_bits, c, balance);
+  // a thread's addition takes 1 / (resident threads) of the chip's throughput at full occupancy
+  // (10.5 us) and never less than ~5.8 us, the latency of one mixed addition with the SM to
+  // itself (2^14 points: 20 K tasks of ~55 additions take 0.33 ms, 74 K tasks of ~19 0.13 ms)
+  double running = tasks < (double)resident_threads ? tasks : (double)resident_threads;
+  if (running < 0.55 * resident_threads) running = 0.55 * resident_threads;
+  const double throughput = (double)n * W, critical = longest * running;
+  return throughput > critical ? throughput : critical;
+}
+
+// Sorting costs the same 0.057 ns per entry for every group while a mixed addition costs 0.155 ns
+// (BN254 G1) to 1.3 ns (BLS12-381 G2): the entry cost in units of one mixed addition.
+inline double EntryCost(double madd_ns) { return 1.0 + 0.057 / madd_ns; }
+
+inline uint32_t ChooseWindowBits(size_t n, uint32_t scalar_bits, size_t ranges = 1,
+                                 double kEntryCost = 1.37) {
   // measured on B200 (BN254 2^24, c = 20): 0.155 ns per mixed addition, 0.057 ns of
-  // sorting per entry, 0.73 ns of reduction per bucket
-  constexpr double kEntryCost = 1.37;
-  const double kBucketCost = 4.7 + kRangeBucketCost * (double)(ranges > 1 ? ranges - 1 : 0);
+  // sorting per entry, 0.75 ns of reduction per bucket (2 full additions + the merge tree = 5.4
+  // mixed additions at 0.138 ns, the same ratio for every field; 2^22 points: c = 17 10.8 ms,
+  // c = 19 11.1 ms)
+  const double kBucketCost = 5.4 + kRangeBucketCost * (double)(ranges > 1 ? ranges - 1 : 0);
   constexpr uint32_t kMaxBuckets = 1u << 24;  // scan_top_kernel capacity
   double best = 1e300;
   uint32_t best_c = kMinWindowBits;
@@ -163,7 +190,10 @@ inline uint32_t ChooseWindowBits(size_t n, uint32_t scalar_bits, size_t ranges =
     uint32_t W = WindowsFor(scalar_bits, c);
     double buckets = (double)W * (double)(1u << (c - 1));
     if (buckets > kMaxBuckets) break;
-    double cost = kEntryCost * (double)n * W + kBucketCost * PopulatedBuckets(scalar_bits, c);
+    // with several point ranges every range is its own accumulation of n / ranges points
+    const size_t per_range = ranges > 1 ? (n + ranges - 1) / ranges : n;
+    double cost = kEntryCost * AccumulateWork(per_range, scalar_bits, c) * (double)(ranges > 1 ? ranges : 1) +
+                  kBucketCost * PopulatedBuckets(scalar_bits, c);
     if (cost < best) {
       best = cost;
       best_c = c;
@@ -174,8 +204,8 @@ inline uint32_t ChooseWindowBits(size_t n, uint32_t scalar_bits, size_t ranges =
 
 // Window choice when all windows share one bucket set (precomputed table of window multiples):
 // the reduction covers 2^(c-1) buckets once instead of once per window, so larger windows pay.
-inline uint32_t ChooseWindowBitsShared(size_t n, uint32_t scalar_bits) {
-  constexpr double kEntryCost = 1.37, kBucketCost = 4.7;
+inline uint32_t ChooseWindowBitsShared(size_t n, uint32_t scalar_bits, double kEntryCost = 1.37) {
+  constexpr double kBucketCost = 5.4;
   double best = 1e300;
   uint32_t best_c = kMinWindowBits;
   for (uint32_t c = kMinWindowBits; c <= 24; ++c) {
@@ -196,9 +226,8 @@ inline uint32_t ChooseWindowBitsShared(size_t n, uint32_t scalar_bits) {
 // have far fewer entries per point than the uniform draw the plain model assumes, and a
 // smaller window (fewer buckets to reduce) wins.
 inline uint32_t ChooseWindowBitsSampled(size_t n, uint32_t scalar_bits, const uint32_t* bit_hist,
-                                        uint32_t samples, size_t ranges = 1) {
-  constexpr double kEntryCost = 1.37;
-  const double kBucketCost = 4.7 + kRangeBucketCost * (double)(ranges > 1 ? ranges - 1 : 0);
+                                        uint32_t samples, size_t ranges = 1, double kEntryCost = 1.37) {
+  const double kBucketCost = 5.4 + kRangeBucketCost * (double)(ranges > 1 ? ranges - 1 : 0);
   constexpr uint32_t kMaxBuckets = 1u << 24;
   double best = 1e300;
   uint32_t best_c = kMinWindowBits;
@@ -399,7 +428,8 @@ class MsmEngine {
     table_c_ = 0;
     uint32_t W = 1;
     if (options_.precompute && n) {
-      table_c_ = options_.window_bits ? options_.window_bits : ChooseWindowBitsShared(n, Fr::kBits);
+      table_c_ = options_.window_bits ? options_.window_bits
+                                      : ChooseWindowBitsShared(n, Fr::kBits, EntryCost(MaddNanos()));
       if (table_c_ < kMinWindowBits) table_c_ = kMinWindowBits;
       W = WindowsFor(Fr::kBits, table_c_);
       if ((uint64_t)n * W >= (uint64_t(1) << 31))
@@ -407,7 +437,13 @@ class MsmEngine {
                         __LINE__};
     }
     registered_.Reserve(n * W * kAffineBytes);
-    if (n) TB_CUDA(cudaMemcpy(registered_.ptr, bases, n * kAffineBytes, cudaMemcpyDefault));
+    // on the engine's stream: a plain cudaMemcpy from pageable memory may return while its last
+    // staged chunk is still on its way, and this (non-blocking) stream does not wait for the
+    // legacy stream — the table kernel below read stale bytes beyond the first MiB
+    if (n) {
+      TB_CUDA(cudaMemcpyAsync(registered_.ptr, bases, n * kAffineBytes, cudaMemcpyDefault, stream_));
+      TB_CUDA(cudaStreamSynchronize(stream_));
+    }
     registered_n_ = n;
     if (table_c_) {
       const uint32_t wide = WideWindowsFor(Fr::kBits, table_c_, options_.balance != 0);
@@ -706,7 +742,7 @@ class MsmEngine {
     for (uint32_t b = 0; b <= 8; ++b) tiny += hist[b];
     skew_hint_ = tiny * 20 > kSamples;  // more than 5 % of the scalars are below 2^8
     if (options_.window_bits || n < (size_t(1) << 22)) return WindowBitsFor(n, ranges);
-    uint32_t c = ChooseWindowBitsSampled(n, Fr::kBits, hist, kSamples, ranges);
+    uint32_t c = ChooseWindowBitsSampled(n, Fr::kBits, hist, kSamples, ranges, EntryCost(MaddNanos()));
     uint32_t by_size = WindowBitsFor(n, ranges);
     if (c > by_size) c = by_size;  // the sample may only argue for FEWER buckets
     if (c < kMinWindowBits) c = kMinWindowBits;
@@ -724,7 +760,8 @@ class MsmEngine {
 
   uint32_t WindowBitsFor(size_t n, size_t ranges = 1) const {
     uint32_t c =
-        options_.window_bits ? options_.window_bits : ChooseWindowBits(n, Fr::kBits, ranges);
+        options_.window_bits ? options_.window_bits
+                             : ChooseWindowBits(n, Fr::kBits, ranges, EntryCost(MaddNanos()));
     if (c < kMinWindowBits) c = kMinWindowBits;
     if (c > 24) c = 24;
     return c;
@@ -888,7 +925,10 @@ class MsmEngine {
     launches_ = 0;
     pd.device_ladder = options_.device_ladder != 0;
     gather = gather && pd.device_ladder;  // host ladder: the partial is gathered after Finish()
-    pd.low = (reserve_only || !pd.device_ladder || table) ? 0u : ChooseLowWindows(big, bound[K] - bound[K - 1]);
+    size_t last_len = 0;  // size of the last non-empty range
+    for (size_t r = 0; r < K; ++r)
+      if (bound[r + 1] > bound[r]) last_len = bound[r + 1] - bound[r];
+    pd.low = (reserve_only || !pd.device_ladder || table) ? 0u : ChooseLowWindows(big, last_len);
 
     // ---- workspace ----------------------------------------------------------------
     // staging ring: kStageSlots slots of one 256-byte-aligned range each, plus one alignment unit
@@ -986,6 +1026,11 @@ class MsmEngine {
     if (pd.any_host) TB_CUDA(cudaEventRecord(ev_copy_begin, copy_stream_));
 
     char* host_out = host_out_ + (size_t)slot * kHostOutBytes;
+    // the window groups are formed in the last NON-EMPTY range (a forced range count can leave
+    // empty ranges at the end, which queue no kernels at all)
+    size_t last_range = 0;
+    for (size_t r = 0; r < K; ++r)
+      if (bound[r + 1] > bound[r]) last_range = r;
     for (size_t r = 0; r < K; ++r) {
       const size_t lo = bound[r], len = bound[r + 1] - bound[r];
       if (len == 0) {  // degenerate split: keep the event bookkeeping of Finish() simple
@@ -1084,7 +1129,7 @@ class MsmEngine {
         LaunchGrid(digits_scatter_kernel, dim3(sgrid, plan.W), 256, digits_.as<uint32_t>(), plan,
                    cursor_.as<uint32_t>(), sorted_.as<uint32_t>());
       // tasks by window group (last range only: high windows first), then descending length
-      const bool split = pd.low > 0 && r + 1 == K;
+      const bool split = pd.low > 0 && r == last_range;
       const uint32_t split_key = split ? pd.low * plan.B : 0u;
       TB_CUDA(cudaMemsetAsync(len_hist_.ptr, 0, (size_t)kOrderBins * 4, stream_));
       uint32_t ogrid = (plan.max_tasks + kOrderThreads * kOrderPerThread - 1) /
@@ -1266,7 +1311,7 @@ class MsmEngine {
         // the range's first accumulate launch ran alone on the device
         TB_CUDA(cudaEventElapsedTime(&ms, ev(r, 2), ev(r, 4)));
         timing_.acc_kernel_ms += ms;
-        timing_.acc_kernel_entries += tot.entries - (r + 1 == pd.K ? tot.entries_lo : 0u);
+        timing_.acc_kernel_entries += tot.entries - tot.entries_lo;  // entries_lo: 0 unless split
       }
     }
     TB_CUDA(cudaEventElapsedTime(&ms, SlotEvent(slot, 6), SlotEvent(slot, 7)));
@@ -1425,6 +1470,11 @@ class MsmEngine {
     return L;
   }
 
+  // Nanoseconds per mixed addition of the accumulation kernel at full occupancy (measured, B200).
+  static constexpr double MaddNanos() {
+    return C::Field::kWords <= 8 ? 0.138 : (C::Field::kWords <= 12 ? 0.34 : (C::Field::kWords <= 16 ? 0.61 : 1.3));
+  }
+
   // How many low windows to accumulate last.  The window combination of the high group is a
   // chain of ~(bits above the split) point doublings, latency-bound on one lane; it is free as
   // long as the low group's accumulation (n mixed additions per window at the pipe rate) lasts
@@ -1443,7 +1493,7 @@ class MsmEngine {
     // full occupancy
     constexpr int kW = C::Field::kWords;
     const double dbl_us = kW <= 8 ? 1.64 : (kW <= 12 ? 3.28 : (kW <= 16 ? 4.41 : 9.6));
-    const double madd_ns = kW <= 8 ? 0.138 : (kW <= 12 ? 0.34 : (kW <= 16 ? 0.61 : 1.3));
+    const double madd_ns = MaddNanos();
     // timeline after the high group's accumulation and running-sum level (t = 0), tail stream:
     // merge tree (latency), doubling chain; compute stream: accumulation of the low windows, then
     // their level + tree, then their chain, which needs the high group's sum.  Minimise what is

@@ -425,6 +425,21 @@ def test_msm_staging_ring_reuse(oracles, torch_cuda, name):
             assert (got == o.msm_affine(bases[:n], scalars[:n])).all(), (n, ranges)
 
 
+# Process-level sharding plumbing that needs no second GPU: the NCCL library resolves, a unique
+# id is produced, joining a world of one is a no-op and an MSM still gives the right point.  (The
+# N > 1 exchange itself runs in bench.py under torchrun, with its own parity check.)
+def test_join_ranks_world_of_one(oracles, torch_cuda):
+    o = oracles["bn254"]
+    uid = msm.nccl_unique_id()
+    assert len(uid) == 128 and any(uid)
+    bases, scalars = o.generate_points(201, 777), o.generate_scalars(202, 777)
+    with msm.MSMGpu("bn254") as ctx:
+        ctx.join_ranks(uid, 0, 1)
+        _check_msm(o, "bn254", ctx, bases, scalars)
+        with pytest.raises(RuntimeError):
+            ctx.join_ranks(uid, 3, 2)               # rank outside the world
+
+
 # bases registered once (the SRS of kzg.h:91-113), then a batch of
 # commitments with fresh scalars (kzg.h:217-313), results batch-normalised (point_xyzz.h:109-163).
 @pytest.mark.parametrize("name", CURVES)
@@ -505,6 +520,19 @@ def test_registered_bases_precomputed_table(oracles, torch_cuda, name):
         got = msm.batch_normalize(name, ctx.commit_batch(scal, sizes))
         for i in range(len(sizes)):
             assert (got[i] == want[i]).all(), i
+    if name == "bls12_381":
+        # more than 1 MiB of pageable host bases: the registration copy must have landed before
+        # the table kernel reads it (a plain cudaMemcpy may return while its last staged chunk is
+        # in flight and the engine's non-blocking stream does not wait for the legacy stream)
+        n = 11708
+        bases, sc = o.generate_points(195, n), o.generate_scalars(196, n)
+        want = np.asarray(o.msm_affine(bases, sc)).reshape(-1)
+        for rep in range(4):
+            with msm.MSMGpu(name) as ctx:
+                ctx.set_option("precompute", 1)
+                ctx.set_option("window_bits", 9)
+                ctx.register_bases(bases)
+                assert (msm.batch_normalize(name, ctx.commit_batch([sc], [n]))[0] == want).all(), rep
 
 
 # BASELINE.json configs[4] in miniature: the four G1 MSMs of a Groth16 proof (A, B1 over the

@@ -1,6 +1,8 @@
 """Randomised parity sweep on a GPU (development aid, uses the CPU oracle as the checker):
-random sizes, window sizes, window balancing, reduction / sort modes, range counts and scalar
-distributions, host and device inputs, both G1 curves (G2 with --g2).
+random sizes, window sizes, window balancing, reduction / sort modes, running-sum block lengths,
+range counts, ladder placement and window groups, task lengths, point staging, registered bases
+with and without the precomputed table, scalar distributions, host and device inputs, both G1
+curves (G2 with --g2).
     python tools/fuzz_gpu.py [cases] [seed] [--g2]"""
 import os
 import random
@@ -37,12 +39,31 @@ for case in range(cases):
         "sort_mode": rng.choice([-1, -1, 0, 1]),
         "ranges": rng.choice([0, 0, 1, 2, 3, 7]),
         "sample_scalars": rng.choice([1, 1, 0]),
+        "device_ladder": rng.choice([0, 0, 1]),
+        "low_windows": rng.choice([-1, 0, 1, 2, 3, 9]),
+        "level_fill": rng.choice([0, 0, 48, 96, 3000]),      # running-sum block lengths 4 .. 64
+        "stage_points": rng.choice([0, 0, 1]),
+        "segment": rng.choice([0, 0, 0, 16, 32]),
     }
     for k, v in opts.items():
         ctx.set_option(k, v)
     s = rng.randrange(1 << 30)
     bases, scalars = o.generate_points(s, n), o.generate_scalars(s + 1, n, dist)
     want = o.msm_affine(bases, scalars)
+    mode = rng.random()
+    if mode < 0.2:
+        # registered bases, with or without the table of window multiples, through the batch call
+        ctx.set_option("precompute", rng.choice([0, 1]))
+        ctx.register_bases(bases)
+        m2 = rng.randint(1, n)
+        out = msm.batch_normalize(c, ctx.commit_batch([scalars, scalars[:m2]], [n, m2]))
+        ctx.set_option("precompute", 0)
+        ok = bool((out[0] == np.asarray(want).reshape(-1)).all()) and \
+            bool((out[1] == np.asarray(o.msm_affine(bases[:m2], scalars[:m2])).reshape(-1)).all())
+        if not ok:
+            bad += 1
+            print("MISMATCH (registered)", c, n, m2, dist, opts, "seed", s, flush=True)
+        continue
     if rng.random() < 0.5:
         got = ctx.affine_msm(bases, scalars)
         where = "host"
