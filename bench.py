@@ -647,26 +647,36 @@ class MsmCase:
             uid = d.broadcast_object(msm.nccl_unique_id() if d.rank == 0 else None)
             self.ctx.join_ranks(uid, d.rank, d.world)
         self.h_bases = self.h_scalars = None
+        self.host_memory = None
 
     def close(self):
         self.ctx.close()
+        for b in (self.h_bases, self.h_scalars):
+            if b is not None:
+                b.free()
         self.bases = self.scalars = self.h_bases = self.h_scalars = None
 
     def resident(self):
         return self.ctx.msm_xyzz(self.bases.data_ptr(), self.scalars.data_ptr(), self.n_local)
 
     def pin_host(self):
+        """The rank's inputs in page-locked HOST memory.  With several ranks on one box the pages
+        are write-combined (tachyon_b200_alloc_host): the bare copy probe (tools/probe/h2d_probe.cu,
+        profiles/r2_h2d_probe_8gpu.txt) shows ordinary pinned memory dropping to ~30 GB/s per GPU
+        when 4-8 GPUs copy at once, write-combined memory holding 39-49."""
         torch = self.d.torch
         if self.h_bases is None:
-            self.h_bases = torch.empty((self.n_local, 2 * self.fq), dtype=torch.int64).pin_memory()
-            self.h_scalars = torch.empty((self.n_local, 4), dtype=torch.int64).pin_memory()
-            self.h_bases.copy_(self.bases)
-            self.h_scalars.copy_(self.scalars)
+            wc = self.d.world >= 4
+            self.h_bases = self.msm.HostBuffer(self.n_local, 2 * self.fq, write_combined=wc)
+            self.h_scalars = self.msm.HostBuffer(self.n_local, 4, write_combined=wc)
+            torch.from_numpy(self.h_bases.array.view(np.int64)).copy_(self.bases)
+            torch.from_numpy(self.h_scalars.array.view(np.int64)).copy_(self.scalars)
             torch.cuda.synchronize()
+            self.host_memory = "page-locked, write-combined" if wc else "page-locked"
 
     def e2e(self):
         """The reference-shaped call (tachyon_<c>_g1_affine_msm_gpu) with pinned HOST buffers."""
-        return self.ctx.affine_msm(self.h_bases.data_ptr(), self.h_scalars.data_ptr(), self.n_local)
+        return self.ctx.affine_msm(self.h_bases.ptr, self.h_scalars.ptr, self.n_local)
 
     def timed(self, fn, steps, stage=None):
         """K steps bracketed by barrier + synchronize, CUDA events on the engine's stream; max over ranks."""
@@ -766,28 +776,32 @@ def measure_in_process_devices(d, curve, log_n, dist_name, steps):
         msm.generate_bases_device(curve, SEED + 2, n, b.data_ptr())
         msm.generate_scalars_device(curve, SEED + 3, n, sc.data_ptr(), dist_name)
         torch.cuda.synchronize()
-        hb = torch.empty((n, 2 * fq), dtype=torch.int64).pin_memory()
-        hs = torch.empty((n, 4), dtype=torch.int64).pin_memory()
-        hb.copy_(b)
-        hs.copy_(sc)
+        wc = k >= 4
+        hbuf, sbuf = msm.HostBuffer(n, 2 * fq, write_combined=wc), msm.HostBuffer(n, 4, write_combined=wc)
+        torch.from_numpy(hbuf.array.view(np.int64)).copy_(b)
+        torch.from_numpy(sbuf.array.view(np.int64)).copy_(sc)
         heads = b[::4096].cpu().numpy().view(np.uint64)
+        folded_in = sc.cpu().numpy().view(np.uint64)      # ordinary memory for the CPU-side check
         del b, sc
         torch.cuda.synchronize()
         ctx = msm.MSMGpu(curve, degree=log_n, device=d.local_rank)
         ctx.set_option("devices", k)
         for _ in range(3):
-            jac = ctx.affine_msm(hb.data_ptr(), hs.data_ptr(), n)
+            jac = ctx.affine_msm(hbuf.ptr, sbuf.ptr, n)
         t0 = time.perf_counter()
         for _ in range(steps):
-            jac = ctx.affine_msm(hb.data_ptr(), hs.data_ptr(), n)
+            jac = ctx.affine_msm(hbuf.ptr, sbuf.ptr, n)
         ms = (time.perf_counter() - t0) * 1e3 / steps
         t = ctx.last_timing()
         o = cpu_oracle.CurveOracle(curve)
-        want = o.msm_affine(heads, o.fold_chain_scalars(hs.numpy().view(np.uint64)))
+        want = o.msm_affine(heads, o.fold_chain_scalars(folded_in))
         ok = bool((o.jacobian_to_affine(jac) == want).all())
         ctx.close()
+        hbuf.free()
+        sbuf.free()
         out = {"workload": f"{curve} MSM 2^{log_n} points through ONE tachyon_{curve}_g1_affine_msm_gpu call, "
-                           f"option devices = {k}, pinned host buffers (H2D inside the timed region)",
+                           f"option devices = {k}, page-locked{' write-combined' if wc else ''} host buffers "
+                           "(H2D inside the timed region)",
                "devices": t["devices"], "ms_per_msm": ms, "points_per_s": n / (ms * 1e-3), "timing": "host wall clock",
                "parity": "bit-exact vs CPU oracle (chain-fold)" if ok else "MISMATCH"}
     d.host_barrier()
@@ -911,6 +925,7 @@ def run_msm(args, rank, world, local_rank):
                     "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ranges": e2e_timing["ranges"], "h2d_ms": e2e_timing["h2d_ms"],
                     "h2d_gbs_per_gpu": (h2d / world) / (e2e_timing["h2d_ms"] * 1e-3) / 1e9 if e2e_timing["h2d_ms"] else None,
+                    "host_memory": case.host_memory,
                     "api": "tachyon_%s_%s_affine_msm_gpu, pinned host buffers; H2D of point range k+1 "
                            "overlaps sort/accumulate of range k" % (curve.replace("_g2", ""),
                                                                     "g2" if curve.endswith("_g2") else "g1")},

@@ -287,6 +287,13 @@ TACHYON_C_EXPORT uint32_t tachyon_b200_window_bits(size_t n, uint32_t scalar_bit
 TACHYON_C_EXPORT uint32_t tachyon_b200_window_count(uint32_t scalar_bits, uint32_t window_bits);
 /* Total kernels launched by this library in this process (all contexts). */
 TACHYON_C_EXPORT uint64_t tachyon_b200_kernel_launch_count(void);
+/* Page-locked host memory for MSM inputs (cudaHostAlloc / cudaFreeHost).  write_combined = 1
+   asks for write-combined pages: the CPU should only fill them front to back (reads are slow),
+   but with several GPUs copying at once the DMA engines read them markedly faster than ordinary
+   pinned memory (bare copy probe on an 8 x B200 box, profiles/r2_h2d_probe_8gpu.txt: 4 GPUs
+   49 vs 31 GB/s each, 8 GPUs 39-49 vs 29-50).  NULL on failure. */
+TACHYON_C_EXPORT void* tachyon_b200_alloc_host(size_t bytes, int write_combined);
+TACHYON_C_EXPORT void tachyon_b200_free_host(void* p);
 
 #ifdef __cplusplus
 }

@@ -60,7 +60,8 @@ CURVE_SYMBOLS = ["tachyon_{c}_groth16_prove_b200", "tachyon_{c}_groth16_prove_fr
                  "tachyon_{c}_groth16_witness_map_from_files_b200"]
 GLOBAL_SYMBOLS = ["tachyon_b200_device_count", "tachyon_b200_last_error", "tachyon_b200_imad_peak",
                   "tachyon_b200_kernel_launch_count", "tachyon_b200_window_bits",
-                  "tachyon_b200_window_count", "tachyon_b200_nccl_unique_id"]
+                  "tachyon_b200_window_count", "tachyon_b200_nccl_unique_id", "tachyon_b200_alloc_host",
+                  "tachyon_b200_free_host"]
 
 
 def all_symbols():
@@ -129,6 +130,10 @@ def load():
     lib.tachyon_b200_imad_peak.argtypes = [i32, i32, i32]
     lib.tachyon_b200_kernel_launch_count.restype = u64
     lib.tachyon_b200_nccl_unique_id.argtypes = [vp]
+    lib.tachyon_b200_alloc_host.restype = vp
+    lib.tachyon_b200_alloc_host.argtypes = [sz, i32]
+    lib.tachyon_b200_free_host.restype = None
+    lib.tachyon_b200_free_host.argtypes = [vp]
     _lib = lib
     return lib
 

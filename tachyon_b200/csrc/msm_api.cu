@@ -54,6 +54,22 @@ int tachyon_b200_nccl_unique_id(void* out128) {
 
 uint64_t tachyon_b200_kernel_launch_count(void) { return g_kernel_launches.load(); }
 
+void* tachyon_b200_alloc_host(size_t bytes, int write_combined) {
+  void* p = nullptr;
+  cudaError_t e = cudaHostAlloc(&p, bytes ? bytes : 1,
+                                write_combined ? cudaHostAllocWriteCombined : cudaHostAllocDefault);
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    g_last_error = std::string("cudaHostAlloc: ") + cudaGetErrorString(e);
+    return nullptr;
+  }
+  return p;
+}
+
+void tachyon_b200_free_host(void* p) {
+  if (p) cudaFreeHost(p);
+}
+
 double tachyon_b200_imad_peak(int device, int variant, int repeats) {
   try {
     TB_CUDA(cudaSetDevice(device));

@@ -298,3 +298,25 @@ def groth16_prove_from_files(g1_ctx, g2_ctx, zkey_path, wtns_path, r=None, s=Non
         _ptr(out), proof_json.encode() if proof_json else None, public_json.encode() if public_json else None)
     _lib.check(rc, "groth16_prove_from_files")
     return out[:2 * fq], out[2 * fq:6 * fq], out[6 * fq:]
+
+
+class HostBuffer:
+    """Page-locked host memory from tachyon_b200_alloc_host, viewed as a (rows, limbs) uint64
+    array.  write_combined pages are for inputs the CPU only writes: several GPUs copying at
+    once read them faster than ordinary pinned memory."""
+
+    def __init__(self, rows, limbs, write_combined=False):
+        self.nbytes = rows * limbs * 8
+        self.ptr = _lib.load().tachyon_b200_alloc_host(self.nbytes, 1 if write_combined else 0)
+        if not self.ptr:
+            raise RuntimeError("alloc_host failed: " + _lib.last_error())
+        raw = (ctypes.c_char * max(self.nbytes, 1)).from_address(self.ptr)
+        self.array = np.frombuffer(raw, dtype=np.uint64, count=rows * limbs).reshape(rows, limbs)
+
+    def free(self):
+        if getattr(self, "ptr", None):
+            self.array = None
+            _lib.load().tachyon_b200_free_host(ctypes.c_void_p(self.ptr))
+            self.ptr = None
+
+    __del__ = free
