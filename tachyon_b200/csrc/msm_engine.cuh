@@ -204,14 +204,23 @@ inline uint32_t ChooseWindowBits(size_t n, uint32_t scalar_bits, size_t ranges =
 
 // Window choice when all windows share one bucket set (precomputed table of window multiples):
 // the reduction covers 2^(c-1) buckets once instead of once per window, so larger windows pay.
-inline uint32_t ChooseWindowBitsShared(size_t n, uint32_t scalar_bits, double kEntryCost = 1.37) {
+inline uint32_t ChooseWindowBitsShared(size_t n, uint32_t scalar_bits, double kEntryCost = 1.37,
+                                       uint32_t resident_threads = 148 * 512) {
   constexpr double kBucketCost = 5.4;
   double best = 1e300;
   uint32_t best_c = kMinWindowBits;
   for (uint32_t c = kMinWindowBits; c <= 24; ++c) {
     uint32_t W = WindowsFor(scalar_bits, c);
     if ((uint64_t)n * W >= (uint64_t(1) << 31)) continue;  // table index + sign bit in one word
-    double cost = kEntryCost * (double)n * W + kBucketCost * (double)(1u << (c - 1));
+    // the same longest-task bound as AccumulateWork: B buckets of n W / B entries on average
+    // (the lower half, shared by the narrow windows, holds more)
+    const double buckets = (double)(1u << (c - 1));
+    const double per_bucket = (double)n * W / buckets * 1.5;
+    const double longest = per_bucket + 4.0 * std::sqrt(per_bucket);
+    double running = buckets < (double)resident_threads ? buckets : (double)resident_threads;
+    if (running < 0.55 * resident_threads) running = 0.55 * resident_threads;
+    const double work = (double)n * W > longest * running ? (double)n * W : longest * running;
+    double cost = kEntryCost * work + kBucketCost * buckets;
     if (cost < best) {
       best = cost;
       best_c = c;
@@ -1450,9 +1459,13 @@ class MsmEngine {
       const uint32_t ctas = nodes >> levels;
       uint32_t* out = set.out[stage & 1].template as<uint32_t>() + (size_t)w0 * slice_words;
       TreeFinal fin{last ? 1u : 0u, w0, plan.c, plan.wide, l0, terms};
+      // more than two CTAs per resident slot: the stage is throughput-bound, its wide levels run
+      // one thread per addition; otherwise every level uses the four-lane latency form
+      const uint32_t thread_items =
+          (uint64_t)wn * ctas > (uint64_t)4 * sm_count_ ? (uint32_t)kTreeThreads / 2 : 0xffffffffu;
       LaunchOn(st, reduce_tree_kernel<C>, wn * ctas, (uint32_t)kTreeThreads, in, vin, levels, ctas,
                slice_words, set.ping.template as<uint32_t>() + (size_t)w0 * slice_words,
-               set.pong.template as<uint32_t>() + (size_t)w0 * slice_words, out, fin);
+               set.pong.template as<uint32_t>() + (size_t)w0 * slice_words, out, fin, thread_items);
       in = out;
       vin += levels;
       nodes >>= levels;

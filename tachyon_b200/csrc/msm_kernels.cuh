@@ -1075,7 +1075,9 @@ __global__ void __launch_bounds__(2 * ReduceSlots<C>()) reduce_blocks_kernel(
 // reduce_tree_kernel runs `levels` levels of that tree in ONE launch: a CTA owns 2^levels
 // consecutive input nodes of one window (vin values each) and ping-pongs between two private
 // scratch regions in global memory (L1/L2 resident; a __syncthreads per level), so a 12-14
-// level tree is two launches instead of 12-14 latency-bound ones.  The stage that ends with one
+// level tree is two launches instead of 12-14 latency-bound ones.  Levels with at least
+// `thread_items` work items use one thread per addition (the throughput form, chosen by the host
+// when the launch has several CTAs per SM slot), the others four lanes per addition.  The stage that ends with one
 // node per window (`fin.enabled`) scatters that node's values to the window's bit positions of
 // the term array Y consumed by window_combine_kernel:
 //   Y[off_w]          = A + P
@@ -1099,7 +1101,8 @@ TB_DEV uint32_t window_bit_offset(uint32_t w, uint32_t c, uint32_t wide) {
 template <class C>
 __global__ void __launch_bounds__(kTreeThreads) reduce_tree_kernel(
     const uint32_t* in, uint32_t vin, uint32_t levels, uint32_t ctas_per_window,
-    size_t slice_words, uint32_t* ping, uint32_t* pong, uint32_t* out, TreeFinal fin) {
+    size_t slice_words, uint32_t* ping, uint32_t* pong, uint32_t* out, TreeFinal fin,
+    uint32_t thread_items) {
   using K = typename C::Field;
   constexpr int kXyzzWords = 4 * K::kWords;
   // every buffer is cut into per-window slices of slice_words; inside its window's slice a CTA
@@ -1117,7 +1120,29 @@ __global__ void __launch_bounds__(kTreeThreads) reduce_tree_kernel(
     uint32_t* dst = (l == levels && !fin.enabled)
                         ? out + (size_t)lw * slice_words + (size_t)chunk * vfinal * kXyzzWords
                         : bufs[l & 1];
-    // one work item (node, value) per group of four lanes (Coop4: an addition is 4
+    if (m * vout >= thread_items) {
+      // throughput form (many CTAs per SM, wide level): one work item per thread, plain additions
+      // — 14 multiplications per thread instead of 16 lane-multiplications plus shuffles
+      for (uint32_t it = threadIdx.x; it < m * vout; it += kTreeThreads) {
+        const uint32_t node = it / vout, v = it % vout;
+        const uint32_t* left = src + (size_t)(2 * node) * vprev * kXyzzWords;
+        const uint32_t* right = left + (size_t)vprev * kXyzzWords;
+        XYZZ<K> a;
+        if (v == vout - 1) {
+          xyzz_load<K>(a, right);
+        } else {
+          XYZZ<K> b;
+          xyzz_load<K>(a, left + (size_t)v * kXyzzWords);
+          xyzz_load<K>(b, right + (size_t)v * kXyzzWords);
+          xyzz_add<K>(a, b);
+        }
+        xyzz_store<K>(dst + (size_t)it * kXyzzWords, a);
+      }
+      __syncthreads();
+      src = dst;
+      continue;
+    }
+    // latency form: one work item (node, value) per group of four lanes (Coop4: an addition is 4
     // multiplication levels deep instead of 14 multiplications)
     for (uint32_t it = group; it < m * vout; it += kTreeThreads / 4) {
       const uint32_t node = it / vout, v = it % vout;

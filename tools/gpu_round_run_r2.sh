@@ -22,24 +22,31 @@ python bench.py -k 16 -k 18 -k 20 -k 22 -k 24 --check_results > $out/${tag}_tabl
 python tools/quick_gpu.py bn254 12,14,16,17,18,19,20,21,22,23,24 > $out/${tag}_sizes_bn254.log 2>&1
 python tools/quick_gpu.py bn254 20,21,24 device_ladder=1 > $out/${tag}_sizes_bn254_device_ladder.log 2>&1
 
+# ncu captures are exported to CSV on the box and the .ncu-rep files deleted: gpurun_out/ comes
+# back only while it stays below 64 MiB
+export_rep() { ncu -i $out/$1.ncu-rep --page raw --csv > $out/$1_raw.csv 2> /dev/null; rm -f $out/$1.ncu-rep; }
 cmd="python bench.py --steps 2 --warmup 3 --no-parity --no-cpu-baseline --no-extra"
 $cmd > $out/${tag}_plain.log 2>&1 &&
   ncu --metrics gpu__time_duration.sum --clock-control none -c 800 --csv \
       --log-file $out/${tag}_launches.csv $cmd > $out/${tag}_ncu1.log 2>&1
 $cmd > $out/${tag}_plain2.log 2>&1 &&
-  ncu --set full --clock-control none --import-source on \
+  ncu --set full --clock-control none \
       -k regex:'accumulate_kernel|reduce_blocks_kernel|reduce_tree_kernel|window_combine_kernel|fine_scatter_kernel|coarse_scatter_kernel|digits_coarse_hist_kernel|fine_hist_kernel|scan_apply_build_tasks_kernel' \
       --launch-skip 33 --launch-count 11 -o $out/${tag}_top -f $cmd > $out/${tag}_ncu2.log 2>&1
+export_rep ${tag}_top
 cmd3="python tools/quick_gpu.py bls12_381 22"
 $cmd3 > $out/${tag}_plain3.log 2>&1 &&
-  ncu --set full --clock-control none --import-source on -k regex:'accumulate_kernel|reduce_blocks_kernel' \
+  ncu --set full --clock-control none -k regex:'accumulate_kernel|reduce_blocks_kernel' \
       --launch-skip 6 --launch-count 2 -o $out/${tag}_bls_acc -f $cmd3 > $out/${tag}_ncu3.log 2>&1
+export_rep ${tag}_bls_acc
 cmd4="python tools/quick_gpu.py bn254_g2 20"
 $cmd4 > $out/${tag}_plain4.log 2>&1 &&
-  ncu --set full --clock-control none --import-source on -k regex:'accumulate_kernel|reduce_blocks_kernel' \
+  ncu --set full --clock-control none -k regex:'accumulate_kernel|reduce_blocks_kernel' \
       --launch-skip 6 --launch-count 2 -o $out/${tag}_g2_acc -f $cmd4 > $out/${tag}_ncu4.log 2>&1
+export_rep ${tag}_g2_acc
 cmd5="python tools/quick_gpu.py bn254 21 device_ladder=1"
 $cmd5 > $out/${tag}_plain5.log 2>&1 &&
   ncu --set full --clock-control none -k regex:'window_combine_kernel|reduce_tree_kernel' \
       --launch-skip 15 --launch-count 6 -o $out/${tag}_ladder -f $cmd5 > $out/${tag}_ncu5.log 2>&1
+export_rep ${tag}_ladder
 ls -la $out/${tag}_* | awk '{print $5, $9}'

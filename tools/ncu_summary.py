@@ -1,6 +1,6 @@
 #!/usr/bin/env python3
-"""Summarise an .ncu-rep (read here, no GPU needed) into profiles/<name>.md:
-tools/ncu_summary.py gpurun_out/x.ncu-rep profiles/name.md ["title"]"""
+"""Summarise an .ncu-rep, or its `--page raw --csv` export, (read here, no GPU needed) into
+profiles/<name>.md:  tools/ncu_summary.py gpurun_out/x.ncu-rep|x.csv profiles/name.md ["title"]"""
 import csv
 import io
 import subprocess
@@ -31,7 +31,10 @@ KEYS = [
 def main():
     rep, out = sys.argv[1], sys.argv[2]
     title = sys.argv[3] if len(sys.argv) > 3 else rep
-    raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    if rep.endswith(".csv"):      # already exported on the GPU box (ncu -i x.ncu-rep --page raw --csv)
+        raw = open(rep).read()
+    else:
+        raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(io.StringIO(raw)))
     hdr, units, data = rows[0], rows[1], rows[2:]
     lines = [f"# {title}", "", f"source: `{rep}` (ncu --set full --clock-control none), read with `ncu -i ... --page raw --csv`", ""]
