@@ -337,67 +337,6 @@ TB_DEV void fp_mul2(Fp<F>& r, const Fp<F>& a, const Fp<F>& b, const Fp<F>& a2, c
   fp_reduce_once<F>(r, t);
 }
 
-// Two independent two-product multiplications, r0 = a0 b0 + a1 b1 and r1 = c0 d0 + c1 d1, with
-// their Montgomery rows alternating in source order.  Each row is a closed carry chain, so the
-// two sequences never share the carry flag, and adjacent rows of different products are
-// independent: a warp that has an SM sub-partition almost to itself (the Fq2 kernels run 2
-// warps per scheduler) gets four carry chains to overlap instead of two.  This is both
-// components of an Fq2 product (quadratic_extension_field.h:326-338).
-template <class F>
-TB_DEV void fp_mul2_pair(Fp<F>& r0, const Fp<F>& a0, const Fp<F>& b0, const Fp<F>& a1, const Fp<F>& b1,
-                         Fp<F>& r1, const Fp<F>& c0, const Fp<F>& d0, const Fp<F>& c1, const Fp<F>& d1) {
-  constexpr int N = Fp<F>::N;
-  uint32_t E[N], O[N], G[N], H[N];  // (E, O): product 0, (G, H): product 1
-#pragma unroll
-  for (int j = 0; j < N; j += 2) {
-    mul_wide(E[j], E[j + 1], a0.l[j], b0.l[0]);
-    mul_wide(O[j], O[j + 1], a0.l[j + 1], b0.l[0]);
-    mul_wide(G[j], G[j + 1], c0.l[j], d0.l[0]);
-    mul_wide(H[j], H[j + 1], c0.l[j + 1], d0.l[0]);
-  }
-  auto second_row0 = [](uint32_t (&X)[N], uint32_t (&Y)[N], const uint32_t (&a2)[N], uint32_t b2) {
-    Y[0] = mad_lo_cc(a2[1], b2, Y[0]);
-    Y[1] = madc_hi_cc(a2[1], b2, Y[1]);
-#pragma unroll
-    for (int j = 2; j < N; j += 2) {
-      Y[j] = madc_lo_cc(a2[j + 1], b2, Y[j]);
-      Y[j + 1] = madc_hi_cc(a2[j + 1], b2, Y[j + 1]);
-    }
-    X[0] = mad_lo_cc(a2[0], b2, X[0]);
-    X[1] = madc_hi_cc(a2[0], b2, X[1]);
-#pragma unroll
-    for (int j = 2; j < N; j += 2) {
-      X[j] = madc_lo_cc(a2[j], b2, X[j]);
-      X[j + 1] = madc_hi_cc(a2[j], b2, X[j + 1]);
-    }
-    Y[N - 1] = addc(Y[N - 1], 0u);
-  };
-  second_row0(E, O, a1.l, b1.l[0]);
-  second_row0(G, H, c1.l, d1.l[0]);
-  mont_reduce_row<F, N>(E, O);
-  mont_reduce_row<F, N>(G, H);
-#pragma unroll
-  for (int i = 1; i < N; i += 2) {
-    mont_mul2_row<F, N>(O, E, a0.l, b0.l[i], a1.l, b1.l[i]);
-    mont_mul2_row<F, N>(H, G, c0.l, d0.l[i], c1.l, d1.l[i]);
-    if (i + 1 < N) {
-      mont_mul2_row<F, N>(E, O, a0.l, b0.l[i + 1], a1.l, b1.l[i + 1]);
-      mont_mul2_row<F, N>(G, H, c0.l, d0.l[i + 1], c1.l, d1.l[i + 1]);
-    }
-  }
-  uint32_t t[N], u[N];
-  t[0] = add_cc(E[0], O[1]);
-#pragma unroll
-  for (int j = 1; j < N - 1; ++j) t[j] = addc_cc(E[j], O[j + 1]);
-  t[N - 1] = addc(E[N - 1], 0u);
-  u[0] = add_cc(G[0], H[1]);
-#pragma unroll
-  for (int j = 1; j < N - 1; ++j) u[j] = addc_cc(G[j], H[j + 1]);
-  u[N - 1] = addc(G[N - 1], 0u);
-  fp_reduce_once<F>(r0, t);
-  fp_reduce_once<F>(r1, u);
-}
-
 // Squaring: a^2 = sum_i a_i * (a_i 2^(32 i) + sum_(j > i) 2 a_j 2^(32 j)) 2^(32 i).  Row i
 // multiplies a_i with the vector m_i = [0, .., 0, a_i, b_(i+1), .., b_(N-1)], b = 2a (fits N limbs:
 // both moduli leave two spare bits; limb i+1 with its lowest bit cleared — that bit is the top
@@ -656,17 +595,11 @@ struct Fp2Field {
     fp_cneg<F>(r.c1, a.c1, n);
   }
   static TB_DEV void mul(El& r, const El& a, const El& b) {
-    Fp<F> nb1, t0, t1;
+    Fp<F> nb1, t0;
     fp_neg<F>(nb1, b.c1);
-#ifdef TB200_FP2_SEQUENTIAL
-    fp_mul2<F>(t0, a.c0, b.c0, a.c1, nb1);   // c0 = a0 b0 - a1 b1
-    fp_mul2<F>(t1, a.c0, b.c1, a.c1, b.c0);  // c1 = a0 b1 + a1 b0
-#else
-    // both components at once, rows interleaved (four carry chains in flight)
-    fp_mul2_pair<F>(t0, a.c0, b.c0, a.c1, nb1, t1, a.c0, b.c1, a.c1, b.c0);
-#endif
+    fp_mul2<F>(t0, a.c0, b.c0, a.c1, nb1);    // c0 = a0 b0 - a1 b1
+    fp_mul2<F>(r.c1, a.c0, b.c1, a.c1, b.c0);  // c1 = a0 b1 + a1 b0
     r.c0 = t0;
-    r.c1 = t1;
   }
   static TB_DEV void sqr(El& r, const El& a) {
     Fp<F> s, d, m;
