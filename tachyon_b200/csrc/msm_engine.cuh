@@ -542,6 +542,7 @@ class MsmEngine {
     uint32_t L0 = 0, M = 0;
     uint32_t low = 0;     // windows of the low group
     uint32_t L0_low = 0;  // its running-sum block length
+    size_t host_bytes = 0;  // bytes that crossed PCIe for this MSM
     bool gathered = false;  // the result is the all-gathered set of rank partials
     bool device_ladder = false;  // the device left one point (else: one sum per window)
     size_t K = 0;
@@ -862,6 +863,7 @@ class MsmEngine {
     const bool scalars_pageable = !scalars_dev && IsPageable(scalars);
     Pending pd;
     pd.any_host = !bases_dev || !scalars_dev;
+    pd.host_bytes = (bases_dev ? 0 : n * kAffineBytes) + (scalars_dev ? 0 : n * kScalarBytes);
     pd.slot = slot;
 
     // ---- how many ranges ----------------------------------------------------------
@@ -912,7 +914,13 @@ class MsmEngine {
     std::vector<size_t> bound(K + 1, n);
     bound[0] = 0;
     if (K > 1 && pd.any_host && options_.ranges == 0 && !memory_bound) {
-      const double q = C::kRangeGrowth;
+      // kRangeGrowth assumes the ~55 GB/s one GPU gets alone.  When the last host-input call saw
+      // less (4-8 GPUs of one box copying at once: 24-30 GB/s each), the copy, not the bucket
+      // work, sets the pace and what remains after the last byte has arrived is the processing of
+      // the LAST range: ranges stop growing (equal ranges; 2^22 points per GPU on 4 GPUs:
+      // 17.6 -> 16.2 ms end to end).
+      double q = C::kRangeGrowth * (h2d_gbs_ > 0 ? h2d_gbs_ / 55.0 : 1.0);
+      if (q < 1.02) q = 1.02;
       double f = (q - 1.0) / (std::pow(q, (double)K) - 1.0), acc = 0;
       for (size_t r = 1; r < K; ++r) {
         acc += f;
@@ -1348,6 +1356,8 @@ class MsmEngine {
       // time the copy engine was busy or waiting for a free slot; overlaps the bucket work
       TB_CUDA(cudaEventElapsedTime(&ms, SlotEvent(slot, 3), ev(pd.K - 1, 0)));
       timing_.h2d_ms += ms;
+      if (pd.host_bytes >= (size_t(32) << 20) && ms > 0)  // the copy rate this call saw
+        h2d_gbs_ = (double)pd.host_bytes / (ms * 1e-3) / 1e9;
     }
     TB_CUDA(cudaEventElapsedTime(&ms, SlotEvent(slot, 1), SlotEvent(slot, 2)));
     timing_.reduce_ms += ms;
@@ -1601,6 +1611,7 @@ class MsmEngine {
   bool bounce_used_[kBounceSlots] = {};
   std::unique_ptr<ParallelMemcpy> copier_;
   size_t budget_ = 0;  // device bytes this engine may use; 0 = ask the driver
+  double h2d_gbs_ = 0;  // host-to-device rate of the last large host-input call (0: none yet)
   bool stage_used_[kStageSlots] = {};
   MsmOptions options_;
   MsmTiming timing_;
