@@ -7,7 +7,7 @@ for n in 8 4; do
   python -m torch.distributed.run --nnodes=1 --nproc-per-node $n --master-addr 127.0.0.1 --master-port 2951$n bench.py --gpus $n --steps 10 --warmup 3 > $out/${tag}_bench$n.json 2> $out/${tag}_bench$n.err
   echo "N=$n rc=$?"
 done
-bash tools/h2d_probe.sh $tag > /dev/null 2>&1
+[ -z "$SKIP_PROBE" ] && bash tools/h2d_probe.sh $tag > /dev/null 2>&1
 python - <<PY
 import json
 for n in (8, 4):
@@ -21,4 +21,4 @@ for n in (8, 4):
             e=d[k]
             print("  ", k, {x:(round(v,3) if isinstance(v,float) else v) for x,v in e.items() if x in ('ms_per_msm','ms_per_step','e2e_ms_per_msm','e2e_ms_per_step','imad_frac','parity','devices')})
 PY
-grep -E "==|device" $out/${tag}_h2d.txt | head -80
+[ -z "$SKIP_PROBE" ] && grep -E "==|device" $out/${tag}_h2d.txt | head -80
