@@ -103,3 +103,41 @@ def test_no_gpu_fails_loudly():
         msm.MSMGpu("bn254")
     with pytest.raises(RuntimeError):
         msm.field_op("bn254", "fq", "mul", np.zeros((1, 4), dtype=np.uint64))
+
+
+def test_bench_reference_arm_runs_without_gpu():
+    """`bench.py --impl reference` (the CPU arm the driver runs beside the GPU arm) needs no GPU,
+    times FULL-size MSMs and prints the same `config` as the GPU arm would."""
+    import json
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--log-n", "12",
+                          "--steps", "2", "--warmup", "1"], capture_output=True, text=True, timeout=300, cwd=root)
+    assert out.returncode == 0, out.stderr[-500:]
+    lines = [l for l in out.stdout.splitlines() if l.startswith("{")]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    sys.path.insert(0, root)
+    import bench
+    assert d["impl"] == "reference" and d["steps"] == 2 and d["warmup"] == 1
+    assert d["config"] == bench.workload_config("bn254", 12, "uniform")
+    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1
+    assert "full 2^12-point MSM per step" in d["cpu_baseline"]["sample"]
+    assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["gpu_launches"] == 0
+
+
+def test_window_model_is_sane():
+    """The exported window rule: defined for every size, never more than 2^24 bucket slots, larger
+    windows for larger inputs (up to the occupancy dip between 2^13 and 2^15 points)."""
+    from tachyon_b200 import msm
+    prev = 0
+    for lg in range(4, 27):
+        c = msm.window_bits(1 << lg, 254)
+        w = msm.window_count(254, c)
+        assert 4 <= c <= 22 and w * (1 << (c - 1)) <= (1 << 24) and w * c >= 255
+        if lg >= 15:
+            assert c >= prev
+        prev = c
+    assert msm.window_bits(1 << 24, 254) == 20 and msm.window_bits(1 << 21, 254) == 17
