@@ -104,6 +104,9 @@ extern "C" {
      multiples 2^(bit offset of window w) * P — the full precompute_factor of                 \
      icicle_msm.h:21 — so that MSMs over the registered bases use one bucket set for all      \
      windows: W times the base memory, a W times smaller bucket reduction, no ladder),        \
+     "acc_variant" (G2 groups: 1 = one lane pair per accumulation task, a lane per Fq2         \
+     component — the default; 2 = the same at the other register budget; 0 = one thread per   \
+     task),                                                                                   \
      "stage_points" (1 = the accumulation stages the next point through shared memory with    \
      cp.async instead of registers),                                                          \
      "device_ladder" (where the final ladder over the W window sums runs — ~255 strictly     \

@@ -6,7 +6,8 @@ import ctypes
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "lib", "libtachyon_msm_b200.so")
+# TACHYON_B200_LIB: load another build of the library (A/B comparisons on one GPU box)
+LIB_PATH = os.environ.get("TACHYON_B200_LIB") or os.path.join(HERE, "lib", "libtachyon_msm_b200.so")
 
 CURVES = {"bn254": 4, "bls12_381": 6}  # curve -> Fq u64 limbs (Fr is 4 for both)
 GROUPS = ("g1", "g2")                  # g2: coordinates in Fq2, twice the limbs

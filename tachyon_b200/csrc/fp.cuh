@@ -337,6 +337,74 @@ TB_DEV void fp_mul2(Fp<F>& r, const Fp<F>& a, const Fp<F>& b, const Fp<F>& a2, c
   fp_reduce_once<F>(r, t);
 }
 
+// ---------------------------------------------------------------------------
+// The same two multiplications with their rows in a LOOP (two rows per trip, so the
+// accumulators keep their roles; the multiplier's limbs move down two places per trip, so every
+// index stays a compile-time constant and everything stays in registers).  Same products, same
+// carry chains, same result — about a third of the code.  The unrolled forms above are ~330
+// (12 limbs) instructions per multiplication and a point addition inlines ten of them: the loop
+// body of the 12-limb accumulation kernel is 144 KB of SASS, the instruction cache serves 79 %
+// of its requests and `no_instruction` is its second largest stall (ncu, BLS12-381 2^22: FMA-
+// heavy pipe 82 % against 91 % for the 8-limb kernel, whose 68 KB loop body still streams
+// through the prefetcher at a 98 % hit rate).  Row 0 is an ordinary row over zeroed
+// accumulators here: the same number of multiply instructions as the mul.wide start.
+// ---------------------------------------------------------------------------
+template <class F>
+TB_DEV void fp_mul_rolled(Fp<F>& r, const Fp<F>& a, const Fp<F>& b) {
+  constexpr int N = Fp<F>::N;
+  static_assert(N % 2 == 0, "limb count must be even");
+  uint32_t E[N], O[N], m[N];
+#pragma unroll
+  for (int j = 0; j < N; ++j) {
+    E[j] = 0u;
+    O[j] = 0u;
+    m[j] = b.l[j];
+  }
+#pragma unroll 1
+  for (int trip = 0; trip < N / 2; ++trip) {
+    mont_mul_row<F, N>(E, O, a.l, m[0]);
+    mont_mul_row<F, N>(O, E, a.l, m[1]);
+#pragma unroll
+    for (int j = 0; j + 2 < N; ++j) m[j] = m[j + 2];
+  }
+  uint32_t t[N];
+  t[0] = add_cc(E[0], O[1]);
+#pragma unroll
+  for (int j = 1; j < N - 1; ++j) t[j] = addc_cc(E[j], O[j + 1]);
+  t[N - 1] = addc(E[N - 1], 0u);
+  fp_reduce_once<F>(r, t);
+}
+
+template <class F>
+TB_DEV void fp_mul2_rolled(Fp<F>& r, const Fp<F>& a, const Fp<F>& b, const Fp<F>& a2,
+                           const Fp<F>& b2) {
+  constexpr int N = Fp<F>::N;
+  uint32_t E[N], O[N], m[N], m2[N];
+#pragma unroll
+  for (int j = 0; j < N; ++j) {
+    E[j] = 0u;
+    O[j] = 0u;
+    m[j] = b.l[j];
+    m2[j] = b2.l[j];
+  }
+#pragma unroll 1
+  for (int trip = 0; trip < N / 2; ++trip) {
+    mont_mul2_row<F, N>(E, O, a.l, m[0], a2.l, m2[0]);
+    mont_mul2_row<F, N>(O, E, a.l, m[1], a2.l, m2[1]);
+#pragma unroll
+    for (int j = 0; j + 2 < N; ++j) {
+      m[j] = m[j + 2];
+      m2[j] = m2[j + 2];
+    }
+  }
+  uint32_t t[N];
+  t[0] = add_cc(E[0], O[1]);
+#pragma unroll
+  for (int j = 1; j < N - 1; ++j) t[j] = addc_cc(E[j], O[j + 1]);
+  t[N - 1] = addc(E[N - 1], 0u);
+  fp_reduce_once<F>(r, t);
+}
+
 // Squaring: a^2 = sum_i a_i * (a_i 2^(32 i) + sum_(j > i) 2 a_j 2^(32 j)) 2^(32 i).  Row i
 // multiplies a_i with the vector m_i = [0, .., 0, a_i, b_(i+1), .., b_(N-1)], b = 2a (fits N limbs:
 // both moduli leave two spare bits; limb i+1 with its lowest bit cleared — that bit is the top
@@ -504,10 +572,15 @@ TB_DEV void fp_store(void* p, const Fp<F>& a) {
 // formulas need; the point and MSM kernels are written once against K and
 // instantiated for the base field (G1) and its quadratic extension (G2).
 // ---------------------------------------------------------------------------
-template <class F>
+// kRoll: 0 = unrolled multiplications, 1 = looped multiplications (fp_mul_rolled /
+// fp_mul2_rolled) and the unrolled squaring, 2 = squarings through the looped multiplication
+// too (28 % more products per squaring for the smallest code).
+template <class F, int kRoll = 0>
 struct FpField {
   using Params = F;
   using El = Fp<F>;
+  template <int R>
+  using WithRoll = FpField<F, R>;  // the same field, other code shape
   static constexpr int kWords = Fp<F>::N;
   static constexpr int kDegree = 1;
   static TB_DEV void set_zero(El& r) { fp_set_zero<F>(r); }
@@ -519,11 +592,18 @@ struct FpField {
   static TB_DEV void dbl(El& r, const El& a) { fp_dbl<F>(r, a); }
   static TB_DEV void neg(El& r, const El& a) { fp_neg<F>(r, a); }
   static TB_DEV void cneg(El& r, const El& a, bool n) { fp_cneg<F>(r, a, n); }
-  static TB_DEV void mul(El& r, const El& a, const El& b) { fp_mul<F>(r, a, b); }
-  static TB_DEV void sqr(El& r, const El& a) { fp_sqr<F>(r, a); }
+  static TB_DEV void mul(El& r, const El& a, const El& b) {
+    if (kRoll) fp_mul_rolled<F>(r, a, b);
+    else fp_mul<F>(r, a, b);
+  }
+  static TB_DEV void sqr(El& r, const El& a) {
+    if (kRoll == 2) fp_mul_rolled<F>(r, a, a);
+    else fp_sqr<F>(r, a);
+  }
   // r = a * b + a2 * b2
   static TB_DEV void mul2(El& r, const El& a, const El& b, const El& a2, const El& b2) {
-    fp_mul2<F>(r, a, b, a2, b2);
+    if (kRoll) fp_mul2_rolled<F>(r, a, b, a2, b2);
+    else fp_mul2<F>(r, a, b, a2, b2);
   }
   static TB_DEV void inv(El& r, const El& a) { fp_inv<F>(r, a); }
   static TB_DEV void select(El& r, bool take_a, const El& a, const El& b) {
@@ -556,10 +636,13 @@ struct Fp2 {
   Fp<F> c0, c1;
 };
 
-template <class F>
+template <class F, int kRoll = 0>
 struct Fp2Field {
   using Params = F;
   using El = Fp2<F>;
+  template <int R>
+  using WithRoll = Fp2Field<F, R>;
+  using Base = FpField<F, kRoll>;  // component arithmetic in the chosen code shape
   static constexpr int kWords = 2 * Fp<F>::N;
   static constexpr int kDegree = 2;
   static TB_DEV void set_zero(El& r) {
@@ -597,16 +680,16 @@ struct Fp2Field {
   static TB_DEV void mul(El& r, const El& a, const El& b) {
     Fp<F> nb1, t0;
     fp_neg<F>(nb1, b.c1);
-    fp_mul2<F>(t0, a.c0, b.c0, a.c1, nb1);    // c0 = a0 b0 - a1 b1
-    fp_mul2<F>(r.c1, a.c0, b.c1, a.c1, b.c0);  // c1 = a0 b1 + a1 b0
+    Base::mul2(t0, a.c0, b.c0, a.c1, nb1);    // c0 = a0 b0 - a1 b1
+    Base::mul2(r.c1, a.c0, b.c1, a.c1, b.c0);  // c1 = a0 b1 + a1 b0
     r.c0 = t0;
   }
   static TB_DEV void sqr(El& r, const El& a) {
     Fp<F> s, d, m;
     fp_add<F>(s, a.c0, a.c1);
     fp_sub<F>(d, a.c0, a.c1);
-    fp_mul<F>(m, a.c0, a.c1);
-    fp_mul<F>(r.c0, s, d);  // c0^2 - c1^2
+    Base::mul(m, a.c0, a.c1);
+    Base::mul(r.c0, s, d);  // c0^2 - c1^2
     fp_dbl<F>(r.c1, m);     // 2 c0 c1
   }
   // r = a * b + a2 * b2: four products per component, still one reduction each
@@ -660,6 +743,89 @@ struct Fp2Field {
       r.c0.l[i] = __shfl_sync(mask, a.c0.l[i], src, width);
       r.c1.l[i] = __shfl_sync(mask, a.c1.l[i], src, width);
     }
+  }
+};
+
+// ---------------------------------------------------------------------------
+// Fq2 with its two components on NEIGHBOURING LANES (lane 2k: c0, lane 2k + 1: c1).
+//
+// The one-thread Fq2 kernels are bound by registers, not by the multiply pipe: a G2 XYZZ
+// accumulator plus the point in flight is 96 (BN254) / 144 (BLS12-381) words before any
+// temporary, so only 8 warps fit an SM and the dependent carry chains of one point addition
+// leave the FMA-heavy pipe idle a third of the time (ncu: 66 %).  Split over a lane pair every
+// lane holds HALF of every element — half the registers, twice the warps — and the
+// multiplication splits without redundancy: with a = (a0, a1), b = (b0, b1) and u^2 = -1
+//   lane 0:  c0 = a0 b0 + a1 (-b1)        lane 1:  c1 = a1 b0 + a0 b1
+// i.e. both lanes run ONE fp_mul2 (two products, one Montgomery reduction: exactly the two
+// sums of products of quadratic_extension_field.h:326-338) on operands exchanged by shuffle.
+// The complex squaring (:371-385) is one fp_mul per lane: (a0 + a1)(a0 - a1) | (2 a1) a0.
+// Addition, subtraction, negation are component-wise and need no exchange.
+//
+// All shuffles use the full-warp mask: the callers keep their warps converged (predicated
+// selects instead of branches), which spares the WARPSYNC / collective bracket ptxas puts
+// around every partial-mask shuffle.  `role` is the lane's component (threadIdx.x & 1).
+// Results are the canonical values of Fp2Field's operations, bit for bit.
+// ---------------------------------------------------------------------------
+template <class F, int kRoll = 0>
+struct Fp2Lanes {
+  using E = Fp<F>;
+  using Base = FpField<F, kRoll>;
+  static constexpr int N = Fp<F>::N;
+  static constexpr uint32_t kFull = 0xffffffffu;
+
+  // the partner lane's component
+  static TB_DEV void other(E& r, const E& a) {
+#pragma unroll
+    for (int i = 0; i < N; ++i) r.l[i] = __shfl_xor_sync(kFull, a.l[i], 1);
+  }
+  // true when the predicate holds on both lanes of the pair
+  static TB_DEV bool both(bool v) {
+    const int partner = __shfl_xor_sync(kFull, (int)v, 1);  // unconditional: every lane takes part
+    return v && partner != 0;
+  }
+  static TB_DEV bool is_zero(const E& a) { return both(fp_is_zero<F>(a)); }
+  static TB_DEV void set_one(E& r, uint32_t role) {
+#pragma unroll
+    for (int i = 0; i < N; ++i) r.l[i] = role ? 0u : F::one(i);
+  }
+  static TB_DEV void select(E& r, bool take_a, const E& a, const E& b) {
+#pragma unroll
+    for (int i = 0; i < N; ++i) r.l[i] = take_a ? a.l[i] : b.l[i];
+  }
+
+  // A multiplier prepared once for several products: (u, v) = (b0, -b1) on lane 0 and
+  // (b0, b1) on lane 1 — the factors of this lane's own and of its partner's component of a.
+  struct Multiplier {
+    E u, v;
+  };
+  static TB_DEV void prepare(Multiplier& m, const E& b, uint32_t role) {
+    E nb, send, recv;
+    fp_neg<F>(nb, b);
+    select(send, role != 0, nb, b);  // lane 1 hands over -b1, lane 0 hands over b0
+    other(recv, send);
+    select(m.u, role != 0, recv, b);  // lane 0: b0        lane 1: b0
+    select(m.v, role != 0, b, recv);  // lane 0: -b1       lane 1: b1
+  }
+  // r = this lane's component of a * b
+  static TB_DEV void mul(E& r, const E& a, const Multiplier& m) {
+    E ao;
+    other(ao, a);
+    // lane 0: a0 b0 + a1 (-b1)      lane 1: a1 b0 + a0 b1
+    Base::mul2(r, a, m.u, ao, m.v);
+  }
+  static TB_DEV void mul(E& r, const E& a, const E& b, uint32_t role) {
+    Multiplier m;
+    prepare(m, b, role);
+    mul(r, a, m);
+  }
+  static TB_DEV void sqr(E& r, const E& a, uint32_t role) {
+    E ao, x, y, d;
+    other(ao, a);
+    select(x, role != 0, a, ao);
+    fp_add<F>(x, a, x);  // lane 0: a0 + a1      lane 1: 2 a1
+    fp_sub<F>(d, a, ao);
+    select(y, role != 0, ao, d);  // lane 0: a0 - a1      lane 1: a0
+    Base::mul(r, x, y);
   }
 };
 

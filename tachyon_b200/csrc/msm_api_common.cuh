@@ -584,6 +584,12 @@ using namespace tb200;
         for (auto& e : ptr->engines) e->options().balance = (int)value;                        \
       } else if (k == "precompute") {                                                          \
         for (auto& e : ptr->engines) e->options().precompute = (int)value;                     \
+      } else if (k == "reduce_roll") {                                                         \
+        for (auto& e : ptr->engines) e->options().reduce_roll = (int)value;                    \
+      } else if (k == "acc_lockstep") {                                                        \
+        for (auto& e : ptr->engines) e->options().acc_lockstep = (int)value;                   \
+      } else if (k == "acc_variant") {                                                         \
+        for (auto& e : ptr->engines) e->options().acc_variant = (int)value;                    \
       } else if (k == "stage_points") {                                                        \
         for (auto& e : ptr->engines) e->options().stage_points = (int)value;                   \
       } else if (k == "device_ladder") {                                                       \

@@ -102,6 +102,17 @@ struct MsmOptions {
                              // 2^(bit offset of window w) * P (precompute_factor of
                              // icicle_msm.h:21, here always the full factor): MSMs over the
                              // registered bases then use ONE set of buckets for all windows
+  int acc_variant = -1;      // G2 groups: 0 = one thread per accumulation task (accumulate_kernel),
+                             // 1 = one LANE PAIR per task, a lane per Fq2 component
+                             // (accumulate_pair_kernel; the default), 2 = the same at the
+                             // alternative register budget (PairMinBlocksAlt).
+                             // G1 groups: 0 = free-running warps, 3 = the warps of a CTA in step
+                             // (accumulate_lockstep_kernel), -1 = the curve's default
+  int acc_lockstep = -1;     // G2 pair kernel: 1 = warps of a CTA in step, 0 = free, -1 = curve default
+  int reduce_roll = -1;      // code shape of the field multiplications in the running-sum kernel:
+                             // 0 = unrolled, 1 = looped multiplications (fp_mul_rolled: a third of
+                             // the code), 2 = looped, squarings through the multiplier too,
+                             // -1 = the curve's measured default (C::kReduceRoll)
   int stage_points = 0;      // 1 = accumulate_staged_kernel: the next point of a task travels
                              // through shared memory (cp.async) instead of registers
   int device_ladder = 0;     // where the final ladder sum_w 2^(offset of w) S_w runs: 0 = on the
@@ -843,6 +854,40 @@ class MsmEngine {
     budget_ = 0;
   }
 
+  // G2: one accumulation task per lane pair (accumulate_pair_kernel).  acc_variant picks the
+  // register budget: 1 (and the default) = the first, 2 = the second entry of PairShapes<C>.
+  template <int kThreads, int kMinBlocks>
+  void LaunchPairShape(uint32_t max_tasks, const uint32_t* d_bases, uint32_t part) {
+    if constexpr (C::Field::kDegree == 2) {
+      uint32_t grid = (uint32_t)(((uint64_t)max_tasks * 2 + kThreads - 1) / kThreads);
+      if (grid == 0) grid = 1;
+      const bool lockstep = options_.acc_lockstep < 0 ? C::kAccLockstep : options_.acc_lockstep != 0;
+      Launch(lockstep ? accumulate_pair_kernel<C, kThreads, kMinBlocks, true>
+                      : accumulate_pair_kernel<C, kThreads, kMinBlocks, false>,
+             grid, (uint32_t)kThreads, d_bases,
+             (const uint32_t*)sorted_.as<uint32_t>(), (const uint2*)tasks_.as<uint2>(),
+             (const uint32_t*)task_meta_.as<uint32_t>(), (const uint32_t*)order_.as<uint32_t>(),
+             (const MsmTotals*)totals_, part, state_.as<uint32_t>(), task_out_.as<uint32_t>());
+    }
+  }
+  void LaunchLockstep(uint32_t agrid, const uint32_t* d_bases, uint32_t part) {
+    if constexpr (C::Field::kDegree == 1) {
+      Launch(accumulate_lockstep_kernel<C>, agrid, (uint32_t)kAccThreads, d_bases,
+             (const uint32_t*)sorted_.as<uint32_t>(), (const uint2*)tasks_.as<uint2>(),
+             (const uint32_t*)task_meta_.as<uint32_t>(), (const uint32_t*)order_.as<uint32_t>(),
+             (const MsmTotals*)totals_, part, state_.as<uint32_t>(), task_out_.as<uint32_t>());
+    }
+  }
+  void LaunchPairAccumulate(uint32_t max_tasks, const uint32_t* d_bases, uint32_t part) {
+    if constexpr (C::Field::kDegree == 2) {
+      constexpr int kFirst = PairMinBlocks<C>(), kSecond = PairMinBlocksAlt<C>();
+      if (options_.acc_variant == 2)
+        LaunchPairShape<kAccThreads, kSecond>(max_tasks, d_bases, part);
+      else
+        LaunchPairShape<kAccThreads, kFirst>(max_tasks, d_bases, part);
+    }
+  }
+
   // One MSM: bucket values live in `state_` for the whole call; the points are consumed
   // as K consecutive ranges, each range sorted by bucket and added into the bucket values
   // (accumulate_kernel starts from the value the earlier ranges left).  With host inputs
@@ -1182,6 +1227,11 @@ class MsmEngine {
           Launch(accumulate_staged_kernel<C>, agrid, kAccThreads, d_bases, sorted_.as<uint32_t>(),
                  tasks_.as<uint2>(), task_meta_.as<uint32_t>(), order_.as<uint32_t>(), totals_, part,
                  state_.as<uint32_t>(), task_out_.as<uint32_t>());
+        else if (C::Field::kDegree == 2 && options_.acc_variant != 0)
+          LaunchPairAccumulate(max_tasks, d_bases, part);
+        else if (C::Field::kDegree == 1 && (uint64_t)plan.n * plan.W >= kAccSmallEntries &&
+                 (options_.acc_variant == 3 || (options_.acc_variant < 0 && C::kAccLockstep)))
+          LaunchLockstep(agrid, d_bases, part);
         else
           Launch((uint64_t)plan.n * plan.W < kAccSmallEntries
                      ? accumulate_kernel<C, false, AccMinBlocksSmall<C>()>
@@ -1444,7 +1494,12 @@ class MsmEngine {
                leaves + kXyzzWords);
     } else {
       constexpr uint32_t kSlots = ReduceSlots<C>();
-      LaunchOn(level_stream, reduce_blocks_kernel<C>, (blocks + kSlots - 1) / kSlots, 2 * kSlots, bucket0,
+      using K0 = typename C::Field;
+      const int roll = options_.reduce_roll < 0 ? C::kReduceRoll : options_.reduce_roll;
+      auto kernel = roll == 2   ? reduce_blocks_kernel<C, typename K0::template WithRoll<2>>
+                    : roll == 1 ? reduce_blocks_kernel<C, typename K0::template WithRoll<1>>
+                                : reduce_blocks_kernel<C, K0>;
+      LaunchOn(level_stream, kernel, (blocks + kSlots - 1) / kSlots, 2 * kSlots, bucket0,
                plan.B, nb, L0, wn, wide_local, leaves, leaves + kXyzzWords);
     }
     if (after_level) {

@@ -35,6 +35,10 @@ struct Bn254Curve {
   using Fr = Bn254FrParams;
   using Gen = Bn254G1Generator;
   static constexpr const char* kName = "bn254";
+  static constexpr int kReduceRoll = 0;  // running-sum kernel: unrolled multiplications (looped: 3.38 -> 3.67 ms at 2^24)
+  // accumulation warps free-running: the 68 KB loop body streams through the instruction cache
+  // at a 98 % hit rate (one barrier per step: 29.96 -> 30.43 ms at 2^24)
+  static constexpr bool kAccLockstep = false;
   // how much larger the next pipelined host range may be: bucket work per point / PCIe time
   // per point (2.4 ns vs 1.75 ns for 96 B at ~55 GB/s), with a margin
   static constexpr double kRangeGrowth = 1.3;
@@ -45,6 +49,10 @@ struct Bls381Curve {
   using Fr = Bls381FrParams;
   using Gen = Bls381G1Generator;
   static constexpr const char* kName = "bls12_381";
+  static constexpr int kReduceRoll = 1;  // running-sum kernel: looped multiplications (2^22: 2.24 -> 2.12 ms)
+  // accumulation warps of a CTA in step (accumulate_lockstep_kernel): 2^22 points 21.64 ->
+  // 19.71 ms, FMA-heavy pipe 82 -> 90 %, instruction-cache hit rate 79 -> 90 %
+  static constexpr bool kAccLockstep = true;
   static constexpr double kRangeGrowth = 2.0;  // 6.3 ns of bucket work vs 2.3 ns of PCIe per point
 };
 
@@ -56,6 +64,8 @@ struct Bn254G2Curve {
   using Fr = Bn254FrParams;
   using Gen = Bn254G2Generator;
   static constexpr const char* kName = "bn254_g2";
+  static constexpr bool kAccLockstep = true;  // pair kernel: warps of a CTA in step
+  static constexpr int kReduceRoll = 1;  // running-sum kernel: looped multiplications (2^20: 1.11 -> 1.06 ms)
   static constexpr double kRangeGrowth = 2.0;
 };
 struct Bls381G2Curve {
@@ -64,6 +74,8 @@ struct Bls381G2Curve {
   using Fr = Bls381FrParams;
   using Gen = Bls381G2Generator;
   static constexpr const char* kName = "bls12_381_g2";
+  static constexpr bool kAccLockstep = true;  // pair kernel: warps of a CTA in step
+  static constexpr int kReduceRoll = 1;  // running-sum kernel: looped multiplications (2^20: 4.09 -> 3.93 ms)
   static constexpr double kRangeGrowth = 2.5;
 };
 
@@ -634,6 +646,170 @@ __global__ void __launch_bounds__(kAccThreads, kMinBlocks) accumulate_kernel(
   xyzz_store<K>((meta & kTaskSingle) ? bucket : task_out + (size_t)g * kXyzzWords, acc);
 }
 
+// G2 accumulation with one task per LANE PAIR: lane 2k holds the c0 components of the bucket
+// value and of the points, lane 2k + 1 the c1 components (fp.cuh Fp2Lanes, xyzz.cuh PairOps).
+// Half the registers per lane of accumulate_kernel<G2> — twice the warps per SM for the same
+// multiply count — and warps that stay converged: every lane pair of a warp walks
+// max(task lengths of the warp) steps (tasks are ordered by length, so the lengths of one warp
+// are nearly equal) with finished pairs predicated off, which is what a diverged warp costs
+// anyway.  Memory layout of points and bucket values is unchanged (c0 | c1 per coordinate): a
+// lane reads and writes its half of every coordinate.
+// Resident CTAs per SM (of kAccThreads lanes) the pair kernel's register budget is held to.
+// Measured (B200, 2^20 points, accumulation only; one thread per task: 11.01 / 22.34 ms):
+//   BN254      3 x 168 registers (12 B of spills)  8.48 ms     4 x 128 (144 B)  8.55 ms
+//   BLS12-381  2 x 242 registers (no spills)      18.14 ms     3 x 168 (240 B) 19.57 ms
+template <class C>
+constexpr int PairMinBlocks() {
+  return C::Field::kWords <= 16 ? 3 : 2;
+}
+template <class C>
+constexpr int PairMinBlocksAlt() {
+  return C::Field::kWords <= 16 ? 4 : 3;
+}
+
+// kLockstep: the warps of a CTA also stay within one addition of each other (one barrier per
+// step, see accumulate_lockstep_kernel) so that they share the instruction stream.
+template <class C, int kThreads, int kMinBlocks, bool kLockstep = false>
+__global__ void __launch_bounds__(kThreads, kMinBlocks) accumulate_pair_kernel(
+    const uint32_t* __restrict__ bases, const uint32_t* __restrict__ sorted,
+    const uint2* __restrict__ tasks, const uint32_t* __restrict__ task_meta,
+    const uint32_t* __restrict__ order, const MsmTotals* __restrict__ totals, uint32_t part,
+    uint32_t* __restrict__ state, uint32_t* __restrict__ task_out) {
+  using F = typename C::Fq;
+  static_assert(C::Field::kDegree == 2, "lane pairs split a quadratic extension");
+  constexpr int N = Fp<F>::N;
+  constexpr int kAffineWords = 4 * N;
+  constexpr int kXyzzWords = 8 * N;
+  const uint32_t role = threadIdx.x & 1;
+  const uint32_t slot = ((blockIdx.x * kThreads + threadIdx.x) >> 1) +
+                        (part == kPartLow ? totals->tasks_hi : 0u);
+  const bool live = slot < (part == kPartHigh ? totals->tasks_hi : totals->tasks);
+  uint32_t g = 0, meta = 0;
+  uint2 task = make_uint2(0u, 0u);
+  if (live) {
+    g = order[slot];
+    task = tasks[g];
+    meta = task_meta[g];
+  }
+  const uint32_t len = live ? task.y : 0u;
+  uint32_t steps = __reduce_max_sync(0xffffffffu, len);  // warp-uniform trip count
+  if (kLockstep) {
+    __shared__ uint32_t cta_steps;
+    if (threadIdx.x == 0) cta_steps = 0;
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) atomicMax(&cta_steps, steps);
+    __syncthreads();
+    steps = cta_steps;
+  }
+  const uint32_t* ent = sorted + task.x;
+  uint32_t* bucket = state + (size_t)(meta & kTaskKeyMask) * kXyzzWords + role * N;
+  auto fetch = [&](PairAffine<F>& p, uint32_t e) {
+    const uint32_t* src = bases + (size_t)(e & 0x7fffffffu) * kAffineWords + role * N;
+    fp_load<F>(p.x, src);
+    fp_load<F>(p.y, src + 2 * N);
+  };
+  uint32_t e = 0;
+  PairAffine<F> nxt;
+  fp_set_zero<F>(nxt.x);
+  fp_set_zero<F>(nxt.y);
+  if (len > 0) {
+    e = ent[0];
+    fetch(nxt, e);
+  }
+  PairPoint<F> acc;
+  if (live && (meta & kTaskFirst)) {
+    fp_load_rw<F>(acc.x, bucket);
+    fp_load_rw<F>(acc.y, bucket + 2 * N);
+    fp_load_rw<F>(acc.zz, bucket + 4 * N);
+    fp_load_rw<F>(acc.zzz, bucket + 6 * N);
+  } else {
+    Fp2Lanes<F>::set_one(acc.x, role);
+    Fp2Lanes<F>::set_one(acc.y, role);
+    fp_set_zero<F>(acc.zz);
+    fp_set_zero<F>(acc.zzz);
+  }
+  for (uint32_t j = 0; j < steps; ++j) {
+    PairAffine<F> cur = nxt;
+    const bool neg = e >> 31;
+    if (j + 1 < len) {
+      e = ent[j + 1];
+      fetch(nxt, e);
+    }
+    PairOps<F>::madd(acc, cur, neg, j < len, role);
+    if (kLockstep) __syncthreads();
+  }
+  if (live) {
+    uint32_t* dst = (meta & kTaskSingle) ? bucket : task_out + (size_t)g * kXyzzWords + role * N;
+    fp_store<F>(dst, acc.x);
+    fp_store<F>(dst + 2 * N, acc.y);
+    fp_store<F>(dst + 4 * N, acc.zz);
+    fp_store<F>(dst + 6 * N, acc.zzz);
+  }
+}
+
+// Experiment: accumulate_kernel with the warps of a CTA kept within one addition of each other
+// (one barrier per step; every thread walks the CTA's longest task length with its own additions
+// predicated), so that the four warps fetch the same stretch of the loop body at about the same
+// time.  The 12-limb loop body is 90 KB of SASS and the instruction cache serves only 79 % of
+// its requests with 16 warps at unrelated places in it (ncu: no_instruction is the second
+// largest stall).
+template <class C, int kMinBlocks = AccMinBlocks<C>()>
+__global__ void __launch_bounds__(kAccThreads, kMinBlocks) accumulate_lockstep_kernel(
+    const uint32_t* __restrict__ bases, const uint32_t* __restrict__ sorted,
+    const uint2* __restrict__ tasks, const uint32_t* __restrict__ task_meta,
+    const uint32_t* __restrict__ order, const MsmTotals* __restrict__ totals, uint32_t part,
+    uint32_t* __restrict__ state, uint32_t* __restrict__ task_out) {
+  using K = typename C::Field;
+  constexpr int kAffineWords = 2 * K::kWords;
+  constexpr int kXyzzWords = 4 * K::kWords;
+  __shared__ uint32_t cta_steps;
+  if (threadIdx.x == 0) cta_steps = 0;
+  __syncthreads();
+  uint32_t slot = blockIdx.x * blockDim.x + threadIdx.x + (part == kPartLow ? totals->tasks_hi : 0u);
+  const bool live = slot < (part == kPartHigh ? totals->tasks_hi : totals->tasks);
+  uint32_t g = 0, meta = 0;
+  uint2 task = make_uint2(0u, 0u);
+  if (live) {
+    g = order[slot];
+    task = tasks[g];
+    meta = task_meta[g];
+  }
+  const uint32_t len = live ? task.y : 0u;
+  const uint32_t warp_steps = __reduce_max_sync(0xffffffffu, len);
+  if ((threadIdx.x & 31) == 0) atomicMax(&cta_steps, warp_steps);
+  __syncthreads();
+  const uint32_t steps = cta_steps;
+  uint32_t* bucket = state + (size_t)(meta & kTaskKeyMask) * kXyzzWords;
+  const uint32_t* ent = sorted + task.x;
+  uint32_t e = 0;
+  Affine<K> nxt;
+  K::set_zero(nxt.x);
+  K::set_zero(nxt.y);
+  if (len > 0) {
+    e = ent[0];
+    affine_load<K>(nxt, bases + (size_t)(e & 0x7fffffffu) * kAffineWords);
+  }
+  XYZZ<K> acc;
+  if (live && (meta & kTaskFirst)) {
+    xyzz_load<K>(acc, bucket);
+  } else {
+    xyzz_set_zero<K>(acc);
+  }
+  for (uint32_t j = 0; j < steps; ++j) {
+    if (j < len) {
+      Affine<K> cur = nxt;
+      bool neg = e >> 31;
+      if (j + 1 < len) {
+        e = ent[j + 1];
+        affine_load<K>(nxt, bases + (size_t)(e & 0x7fffffffu) * kAffineWords);
+      }
+      xyzz_madd<K>(acc, cur, neg);
+    }
+    __syncthreads();
+  }
+  if (live) xyzz_store<K>((meta & kTaskSingle) ? bucket : task_out + (size_t)g * kXyzzWords, acc);
+}
+
 // The same accumulation with the NEXT point staged through shared memory instead of registers:
 // cp.async (LDGSTS) copies the gathered point straight from L2 into the thread's private slot
 // while the current mixed addition runs, so nothing of the point in flight is live in registers
@@ -1009,11 +1185,10 @@ constexpr int ReduceSlots() {
   return 4 * C::Field::kWords > 64 ? 32 : 64;
 }
 
-template <class C>
+template <class C, class K = typename C::Field>
 __global__ void __launch_bounds__(2 * ReduceSlots<C>()) reduce_blocks_kernel(
     const uint32_t* __restrict__ state, uint32_t n_in, uint32_t n_out, uint32_t L,
     uint32_t windows, uint32_t wide, uint32_t* __restrict__ out_a, uint32_t* __restrict__ out_c) {
-  using K = typename C::Field;
   constexpr int kXyzzWords = 4 * K::kWords;
   constexpr int kSlots = kXyzzWords > 64 ? 32 : 64;  // = ReduceSlots<C>()
   constexpr int kStride = kXyzzWords + 4;  // 16-byte accesses of neighbouring slots hit distinct banks

@@ -294,4 +294,116 @@ struct Coop4 {
   }
 };
 
+// ---------------------------------------------------------------------------
+// G2 point operations with every Fq2 coordinate split over a LANE PAIR (fp.cuh, Fp2Lanes): a
+// lane holds its component of x, y, zz, zzz.  Same formulas and the same case analysis as
+// xyzz_madd / xyzz_dbl_nz above, but written for warps that stay CONVERGED: the general
+// formula always runs and the exceptional cases (identity operands, inactive lane pairs, the
+// P == R == 0 doubling) are selects or warp-uniform branches, so every shuffle inside is a
+// plain full-mask SHFL.
+// ---------------------------------------------------------------------------
+template <class F>
+struct PairPoint {
+  Fp<F> x, y, zz, zzz;  // this lane's components
+};
+template <class F>
+struct PairAffine {
+  Fp<F> x, y;
+};
+
+template <class F, int kRoll = 0>
+struct PairOps {
+  using L = Fp2Lanes<F, kRoll>;
+  using E = Fp<F>;
+
+  // p = 2 p for the lane pairs with `take` set (p != identity there); all lanes compute.
+  static __device__ __noinline__ void dbl_where(PairPoint<F>& p, bool take, uint32_t role) {
+    E u, v, w, s, m, t, nzz, nzzz, nx;
+    fp_dbl<F>(u, p.y);         // U = 2 Y1
+    L::sqr(v, u, role);        // V = U^2
+    typename L::Multiplier mv;
+    L::prepare(mv, v, role);
+    L::mul(w, u, mv);          // W = U V
+    L::mul(s, p.x, mv);        // S = X1 V
+    L::mul(nzz, p.zz, mv);     // ZZ3 = V ZZ1
+    L::sqr(m, p.x, role);      // M = 3 X1^2
+    fp_dbl<F>(t, m);
+    fp_add<F>(m, m, t);
+    typename L::Multiplier mw;
+    L::prepare(mw, w, role);
+    L::mul(nzzz, p.zzz, mw);   // ZZZ3 = W ZZZ1
+    L::sqr(nx, m, role);       // X3 = M^2 - 2 S
+    fp_dbl<F>(t, s);
+    fp_sub<F>(nx, nx, t);
+    fp_sub<F>(t, s, nx);       // Y3 = M (S - X3) - W Y1
+    L::mul(t, t, m, role);
+    L::mul(u, p.y, mw);
+    fp_sub<F>(t, t, u);
+    L::select(p.x, take, nx, p.x);
+    L::select(p.y, take, t, p.y);
+    L::select(p.zz, take, nzz, p.zz);
+    L::select(p.zzz, take, nzzz, p.zzz);
+  }
+
+  // acc += (neg ? -q : q) for the lane pairs with `active` set; q affine.  madd-2008-s with
+  // the case analysis of point_xyzz_impl.h:114-176.
+  static TB_DEV void madd(PairPoint<F>& acc, const PairAffine<F>& q, bool neg, bool active,
+                          uint32_t role) {
+    const bool qz = L::both(fp_is_zero<F>(q.x) && fp_is_zero<F>(q.y));
+    const bool az = L::is_zero(acc.zz);
+    const bool adds = active && !qz;  // something is added at all
+    const bool plain = adds && !az;   // ... to a non-identity accumulator: the formula
+    const bool copy = adds && az;     // ... to the identity: acc = q
+    E y2;
+    fp_cneg<F>(y2, q.y, neg);
+    // Both blocks are warp-uniform branches.  The copy comes first so that q is not live across
+    // the formula; the formula's selects skip the pairs that copied (`plain` is false there).
+    if (__any_sync(L::kFull, copy)) {  // first point of fresh tasks, mostly
+      E one;
+      L::set_one(one, role);
+      L::select(acc.x, copy, q.x, acc.x);
+      L::select(acc.y, copy, y2, acc.y);
+      L::select(acc.zz, copy, one, acc.zz);
+      L::select(acc.zzz, copy, one, acc.zzz);
+    }
+    if (__any_sync(L::kFull, plain)) {
+      E p, r, pp, ppp, qq, t, u, nx, nzz, nzzz;
+      L::mul(p, q.x, acc.zz, role);       // P = X2 ZZ1 - X1
+      fp_sub<F>(p, p, acc.x);
+      L::mul(r, y2, acc.zzz, role);       // R = Y2 ZZZ1 - Y1
+      fp_sub<F>(r, r, acc.y);
+      const bool pr_zero = L::both(fp_is_zero<F>(p) && fp_is_zero<F>(r));  // every lane takes part
+      const bool same = plain && pr_zero;
+      const bool take = plain && !same;
+      L::sqr(pp, p, role);                // PP = P^2
+      {
+        typename L::Multiplier mpp;
+        L::prepare(mpp, pp, role);
+        L::mul(ppp, p, mpp);              // PPP = P PP
+        L::mul(qq, acc.x, mpp);           // Q = X1 PP
+        L::mul(nzz, acc.zz, mpp);         // ZZ3 = ZZ1 PP
+      }
+      L::select(acc.zz, take, nzz, acc.zz);
+      {
+        typename L::Multiplier mppp;
+        L::prepare(mppp, ppp, role);
+        L::mul(nzzz, acc.zzz, mppp);      // ZZZ3 = ZZZ1 PPP
+        L::mul(u, acc.y, mppp);           // Y1 PPP
+      }
+      L::select(acc.zzz, take, nzzz, acc.zzz);
+      L::sqr(nx, r, role);                // X3 = R^2 - PPP - 2 Q
+      fp_sub<F>(nx, nx, ppp);
+      fp_dbl<F>(t, qq);
+      fp_sub<F>(nx, nx, t);
+      fp_sub<F>(t, qq, nx);               // Y3 = R (Q - X3) - Y1 PPP
+      L::mul(t, t, r, role);
+      fp_sub<F>(t, t, u);
+      L::select(acc.x, take, nx, acc.x);
+      L::select(acc.y, take, t, acc.y);
+      // P == R == 0: the operands are equal, double instead (those pairs' acc is still untouched)
+      if (__any_sync(L::kFull, same)) dbl_where(acc, same, role);
+    }
+  }
+};
+
 }  // namespace tb200

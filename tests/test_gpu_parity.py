@@ -174,6 +174,69 @@ def test_g2_msm_host_inputs(oracles, torch_cuda, name, n):
         _check_msm(o, name, ctx, bases, scalars, entry="point2")
 
 
+@pytest.mark.parametrize("name", G2)
+@pytest.mark.parametrize("variant", [0, 1, 2])
+def test_g2_accumulate_variants(oracles, torch_cuda, name, variant):
+    # 0: one thread per accumulation task; 1 / 2: one LANE PAIR per task (a lane per Fq2 component)
+    # at both register budgets.  Covers what only the accumulation sees: bucket values carried
+    # across point ranges, buckets split into several tasks, identity bases, equal points
+    # (the doubling branch) and warps whose pairs run different task lengths.
+    o = oracles[name]
+    r_mod, el = _consts(name)
+    n = 3000
+    bases, scalars = o.generate_points(51, n), o.generate_scalars(52, n, "non_uniform")
+    bases[5] = 0
+    bases[9] = bases[8]
+    scalars[9] = scalars[8]
+    bases[200:260] = bases[200]
+    with msm.MSMGpu(name) as ctx:
+        ctx.set_option("acc_variant", variant)
+        _check_msm(o, name, ctx, bases, scalars)
+        ctx.set_option("ranges", 3)            # later ranges start from the stored bucket values
+        _check_msm(o, name, ctx, bases, scalars)
+        ctx.set_option("segment", 16)          # split buckets: partial sums to task_out, folded
+        ctx.set_option("window_bits", 6)
+        _check_msm(o, name, ctx, bases, scalars)
+        same = bases.copy()
+        same[:] = bases[7]
+        _check_msm(o, name, ctx, same, o.generate_scalars(53, n))
+
+
+@pytest.mark.parametrize("name", CURVES)
+def test_msm_accumulate_lockstep(oracles, torch_cuda, name):
+    # acc_variant 3 (G1): the warps of a CTA walk their tasks one addition per barrier
+    o = oracles[name]
+    n = 5000
+    bases, scalars = o.generate_points(71, n), o.generate_scalars(72, n, "non_uniform")
+    bases[5] = 0
+    bases[9] = bases[8]
+    scalars[9] = scalars[8]
+    with msm.MSMGpu(name) as ctx:
+        ctx.set_option("acc_variant", 3)
+        _check_msm(o, name, ctx, bases, scalars)
+        ctx.set_option("ranges", 3)
+        ctx.set_option("segment", 16)
+        _check_msm(o, name, ctx, bases, scalars)
+
+
+@pytest.mark.parametrize("name", ALL)
+@pytest.mark.parametrize("roll", [0, 1, 2])
+def test_msm_reduce_code_shapes(oracles, torch_cuda, name, roll):
+    # the field multiplications of the running-sum kernel unrolled (0), looped (1), looped with
+    # the squarings through the multiplier (2): same values
+    o = oracles[name]
+    n = 4000
+    bases, scalars = o.generate_points(61, n), o.generate_scalars(62, n)
+    bases[9] = bases[8]
+    scalars[9] = scalars[8]
+    with msm.MSMGpu(name) as ctx:
+        ctx.set_option("reduce_roll", roll)
+        _check_msm(o, name, ctx, bases, scalars)
+        ctx.set_option("window_bits", 7)
+        ctx.set_option("ranges", 2)
+        _check_msm(o, name, ctx, bases, o.generate_scalars(63, n, "non_uniform"))
+
+
 @pytest.mark.parametrize("name", ALL)
 @pytest.mark.parametrize("dist", ["non_uniform", "witness"])
 def test_msm_skewed_scalars(oracles, torch_cuda, name, dist):

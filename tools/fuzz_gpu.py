@@ -43,6 +43,7 @@ for case in range(cases):
         "low_windows": rng.choice([-1, 0, 1, 2, 3, 9]),
         "level_fill": rng.choice([0, 0, 48, 96, 3000]),      # running-sum block lengths 4 .. 64
         "stage_points": rng.choice([0, 0, 1]),
+        "acc_variant": rng.choice([-1, 0, 1, 2]),
         "segment": rng.choice([0, 0, 0, 16, 32]),
     }
     for k, v in opts.items():
