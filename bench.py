@@ -50,10 +50,13 @@ def algorithmic_products(curve, n):
     # What the accumulation kernel ISSUES per mixed addition (xyzz.cuh xyzz_madd: 6 mul + 2 sqr
     # + 1 fused two-product mul2; fp.cuh: mul 2L^2+L, sqr L(L+1)/2+L^2+L, mul2 3L^2+L wide
     # products) — fewer than the canonical 10 multiplications, which is why `frac` can exceed 1.
-    issued_per_add = None
+    L = limbs
     if not curve.endswith("_g2"):
-        L = limbs
         issued_per_add = 6 * (2 * L * L + L) + 2 * (L * (L + 1) // 2 + L * L + L) + (3 * L * L + L)
+    else:
+        # G2 (fp.cuh Fp2Field / Fp2Lanes): an Fq2 multiplication is two fp_mul2 (3L^2+L each), an Fq2
+        # squaring two fp_mul (2L^2+L each), the fused Y3 two Fq2 multiplications
+        issued_per_add = 6 * 2 * (3 * L * L + L) + 2 * 2 * (2 * L * L + L) + 2 * 2 * (3 * L * L + L)
     return dict(c=c, W=W, modmuls=modmuls, products=modmuls * per_mul,
                 accumulate_products=n * W * 10 * per_mul, issued_per_add=issued_per_add)
 
@@ -934,7 +937,10 @@ def run_msm(args, rank, world, local_rank):
             # 32x32->64 products per addition in xyzz_madd) per second of that kernel's own launch
             # time, over the measured pipe peak.  frac_alg uses the canonical 10 multiplications of
             # 2 L^2 + L products per addition instead and can exceed 1.
-            "roofline": {"bound": "int32-imad", "kernel": "accumulate_kernel",
+            "roofline": {"bound": "int32-imad",
+                         "kernel": "accumulate_pair_kernel" if curve.endswith("_g2") else
+                                   ("accumulate_lockstep_kernel" if curve == "bls12_381" and n_local * timing["windows"] >= (12 << 20)
+                                    else "accumulate_kernel"),
                          "achieved": rate(issued) / 1e9 if rate(issued) else None,
                          "peak": peak / 1e9, "unit": "G products/s (32x32->64)",
                          "frac": rate(issued) / peak if rate(issued) and peak else None,

@@ -96,8 +96,9 @@ extern "C" {
      "sort_mode" (0 = one-level atomic counting sort, 1 = two-level shared-memory sort       \
      where eligible, -1 = automatic),                                                        \
      "balance" (1 = balanced window widths, the default; 0 = equal widths),                  \
-     "reduce_mode" (1 = two threads per block of buckets in the running-sum level, the       \
-     default; 0 = one), "host_ranges" (most ranges of the automatic host-input pipeline),    \
+     "reduce_mode" (1 = two threads — G2: two lane pairs — per block of buckets in the       \
+     running-sum level, the default; 2 = two threads for G2 as well; 0 = one thread),        \
+     "host_ranges" (most ranges of the automatic host-input pipeline),                       \
      "prewarm" (reserve workspace, staging and copy threads for an MSM of `value` points now),\
      "release_workspace" (free the grow-only workspace; registered bases are kept),           \
      "precompute" (1 = the next register_bases call also builds the table of window           \
@@ -106,7 +107,11 @@ extern "C" {
      windows: W times the base memory, a W times smaller bucket reduction, no ladder),        \
      "acc_variant" (G2 groups: 1 = one lane pair per accumulation task, a lane per Fq2         \
      component — the default; 2 = the same at the other register budget; 0 = one thread per   \
-     task),                                                                                   \
+     task.  G1 groups: 3 = the warps of a CTA walk their tasks in step, the default for       \
+     BLS12-381; 0 = free-running warps, the default for BN254),                               \
+     "acc_lockstep" (G2 lane-pair kernel: 1 = warps of a CTA in step, the default; 0 = free), \
+     "reduce_roll" (field multiplications of the running-sum kernel: 0 = unrolled, 1 = as a   \
+     loop over row pairs, 2 = squarings through that loop too, -1 = per-curve default),       \
      "stage_points" (1 = the accumulation stages the next point through shared memory with    \
      cp.async instead of registers),                                                          \
      "device_ladder" (where the final ladder over the W window sums runs — ~255 strictly     \

@@ -46,21 +46,24 @@ struct CudaError {
 struct DeviceBuffer {
   void* ptr = nullptr;
   size_t bytes = 0;
+  bool in_arena = false;  // a slice of the engine's workspace arena (not freed on its own)
+  // 2 MiB granules, 12.5 % slack so slightly larger follow-up calls reuse the buffer
+  static size_t Rounded(size_t want) {
+    size_t sz = want + want / 8;
+    return (sz + (size_t(2) << 20) - 1) & ~((size_t(2) << 20) - 1);
+  }
   void Reserve(size_t want) {
     if (want <= bytes) return;
-    if (ptr) TB_CUDA(cudaFree(ptr));
-    ptr = nullptr;
-    bytes = 0;
-    // round up to 2 MiB, 12.5 % slack so slightly larger follow-up calls reuse it
-    size_t sz = want + want / 8;
-    sz = (sz + (size_t(2) << 20) - 1) & ~((size_t(2) << 20) - 1);
+    Free();
+    size_t sz = Rounded(want);
     TB_CUDA(cudaMalloc(&ptr, sz));
     bytes = sz;
   }
   void Free() {
-    if (ptr) cudaFree(ptr);
+    if (ptr && !in_arena) cudaFree(ptr);
     ptr = nullptr;
     bytes = 0;
+    in_arena = false;
   }
   template <class T>
   T* as() const {
@@ -93,8 +96,9 @@ struct MsmOptions {
   int pair_rounds = -1;      // batched-affine pair rounds before the XYZZ accumulation:
                              // -1 = none (default), -2 = from bucket occupancy, >= 0 = forced
   uint32_t host_ranges = 8;  // most ranges the automatic host-input pipeline cuts an MSM into
-  int reduce_mode = 1;       // 1 = two threads per block of buckets (reduce_blocks_kernel),
-                             // 0 = one thread per block (reduce_level_kernel)
+  int reduce_mode = 1;       // 1 = two threads per block of buckets (reduce_blocks_kernel; G2: two
+                             // lane pairs, reduce_blocks_pair_kernel), 2 = two threads per block
+                             // for G2 as well, 0 = one thread per block (reduce_level_kernel)
   uint32_t level_fill = 0;   // blocks per SM the running-sum level wants before it shortens its
                              // blocks (0 = default: 384, 768 from 1.5 M bucket slots)
   int balance = 1;           // balanced windows (WideWindowsFor); 0 = equal widths, slack on top
@@ -330,6 +334,7 @@ class MsmEngine {
     cudaStreamSynchronize(tail_stream_);
     cudaStreamSynchronize(copy_stream_);
     for (const DeviceBuffer* b : AllBuffers()) const_cast<DeviceBuffer*>(b)->Free();
+    if (arena_) cudaFree(arena_);
     if (totals_) cudaFree(totals_);
     if (host_out_) cudaFreeHost(host_out_);
     if (bounce_) cudaFreeHost(bounce_);
@@ -420,6 +425,8 @@ class MsmEngine {
     TB_CUDA(cudaStreamSynchronize(tail_stream_));
     for (const DeviceBuffer* b : AllBuffers())
       if (b != &registered_) const_cast<DeviceBuffer*>(b)->Free();
+    if (arena_) cudaFree(arena_);
+    arena_ = nullptr;
     for (auto& u : stage_used_) u = false;
     budget_ = 0;
   }
@@ -829,27 +836,61 @@ class MsmEngine {
     for (auto& w : wants) grow = grow || w.second > w.first->bytes;
     if (!grow) return;
     static const bool trace = getenv("TACHYON_B200_TRACE") != nullptr;
+    // TACHYON_B200_ARENA=0: one cudaMalloc per buffer (the round-1 layout)
+    static const bool use_arena = !(getenv("TACHYON_B200_ARENA") && atoi(getenv("TACHYON_B200_ARENA")) == 0);
+    // experiment hook: a gap of TACHYON_B200_PAD_MB between consecutive buffers
+    static const size_t pad = (getenv("TACHYON_B200_PAD_MB") ? (size_t)atol(getenv("TACHYON_B200_PAD_MB")) : 0) << 20;
     auto t0 = std::chrono::steady_clock::now();
     TB_CUDA(cudaStreamSynchronize(copy_stream_));
     TB_CUDA(cudaStreamSynchronize(stream_));
     TB_CUDA(cudaStreamSynchronize(tail_stream_));
-    int index = 0;
-    for (auto& w : wants) {
-      if (trace && w.second > w.first->bytes) {
-        auto t1 = std::chrono::steady_clock::now();
-        size_t had = w.first->bytes;
-        w.first->Reserve(w.second);
-        fprintf(stderr, "[tachyon_b200] workspace buffer %d grows %zu -> %zu bytes: %.2f ms\n", index,
-                had, w.first->bytes,
-                std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t1).count());
-      } else {
-        w.first->Reserve(w.second);
+    if (use_arena) {
+      // ONE allocation for the whole workspace, cut into 2 MiB-aligned slices in list order: the
+      // placement of the buffers relative to each other no longer depends on what the driver's
+      // allocator did before (sizes stay grow-only per buffer; contents are scratch)
+      std::vector<size_t> sz;
+      size_t total = 0;
+      for (auto& w : wants) {
+        size_t have = w.first->bytes, s = w.second > have ? DeviceBuffer::Rounded(w.second) : have;
+        sz.push_back(s);
+        total += s + (s ? pad : 0);
       }
-      ++index;
+      for (auto& w : wants) w.first->Free();
+      if (arena_) TB_CUDA(cudaFree(arena_));
+      arena_ = nullptr;
+      TB_CUDA(cudaMalloc(&arena_, total ? total : 1));
+      size_t off = 0, k = 0;
+      for (auto& w : wants) {
+        if (sz[k]) {
+          w.first->ptr = static_cast<char*>(arena_) + off;
+          w.first->bytes = sz[k];
+          w.first->in_arena = true;
+          off += sz[k] + pad;
+        }
+        ++k;
+      }
+      if (trace)
+        fprintf(stderr, "[tachyon_b200] workspace arena: %zu bytes at %p, %.2f ms\n", total, arena_,
+                std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t0).count());
+    } else {
+      int index = 0;
+      for (auto& w : wants) {
+        if (trace && w.second > w.first->bytes) {
+          auto t1 = std::chrono::steady_clock::now();
+          size_t had = w.first->bytes;
+          w.first->Reserve(w.second);
+          fprintf(stderr, "[tachyon_b200] workspace buffer %d grows %zu -> %zu bytes at %p: %.2f ms\n", index,
+                  had, w.first->bytes, w.first->ptr,
+                  std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t1).count());
+        } else {
+          w.first->Reserve(w.second);
+        }
+        ++index;
+      }
+      if (trace)
+        fprintf(stderr, "[tachyon_b200] workspace growth took %.2f ms\n",
+                std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t0).count());
     }
-    if (trace)
-      fprintf(stderr, "[tachyon_b200] workspace growth took %.2f ms\n",
-              std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t0).count());
     for (auto& u : stage_used_) u = false;
     budget_ = 0;
   }
@@ -868,6 +909,18 @@ class MsmEngine {
              (const uint32_t*)sorted_.as<uint32_t>(), (const uint2*)tasks_.as<uint2>(),
              (const uint32_t*)task_meta_.as<uint32_t>(), (const uint32_t*)order_.as<uint32_t>(),
              (const MsmTotals*)totals_, part, state_.as<uint32_t>(), task_out_.as<uint32_t>());
+    }
+  }
+  // G2 running-sum level on lane pairs (reduce_blocks_pair_kernel)
+  void LaunchPairReduce(cudaStream_t st, uint32_t blocks, const uint32_t* bucket0, uint32_t B,
+                        uint32_t nb, uint32_t L0, uint32_t wn, uint32_t wide_local, uint32_t* leaves) {
+    if constexpr (C::Field::kDegree == 2) {
+      constexpr uint32_t kSlots = kPairReduceSlots;
+      constexpr int kMin = PairMinBlocks<C>();
+      const int roll = options_.reduce_roll < 0 ? C::kReduceRoll : options_.reduce_roll;
+      auto kernel = roll ? reduce_blocks_pair_kernel<C, 1, kMin> : reduce_blocks_pair_kernel<C, 0, kMin>;
+      LaunchOn(st, kernel, (blocks + kSlots - 1) / kSlots, 4 * kSlots, bucket0, B, nb, L0, wn,
+               wide_local, leaves, leaves + kXyzzWords);
     }
   }
   void LaunchLockstep(uint32_t agrid, const uint32_t* d_bases, uint32_t part) {
@@ -1492,6 +1545,8 @@ class MsmEngine {
       LaunchOn(level_stream, reduce_level_kernel<C, true>, (blocks + kReduceThreads - 1) / kReduceThreads,
                kReduceThreads, bucket0, (const uint32_t*)nullptr, plan.B, nb, L0, 0u, wn, leaves,
                leaves + kXyzzWords);
+    } else if (C::Field::kDegree == 2 && options_.reduce_mode == 1) {
+      LaunchPairReduce(level_stream, blocks, bucket0, plan.B, nb, L0, wn, wide_local, leaves);
     } else {
       constexpr uint32_t kSlots = ReduceSlots<C>();
       using K0 = typename C::Field;
@@ -1550,7 +1605,8 @@ class MsmEngine {
 
   // Nanoseconds per mixed addition of the accumulation kernel at full occupancy (measured, B200).
   static constexpr double MaddNanos() {
-    return C::Field::kWords <= 8 ? 0.138 : (C::Field::kWords <= 12 ? 0.34 : (C::Field::kWords <= 16 ? 0.61 : 1.3));
+    // (BLS12-381 G1 with its warps in step: 0.313; G2 on lane pairs: 0.475 / 1.08)
+    return C::Field::kWords <= 8 ? 0.138 : (C::Field::kWords <= 12 ? 0.313 : (C::Field::kWords <= 16 ? 0.475 : 1.08));
   }
 
   // How many low windows to accumulate last.  The window combination of the high group is a
@@ -1672,6 +1728,7 @@ class MsmEngine {
   MsmTiming timing_;
   uint32_t launches_ = 0;
   MsmTotals* totals_ = nullptr;
+  void* arena_ = nullptr;  // backing store of the workspace buffers (ReserveAll)
   char* host_out_ = nullptr;
   size_t registered_n_ = 0;
   uint32_t table_c_ = 0, table_wide_ = 0;  // window size of the precomputed table (0: none)

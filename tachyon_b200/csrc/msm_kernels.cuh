@@ -1239,6 +1239,80 @@ __global__ void __launch_bounds__(2 * ReduceSlots<C>()) reduce_blocks_kernel(
   if (live) xyzz_store<K>((summing ? out_c : out_a) + (size_t)g * 2 * kXyzzWords, acc);
 }
 
+// The same running-sum level for G2 with every block handled by a LANE PAIR per role (a lane per
+// Fq2 component, xyzz.cuh PairOps::add): kSlots blocks per CTA, 2 x 2 x kSlots threads — warps
+// [0, kSlots / 16) keep the running sums, the others the weighted sums.  Warps are role-uniform
+// and in step by the per-step barrier, so every shuffle is a full-mask one.  Same values, same
+// memory layout as reduce_blocks_kernel.
+constexpr int kPairReduceSlots = 32;
+
+template <class C, int kRoll, int kMinBlocks>
+__global__ void __launch_bounds__(4 * kPairReduceSlots, kMinBlocks) reduce_blocks_pair_kernel(
+    const uint32_t* __restrict__ state, uint32_t n_in, uint32_t n_out, uint32_t L,
+    uint32_t windows, uint32_t wide, uint32_t* __restrict__ out_a, uint32_t* __restrict__ out_c) {
+  using F = typename C::Fq;
+  static_assert(C::Field::kDegree == 2, "lane pairs split a quadratic extension");
+  using Ops = PairOps<F, kRoll>;
+  constexpr int N = Fp<F>::N;
+  constexpr int kXyzzWords = 8 * N;
+  constexpr int kSlots = kPairReduceSlots;
+  constexpr int kStride = kXyzzWords + 4;
+  __shared__ __align__(16) uint32_t sh[2 * kSlots * kStride];
+  const uint32_t role = threadIdx.x & 1;
+  const uint32_t pair = threadIdx.x >> 1;
+  const uint32_t slot = pair % kSlots;
+  const bool summing = pair >= (uint32_t)kSlots;  // second half of the CTA: wt += run
+  const uint32_t total = n_out * windows;
+  const uint32_t g0 = blockIdx.x * kSlots;
+  const uint32_t g = g0 + slot;
+  auto load = [&](PairPoint<F>& p, const uint32_t* src) {
+    fp_load_rw<F>(p.x, src + role * N);
+    fp_load_rw<F>(p.y, src + 2 * N + role * N);
+    fp_load_rw<F>(p.zz, src + 4 * N + role * N);
+    fp_load_rw<F>(p.zzz, src + 6 * N + role * N);
+  };
+  auto store = [&](uint32_t* dst, const PairPoint<F>& p) {
+    fp_store<F>(dst + role * N, p.x);
+    fp_store<F>(dst + 2 * N + role * N, p.y);
+    fp_store<F>(dst + 4 * N + role * N, p.zz);
+    fp_store<F>(dst + 6 * N + role * N, p.zzz);
+  };
+  PairPoint<F> acc, in;
+  Fp2Lanes<F>::set_one(acc.x, role);
+  Fp2Lanes<F>::set_one(acc.y, role);
+  fp_set_zero<F>(acc.zz);
+  fp_set_zero<F>(acc.zzz);
+  {
+    // known-empty CTA (uniform decision: first and last block of the CTA)
+    uint32_t g1 = min(g0 + kSlots, total) - 1;
+    uint32_t w0 = g0 / n_out, w1 = g1 / n_out;
+    if (w0 == w1 && w0 >= wide && (g0 % n_out) * L >= n_in / 2) {
+      if (g < total) store((summing ? out_c : out_a) + (size_t)g * 2 * kXyzzWords, acc);
+      return;
+    }
+  }
+  const bool live = g < total;
+  const uint32_t w = live ? g / n_out : 0, t = live ? g % n_out : 0;
+  const uint32_t lo = t * L, hi = min(n_in, lo + L);
+  const uint32_t steps = live ? hi - lo : 0;
+  uint32_t* mine = sh + slot * kStride;
+  in = acc;
+  for (uint32_t i = 0; i < L; ++i) {
+    if (!summing) {  // warp-uniform
+      const bool active = i < steps;
+      if (active) load(in, state + (size_t)(w * n_in + (hi - 1 - i)) * kXyzzWords);
+      Ops::add(acc, in, active, role);
+      if (i + 1 < steps) store(mine + (i & 1) * (kSlots * kStride), acc);
+    } else {
+      const bool active = i >= 1 && i < steps;
+      if (active) load(in, mine + ((i - 1) & 1) * (kSlots * kStride));
+      Ops::add(acc, in, active, role);
+    }
+    __syncthreads();
+  }
+  if (live) store((summing ? out_c : out_a) + (size_t)g * 2 * kXyzzWords, acc);
+}
+
 // Tail of the bucket reduction.  After level 0 every window has nb = 2^M blocks t with
 // (A_t, P_t) and  S_w = sum_t A_t + sum_t P_t + L * sum_t t A_t.  Writing t in binary,
 // sum_t t A_t = sum_j 2^j D_j with D_j = sum of A_t over the t whose bit j is set, so only

@@ -345,6 +345,63 @@ struct PairOps {
     L::select(p.zzz, take, nzzz, p.zzz);
   }
 
+  // acc += b for the lane pairs with `active` set (add-2008-s, case analysis of
+  // point_xyzz_impl.h:14-97); all lanes compute, warp-uniform branches only.
+  static TB_DEV void add(PairPoint<F>& acc, const PairPoint<F>& b, bool active, uint32_t role) {
+    const bool az = L::is_zero(acc.zz), bz = L::is_zero(b.zz);
+    const bool copy = active && az && !bz;
+    const bool plain = active && !az && !bz;
+    if (__any_sync(L::kFull, copy)) {
+      L::select(acc.x, copy, b.x, acc.x);
+      L::select(acc.y, copy, b.y, acc.y);
+      L::select(acc.zz, copy, b.zz, acc.zz);
+      L::select(acc.zzz, copy, b.zzz, acc.zzz);
+    }
+    if (__any_sync(L::kFull, plain)) {
+      E u1, s1, p, r, pp, ppp, qq, t, u, nx, nzz, nzzz;
+      {
+        typename L::Multiplier m;
+        L::prepare(m, b.zz, role);
+        L::mul(u1, acc.x, m);            // U1 = X1 ZZ2
+        L::mul(nzz, acc.zz, m);          // ZZ1 ZZ2
+        L::prepare(m, b.zzz, role);
+        L::mul(s1, acc.y, m);            // S1 = Y1 ZZZ2
+        L::mul(nzzz, acc.zzz, m);        // ZZZ1 ZZZ2
+      }
+      L::mul(p, b.x, acc.zz, role);      // P = X2 ZZ1 - U1
+      fp_sub<F>(p, p, u1);
+      L::mul(r, b.y, acc.zzz, role);     // R = Y2 ZZZ1 - S1
+      fp_sub<F>(r, r, s1);
+      const bool pr_zero = L::both(fp_is_zero<F>(p) && fp_is_zero<F>(r));  // every lane takes part
+      const bool same = plain && pr_zero;
+      const bool take = plain && !same;
+      L::sqr(pp, p, role);               // PP = P^2
+      {
+        typename L::Multiplier m;
+        L::prepare(m, pp, role);
+        L::mul(ppp, p, m);               // PPP = P PP
+        L::mul(qq, u1, m);               // Q = U1 PP
+        L::mul(nzz, nzz, m);             // ZZ3 = ZZ1 ZZ2 PP
+        L::prepare(m, ppp, role);
+        L::mul(nzzz, nzzz, m);           // ZZZ3 = ZZZ1 ZZZ2 PPP
+        L::mul(u, s1, m);                // S1 PPP
+      }
+      L::select(acc.zz, take, nzz, acc.zz);
+      L::select(acc.zzz, take, nzzz, acc.zzz);
+      L::sqr(nx, r, role);               // X3 = R^2 - PPP - 2 Q
+      fp_sub<F>(nx, nx, ppp);
+      fp_dbl<F>(t, qq);
+      fp_sub<F>(nx, nx, t);
+      fp_sub<F>(t, qq, nx);              // Y3 = R (Q - X3) - S1 PPP
+      L::mul(t, t, r, role);
+      fp_sub<F>(t, t, u);
+      L::select(acc.x, take, nx, acc.x);
+      L::select(acc.y, take, t, acc.y);
+      // equal operands: double instead (those pairs' acc is still untouched)
+      if (__any_sync(L::kFull, same)) dbl_where(acc, same, role);
+    }
+  }
+
   // acc += (neg ? -q : q) for the lane pairs with `active` set; q affine.  madd-2008-s with
   // the case analysis of point_xyzz_impl.h:114-176.
   static TB_DEV void madd(PairPoint<F>& acc, const PairAffine<F>& q, bool neg, bool active,

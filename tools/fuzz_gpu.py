@@ -35,7 +35,9 @@ for case in range(cases):
     opts = {
         "window_bits": rng.choice([0, 0, 0] + list(range(4, 19))),
         "balance": rng.choice([1, 1, 0]),
-        "reduce_mode": rng.choice([1, 1, 0]),
+        "reduce_mode": rng.choice([1, 1, 0, 2]),
+        "reduce_roll": rng.choice([-1, -1, 0, 1, 2]),
+        "acc_lockstep": rng.choice([-1, 0, 1]),
         "sort_mode": rng.choice([-1, -1, 0, 1]),
         "ranges": rng.choice([0, 0, 1, 2, 3, 7]),
         "sample_scalars": rng.choice([1, 1, 0]),
@@ -43,7 +45,7 @@ for case in range(cases):
         "low_windows": rng.choice([-1, 0, 1, 2, 3, 9]),
         "level_fill": rng.choice([0, 0, 48, 96, 3000]),      # running-sum block lengths 4 .. 64
         "stage_points": rng.choice([0, 0, 1]),
-        "acc_variant": rng.choice([-1, 0, 1, 2]),
+        "acc_variant": rng.choice([-1, -1, 0, 1, 2, 3]),
         "segment": rng.choice([0, 0, 0, 16, 32]),
     }
     for k, v in opts.items():

@@ -25,6 +25,9 @@ KEYS = [
     "smsp__average_warps_issue_stalled_dispatch_stall_per_issue_active.ratio",
     "smsp__average_warps_issue_stalled_not_selected_per_issue_active.ratio",
     "smsp__average_warps_issue_stalled_lg_throttle_per_issue_active.ratio",
+    "smsp__average_warps_issue_stalled_no_instruction_per_issue_active.ratio",
+    "smsp__average_warps_issue_stalled_barrier_per_issue_active.ratio",
+    "sm__icc_request_hit_rate.pct",
 ]
 
 
