@@ -70,7 +70,8 @@ class ClockSampler:
 
     def __init__(self, uuid, gpu_index):
         self.uuid, self.gpu = uuid, gpu_index
-        self.sm, self.power, self.bits = [], [], 0
+        self.sm, self.mem, self.power, self.bits = [], [], [], 0
+        self.ecc = None
         self.max_sm = None
         self.stop_flag = threading.Event()
         self.thread = None
@@ -85,6 +86,10 @@ class ClockSampler:
             except Exception:
                 h = pynvml.nvmlDeviceGetHandleByIndex(self.gpu)
             self.max_sm = float(pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM))
+            try:  # what kind of box this is: the memory-bound stages vary from box to box
+                self.ecc = bool(pynvml.nvmlDeviceGetEccMode(h)[0])
+            except Exception:
+                self.ecc = None
             self.nvml, self.handle = pynvml, h
             self.thread = threading.Thread(target=self._poll, daemon=True)
             self.thread.start()
@@ -96,6 +101,7 @@ class ClockSampler:
         while not self.stop_flag.is_set():
             try:
                 self.sm.append(float(n.nvmlDeviceGetClockInfo(h, n.NVML_CLOCK_SM)))
+                self.mem.append(float(n.nvmlDeviceGetClockInfo(h, n.NVML_CLOCK_MEM)))
                 self.power.append(n.nvmlDeviceGetPowerUsage(h) / 1000.0)
                 self.bits |= int(n.nvmlDeviceGetCurrentClocksThrottleReasons(h))
             except Exception:
@@ -109,6 +115,7 @@ class ClockSampler:
         self.thread.join(timeout=1)
         return {"sm_mhz": statistics.median(self.sm) if self.sm else None, "sm_max_mhz": self.max_sm,
                 "power_w_max": max(self.power) if self.power else None, "samples": len(self.sm),
+                "mem_mhz": statistics.median(self.mem) if self.mem else None, "ecc": self.ecc,
                 "reasons": [name for name, bit in self.REASONS if self.bits & bit], "source": "nvml, 5 ms poll"}
 
     def _smi_once(self):

@@ -584,6 +584,8 @@ using namespace tb200;
         for (auto& e : ptr->engines) e->options().balance = (int)value;                        \
       } else if (k == "precompute") {                                                          \
         for (auto& e : ptr->engines) e->options().precompute = (int)value;                     \
+      } else if (k == "reduce_inline") {                                                       \
+        for (auto& e : ptr->engines) e->options().reduce_inline = (int)value;                  \
       } else if (k == "reduce_roll") {                                                         \
         for (auto& e : ptr->engines) e->options().reduce_roll = (int)value;                    \
       } else if (k == "acc_lockstep") {                                                        \

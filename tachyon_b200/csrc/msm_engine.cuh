@@ -113,6 +113,8 @@ struct MsmOptions {
                              // G1 groups: 0 = free-running warps, 3 = the warps of a CTA in step
                              // (accumulate_lockstep_kernel), -1 = the curve's default
   int acc_lockstep = -1;     // G2 pair kernel: 1 = warps of a CTA in step, 0 = free, -1 = curve default
+  int reduce_inline = -1;    // G1 running-sum kernel: 1 = both roles share one inlined call site of the
+                             // addition, 0 = out-of-line addition, -1 = the curve's default
   int reduce_roll = -1;      // code shape of the field multiplications in the running-sum kernel:
                              // 0 = unrolled, 1 = looped multiplications (fp_mul_rolled: a third of
                              // the code), 2 = looped, squarings through the multiplier too,
@@ -1554,6 +1556,11 @@ class MsmEngine {
       auto kernel = roll == 2   ? reduce_blocks_kernel<C, typename K0::template WithRoll<2>>
                     : roll == 1 ? reduce_blocks_kernel<C, typename K0::template WithRoll<1>>
                                 : reduce_blocks_kernel<C, K0>;
+      if constexpr (C::Field::kDegree == 1) {  // one inlined call site of the addition
+        const bool inl = options_.reduce_inline < 0 ? C::kReduceInline : options_.reduce_inline != 0;
+        if (inl && roll == 0) kernel = reduce_blocks_kernel<C, K0, true>;
+        if (inl && roll == 1) kernel = reduce_blocks_kernel<C, typename K0::template WithRoll<1>, true>;
+      }
       LaunchOn(level_stream, kernel, (blocks + kSlots - 1) / kSlots, 2 * kSlots, bucket0,
                plan.B, nb, L0, wn, wide_local, leaves, leaves + kXyzzWords);
     }

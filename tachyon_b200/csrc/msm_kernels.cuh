@@ -35,6 +35,9 @@ struct Bn254Curve {
   using Fr = Bn254FrParams;
   using Gen = Bn254G1Generator;
   static constexpr const char* kName = "bn254";
+  // running-sum kernel: both roles share ONE inlined call site of the addition (2^24: reduce
+  // 3.45 -> 2.75 ms; every product a fused IMAD.WIDE, no operands through the stack)
+  static constexpr bool kReduceInline = true;
   static constexpr int kReduceRoll = 0;  // running-sum kernel: unrolled multiplications (looped: 3.38 -> 3.67 ms at 2^24)
   // accumulation warps free-running: the 68 KB loop body streams through the instruction cache
   // at a 98 % hit rate (one barrier per step: 29.96 -> 30.43 ms at 2^24)
@@ -49,6 +52,7 @@ struct Bls381Curve {
   using Fr = Bls381FrParams;
   using Gen = Bls381G1Generator;
   static constexpr const char* kName = "bls12_381";
+  static constexpr bool kReduceInline = false;  // running-sum kernel: addition out of line (inlined: 2.13 -> 2.21 ms at 2^22)
   static constexpr int kReduceRoll = 1;  // running-sum kernel: looped multiplications (2^22: 2.24 -> 2.12 ms)
   // accumulation warps of a CTA in step (accumulate_lockstep_kernel): 2^22 points 21.64 ->
   // 19.71 ms, FMA-heavy pipe 82 -> 90 %, instruction-cache hit rate 79 -> 90 %
@@ -1185,8 +1189,10 @@ constexpr int ReduceSlots() {
   return 4 * C::Field::kWords > 64 ? 32 : 64;
 }
 
-template <class C, class K = typename C::Field>
-__global__ void __launch_bounds__(2 * ReduceSlots<C>()) reduce_blocks_kernel(
+// kInline: both roles share ONE call site of the addition, inlined there (no out-of-line call, no
+// operands through the stack).
+template <class C, class K = typename C::Field, bool kInline = false>
+__global__ void __launch_bounds__(2 * ReduceSlots<C>(), (kInline && K::kWords == 8) ? 4 : 0) reduce_blocks_kernel(
     const uint32_t* __restrict__ state, uint32_t n_in, uint32_t n_out, uint32_t L,
     uint32_t windows, uint32_t wide, uint32_t* __restrict__ out_a, uint32_t* __restrict__ out_c) {
   constexpr int kXyzzWords = 4 * K::kWords;
@@ -1221,7 +1227,16 @@ __global__ void __launch_bounds__(2 * ReduceSlots<C>()) reduce_blocks_kernel(
   // step i: role A adds bucket hi - 1 - i and publishes run in buffer i & 1; role B adds what
   // was published in step i - 1 (all but the run that includes the block's lowest bucket)
   for (uint32_t i = 0; i < L; ++i) {
-    if (!summing) {
+    if (kInline) {
+      const bool have = summing ? (i >= 1 && i < steps) : (i < steps);
+      if (have) {
+        const uint32_t* src = summing ? mine + ((i - 1) & 1) * (kSlots * kStride)
+                                      : state + (size_t)(w * n_in + (hi - 1 - i)) * kXyzzWords;
+        xyzz_load<K>(in, src);
+        xyzz_add_inlined<K>(acc, in);
+        if (!summing && i + 1 < steps) xyzz_store<K>(mine + (i & 1) * (kSlots * kStride), acc);
+      }
+    } else if (!summing) {
       if (i < steps) {
         uint32_t idx = w * n_in + (hi - 1 - i);
         xyzz_load<K>(in, state + (size_t)idx * kXyzzWords);
@@ -1347,8 +1362,10 @@ TB_DEV uint32_t window_bit_offset(uint32_t w, uint32_t c, uint32_t wide) {
   return w * c - (w > wide ? w - wide : 0u);
 }
 
+// (8-limb curve: held to 2 CTAs per SM — left alone, ptxas has chosen anything from 113 to 170
+// registers for this kernel from build to build)
 template <class C>
-__global__ void __launch_bounds__(kTreeThreads) reduce_tree_kernel(
+__global__ void __launch_bounds__(kTreeThreads, C::Field::kWords == 8 ? 2 : 0) reduce_tree_kernel(
     const uint32_t* in, uint32_t vin, uint32_t levels, uint32_t ctas_per_window,
     size_t slice_words, uint32_t* ping, uint32_t* pong, uint32_t* out, TreeFinal fin,
     uint32_t thread_items) {

@@ -138,7 +138,7 @@ TB_DEV void xyzz_madd(XYZZ<K>& acc, const Affine<K>& q, bool neg) {
 // Returns true when the operands are equal (caller must double instead; acc is
 // left untouched in that case).
 template <class K>
-__device__ __noinline__ bool xyzz_add_nz(XYZZ<K>& acc, const XYZZ<K>& b) {
+TB_DEV bool xyzz_add_nz_body(XYZZ<K>& acc, const XYZZ<K>& b) {
   typename K::El u1, s1, p, r, pp, ppp, qq, t;
   K::mul(u1, acc.x, b.zz);   // U1 = X1 ZZ2
   K::mul(s1, acc.y, b.zzz);  // S1 = Y1 ZZZ2
@@ -168,6 +168,10 @@ __device__ __noinline__ bool xyzz_add_nz(XYZZ<K>& acc, const XYZZ<K>& b) {
   K::select(acc.zzz, same, acc.zzz, o.zzz);
   return same;
 }
+template <class K>
+__device__ __noinline__ bool xyzz_add_nz(XYZZ<K>& acc, const XYZZ<K>& b) {
+  return xyzz_add_nz_body<K>(acc, b);
+}
 
 template <class K>
 TB_DEV void xyzz_copy(XYZZ<K>& dst, const XYZZ<K>& src) {
@@ -181,6 +185,16 @@ TB_DEV void xyzz_add(XYZZ<K>& acc, const XYZZ<K>& b) {
   if (az && !bz) xyzz_copy<K>(acc, b);
   if (!az && !bz) {
     if (xyzz_add_nz<K>(acc, b)) xyzz_dbl_nz<K>(acc);
+  }
+}
+
+// xyzz_add with the addition itself inlined at the call site (for kernels that have exactly one)
+template <class K>
+TB_DEV void xyzz_add_inlined(XYZZ<K>& acc, const XYZZ<K>& b) {
+  bool bz = xyzz_is_zero<K>(b), az = xyzz_is_zero<K>(acc);
+  if (az && !bz) xyzz_copy<K>(acc, b);
+  if (!az && !bz) {
+    if (xyzz_add_nz_body<K>(acc, b)) xyzz_dbl_nz<K>(acc);
   }
 }
 

@@ -417,6 +417,12 @@ def test_msm_reduce_modes(oracles, torch_cuda, name):
                 assert (got == want).all(), (mode, balance, cbits)
         ctx.set_option("reduce_mode", 1)
         ctx.set_option("balance", 1)
+        for inline in (1, 0, -1):              # G1: one inlined call site of the addition
+            ctx.set_option("reduce_inline", inline)
+            for cbits in (0, 9, 14):
+                ctx.set_option("window_bits", cbits)
+                got = o.jacobian_to_affine(ctx.affine_msm(bases, scalars))
+                assert (got == want).all(), (inline, cbits)
         ctx.set_option("window_bits", 0)
         for host_ranges in (1, 3, 16):
             ctx.set_option("host_ranges", host_ranges)
