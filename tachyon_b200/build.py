@@ -15,7 +15,10 @@ LIB_DIR = os.path.join(HERE, "lib")
 LIB = os.path.join(LIB_DIR, "libtachyon_msm_b200.so")
 # one translation unit per (curve, group) + the common part: compiled in parallel
 SOURCES = ["msm_api.cu", "msm_api_bn254_g1.cu", "msm_api_bls12_381_g1.cu", "msm_api_bn254_g2.cu",
-           "msm_api_bls12_381_g2.cu", "groth16_api.cu"]
+           "msm_api_bls12_381_g2.cu", "groth16_api.cu", "msm_sort_kernels.cu"]
+# compiled as ONE piece (no --split-compile): the split changed the generated code of identical
+# kernels from one translation unit to the next (msm_sort.cuh)
+WHOLE = {"msm_sort_kernels.cu"}
 OBJ_DIR = os.path.join(HERE, "build")
 REPLAY = os.path.join(LIB_DIR, "msm_gpu_replay")
 REPLAY_SRC = os.path.join(CSRC, "tools", "msm_gpu_replay.cc")
@@ -65,7 +68,11 @@ def build(force=False, verbose=False):
     procs = []
     for src in SOURCES:
         obj = os.path.join(OBJ_DIR, src.replace(".cu", ".o"))
-        cmd = [nvcc()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + \
+        flags = list(NVCC_FLAGS)
+        if src in WHOLE:
+            k = flags.index("--split-compile")
+            del flags[k:k + 2]
+        cmd = [nvcc()] + flags + (["-Xptxas", "-v"] if verbose else []) + \
               ["-c", "-o", obj, os.path.join(CSRC, src)]
         procs.append((src, obj, subprocess.Popen(cmd, cwd=CSRC, env=env, stdout=subprocess.PIPE,
                                                  stderr=subprocess.STDOUT, text=True)))

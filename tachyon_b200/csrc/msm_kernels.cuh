@@ -239,7 +239,7 @@ TB_DEV uint32_t bucket_inc(uint32_t* counter_base, uint32_t key, bool valid, boo
 // (digits[w * n + i] = |d| | sign << 31, 0 for a zero digit; coalesced per window) and count
 // bucket sizes.
 template <class C>
-__global__ void __launch_bounds__(256) digits_hist_kernel(const uint32_t* __restrict__ scalars,
+__global__ void __launch_bounds__(256, 6) digits_hist_kernel(const uint32_t* __restrict__ scalars,
                                                           MsmPlan plan,
                                                           uint32_t* __restrict__ digits,
                                                           uint32_t* __restrict__ count,
@@ -279,7 +279,7 @@ __global__ void __launch_bounds__(256) digits_hist_kernel(const uint32_t* __rest
 // The scalar-major form wrote 4-byte words at random over the whole n*W array: 14.7 GB of
 // DRAM traffic and L2-missing atomics at n = 2^24 (profiles/r1_b_*).
 // cursor[key] starts at offset[key]; the value returned by the atomic is the slot.
-static __global__ void __launch_bounds__(256) digits_scatter_kernel(const uint32_t* __restrict__ digits,
+static __global__ void __launch_bounds__(256, 8) digits_scatter_kernel(const uint32_t* __restrict__ digits,
                                                              MsmPlan plan,
                                                              uint32_t* __restrict__ cursor,
                                                              uint32_t* __restrict__ sorted) {
@@ -487,7 +487,7 @@ TB_DEV uint32_t order_bin(uint32_t len, uint32_t meta, uint32_t split_key) {
   return low * (kMaxSegment + 1) + (kMaxSegment - len);
 }
 
-static __global__ void __launch_bounds__(kOrderThreads) order_hist_kernel(
+static __global__ void __launch_bounds__(kOrderThreads, 8) order_hist_kernel(
     const uint2* __restrict__ tasks, const uint32_t* __restrict__ task_meta,
     const MsmTotals* __restrict__ totals, uint32_t split_key, uint32_t* __restrict__ len_hist) {
   __shared__ uint32_t sh[kOrderBins];
@@ -550,7 +550,7 @@ static __global__ void __launch_bounds__(1024) order_scan_kernel(
   if (threadIdx.x == 0) totals->entries_lo = split_key ? offset[split_key] : 0u;
 }
 
-static __global__ void __launch_bounds__(kOrderThreads) order_scatter_kernel(
+static __global__ void __launch_bounds__(kOrderThreads, 8) order_scatter_kernel(
     const uint2* __restrict__ tasks, const uint32_t* __restrict__ task_meta,
     const MsmTotals* __restrict__ totals, uint32_t split_key, uint32_t* __restrict__ len_cursor,
     uint32_t* __restrict__ order) {
@@ -1192,7 +1192,7 @@ constexpr int ReduceSlots() {
 // kInline: both roles share ONE call site of the addition, inlined there (no out-of-line call, no
 // operands through the stack).
 template <class C, class K = typename C::Field, bool kInline = false>
-__global__ void __launch_bounds__(2 * ReduceSlots<C>(), (kInline && K::kWords == 8) ? 4 : 0) reduce_blocks_kernel(
+__global__ void __launch_bounds__(2 * ReduceSlots<C>(), K::kWords <= 12 ? 4 : 0) reduce_blocks_kernel(
     const uint32_t* __restrict__ state, uint32_t n_in, uint32_t n_out, uint32_t L,
     uint32_t windows, uint32_t wide, uint32_t* __restrict__ out_a, uint32_t* __restrict__ out_c) {
   constexpr int kXyzzWords = 4 * K::kWords;

@@ -106,7 +106,7 @@ TB_DEV void block_exclusive_scan_bins(uint32_t* bins, uint32_t nbins, uint32_t* 
 
 // dynamic shared memory: W * Cw counters
 template <class C>
-__global__ void __launch_bounds__(kSortThreads) digits_coarse_hist_kernel(
+__global__ void __launch_bounds__(kSortThreads, 6) digits_coarse_hist_kernel(
     const uint32_t* __restrict__ scalars, MsmPlan plan, SortPlan sp,
     uint32_t* __restrict__ digits, uint32_t* __restrict__ coarse_count) {
   using Fr = typename C::Fr;
@@ -135,11 +135,17 @@ __global__ void __launch_bounds__(kSortThreads) digits_coarse_hist_kernel(
 
 // One CTA.  coarse_offset[r], coarse_cursor[r] = entries before region r; tile_offset[r] = tiles
 // before region r; totals->tiles.
-static __global__ void __launch_bounds__(1024) coarse_scan_kernel(
+__global__ void __launch_bounds__(1024) coarse_scan_kernel(
     const uint32_t* __restrict__ coarse_count, uint32_t regions,
     uint32_t* __restrict__ coarse_offset, uint32_t* __restrict__ coarse_cursor,
     uint32_t* __restrict__ tile_offset, SortTotals* __restrict__ totals,
-    uint32_t* __restrict__ nonzero_slots) {
+    uint32_t* __restrict__ nonzero_slots);
+#ifdef TB200_DEFINE_SORT_KERNELS
+__global__ void __launch_bounds__(1024) coarse_scan_kernel(
+    const uint32_t* __restrict__ coarse_count, uint32_t regions,
+    uint32_t* __restrict__ coarse_offset, uint32_t* __restrict__ coarse_cursor,
+    uint32_t* __restrict__ tile_offset, SortTotals* __restrict__ totals,
+    uint32_t* __restrict__ nonzero_slots){
   __shared__ uint32_t warp_e[32], warp_t[32];
   const uint32_t per = (regions + 1023) / 1024;
   const uint32_t lo = threadIdx.x * per, hi = min(regions, lo + per);
@@ -195,13 +201,30 @@ static __global__ void __launch_bounds__(1024) coarse_scan_kernel(
     nonzero_slots[0] = warp_e[31];  // the other slots were zeroed by the host
   }
 }
+#endif
 
+// The four non-template kernels are DEFINED in one translation unit of their own
+// (msm_sort_kernels.cu, which sets TB200_DEFINE_SORT_KERNELS and is compiled without nvcc's
+// --split-compile) and only declared everywhere else: as `static` kernels of this header every
+// curve's translation unit carried its own copy, and the copies came out of the split compile
+// with different code from the same source — 64 registers in one unit, 128 (or, once capped,
+// 64 with the per-thread arrays demoted to local memory) in another.
+//
+// Every kernel of this file states its resident CTAs per SM in __launch_bounds__: left to its
+// own heuristics ptxas gave the SAME source 64 registers in one translation unit and 128 in
+// another (and differently from build to build), which halved the occupancy of the two scatter
+// kernels and cost 0.8 ms of a 2^24-point sort (3.43 -> 4.24 ms) in "unlucky" builds.
+//
 // grid (tiles of kSortTile points, W).  The tile is counting-sorted by coarse bin in shared
 // memory first, so that the entries of one bin leave as one contiguous run: a warp then
 // stores a handful of 64-byte segments instead of 32 scattered 8-byte words.
-static __global__ void __launch_bounds__(kSortThreads) coarse_scatter_kernel(
+__global__ void __launch_bounds__(kSortThreads, 4) coarse_scatter_kernel(
     const uint32_t* __restrict__ digits, MsmPlan plan, SortPlan sp,
-    uint32_t* __restrict__ coarse_cursor, uint2* __restrict__ mid) {
+    uint32_t* __restrict__ coarse_cursor, uint2* __restrict__ mid);
+#ifdef TB200_DEFINE_SORT_KERNELS
+__global__ void __launch_bounds__(kSortThreads, 4) coarse_scatter_kernel(
+    const uint32_t* __restrict__ digits, MsmPlan plan, SortPlan sp,
+    uint32_t* __restrict__ coarse_cursor, uint2* __restrict__ mid){
   __shared__ uint32_t hist[kMaxCoarsePerWindow];   // counts, then local offsets
   __shared__ uint32_t delta[kMaxCoarsePerWindow];  // global run start - local offset
   __shared__ uint2 staged[kSortTile];
@@ -251,6 +274,7 @@ static __global__ void __launch_bounds__(kSortThreads) coarse_scatter_kernel(
     mid[delta[e.y >> kFineBits] + j] = e;
   }
 }
+#endif
 
 // Region and entry span of tile t.
 TB_DEV bool tile_span(uint32_t t, const uint32_t* __restrict__ tile_offset,
@@ -267,10 +291,15 @@ TB_DEV bool tile_span(uint32_t t, const uint32_t* __restrict__ tile_offset,
   return start < end;
 }
 
-static __global__ void __launch_bounds__(kSortThreads) fine_hist_kernel(
+__global__ void __launch_bounds__(kSortThreads, 8) fine_hist_kernel(
     const uint2* __restrict__ mid, SortPlan sp, const uint32_t* __restrict__ tile_offset,
     const uint32_t* __restrict__ coarse_offset, const SortTotals* __restrict__ totals,
-    uint32_t* __restrict__ count) {
+    uint32_t* __restrict__ count);
+#ifdef TB200_DEFINE_SORT_KERNELS
+__global__ void __launch_bounds__(kSortThreads, 8) fine_hist_kernel(
+    const uint2* __restrict__ mid, SortPlan sp, const uint32_t* __restrict__ tile_offset,
+    const uint32_t* __restrict__ coarse_offset, const SortTotals* __restrict__ totals,
+    uint32_t* __restrict__ count){
   __shared__ uint32_t hist[kFineBins];
   if (blockIdx.x >= totals->tiles) return;
   uint32_t region, start, end;
@@ -289,11 +318,17 @@ static __global__ void __launch_bounds__(kSortThreads) fine_hist_kernel(
   for (uint32_t k = threadIdx.x; k < kFineBins; k += kSortThreads)
     if (hist[k]) atomicAdd(dst + k, hist[k]);
 }
+#endif
 
-static __global__ void __launch_bounds__(kSortThreads) fine_scatter_kernel(
+__global__ void __launch_bounds__(kSortThreads, 4) fine_scatter_kernel(
     const uint2* __restrict__ mid, SortPlan sp, const uint32_t* __restrict__ tile_offset,
     const uint32_t* __restrict__ coarse_offset, const SortTotals* __restrict__ totals,
-    uint32_t* __restrict__ cursor, uint32_t* __restrict__ sorted) {
+    uint32_t* __restrict__ cursor, uint32_t* __restrict__ sorted);
+#ifdef TB200_DEFINE_SORT_KERNELS
+__global__ void __launch_bounds__(kSortThreads, 4) fine_scatter_kernel(
+    const uint2* __restrict__ mid, SortPlan sp, const uint32_t* __restrict__ tile_offset,
+    const uint32_t* __restrict__ coarse_offset, const SortTotals* __restrict__ totals,
+    uint32_t* __restrict__ cursor, uint32_t* __restrict__ sorted){
   __shared__ uint32_t hist[kFineBins];   // counts, then local offsets
   __shared__ uint32_t delta[kFineBins];  // global run start - local offset
   __shared__ uint32_t staged[kSortTile];
@@ -335,5 +370,6 @@ static __global__ void __launch_bounds__(kSortThreads) fine_scatter_kernel(
   for (uint32_t j = threadIdx.x; j < count; j += kSortThreads)
     sorted[delta[staged_bin[j]] + j] = staged[j];
 }
+#endif
 
 }  // namespace tb200
