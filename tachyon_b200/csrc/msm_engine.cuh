@@ -1693,13 +1693,17 @@ class MsmEngine {
 
   // Blocks of the running-sum level: as long as possible while the grid still fills the chip
   // (a block costs 2 L full additions, the merge tree ~3 per block).  Measured sweep of the
-  // blocks wanted per SM (option "level_fill"): 384 is best up to ~1.5 M bucket slots; longer
-  // blocks (192, 96) lose although they drop merge-tree levels (2^21 points: 0.75 -> 0.82 ms);
-  // above, the equal-length CTAs run in few rounds and shorter blocks even out the last one
-  // (768: 2^24 points 3.34 -> 3.25 ms, BLS12-381 2^22 2.04 -> 1.86 ms).
+  // blocks wanted per SM (option "level_fill"); with the round-1 kernels 384 was best up to ~1.5 M
+  // bucket slots and 768 above (2^24 points 3.34 -> 3.25 ms).
   uint32_t ChooseLevelLength(uint32_t buckets_per_window, uint32_t windows) const {
     uint64_t items = (uint64_t)buckets_per_window * windows;
-    uint32_t fill = options_.level_fill ? options_.level_fill : (items >= 1500000 ? 768 : 384);
+    // Re-measured with the final running-sum kernels (profiles/r2_zz_level_fill_sweep.txt): 384 blocks
+    // per SM everywhere (the 768 of the earlier kernels now loses: BN254 2^23 1.36 -> 1.26 ms,
+    // BLS12-381 2^22 2.16 -> 1.87 ms), 96 for the 8-limb curve below ~400 K bucket slots (c <= 15:
+    // 0.31 -> 0.27 ms), 48 for G2, whose lane-pair kernel holds 96 / 64 blocks per SM at a time
+    // (BN254 G2 2^20 0.96 -> 0.85 ms, 2^16 1.06 -> 0.90 ms).
+    uint32_t fill = options_.level_fill ? options_.level_fill
+                    : (C::Field::kDegree == 2 ? 48u : (C::Field::kWords == 8 && items < 400000 ? 96u : 384u));
     uint64_t want_blocks = (uint64_t)sm_count_ * fill;
     uint32_t L = 64;
     while (L > 4 && items / L < want_blocks) L >>= 1;
