@@ -30,9 +30,12 @@ NVCC_FLAGS = [
     "-O3", "-std=c++17",
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-lineinfo",
-    # kernels of one translation unit are optimised by parallel ptxas jobs (the 24-limb G2
-    # instantiations dominate the build otherwise)
-    "--split-compile", "0",
+    # kernels of one translation unit are optimised by parallel jobs (the 24-limb G2
+    # instantiations dominate the build otherwise: 10 minutes in one piece).  A FIXED job count:
+    # the split changes the generated code, and with "0" (= one job per CPU) the same source gave
+    # different SASS from machine to machine and from run to run; with a fixed count the build is
+    # reproducible (checked: identical SASS over repeated builds).
+    "--split-compile", "8",
     "-Xcompiler", "-fPIC,-fvisibility=hidden,-march=x86-64-v3,-mtune=generic",
 ]
 LINK_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-cudart", "static", "-shared",
