@@ -112,6 +112,8 @@ extern "C" {
      "acc_lockstep" (G2 lane-pair kernel: 1 = warps of a CTA in step, the default; 0 = free), \
      "reduce_roll" (field multiplications of the running-sum kernel: 0 = unrolled, 1 = as a   \
      loop over row pairs, 2 = squarings through that loop too, -1 = per-curve default),       \
+     "reduce_inline" (G1 running-sum kernel: 1 = both roles share one inlined call site of    \
+     the point addition, the default for BN254; 0 = out-of-line addition; -1 = per curve),    \
      "stage_points" (1 = the accumulation stages the next point through shared memory with    \
      cp.async instead of registers),                                                          \
      "device_ladder" (where the final ladder over the W window sums runs — ~255 strictly     \

@@ -37,6 +37,7 @@ for case in range(cases):
         "balance": rng.choice([1, 1, 0]),
         "reduce_mode": rng.choice([1, 1, 0, 2]),
         "reduce_roll": rng.choice([-1, -1, 0, 1, 2]),
+        "reduce_inline": rng.choice([-1, -1, 0, 1]),
         "acc_lockstep": rng.choice([-1, 0, 1]),
         "sort_mode": rng.choice([-1, -1, 0, 1]),
         "ranges": rng.choice([0, 0, 1, 2, 3, 7]),
