@@ -31,10 +31,12 @@ NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-lineinfo",
     # kernels of one translation unit are optimised by parallel jobs (the 24-limb G2
-    # instantiations dominate the build otherwise: 10 minutes in one piece).  A FIXED job count:
-    # the split changes the generated code, and with "0" (= one job per CPU) the same source gave
-    # different SASS from machine to machine and from run to run; with a fixed count the build is
-    # reproducible (checked: identical SASS over repeated builds).
+    # instantiations dominate the build otherwise: 10 minutes in one piece).  The split changes
+    # the generated code: a FIXED job count instead of "0" (= one job per CPU) takes the machine
+    # out of it (one unit compiled alone gives identical SASS every time), but with all units
+    # compiling at once a few kernels still come out with slightly different stack frames from
+    # build to build.  What the measured numbers rely on is pinned in the source (launch bounds,
+    # msm_sort_kernels.cu compiled in one piece) and checked by tests/test_build_resources.py.
     "--split-compile", "8",
     "-Xcompiler", "-fPIC,-fvisibility=hidden,-march=x86-64-v3,-mtune=generic",
 ]
